@@ -1,0 +1,95 @@
+/* libsinkfa -- C ABI of the B200 (sm_100a) sink-flash-attention kernels.
+ *
+ * This is the drop-in boundary for the hot path of RulinShao/sink-flash-attention-kernel.
+ * Each entry point replaces a Triton launch site of the reference (paths relative to the
+ * reference's sink_attention/ package):
+ *
+ *   sfa_fwd      <- SinkFlashAttentionFunc.forward   sink_flash_attention.py:491-566
+ *                   (_sink_flash_attn_fwd_kernel, :93-194)
+ *   sfa_bwd      <- SinkFlashAttentionFunc.backward  sink_flash_attention.py:568-667
+ *                   (delta :582, _bwd_dkdv_kernel :256-364, _bwd_dq_kernel :371-484,
+ *                    GQA group sum :648-651, ds_aux :653-665)
+ *   sfa_decode   <- sink_decode_attention            decode_kernel.py:120-226
+ *                   (_decode_split_kv_kernel :28-113 + the torch phase-2 reduce :201-226)
+ *   sfa_decode_ring <- SinkCacheLayer.get_kv() + sink_decode_attention, fused: reads the
+ *                   sink buffer and the ring window buffer in place  (cache.py:185-216)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers; the library never
+ *     allocates or frees device memory and never synchronises the stream.
+ *   - strides are in ELEMENTS, ordered (batch, head, position, channel); the channel stride
+ *     must be 1.  Both the reference's [B,H,N,D] layout and HF's [B,N,H,D] layout (passed
+ *     as a transposed view) are accepted without copies.
+ *   - softmax scale is 1/sqrt(D) (sink_flash_attention.py:505); s_aux is one fp32 logit
+ *     per Q head or NULL; lse is fp32 [B,Hq,N] contiguous, natural log, sink term included.
+ *   - mask: valid(i,j) = j<=i && (j<num_sink || j>=i-window+1)   (sink_flash_attention.py:30-39)
+ *   - return value: 0 ok; <0 argument error; >0 a cudaError_t.  sfa_last_error() returns a
+ *     thread-local description of the last non-zero return.
+ *   - `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef SINKFA_H_
+#define SINKFA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFA_DTYPE_BF16 0
+#define SFA_DTYPE_FP16 1
+#define SFA_DTYPE_FP32 2
+
+#define SFA_OP_FWD 0
+#define SFA_OP_BWD 1
+#define SFA_OP_DECODE 2
+
+/* implementation selector for sfa_set_impl (testing / cross-checking only) */
+#define SFA_IMPL_AUTO 0    /* tcgen05 kernels where the shape allows, CUDA-core kernels otherwise */
+#define SFA_IMPL_SIMT 1    /* force the CUDA-core (fp32 math) kernels */
+
+int sfa_version(void);
+const char* sfa_last_error(void);
+int sfa_set_impl(int impl);
+/* name of the kernel family the last call on this thread dispatched to ("tcgen05", "simt", "mma") */
+const char* sfa_last_impl(void);
+
+size_t sfa_workspace_bytes(int op, int B, int Hq, int Hkv, int N, int D, int dtype);
+
+int sfa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux,
+            int B, int Hq, int Hkv, int N, int D, int num_sink, int window, int dtype,
+            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+            const int64_t o_strides[4], void* workspace, size_t workspace_bytes, void* stream);
+
+int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+            const float* s_aux, void* dq, void* dk, void* dv, float* ds_aux,
+            int B, int Hq, int Hkv, int N, int D, int num_sink, int window, int dtype,
+            const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+            const int64_t o_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
+            const int64_t dk_strides[4], const int64_t dv_strides[4],
+            void* workspace, size_t workspace_bytes, void* stream);
+
+/* q,o: [B,Hq,1,D] (strides for batch, head); k,v: [B,Hkv,Nkv,D] (strides for batch, head, position) */
+int sfa_decode(const void* q, const void* k, const void* v, void* o, const float* s_aux,
+               int B, int Hq, int Hkv, int Nkv, int D, int dtype,
+               const int64_t q_strides[2], const int64_t k_strides[3], const int64_t v_strides[3],
+               const int64_t o_strides[2], void* workspace, size_t workspace_bytes, void* stream);
+
+/* Ring-aware decode: attends sink_k/v[:, :, :sink_len] and window_k/v[:, :, :window_len] in place
+ * (softmax is order-invariant, so the ring needs no linearisation).  Buffers are
+ * [B,Hkv,num_sink,D] and [B,Hkv,window_size,D] with the given (batch, head, position) strides. */
+int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const void* win_k, const void* win_v,
+                    void* o, const float* s_aux, int B, int Hq, int Hkv, int sink_len, int window_len, int D,
+                    int dtype, const int64_t q_strides[2], const int64_t sink_strides[3],
+                    const int64_t win_strides[3], const int64_t o_strides[2],
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* tcgen05/TMA self-test: C[M=128,N] = A[128,K] * B^T (+ variants).  Returns 0 and fills c (fp32, device).
+ * mode 0: A,B K-major in smem; mode 1: B given as [K,N] (MN-major); mode 2: A through TMEM (TS form). */
+int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SINKFA_H_ */
