@@ -1,0 +1,239 @@
+// extern "C" surface of libsinkfa (declared in include/sinkfa.h): argument validation,
+// workspace carving and dispatch to the kernel families.  No device allocation, no stream sync.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sfa {
+
+static thread_local char g_err[512] = "";
+static thread_local const char* g_impl = "";
+static int g_force_impl = SFA_IMPL_AUTO;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void set_impl_name(const char* name) { g_impl = name; }
+
+static Strides4 mk(const int64_t* s) { return Strides4{s[0], s[1], s[2]}; }
+
+static int check_common(int B, int Hq, int Hkv, int N, int D, int dtype, const int64_t* const* strides, int nstr) {
+  if (B < 1 || Hq < 1 || Hkv < 1 || N < 1 || D < 1) {
+    set_error("invalid sizes B=%d Hq=%d Hkv=%d N=%d D=%d", B, Hq, Hkv, N, D);
+    return -1;
+  }
+  if (Hq % Hkv != 0) {
+    set_error("H_q (%d) must be divisible by H_kv (%d)", Hq, Hkv);
+    return -2;
+  }
+  if (D > 256) {
+    set_error("head_dim %d > 256 not supported", D);
+    return -3;
+  }
+  if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16 && dtype != SFA_DTYPE_FP32) {
+    set_error("unknown dtype %d", dtype);
+    return -4;
+  }
+  for (int t = 0; t < nstr; ++t)
+    if (strides[t][3] != 1) {
+      set_error("channel stride must be 1 (tensor %d has %lld)", t, (long long)strides[t][3]);
+      return -5;
+    }
+  return 0;
+}
+
+static int cuda_ret(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace sfa
+
+using namespace sfa;
+
+extern "C" {
+
+int sfa_version(void) { return 100; }
+const char* sfa_last_error(void) { return g_err; }
+const char* sfa_last_impl(void) { return g_impl; }
+int sfa_set_impl(int impl) {
+  if (impl != SFA_IMPL_AUTO && impl != SFA_IMPL_SIMT) {
+    set_error("unknown impl %d", impl);
+    return -1;
+  }
+  g_force_impl = impl;
+  return 0;
+}
+
+size_t sfa_workspace_bytes(int op, int B, int Hq, int Hkv, int N, int D, int dtype) {
+  (void)dtype;
+  if (op == SFA_OP_FWD) return 0;
+  if (op == SFA_OP_BWD) {
+    // delta [B,Hq,N] + ds_aux partials [B,Hq,ceil(N/8)]
+    return align_up((size_t)B * Hq * N * 4, 256) + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256);
+  }
+  if (op == SFA_OP_DECODE) {
+    const int splits = mma_decode_splits(B, Hkv, N);
+    return align_up((size_t)B * Hq * splits * 2 * 4, 256) + align_up((size_t)B * Hq * splits * D * 4, 256);
+  }
+  return 0;
+}
+
+int sfa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux, int B, int Hq, int Hkv,
+            int N, int D, int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
+            const int64_t v_strides[4], const int64_t o_strides[4], void* workspace, size_t workspace_bytes,
+            void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  const int64_t* ss[4] = {q_strides, k_strides, v_strides, o_strides};
+  if (int r = check_common(B, Hq, Hkv, N, D, dtype, ss, 4)) return r;
+  if (!q || !k || !v || !o || !lse) {
+    set_error("null tensor pointer");
+    return -6;
+  }
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.k = k; p.v = v; p.o = o; p.lse = lse; p.s_aux = s_aux;
+  p.sq = mk(q_strides); p.sk = mk(k_strides); p.sv = mk(v_strides); p.so = mk(o_strides);
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.N = N; p.D = D;
+  p.S = num_sink < 0 ? 0 : num_sink;
+  p.W = window < 0 ? 0 : window;
+  p.scale = 1.0f / sqrtf((float)D);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_force_impl != SFA_IMPL_SIMT && tc_fwd_supported(p, dtype)) {
+    set_impl_name("tcgen05");
+    return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");
+  }
+  set_impl_name("simt");
+  return cuda_ret(simt_fwd(p, dtype, st), "sfa_fwd(simt)");
+}
+
+int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+            const float* s_aux, void* dq, void* dk, void* dv, float* ds_aux, int B, int Hq, int Hkv, int N, int D,
+            int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
+            const int64_t v_strides[4], const int64_t o_strides[4], const int64_t do_strides[4],
+            const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], void* workspace,
+            size_t workspace_bytes, void* stream) {
+  const int64_t* ss[8] = {q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides};
+  if (int r = check_common(B, Hq, Hkv, N, D, dtype, ss, 8)) return r;
+  if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv) {
+    set_error("null tensor pointer");
+    return -6;
+  }
+  const size_t need = sfa_workspace_bytes(SFA_OP_BWD, B, Hq, Hkv, N, D, dtype);
+  if (!workspace || workspace_bytes < need) {
+    set_error("backward workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    return -7;
+  }
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.k = k; p.v = v; p.o = const_cast<void*>(o); p.lse = const_cast<float*>(lse); p.s_aux = s_aux;
+  p.dout = dout; p.dq = dq; p.dk = dk; p.dv = dv; p.ds_aux = ds_aux;
+  p.sq = mk(q_strides); p.sk = mk(k_strides); p.sv = mk(v_strides); p.so = mk(o_strides);
+  p.sdo = mk(do_strides); p.sdq = mk(dq_strides); p.sdk = mk(dk_strides); p.sdv = mk(dv_strides);
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.N = N; p.D = D;
+  p.S = num_sink < 0 ? 0 : num_sink;
+  p.W = window < 0 ? 0 : window;
+  p.scale = 1.0f / sqrtf((float)D);
+  p.delta = static_cast<float*>(workspace);
+  float* ds_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)B * Hq * N * 4, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
+  if (g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype)) {
+    set_impl_name("tcgen05");
+    return cuda_ret(tc_bwd(p, dtype, st), "sfa_bwd(tcgen05)");
+  }
+  set_impl_name("simt");
+  return cuda_ret(simt_bwd(p, dtype, st), "sfa_bwd(simt)");
+}
+
+static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int L = p.len[0] + p.len[1];
+  if (L < 1) {
+    set_error("decode needs at least one cached key");
+    return -8;
+  }
+  for (int s = 0; s < 2; ++s)
+    if (p.len[s] <= 0) {  // keep pointers dereferenceable for zero-sized segments
+      p.len[s] = 0;
+      p.k[s] = p.k[1 - s];
+      p.v[s] = p.v[1 - s];
+      p.sk[s] = p.sk[1 - s];
+      p.sv[s] = p.sv[1 - s];
+    }
+  if (g_force_impl != SFA_IMPL_SIMT && mma_decode_supported(p, dtype)) {
+    p.splits = mma_decode_splits(p.B, p.Hkv, L);
+    if (p.splits > 1) {
+      const size_t ml = align_up((size_t)p.B * p.Hq * p.splits * 2 * 4, 256);
+      const size_t po = align_up((size_t)p.B * p.Hq * p.splits * p.D * 4, 256);
+      if (!workspace || workspace_bytes < ml + po) {
+        set_error("decode workspace too small: need %zu bytes, got %zu", ml + po, workspace_bytes);
+        return -7;
+      }
+      p.part_ml = static_cast<float*>(workspace);
+      p.part_o = reinterpret_cast<float*>(static_cast<char*>(workspace) + ml);
+    }
+    set_impl_name("mma");
+    return cuda_ret(mma_decode(p, dtype, st), "sfa_decode(mma)");
+  }
+  p.splits = 1;
+  set_impl_name("simt");
+  return cuda_ret(simt_decode(p, dtype, st), "sfa_decode(simt)");
+}
+
+int sfa_decode(const void* q, const void* k, const void* v, void* o, const float* s_aux, int B, int Hq, int Hkv, int Nkv,
+               int D, int dtype, const int64_t q_strides[2], const int64_t k_strides[3], const int64_t v_strides[3],
+               const int64_t o_strides[2], void* workspace, size_t workspace_bytes, void* stream) {
+  const int64_t* none[1] = {nullptr};
+  if (int r = check_common(B, Hq, Hkv, Nkv, D, dtype, none, 0)) return r;
+  if (!q || !k || !v || !o) {
+    set_error("null tensor pointer");
+    return -6;
+  }
+  DecodeParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.o = o; p.s_aux = s_aux;
+  p.k[0] = k; p.v[0] = v; p.len[0] = Nkv; p.len[1] = 0;
+  p.sk[0] = mk(k_strides); p.sv[0] = mk(v_strides);
+  p.sq_b = q_strides[0]; p.sq_h = q_strides[1]; p.so_b = o_strides[0]; p.so_h = o_strides[1];
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.D = D;
+  p.scale = 1.0f / sqrtf((float)D);
+  return decode_impl(p, dtype, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const void* win_k, const void* win_v, void* o,
+                    const float* s_aux, int B, int Hq, int Hkv, int sink_len, int window_len, int D, int dtype,
+                    const int64_t q_strides[2], const int64_t sink_strides[3], const int64_t win_strides[3],
+                    const int64_t o_strides[2], void* workspace, size_t workspace_bytes, void* stream) {
+  const int64_t* none[1] = {nullptr};
+  if (int r = check_common(B, Hq, Hkv, sink_len + window_len, D, dtype, none, 0)) return r;
+  if (!q || !o || (sink_len > 0 && (!sink_k || !sink_v)) || (window_len > 0 && (!win_k || !win_v))) {
+    set_error("null tensor pointer");
+    return -6;
+  }
+  DecodeParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.o = o; p.s_aux = s_aux;
+  p.k[0] = sink_k; p.v[0] = sink_v; p.len[0] = sink_len;
+  p.k[1] = win_k; p.v[1] = win_v; p.len[1] = window_len;
+  p.sk[0] = p.sv[0] = mk(sink_strides);
+  p.sk[1] = p.sv[1] = mk(win_strides);
+  p.sq_b = q_strides[0]; p.sq_h = q_strides[1]; p.so_b = o_strides[0]; p.so_h = o_strides[1];
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.D = D;
+  p.scale = 1.0f / sqrtf((float)D);
+  return decode_impl(p, dtype, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream) {
+  return cuda_ret(probe_umma(a, b, c, N, K, mode, dtype, static_cast<cudaStream_t>(stream)), "sfa_probe_umma");
+}
+
+}  // extern "C"

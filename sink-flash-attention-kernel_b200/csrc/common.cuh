@@ -1,0 +1,87 @@
+// Shared declarations for libsinkfa: problem descriptors, dtype helpers, error plumbing.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/sinkfa.h"
+
+namespace sfa {
+
+struct Strides4 {  // element strides for (batch, head, position); channel stride is 1
+  int64_t b, h, n;
+};
+
+// Prefill / training problem.  Mask: sink_flash_attention.py:30-39 of the reference.
+struct AttnParams {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;          // fwd: output; bwd: input
+  float* lse;       // [B,Hq,N]
+  const float* s_aux;
+  const void* dout;
+  void* dq;
+  void* dk;
+  void* dv;
+  float* ds_aux;
+  float* delta;     // workspace [B,Hq,N]
+  Strides4 sq, sk, sv, so, sdo, sdq, sdk, sdv;
+  int B, Hq, Hkv, N, D, S, W;
+  float scale;
+};
+
+struct DecodeParams {
+  const void* q;
+  const void* k[2];   // up to two KV segments (sink buffer, window buffer); segment 1 may be empty
+  const void* v[2];
+  int len[2];
+  Strides4 sk[2];     // (b, h, n)
+  Strides4 sv[2];
+  void* o;
+  const float* s_aux;
+  int64_t sq_b, sq_h, so_b, so_h;
+  int B, Hq, Hkv, D;
+  float scale;
+  float* part_ml;     // workspace: [B,Hq,splits,2]
+  float* part_o;      // workspace: [B,Hq,splits,D]
+  int splits;
+};
+
+void set_error(const char* fmt, ...);
+void set_impl_name(const char* name);
+
+template <typename T> __device__ __forceinline__ float to_f(T x);
+template <> __device__ __forceinline__ float to_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ float to_f<__half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// attended-set predicate, shared by every kernel (reference: sink_flash_attention.py:36-39)
+__host__ __device__ __forceinline__ bool attended(int i, int j, int S, int W) {
+  return (j <= i) && ((j < S) || (j >= i - W + 1));
+}
+
+// launchers implemented in the .cu files; every one returns a cudaError_t
+cudaError_t simt_fwd(const AttnParams& p, int dtype, cudaStream_t st);
+cudaError_t simt_bwd(const AttnParams& p, int dtype, cudaStream_t st);
+cudaError_t simt_decode(const DecodeParams& p, int dtype, cudaStream_t st);
+cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st);
+
+bool tc_fwd_supported(const AttnParams& p, int dtype);
+cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st);
+bool tc_bwd_supported(const AttnParams& p, int dtype);
+cudaError_t tc_bwd(const AttnParams& p, int dtype, cudaStream_t st);
+
+bool mma_decode_supported(const DecodeParams& p, int dtype);
+int mma_decode_splits(int B, int Hkv, int total_len);
+cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st);
+
+cudaError_t probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, cudaStream_t st);
+
+}  // namespace sfa

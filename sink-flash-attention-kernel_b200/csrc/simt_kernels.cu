@@ -1,0 +1,401 @@
+// CUDA-core (fp32 math) sink-attention kernels: the fp32-I/O path of the library (the tcgen05
+// tensor path is 16-bit only), the path for head dims the tensor kernels do not tile
+// (D not in {64,128}), and the on-device cross-check used by the parity tests at sizes the
+// CPU oracle cannot reach.  One warp owns one query row (fwd, dQ) or one key row (dK/dV);
+// lanes split the 32 keys of a chunk for the scores and the channels for the accumulators.
+//
+// Reference semantics: sink_flash_attention.py:30-39 (mask), :139-146 (s_aux seed),
+// :183-194 (normalise, LSE), :242-251 (P, dV, dP, dS, dK), :449,481 (dQ), :582 (delta),
+// :653-665 (ds_aux); decode_kernel.py:201-226 (s_aux as a virtual split).
+#include "common.cuh"
+
+namespace sfa {
+namespace {
+
+constexpr int kMaxD = 256;
+constexpr int kDPL = kMaxD / 32;  // channels per lane
+
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <typename T>
+__device__ __forceinline__ float dot_row(const T* __restrict__ row, const float* __restrict__ qs, int D) {
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s = fmaf(to_f<T>(row[d]), qs[d], s);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <typename T>
+__global__ void __launch_bounds__(128) simt_fwd_kernel(AttnParams p) {
+  __shared__ float qs[4][kMaxD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp, h = blockIdx.y, b = blockIdx.z;
+  if (i >= p.N) return;
+  const int D = p.D, S = p.S, W = p.W;
+  const int kvh = h / (p.Hq / p.Hkv);
+  const T* q = static_cast<const T*>(p.q) + b * p.sq.b + h * p.sq.h + (int64_t)i * p.sq.n;
+  const T* kb = static_cast<const T*>(p.k) + b * p.sk.b + kvh * p.sk.h;
+  const T* vb = static_cast<const T*>(p.v) + b * p.sv.b + kvh * p.sv.h;
+  for (int d = lane; d < D; d += 32) qs[warp][d] = to_f<T>(q[d]);
+  __syncwarp();
+
+  float m = p.s_aux ? p.s_aux[h] : -INFINITY;
+  float l = p.s_aux ? 1.f : 0.f;
+  float acc[kDPL];
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) acc[t] = 0.f;
+
+  // two disjoint key ranges: sinks [0, min(S, i+1)) and the window [max(S, i-W+1, 0), i]
+  int lo[2] = {0, max(max(S, i - W + 1), 0)};
+  int hi[2] = {min(S, i + 1), (W > 0) ? i + 1 : 0};
+  for (int r = 0; r < 2; ++r) {
+    for (int j0 = lo[r]; j0 < hi[r]; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < hi[r];
+      float s = valid ? dot_row<T>(kb + (int64_t)j * p.sk.n, qs[warp], D) * p.scale : -INFINITY;
+      const float m_new = fmaxf(m, warp_max(s));
+      const float alpha = (m == -INFINITY) ? 0.f : expf(m - m_new);
+      const float pj = valid ? expf(s - m_new) : 0.f;
+      l = l * alpha + warp_sum(pj);
+#pragma unroll
+      for (int t = 0; t < kDPL; ++t) acc[t] *= alpha;
+      const int cnt = min(32, hi[r] - j0);
+      for (int jj = 0; jj < cnt; ++jj) {
+        const float pjj = __shfl_sync(0xffffffffu, pj, jj);
+        const T* vr = vb + (int64_t)(j0 + jj) * p.sv.n;
+#pragma unroll
+        for (int t = 0; t < kDPL; ++t) {
+          const int d = lane + 32 * t;
+          if (d < D) acc[t] = fmaf(pjj, to_f<T>(vr[d]), acc[t]);
+        }
+      }
+      m = m_new;
+    }
+  }
+  T* o = static_cast<T*>(p.o) + b * p.so.b + h * p.so.h + (int64_t)i * p.so.n;
+  const float inv = (l == 0.f) ? 0.f : 1.f / l;
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) {
+    const int d = lane + 32 * t;
+    if (d < D) o[d] = from_f<T>(acc[t] * inv);
+  }
+  if (lane == 0) p.lse[((int64_t)b * p.Hq + h) * p.N + i] = (l == 0.f) ? -INFINITY : m + logf(l);
+}
+
+// ------------------------------------------------------------------------------------ dQ
+template <typename T>
+__global__ void __launch_bounds__(128) simt_dq_kernel(AttnParams p) {
+  __shared__ float qs[4][kMaxD];
+  __shared__ float dos[4][kMaxD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp, h = blockIdx.y, b = blockIdx.z;
+  if (i >= p.N) return;
+  const int D = p.D, S = p.S, W = p.W;
+  const int kvh = h / (p.Hq / p.Hkv);
+  const T* q = static_cast<const T*>(p.q) + b * p.sq.b + h * p.sq.h + (int64_t)i * p.sq.n;
+  const T* dO = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h + (int64_t)i * p.sdo.n;
+  const T* kb = static_cast<const T*>(p.k) + b * p.sk.b + kvh * p.sk.h;
+  const T* vb = static_cast<const T*>(p.v) + b * p.sv.b + kvh * p.sv.h;
+  for (int d = lane; d < D; d += 32) {
+    qs[warp][d] = to_f<T>(q[d]);
+    dos[warp][d] = to_f<T>(dO[d]);
+  }
+  __syncwarp();
+  const int64_t row = ((int64_t)b * p.Hq + h) * p.N + i;
+  const float lse = p.lse[row], delta = p.delta[row];
+  float acc[kDPL];
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) acc[t] = 0.f;
+  int lo[2] = {0, max(max(S, i - W + 1), 0)};
+  int hi[2] = {min(S, i + 1), (W > 0) ? i + 1 : 0};
+  for (int r = 0; r < 2; ++r) {
+    for (int j0 = lo[r]; j0 < hi[r]; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = (j < hi[r]) && (lse != -INFINITY);
+      float ds = 0.f;
+      if (valid) {
+        const float s = dot_row<T>(kb + (int64_t)j * p.sk.n, qs[warp], D) * p.scale;
+        const float pr = expf(s - lse);
+        const float dp = dot_row<T>(vb + (int64_t)j * p.sv.n, dos[warp], D);
+        ds = pr * (dp - delta);
+      }
+      const int cnt = min(32, hi[r] - j0);
+      for (int jj = 0; jj < cnt; ++jj) {
+        const float dsj = __shfl_sync(0xffffffffu, ds, jj);
+        const T* kr = kb + (int64_t)(j0 + jj) * p.sk.n;
+#pragma unroll
+        for (int t = 0; t < kDPL; ++t) {
+          const int d = lane + 32 * t;
+          if (d < D) acc[t] = fmaf(dsj, to_f<T>(kr[d]), acc[t]);
+        }
+      }
+    }
+  }
+  T* dq = static_cast<T*>(p.dq) + b * p.sdq.b + h * p.sdq.h + (int64_t)i * p.sdq.n;
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) {
+    const int d = lane + 32 * t;
+    if (d < D) dq[d] = from_f<T>(acc[t] * p.scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------ dK, dV
+template <typename T>
+__global__ void __launch_bounds__(128) simt_dkdv_kernel(AttnParams p) {
+  __shared__ float ks[4][kMaxD];
+  __shared__ float vs[4][kMaxD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + warp, kvh = blockIdx.y, b = blockIdx.z;
+  if (j >= p.N) return;
+  const int D = p.D, S = p.S, W = p.W, N = p.N;
+  const int g = p.Hq / p.Hkv;
+  const T* kr = static_cast<const T*>(p.k) + b * p.sk.b + kvh * p.sk.h + (int64_t)j * p.sk.n;
+  const T* vr = static_cast<const T*>(p.v) + b * p.sv.b + kvh * p.sv.h + (int64_t)j * p.sv.n;
+  for (int d = lane; d < D; d += 32) {
+    ks[warp][d] = to_f<T>(kr[d]);
+    vs[warp][d] = to_f<T>(vr[d]);
+  }
+  __syncwarp();
+  float dk[kDPL], dv[kDPL];
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) dk[t] = dv[t] = 0.f;
+  // queries that attend key j: i >= j and (j < S or i <= j + W - 1)
+  const int i_end = (j < S) ? N : ((W > 0) ? min(N, j + W) : j);
+  for (int hh = 0; hh < g; ++hh) {
+    const int h = kvh * g + hh;
+    const T* qb = static_cast<const T*>(p.q) + b * p.sq.b + h * p.sq.h;
+    const T* dob = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h;
+    const int64_t rowb = ((int64_t)b * p.Hq + h) * N;
+    for (int i0 = j; i0 < i_end; i0 += 32) {
+      const int i = i0 + lane;
+      float pr = 0.f, ds = 0.f;
+      if (i < i_end) {
+        const float lse = p.lse[rowb + i];
+        if (lse != -INFINITY) {
+          const float s = dot_row<T>(qb + (int64_t)i * p.sq.n, ks[warp], D) * p.scale;
+          pr = expf(s - lse);
+          const float dp = dot_row<T>(dob + (int64_t)i * p.sdo.n, vs[warp], D);
+          ds = pr * (dp - p.delta[rowb + i]);
+        }
+      }
+      const int cnt = min(32, i_end - i0);
+      for (int ii = 0; ii < cnt; ++ii) {
+        const float pi = __shfl_sync(0xffffffffu, pr, ii);
+        const float dsi = __shfl_sync(0xffffffffu, ds, ii);
+        const T* qr = qb + (int64_t)(i0 + ii) * p.sq.n;
+        const T* dor = dob + (int64_t)(i0 + ii) * p.sdo.n;
+#pragma unroll
+        for (int t = 0; t < kDPL; ++t) {
+          const int d = lane + 32 * t;
+          if (d < D) {
+            dv[t] = fmaf(pi, to_f<T>(dor[d]), dv[t]);
+            dk[t] = fmaf(dsi, to_f<T>(qr[d]), dk[t]);
+          }
+        }
+      }
+    }
+  }
+  T* dkr = static_cast<T*>(p.dk) + b * p.sdk.b + kvh * p.sdk.h + (int64_t)j * p.sdk.n;
+  T* dvr = static_cast<T*>(p.dv) + b * p.sdv.b + kvh * p.sdv.h + (int64_t)j * p.sdv.n;
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) {
+    const int d = lane + 32 * t;
+    if (d < D) {
+      dkr[d] = from_f<T>(dk[t] * p.scale);
+      dvr[d] = from_f<T>(dv[t]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ delta + ds_aux
+// delta[b,h,i] = sum_d dO*O (sink_flash_attention.py:582); per-block partial of
+// ds_aux[h] = -sum exp(s_aux[h]-lse)*delta (:653-665), reduced deterministically by a second kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) preprocess_kernel(AttnParams p, float* ds_partial) {
+  __shared__ float part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp, h = blockIdx.y, b = blockIdx.z;
+  float contrib = 0.f;
+  if (i < p.N) {
+    const T* o = static_cast<const T*>(p.o) + b * p.so.b + h * p.so.h + (int64_t)i * p.so.n;
+    const T* dO = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h + (int64_t)i * p.sdo.n;
+    float s = 0.f;
+    for (int d = lane; d < p.D; d += 32) s = fmaf(to_f<T>(o[d]), to_f<T>(dO[d]), s);
+    s = warp_sum(s);
+    const int64_t row = ((int64_t)b * p.Hq + h) * p.N + i;
+    if (lane == 0) p.delta[row] = s;
+    if (p.s_aux) {
+      const float lse = p.lse[row];
+      contrib = (lse == -INFINITY) ? 0.f : -expf(p.s_aux[h] - lse) * s;
+    }
+  }
+  if (ds_partial) {
+    if (lane == 0) part[warp] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += part[w];
+      ds_partial[((int64_t)b * p.Hq + h) * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ds_aux_reduce_kernel(const float* __restrict__ ds_partial, float* ds_aux, int B,
+                                                            int Hq, int nblk) {
+  __shared__ float red[256];
+  const int h = blockIdx.x;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b)
+    for (int t = threadIdx.x; t < nblk; t += 256) s += ds_partial[((int64_t)b * Hq + h) * nblk + t];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ds_aux[h] = red[0];
+}
+
+// ------------------------------------------------------------------------------------ decode
+template <typename T>
+__global__ void __launch_bounds__(128) simt_decode_kernel(DecodeParams p) {
+  __shared__ float qs[kMaxD];
+  __shared__ float sm_m[4], sm_l[4];
+  __shared__ float sm_o[4][kMaxD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int D = p.D;
+  const int kvh = h / (p.Hq / p.Hkv);
+  const T* q = static_cast<const T*>(p.q) + b * p.sq_b + h * p.sq_h;
+  for (int d = threadIdx.x; d < D; d += 128) qs[d] = to_f<T>(q[d]);
+  __syncthreads();
+  float m = -INFINITY, l = 0.f;
+  float acc[kDPL];
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) acc[t] = 0.f;
+  for (int seg = 0; seg < 2; ++seg) {
+    const int len = p.len[seg];
+    if (len <= 0) continue;
+    const T* kb = static_cast<const T*>(p.k[seg]) + b * p.sk[seg].b + kvh * p.sk[seg].h;
+    const T* vb = static_cast<const T*>(p.v[seg]) + b * p.sv[seg].b + kvh * p.sv[seg].h;
+    const int64_t sn = p.sk[seg].n, svn = p.sv[seg].n;
+    for (int j0 = warp * 32; j0 < len; j0 += 128) {
+      const int j = j0 + lane;
+      const bool valid = j < len;
+      const float s = valid ? dot_row<T>(kb + (int64_t)j * sn, qs, D) * p.scale : -INFINITY;
+      const float m_new = fmaxf(m, warp_max(s));
+      const float alpha = (m == -INFINITY) ? 0.f : expf(m - m_new);
+      const float pj = valid ? expf(s - m_new) : 0.f;
+      l = l * alpha + warp_sum(pj);
+#pragma unroll
+      for (int t = 0; t < kDPL; ++t) acc[t] *= alpha;
+      const int cnt = min(32, len - j0);
+      for (int jj = 0; jj < cnt; ++jj) {
+        const float pjj = __shfl_sync(0xffffffffu, pj, jj);
+        const T* vr = vb + (int64_t)(j0 + jj) * svn;
+#pragma unroll
+        for (int t = 0; t < kDPL; ++t) {
+          const int d = lane + 32 * t;
+          if (d < D) acc[t] = fmaf(pjj, to_f<T>(vr[d]), acc[t]);
+        }
+      }
+      m = m_new;
+    }
+  }
+  if (lane == 0) {
+    sm_m[warp] = m;
+    sm_l[warp] = l;
+  }
+#pragma unroll
+  for (int t = 0; t < kDPL; ++t) {
+    const int d = lane + 32 * t;
+    if (d < D) sm_o[warp][d] = acc[t];
+  }
+  __syncthreads();
+  // merge the four warps plus the s_aux virtual split (m = s_aux, l = 1, o = 0)
+  float mg = p.s_aux ? p.s_aux[h] : -INFINITY;
+  for (int w = 0; w < 4; ++w) mg = fmaxf(mg, sm_m[w]);
+  float lg = p.s_aux ? expf(p.s_aux[h] - mg) : 0.f;
+  float a[4];
+  for (int w = 0; w < 4; ++w) {
+    a[w] = (sm_m[w] == -INFINITY) ? 0.f : expf(sm_m[w] - mg);
+    lg += sm_l[w] * a[w];
+  }
+  lg = fmaxf(lg, 1e-8f);  // decode_kernel.py:222
+  T* o = static_cast<T*>(p.o) + b * p.so_b + h * p.so_h;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    float s = 0.f;
+    for (int w = 0; w < 4; ++w) s += sm_o[w][d] * a[w];
+    o[d] = from_f<T>(s / lg);
+  }
+}
+
+template <typename F>
+cudaError_t dispatch_dtype(int dtype, F&& f) {
+  switch (dtype) {
+    case SFA_DTYPE_BF16: return f(__nv_bfloat16{});
+    case SFA_DTYPE_FP16: return f(__half{});
+    case SFA_DTYPE_FP32: return f(float{});
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+cudaError_t simt_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    dim3 grid((p.N + 3) / 4, p.Hq, p.B);
+    simt_fwd_kernel<T><<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st) {
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    const int nblk = (p.N + 7) / 8;
+    dim3 grid(nblk, p.Hq, p.B);
+    preprocess_kernel<T><<<grid, 256, 0, st>>>(p, p.s_aux ? ds_partial : nullptr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (p.s_aux && p.ds_aux) {
+      ds_aux_reduce_kernel<<<p.Hq, 256, 0, st>>>(ds_partial, p.ds_aux, p.B, p.Hq, nblk);
+      e = cudaGetLastError();
+    }
+    return e;
+  });
+}
+
+cudaError_t simt_bwd(const AttnParams& p, int dtype, cudaStream_t st) {
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    dim3 gq((p.N + 3) / 4, p.Hq, p.B);
+    simt_dq_kernel<T><<<gq, 128, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 gk((p.N + 3) / 4, p.Hkv, p.B);
+    simt_dkdv_kernel<T><<<gk, 128, 0, st>>>(p);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t simt_decode(const DecodeParams& p, int dtype, cudaStream_t st) {
+  return dispatch_dtype(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    dim3 grid(p.Hq, p.B);
+    simt_decode_kernel<T><<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+  });
+}
+
+}  // namespace sfa

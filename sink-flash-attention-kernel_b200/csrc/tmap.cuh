@@ -1,0 +1,88 @@
+// Host-side construction of 4-D TMA tensor maps over [B,H,N,D]-shaped tensors with arbitrary
+// (batch, head, position) element strides.  libcuda is not linked: cuTensorMapEncodeTiled is
+// resolved at run time through cudaGetDriverEntryPoint.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace sfa {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct TileMap {
+  CUtensorMap map;
+  int swap_nh;  // 1: the map's dim order is (D, H, N, B) -- coordinates must be passed (d, h, n, b)
+};
+
+// Tensor viewed as (D, N, H, B) with element strides (1, sn, sh, sb); 16-bit elements.
+// Box = 64 channels x box_n positions x box_h heads x 1 batch, SWIZZLE_128B, OOB -> zero.
+// The two middle dims are ordered by increasing stride, so a multi-head box lands in shared
+// memory as rows (h*box_n + n) when swap_nh == 0 and as rows (n*box_h + h) when swap_nh == 1.
+inline bool make_tile_map(TileMap* out, const void* ptr, int dtype, int D, int N, int H, int B, const Strides4& s,
+                          int box_n, int box_h) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return false;
+  }
+  const CUtensorMapDataType dt = (dtype == SFA_DTYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const bool swap = (H > 1 && N > 1) ? (s.h < s.n) : false;
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  dims[0] = (cuuint64_t)D;
+  box[0] = 64;
+  if (!swap) {
+    dims[1] = N; dims[2] = H;
+    strides[0] = (cuuint64_t)s.n * 2; strides[1] = (cuuint64_t)s.h * 2;
+    box[1] = box_n; box[2] = box_h;
+  } else {
+    dims[1] = H; dims[2] = N;
+    strides[0] = (cuuint64_t)s.h * 2; strides[1] = (cuuint64_t)s.n * 2;
+    box[1] = box_h; box[2] = box_n;
+  }
+  dims[3] = B;
+  strides[2] = (cuuint64_t)s.b * 2;
+  box[3] = 1;
+  // size-1 dims may carry arbitrary strides in torch; any 16-B multiple is acceptable for the encoder
+  for (int i = 0; i < 3; ++i)
+    if (dims[i + 1] == 1 || strides[i] == 0) strides[i] = (cuuint64_t)16 * ((dims[0] * 2 + 15) / 16);
+  if (D < 64) box[0] = D;
+  CUresult r = enc(&out->map, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u,%u,%u)",
+              (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+              (unsigned long long)strides[2], box[0], box[1], box[2], box[3]);
+    return false;
+  }
+  out->swap_nh = swap ? 1 : 0;
+  return true;
+}
+
+// TMA needs 16-B aligned base and 16-B multiple strides
+inline bool tma_compatible(const void* ptr, const Strides4& s) {
+  return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (s.n % 8 == 0) && (s.h % 8 == 0) && (s.b % 8 == 0);
+}
+
+}  // namespace sfa

@@ -1,0 +1,214 @@
+"""ctypes binding of libsinkfa.so (C ABI declared in include/sinkfa.h).
+
+There is no fallback: if the CUDA library is missing or a tensor is not on a CUDA device the
+call raises.  PyTorch is used only for device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsinkfa.so")
+
+DTYPE_CODE = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+OP_FWD, OP_BWD, OP_DECODE = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT = 0, 1
+
+EXPORTS = (
+    "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_last_impl", "sfa_workspace_bytes",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma",
+)
+
+_lib = None
+
+
+class SinkFAError(RuntimeError):
+    pass
+
+
+def _i64(vals: Sequence[int]):
+    return (ctypes.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def load() -> ctypes.CDLL:
+    """Load libsinkfa.so (built in-tree by `make` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SinkFAError(
+            f"{LIB_PATH} not found: build it with `make -C {os.path.dirname(_HERE)}` "
+            "(hand-written sm_100a kernels; there is no CPU or Triton fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    p, i, i64p, f32p = c.c_void_p, c.c_int, c.POINTER(c.c_int64), c.c_void_p
+    lib.sfa_version.restype = i
+    lib.sfa_last_error.restype = c.c_char_p
+    lib.sfa_last_impl.restype = c.c_char_p
+    lib.sfa_set_impl.argtypes = [i]
+    lib.sfa_set_impl.restype = i
+    lib.sfa_workspace_bytes.argtypes = [i] * 7
+    lib.sfa_workspace_bytes.restype = c.c_size_t
+    lib.sfa_fwd.argtypes = [p, p, p, p, f32p, f32p] + [i] * 8 + [i64p] * 4 + [p, c.c_size_t, p]
+    lib.sfa_fwd.restype = i
+    lib.sfa_bwd.argtypes = [p] * 5 + [f32p, f32p] + [p] * 3 + [f32p] + [i] * 8 + [i64p] * 8 + [p, c.c_size_t, p]
+    lib.sfa_bwd.restype = i
+    lib.sfa_decode.argtypes = [p, p, p, p, f32p] + [i] * 6 + [i64p] * 4 + [p, c.c_size_t, p]
+    lib.sfa_decode.restype = i
+    lib.sfa_decode_ring.argtypes = [p] * 6 + [f32p] + [i] * 7 + [i64p] * 4 + [p, c.c_size_t, p]
+    lib.sfa_decode_ring.restype = i
+    lib.sfa_probe_umma.argtypes = [p, p, f32p, i, i, i, i, p]
+    lib.sfa_probe_umma.restype = i
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().sfa_last_error().decode(errors="replace")
+        if rc < 0:
+            raise ValueError(f"{what}: {msg} (code {rc})")
+        raise SinkFAError(f"{what}: {msg} (cudaError {rc})")
+
+
+def _require_cuda(*ts: torch.Tensor):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise SinkFAError(
+                "sink_attention runs only on CUDA tensors (sm_100a kernels; no CPU fallback); "
+                f"got a tensor on {t.device}")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _unit_last(t: torch.Tensor) -> torch.Tensor:
+    """Kernels accept any (batch, head, position) strides but need channel stride 1."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def last_impl() -> str:
+    return load().sfa_last_impl().decode()
+
+
+def set_impl(code: int):
+    _check(load().sfa_set_impl(int(code)), "sfa_set_impl")
+
+
+def _s_aux_f32(s_aux: Optional[torch.Tensor], hq: int) -> Optional[torch.Tensor]:
+    if s_aux is None:
+        return None
+    if tuple(s_aux.shape) != (hq,):
+        raise AssertionError(f"s_aux shape must be [H_q={hq}], got {tuple(s_aux.shape)}")
+    return s_aux.detach().contiguous().float()
+
+
+def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32):
+    """-> (o, lse).  q [B,Hq,N,D] (any strides with unit channel stride), k/v [B,Hkv,N,D]."""
+    lib = load()
+    _require_cuda(q, k, v, s_aux_f32)
+    B, Hq, N, D = q.shape
+    Hkv = k.shape[1]
+    q, k, v = _unit_last(q), _unit_last(k), _unit_last(v)
+    o = torch.empty_like(q)   # keeps q's memory layout: an HF [B,N,H,D] view gets an HF-layout output
+    if o.stride(-1) != 1:
+        o = torch.empty((B, Hq, N, D), device=q.device, dtype=q.dtype)
+    lse = torch.empty((B, Hq, N), device=q.device, dtype=torch.float32)
+    with torch.cuda.device(q.device):
+        rc = lib.sfa_fwd(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+            s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
+            B, Hq, Hkv, N, D, int(num_sink), int(window_size), DTYPE_CODE[q.dtype],
+            _i64(q.stride()), _i64(k.stride()), _i64(v.stride()), _i64(o.stride()),
+            None, 0, _stream(q))
+    _check(rc, "sfa_fwd")
+    return o, lse
+
+
+def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32):
+    """-> (dq, dk, dv, ds_aux|None); dk/dv are already reduced over the GQA group (fp32 accumulate)."""
+    lib = load()
+    _require_cuda(q, k, v, o, do, lse, s_aux_f32)
+    B, Hq, N, D = q.shape
+    Hkv = k.shape[1]
+    q, k, v, o, do = (_unit_last(t) for t in (q, k, v, o, do))
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ds_aux = torch.empty((Hq,), device=q.device, dtype=torch.float32) if s_aux_f32 is not None else None
+    code = DTYPE_CODE[q.dtype]
+    ws_bytes = lib.sfa_workspace_bytes(OP_BWD, B, Hq, Hkv, N, D, code)
+    ws = torch.empty((ws_bytes,), device=q.device, dtype=torch.uint8)
+    with torch.cuda.device(q.device):
+        rc = lib.sfa_bwd(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+            s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
+            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ds_aux.data_ptr() if ds_aux is not None else None,
+            B, Hq, Hkv, N, D, int(num_sink), int(window_size), code,
+            _i64(q.stride()), _i64(k.stride()), _i64(v.stride()), _i64(o.stride()), _i64(do.stride()),
+            _i64(dq.stride()), _i64(dk.stride()), _i64(dv.stride()),
+            ws.data_ptr(), ws_bytes, _stream(q))
+    _check(rc, "sfa_bwd")
+    return dq, dk, dv, ds_aux
+
+
+def decode(q, k, v, s_aux_f32):
+    """q [B,Hq,1,D]; k,v [B,Hkv,Nkv,D] -> o [B,Hq,1,D]."""
+    lib = load()
+    _require_cuda(q, k, v, s_aux_f32)
+    B, Hq, _, D = q.shape
+    Hkv, Nkv = k.shape[1], k.shape[2]
+    q, k, v = _unit_last(q), _unit_last(k), _unit_last(v)
+    o = torch.empty((B, Hq, 1, D), device=q.device, dtype=q.dtype)
+    code = DTYPE_CODE[q.dtype]
+    ws_bytes = lib.sfa_workspace_bytes(OP_DECODE, B, Hq, Hkv, Nkv, D, code)
+    ws = torch.empty((max(ws_bytes, 1),), device=q.device, dtype=torch.uint8)
+    with torch.cuda.device(q.device):
+        rc = lib.sfa_decode(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+            s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
+            B, Hq, Hkv, Nkv, D, code,
+            _i64(q.stride()[:2]), _i64(k.stride()[:3]), _i64(v.stride()[:3]), _i64(o.stride()[:2]),
+            ws.data_ptr(), ws_bytes, _stream(q))
+    _check(rc, "sfa_decode")
+    return o
+
+
+def decode_ring(q, sink_k, sink_v, win_k, win_v, sink_len: int, window_len: int, s_aux_f32):
+    """Decode straight from a SinkCacheLayer's buffers (no linearisation copy)."""
+    lib = load()
+    _require_cuda(q, sink_k, sink_v, win_k, win_v, s_aux_f32)
+    B, Hq, _, D = q.shape
+    Hkv = win_k.shape[1]
+    q = _unit_last(q)
+    for t in (sink_k, sink_v, win_k, win_v):
+        if t.stride(-1) != 1:
+            raise ValueError("cache buffers must have unit channel stride")
+    if sink_k.stride() != sink_v.stride() or win_k.stride() != win_v.stride():
+        raise ValueError("K and V cache buffers must share strides")
+    o = torch.empty((B, Hq, 1, D), device=q.device, dtype=q.dtype)
+    code = DTYPE_CODE[q.dtype]
+    ws_bytes = lib.sfa_workspace_bytes(OP_DECODE, B, Hq, Hkv, sink_len + window_len, D, code)
+    ws = torch.empty((max(ws_bytes, 1),), device=q.device, dtype=torch.uint8)
+    with torch.cuda.device(q.device):
+        rc = lib.sfa_decode_ring(
+            q.data_ptr(), sink_k.data_ptr(), sink_v.data_ptr(), win_k.data_ptr(), win_v.data_ptr(), o.data_ptr(),
+            s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
+            B, Hq, Hkv, int(sink_len), int(window_len), D, code,
+            _i64(q.stride()[:2]), _i64(sink_k.stride()[:3]), _i64(win_k.stride()[:3]), _i64(o.stride()[:2]),
+            ws.data_ptr(), ws_bytes, _stream(q))
+    _check(rc, "sfa_decode_ring")
+    return o
+
+
+def probe_umma(a: torch.Tensor, b: torch.Tensor, n: int, k: int, mode: int) -> torch.Tensor:
+    lib = load()
+    _require_cuda(a, b)
+    c = torch.empty((128, n), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        rc = lib.sfa_probe_umma(a.data_ptr(), b.data_ptr(), c.data_ptr(), n, k, mode, DTYPE_CODE[a.dtype], _stream(a))
+    _check(rc, "sfa_probe_umma")
+    return c

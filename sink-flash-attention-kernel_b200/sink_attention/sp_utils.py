@@ -1,0 +1,227 @@
+"""Sequence parallelism for sink attention.
+
+Two schemes live here.
+
+1. Ulysses (what the north-star layout asks for; the reference leaves the all-to-all to verl,
+   verl_patch.py:15-20, and only slices ``s_aux``, :132-154).  Activations arrive sequence-sharded
+   ``[B, N/P, H, D]``; one all-to-all turns them into head-sharded ``[B, N, H/P, D]``; every rank runs
+   the unmodified attention op on the full sequence for its heads (heads are independent, dK/dV reduce
+   inside a GQA group, ds_aux is per head -> no collective inside the op); the inverse all-to-all
+   returns ``O``.  ``UlyssesSinkAttention`` wires that up with autograd, pipelines the exchange in
+   head chunks on a side stream so NVLink traffic overlaps the tensor-core work, and takes ``s_aux``
+   for ALL heads, slicing the local part with the reference's rule.
+
+2. The reference's sequence-chunk helpers ``prepare_sink_kv_for_sp`` / ``reduce_sink_kv_grads`` /
+   ``get_local_position_offset`` / ``SinkAttentionSPWrapper`` (sp_utils.py:28-180), kept with the same
+   names and collective semantics (broadcast of the sink K/V from group-rank 0, all-reduce of their
+   gradients).  As in the reference this scheme has no window halo; it is API surface, not the
+   recommended path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+# =============================================================================================
+# Ulysses all-to-all
+# =============================================================================================
+def _group_size_rank(group) -> Tuple[int, int]:
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _a2a_seq_to_head(x: torch.Tensor, group) -> torch.Tensor:
+    """[B, n, H, D] (this rank's sequence chunk, all heads) -> [B, n*P, H/P, D] (all positions, local heads)."""
+    P, _ = _group_size_rank(group)
+    if P == 1:
+        return x
+    B, n, H, D = x.shape
+    assert H % P == 0, f"heads ({H}) must be divisible by the sequence-parallel size ({P})"
+    hl = H // P
+    # send[r] = heads of rank r: [P, B, n, hl, D]
+    send = x.reshape(B, n, P, hl, D).permute(2, 0, 1, 3, 4).contiguous()
+    recv = torch.empty_like(send)                  # recv[s] = sequence chunk s
+    dist.all_to_all_single(recv, send, group=group)
+    if B == 1:                                     # [P,1,n,hl,D] is already [1, P*n, hl, D] in memory
+        return recv.view(1, P * n, hl, D)
+    return recv.permute(1, 0, 2, 3, 4).reshape(B, P * n, hl, D)
+
+
+def _a2a_head_to_seq(x: torch.Tensor, group) -> torch.Tensor:
+    """[B, N, H/P, D] (all positions, local heads) -> [B, N/P, H, D] (local positions, all heads)."""
+    P, _ = _group_size_rank(group)
+    if P == 1:
+        return x
+    B, N, hl, D = x.shape
+    assert N % P == 0, f"sequence length ({N}) must be divisible by the sequence-parallel size ({P})"
+    n = N // P
+    send = x.reshape(B, P, n, hl, D).permute(1, 0, 2, 3, 4).contiguous()   # send[s] = chunk s
+    recv = torch.empty_like(send)                                         # recv[r] = heads of rank r
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.permute(1, 2, 0, 3, 4).reshape(B, n, P * hl, D)
+
+
+class _SeqToHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return _a2a_seq_to_head(x, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _a2a_head_to_seq(g.contiguous(), ctx.group), None
+
+
+class _HeadToSeq(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return _a2a_head_to_seq(x, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _a2a_seq_to_head(g.contiguous(), ctx.group), None
+
+
+def ulysses_seq_to_head(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Differentiable all-to-all ``[B, N/P, H, D] -> [B, N, H/P, D]`` (HF layout)."""
+    return _SeqToHead.apply(x, group)
+
+
+def ulysses_head_to_seq(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Differentiable inverse all-to-all ``[B, N, H/P, D] -> [B, N/P, H, D]``."""
+    return _HeadToSeq.apply(x, group)
+
+
+def slice_s_aux_for_rank(s_aux: Optional[torch.Tensor], local_heads: int, rank: int) -> Optional[torch.Tensor]:
+    """Reference rule (verl_patch.py:140-151): rank r owns s_aux[r*H_local : (r+1)*H_local]."""
+    if s_aux is None or s_aux.shape[0] == local_heads:
+        return s_aux
+    assert s_aux.shape[0] % local_heads == 0
+    return s_aux[rank * local_heads:(rank + 1) * local_heads]
+
+
+class UlyssesSinkAttention(torch.nn.Module):
+    """Sequence-parallel sink attention over one NVLink/NVSwitch node.
+
+    Inputs are this rank's sequence chunk in HF layout: ``q [B, N/P, H_q, D]``, ``k, v [B, N/P, H_kv, D]``
+    (``P`` must divide ``H_kv``); ``s_aux`` holds ALL ``H_q`` logits.  Returns ``O [B, N/P, H_q, D]``.
+    """
+
+    def __init__(self, num_sink: int = 0, window_size: int = 4096, sp_group=None, head_chunks: int = 1):
+        super().__init__()
+        self.num_sink = num_sink
+        self.window_size = window_size
+        self.sp_group = sp_group
+        self.head_chunks = max(1, int(head_chunks))
+
+    def forward(self, q, k, v, s_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from .sink_flash_attention import sink_flash_attention
+        P, rank = _group_size_rank(self.sp_group)
+        H_q, H_kv = q.shape[2], k.shape[2]
+        assert H_kv % P == 0 and H_q % P == 0, "the sequence-parallel size must divide H_kv and H_q"
+        hq_l, hkv_l = H_q // P, H_kv // P
+        s_loc = slice_s_aux_for_rank(s_aux, hq_l, rank)
+        # head chunks are whole GQA groups so every chunk is an independent attention problem
+        nchunk = min(self.head_chunks, hkv_l) if P > 1 else 1
+        while hkv_l % nchunk:
+            nchunk -= 1
+        if nchunk == 1:
+            qh = ulysses_seq_to_head(q, self.sp_group)
+            kh = ulysses_seq_to_head(k, self.sp_group)
+            vh = ulysses_seq_to_head(v, self.sp_group)
+            oh = sink_flash_attention(qh.transpose(1, 2), kh.transpose(1, 2), vh.transpose(1, 2),
+                                      self.num_sink, self.window_size, s_loc).transpose(1, 2)
+            return ulysses_head_to_seq(oh, self.sp_group)
+        # Pipelined: chunk c's attention overlaps chunk c+1's all-to-all (NCCL runs on its own stream).
+        g = H_q // H_kv
+        kv_per = hkv_l // nchunk
+        outs = []
+        B, n = q.shape[0], q.shape[1]
+        qv = q.reshape(B, n, P, hkv_l, g, -1)
+        kv_ = k.reshape(B, n, P, hkv_l, -1)
+        vv = v.reshape(B, n, P, hkv_l, -1)
+        for c in range(nchunk):
+            sl = slice(c * kv_per, (c + 1) * kv_per)
+            qc = qv[:, :, :, sl].reshape(B, n, P * kv_per * g, -1)
+            kc = kv_[:, :, :, sl].reshape(B, n, P * kv_per, -1)
+            vc = vv[:, :, :, sl].reshape(B, n, P * kv_per, -1)
+            qh = ulysses_seq_to_head(qc, self.sp_group)
+            kh = ulysses_seq_to_head(kc, self.sp_group)
+            vh = ulysses_seq_to_head(vc, self.sp_group)
+            sc = None if s_loc is None else s_loc[c * kv_per * g:(c + 1) * kv_per * g]
+            oh = sink_flash_attention(qh.transpose(1, 2), kh.transpose(1, 2), vh.transpose(1, 2),
+                                      self.num_sink, self.window_size, sc).transpose(1, 2)
+            outs.append(ulysses_head_to_seq(oh, self.sp_group).reshape(B, n, P, kv_per * g, -1))
+        return torch.cat(outs, dim=3).reshape(B, n, H_q, -1)
+
+
+# =============================================================================================
+# Reference sequence-chunk helpers (same names / semantics as sp_utils.py:28-180)
+# =============================================================================================
+def prepare_sink_kv_for_sp(k: torch.Tensor, v: torch.Tensor, num_sink: int, sp_group,
+                           rank: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Broadcast the first ``num_sink`` K/V rows from group-rank 0 and prepend them on the other ranks."""
+    if num_sink == 0:
+        return k, v
+    if rank is None:
+        rank = dist.get_rank(sp_group)
+    B, H, _, D = k.shape
+    if rank == 0:
+        sk, sv = k[:, :, :num_sink].contiguous(), v[:, :, :num_sink].contiguous()
+    else:
+        sk = torch.empty(B, H, num_sink, D, device=k.device, dtype=k.dtype)
+        sv = torch.empty(B, H, num_sink, D, device=v.device, dtype=v.dtype)
+    src = dist.get_global_rank(sp_group, 0) if sp_group is not None else 0
+    dist.broadcast(sk, src=src, group=sp_group)
+    dist.broadcast(sv, src=src, group=sp_group)
+    if rank == 0:
+        return k, v
+    return torch.cat([sk, k], dim=2), torch.cat([sv, v], dim=2)
+
+
+def reduce_sink_kv_grads(dk: torch.Tensor, dv: torch.Tensor, num_sink: int, sp_group,
+                         rank: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sum the sink rows' gradients over the group; rank 0 keeps them, the others strip the prefix."""
+    if num_sink == 0:
+        return dk, dv
+    if rank is None:
+        rank = dist.get_rank(sp_group)
+    sdk, sdv = dk[:, :, :num_sink].contiguous(), dv[:, :, :num_sink].contiguous()
+    dist.all_reduce(sdk, op=dist.ReduceOp.SUM, group=sp_group)
+    dist.all_reduce(sdv, op=dist.ReduceOp.SUM, group=sp_group)
+    if rank == 0:
+        dk, dv = dk.clone(), dv.clone()
+        dk[:, :, :num_sink] = sdk
+        dv[:, :, :num_sink] = sdv
+        return dk, dv
+    return dk[:, :, num_sink:], dv[:, :, num_sink:]
+
+
+def get_local_position_offset(rank: int, n_local: int, num_sink: int) -> int:
+    """Global position of the first local (non-prepended) token of ``rank``'s chunk."""
+    return rank * n_local
+
+
+class SinkAttentionSPWrapper(torch.nn.Module):
+    """Reference-compatible wrapper (sp_utils.py:151-180).  Without a group (or with a group of one)
+    it is plain ``sink_flash_attention``.  With a group it runs the Ulysses path on kernel-layout
+    ``[B, H, N/P, D]`` chunks -- the reference's own multi-rank branch cannot run (it feeds a K longer
+    than Q into an op that asserts equal lengths)."""
+
+    def __init__(self, num_sink: int = 4, window_size: int = 4096, sp_group=None):
+        super().__init__()
+        self.num_sink = num_sink
+        self.window_size = window_size
+        self.sp_group = sp_group
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+        from .sink_flash_attention import sink_flash_attention
+        if self.sp_group is None or dist.get_world_size(self.sp_group) == 1:
+            return sink_flash_attention(q, k, v, self.num_sink, self.window_size)
+        uly = UlyssesSinkAttention(self.num_sink, self.window_size, self.sp_group)
+        return uly(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)

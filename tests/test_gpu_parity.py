@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes) against the CPU oracle, the golden
+fixtures generated from the reference, and size-independent properties at the BASELINE sizes.
+
+Tolerances (stated per test) follow BASELINE.json's north star: O/LSE within 2e-2 max-abs in
+bf16/fp16 and 1e-3 in fp32; gradients within the reference's test tolerance 5e-2
+(tests/test_sink_attention.py:94-96); ds_aux within 2e-3; masks bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+import golden_cases as gc
+import sink_oracle as orc
+from _util import load_decode, load_prefill, maxdiff, to_dev
+
+pytestmark = pytest.mark.gpu
+
+import sink_attention as sa
+from sink_attention import _lib
+
+LOW = [torch.bfloat16, torch.float16]
+
+
+def _fwd(q, k, v, S, W, s_aux, impl=None):
+    if impl is not None:
+        _lib.set_impl(impl)
+    try:
+        o, lse = sa.sink_flash_attention_with_lse(q, k, v, S, W, s_aux)
+        name = _lib.last_impl()
+    finally:
+        _lib.set_impl(_lib.IMPL_AUTO)
+    return o, lse, name
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 / TMA descriptor self-test
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", LOW)
+@pytest.mark.parametrize("mode,n,k", [(0, 64, 64), (0, 144, 64), (0, 128, 128), (0, 256, 256), (0, 16, 64),
+                                      (1, 64, 64), (1, 128, 128), (1, 64, 192),
+                                      (2, 64, 16), (2, 64, 144), (2, 128, 128), (2, 64, 256)])
+def test_probe_umma(dtype, mode, n, k):
+    g = torch.Generator().manual_seed(7 + mode + n + k)
+    a = torch.randn(128, k, generator=g).to("cuda", dtype)
+    if mode == 0:
+        b = torch.randn(n, k, generator=g).to("cuda", dtype)
+        ref = a.float() @ b.float().t()
+    else:
+        b = torch.randn(k, n, generator=g).to("cuda", dtype)
+        ref = a.float() @ b.float()
+    c = _lib.probe_umma(a, b, n, k, mode)
+    torch.cuda.synchronize()
+    assert maxdiff(c, ref) < 1e-3 * math.sqrt(k) + 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# forward / backward vs golden fixtures (reference outputs) and the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", gc.PREFILL_CASES, ids=[c[0] for c in gc.PREFILL_CASES])
+def test_prefill_fp32_golden(case):
+    (q, k, v, do, s_aux), z = load_prefill(case)
+    S, W = case[6], case[7]
+    qd, kd, vd = (to_dev(t).requires_grad_(True) for t in (q, k, v))
+    sd = to_dev(s_aux).requires_grad_(True) if s_aux is not None else None
+    o = sa.sink_flash_attention(qd, kd, vd, S, W, sd)
+    assert _lib.last_impl() == "simt"
+    o.backward(to_dev(do))
+    _, lse, _ = _fwd(qd.detach(), kd.detach(), vd.detach(), S, W, sd.detach() if sd is not None else None)
+    tol = 1e-4   # fp32 bar is 1e-3 (north star); the CUDA-core path is far inside it
+    assert maxdiff(o, torch.from_numpy(z["o"])) < tol
+    assert maxdiff(lse, torch.from_numpy(z["lse"])) < tol
+    if z["lse_triton"].size:
+        assert maxdiff(lse, torch.from_numpy(z["lse_triton"])) < tol
+    if z["dq"].size:
+        assert maxdiff(qd.grad, torch.from_numpy(z["dq"])) < tol
+        assert maxdiff(kd.grad, torch.from_numpy(z["dk"])) < 2 * tol
+        assert maxdiff(vd.grad, torch.from_numpy(z["dv"])) < 2 * tol
+    if s_aux is not None:
+        assert maxdiff(sd.grad, torch.from_numpy(z["ds_aux"])) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", LOW)
+@pytest.mark.parametrize("case", gc.PREFILL_CASES, ids=[c[0] for c in gc.PREFILL_CASES])
+def test_prefill_lowp_vs_oracle(case, dtype):
+    (q, k, v, do, s_aux), z = load_prefill(case)
+    S, W, D = case[6], case[7], case[5]
+    ql, kl, vl, dol = (t.to(dtype) for t in (q, k, v, do))
+    o_ref, lse_ref = orc.sink_attention_fwd(ql, kl, vl, S, W, s_aux)
+    dq_r, dk_r, dv_r, ds_r = orc.sink_attention_bwd(ql, kl, vl, dol, S, W, s_aux)
+    qd, kd, vd = (to_dev(t).requires_grad_(True) for t in (ql, kl, vl))
+    sd = to_dev(s_aux).requires_grad_(True) if s_aux is not None else None
+    o = sa.sink_flash_attention(qd, kd, vd, S, W, sd)
+    assert _lib.last_impl() == ("tcgen05" if D in (64, 128) else "simt")
+    o.backward(to_dev(dol))
+    _, lse, _ = _fwd(qd.detach(), kd.detach(), vd.detach(), S, W, sd.detach() if sd is not None else None)
+    assert maxdiff(o, o_ref) < 2e-2
+    assert maxdiff(lse, lse_ref) < 2e-2
+    # also against the reference's stored fp32-input output: input rounding adds to the budget
+    assert maxdiff(o, torch.from_numpy(z["o"])) < 5e-2
+    assert maxdiff(qd.grad, dq_r) < 5e-2
+    assert maxdiff(kd.grad, dk_r) < 5e-2
+    assert maxdiff(vd.grad, dv_r) < 5e-2
+    if s_aux is not None:
+        assert maxdiff(sd.grad, ds_r) < 5e-2
+
+
+@pytest.mark.parametrize("dtype", LOW)
+@pytest.mark.parametrize("shape", [
+    # B, Hq, Hkv, N, D, S, W, s_aux
+    (1, 16, 2, 1024, 64, 0, 128, True),      # gpt-oss head ratio 8:1, narrow window (C1 scaled down)
+    (2, 8, 2, 777, 128, 4, 300, False),      # Llama-style ratio 4:1, D=128, ragged N, sinks
+    (1, 4, 4, 512, 64, 16, 128, True),       # MHA, sinks + s_aux (test_sink_attention.py:194)
+    (1, 32, 2, 300, 64, 3, 50, True),        # group 16 -> 8 positions per tile
+    (1, 6, 2, 260, 64, 2, 70, False),        # group 3 -> unpacked tiles
+    (1, 4, 2, 1500, 128, 0, 1500, True),     # full causal (window = N), many KV tiles
+    (1, 8, 1, 200, 64, 150, 8, True),        # sinks spanning more than one KV tile of a narrow band
+    (1, 2, 2, 130, 64, 0, 1, False),         # window 1: self only
+])
+def test_fwd_tcgen05_vs_simt_and_oracle(shape, dtype):
+    B, Hq, Hkv, N, D, S, W, use_aux = shape
+    g = torch.Generator().manual_seed(N + D + S)
+    q = torch.randn(B, Hq, N, D, generator=g).to("cuda", dtype)
+    k = torch.randn(B, Hkv, N, D, generator=g).to("cuda", dtype)
+    v = torch.randn(B, Hkv, N, D, generator=g).to("cuda", dtype)
+    s_aux = (torch.randn(Hq, generator=g) * 0.5 + 1.0).cuda() if use_aux else None
+    o_t, lse_t, name_t = _fwd(q, k, v, S, W, s_aux)
+    o_s, lse_s, name_s = _fwd(q, k, v, S, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert (name_t, name_s) == ("tcgen05", "simt")
+    assert maxdiff(o_t, o_s) < 2e-2
+    assert maxdiff(lse_t, lse_s) < 2e-3
+    o_ref, lse_ref = orc.sink_attention_fwd(q.cpu(), k.cpu(), v.cpu(), S, W, s_aux.cpu() if use_aux else None)
+    assert maxdiff(o_t, o_ref) < 2e-2
+    assert maxdiff(lse_t, lse_ref) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# mask: bit-exact attended index set (one-hot V probe: O[i, j] > 0  <=>  key j attended by query i)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("N,S,W", [(128, 0, 128), (128, 4, 32), (128, 2, 3), (128, 200, 5), (128, 0, 1), (128, 7, 0),
+                                   (256, 4, 100), (256, 130, 17), (200, 0, 64)])
+def test_mask_bit_exact(N, S, W, dtype):
+    D, Hq, Hkv = 128, 4, 2
+    q = torch.zeros(1, Hq, N, D, device="cuda", dtype=dtype)
+    k = torch.zeros(1, Hkv, N, D, device="cuda", dtype=dtype)
+    mask = orc.attended_mask(N, S, W)
+    got = torch.zeros(N, N, dtype=torch.bool)
+    for off in range(0, N, D):
+        v = torch.zeros(1, Hkv, N, D, device="cuda", dtype=dtype)
+        idx = torch.arange(off, min(off + D, N))
+        v[:, :, idx, idx - off] = 1.0
+        o, _, name = _fwd(q, k, v, S, W, None)
+        assert name == ("simt" if dtype == torch.float32 else "tcgen05")
+        hit = (o[0] > 0).cpu()                                   # [Hq, N, D]
+        assert bool((hit == hit[0:1]).all()), "heads disagree on the attended set"
+        got[:, off:off + len(idx)] = hit[0][:, :len(idx)]
+    assert torch.equal(got, mask)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout: HF [B,N,H,D] transposed views are consumed in place and give identical results
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_strided_hf_layout(dtype):
+    B, N, Hq, Hkv, D, S, W = 2, 300, 8, 2, 64, 2, 96
+    g = torch.Generator().manual_seed(5)
+    qh = torch.randn(B, N, Hq, D, generator=g).to("cuda", dtype)
+    kh = torch.randn(B, N, Hkv, D, generator=g).to("cuda", dtype)
+    vh = torch.randn(B, N, Hkv, D, generator=g).to("cuda", dtype)
+    s_aux = torch.randn(Hq, generator=g).cuda()
+    do = torch.randn(B, N, Hq, D, generator=g).to("cuda", dtype)
+    outs = []
+    for contiguous in (False, True):
+        q, k, v = (t.transpose(1, 2) for t in (qh, kh, vh))
+        if contiguous:
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
+        o = sa.sink_flash_attention(q, k, v, S, W, s_aux)
+        if not contiguous:
+            assert o.transpose(1, 2).is_contiguous(), "output should come back in HF memory layout"
+        o.backward(do.transpose(1, 2))
+        outs.append((o, q.grad, k.grad, v.grad))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", gc.DECODE_CASES, ids=[c[0] for c in gc.DECODE_CASES])
+def test_decode_fp32_golden(case):
+    (q, k, v, s_aux), z = load_decode(case)
+    o = sa.sink_decode_attention(to_dev(q), to_dev(k), to_dev(v), to_dev(s_aux))
+    assert _lib.last_impl() == "simt"
+    assert maxdiff(o, torch.from_numpy(z["o"])) < 1e-4          # tests/test_inference.py:86 bar
+    if case[6] == "big":
+        assert o.abs().max().item() < 0.01                      # tests/test_decode_kernel.py:165-186
+
+
+@pytest.mark.parametrize("dtype", LOW)
+@pytest.mark.parametrize("case", gc.DECODE_CASES, ids=[c[0] for c in gc.DECODE_CASES])
+def test_decode_lowp(case, dtype):
+    (q, k, v, s_aux), z = load_decode(case)
+    ql, kl, vl = (t.to(dtype) for t in (q, k, v))
+    ref = orc.decode_attention(ql, kl, vl, s_aux)
+    o = sa.sink_decode_attention(to_dev(ql), to_dev(kl), to_dev(vl), to_dev(s_aux))
+    assert _lib.last_impl() == ("mma" if case[5] in (64, 128, 256) else "simt")
+    assert maxdiff(o, ref) < 1e-2                               # tests/test_decode_kernel.py:76
+    assert maxdiff(o, torch.from_numpy(z["o"])) < 2e-2
+
+
+@pytest.mark.parametrize("dtype", LOW)
+@pytest.mark.parametrize("B,Hq,Hkv,Nkv,D", [(2, 64, 8, 4100, 64), (1, 32, 8, 8192, 128), (3, 8, 8, 1000, 64),
+                                             (1, 48, 2, 515, 64), (1, 8, 2, 16384, 64), (2, 4, 4, 33, 256)])
+def test_decode_long(B, Hq, Hkv, Nkv, D, dtype):
+    g = torch.Generator().manual_seed(Nkv + D)
+    q = torch.randn(B, Hq, 1, D, generator=g).to(dtype)
+    k = torch.randn(B, Hkv, Nkv, D, generator=g).to(dtype)
+    v = torch.randn(B, Hkv, Nkv, D, generator=g).to(dtype)
+    s_aux = torch.randn(Hq, generator=g) + 1.0
+    ref = orc.decode_attention(q, k, v, s_aux)
+    o = sa.sink_decode_attention(q.cuda(), k.cuda(), v.cuda(), s_aux.cuda())
+    assert _lib.last_impl() == "mma"
+    assert maxdiff(o, ref) < 2e-2                               # tests/test_decode_kernel.py:223
+    o2 = sa.sink_decode_attention(q.cuda(), k.cuda(), v.cuda(), None)
+    assert maxdiff(o2, orc.decode_attention(q, k, v, None)) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# cache: decode through the ring equals the last row of full attention; in-place ring read
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_cache_decode_matches_prefill_row(dtype, tol):
+    B, Hq, Hkv, D, S, W = 1, 8, 2, 64, 4, 32
+    n_prefill, n_steps = 50, 45                                   # wraps the ring more than once
+    N = n_prefill + n_steps
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(B, Hq, N, D, generator=g).to(dtype)
+    k = torch.randn(B, Hkv, N, D, generator=g).to(dtype)
+    v = torch.randn(B, Hkv, N, D, generator=g).to(dtype)
+    full, _ = orc.sink_attention_fwd(q, k, v, S, W, None)
+    layer = sa.SinkCacheLayer(S, W)
+    kd, vd, qd = k.cuda(), v.cuda(), q.cuda()
+    k_out, v_out = layer.update(kd[:, :, :n_prefill], vd[:, :, :n_prefill])
+    assert k_out.shape[2] == n_prefill                            # prefill returns the full K/V
+    for t in range(n_prefill, N):
+        k_lin, v_lin = layer.update(kd[:, :, t:t + 1], vd[:, :, t:t + 1])
+        o_lin = sa.sink_decode_attention(qd[:, :, t:t + 1], k_lin, v_lin)
+        o_ring = layer.decode_attention(qd[:, :, t:t + 1])
+        assert maxdiff(o_lin, full[:, :, t:t + 1]) < tol
+        assert maxdiff(o_ring, full[:, :, t:t + 1]) < tol
+        assert maxdiff(o_ring, o_lin) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties + on-device cross-check against the CUDA-core path
+# ------------------------------------------------------------------------------------------------
+def test_c1_full_size_properties():
+    """gpt-oss shape (BASELINE configs[1]): B=1 N=8192 Hq=64 Hkv=8 D=64 W=128 s_aux bf16."""
+    B, N, Hq, Hkv, D, W = 1, 8192, 64, 8, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(42)
+    q = torch.randn(B, Hq, N, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    k = torch.randn(B, Hkv, N, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    s_aux = torch.randn(Hq, device="cuda", generator=g) * 0.5
+    ones = torch.ones(B, Hkv, N, D, device="cuda", dtype=torch.bfloat16)
+    o, lse, name = _fwd(q, k, ones, 0, W, s_aux)
+    assert name == "tcgen05"
+    # rows of P sum to 1 - P(sink): with V = 1 every output channel equals 1 - exp(s_aux - lse)
+    expect = 1.0 - torch.exp(s_aux[None, :, None] - lse)
+    assert (o.float() - expect[..., None]).abs().max().item() < 1e-2
+    # cross-check the whole tensor against the CUDA-core path on the same inputs
+    v = torch.randn(B, Hkv, N, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    o_t, lse_t, _ = _fwd(q, k, v, 0, W, s_aux)
+    o_s, lse_s, _ = _fwd(q, k, v, 0, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert maxdiff(o_t, o_s) < 2e-2
+    assert maxdiff(lse_t, lse_s) < 2e-3
+    # causality: perturbing the last 100 keys/values must not change earlier rows
+    k2, v2 = k.clone(), v.clone()
+    k2[:, :, -100:] += 1.0
+    v2[:, :, -100:] -= 1.0
+    o_p, _, _ = _fwd(q, k2, v2, 0, W, s_aux)
+    assert torch.equal(o_p[:, :, : N - 100], o_t[:, :, : N - 100])
+    # locality: rows i >= j + W never see key j
+    k3 = k.clone()
+    k3[:, :, :1000] *= -1.0
+    o_l, _, _ = _fwd(q, k3, v, 0, W, s_aux)
+    assert torch.equal(o_l[:, :, 1000 + W - 1:], o_t[:, :, 1000 + W - 1:])
+
+
+def test_c3_decode_full_size():
+    """BASELINE configs[3]: batch 64, sink 4 + window 4096 cache, Hq=64/Hkv=8, D=64, s_aux, bf16."""
+    B, Hq, Hkv, Nkv, D = 64, 64, 8, 4100, 64
+    g = torch.Generator(device="cuda").manual_seed(42)
+    q = torch.randn(B, Hq, 1, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    k = torch.randn(B, Hkv, Nkv, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    v = torch.randn(B, Hkv, Nkv, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    s_aux = torch.randn(Hq, device="cuda", generator=g) + 2.0
+    o = sa.sink_decode_attention(q, k, v, s_aux)
+    assert _lib.last_impl() == "mma"
+    # oracle on a slice of the batch (fp64 on the CPU), CUDA-core path on everything
+    ref = orc.decode_attention(q[:2].cpu(), k[:2].cpu(), v[:2].cpu(), s_aux.cpu())
+    assert maxdiff(o[:2], ref) < 1e-2
+    _lib.set_impl(_lib.IMPL_SIMT)
+    try:
+        o_s = sa.sink_decode_attention(q, k, v, s_aux)
+    finally:
+        _lib.set_impl(_lib.IMPL_AUTO)
+    assert maxdiff(o, o_s) < 1e-2
+    # order invariance: a rotated cache gives the same answer (the ring is read in place)
+    perm = torch.roll(torch.arange(Nkv, device="cuda"), 1234)
+    o_r = sa.sink_decode_attention(q, k[:, :, perm].contiguous(), v[:, :, perm].contiguous(), s_aux)
+    assert maxdiff(o, o_r) < 1e-2
+
+
+def test_errors_are_loud():
+    q = torch.randn(1, 4, 16, 64)
+    with pytest.raises(RuntimeError):
+        sa.sink_flash_attention(q, q, q, 0, 8)                     # CPU tensors: no fallback
+    qc = torch.randn(1, 4, 16, 64, device="cuda")
+    with pytest.raises(AssertionError):
+        sa.sink_flash_attention(qc, qc[:, :3], qc[:, :3], 0, 8)    # H_q % H_kv != 0
+    with pytest.raises(AssertionError):
+        sa.sink_decode_attention(qc, qc, qc)                       # N_q != 1

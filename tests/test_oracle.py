@@ -1,0 +1,92 @@
+"""CPU: the oracle replays the golden fixtures that oracle/make_golden.py generated from the
+REFERENCE (eager paths + Triton kernels under the interpreter).  This is what pins the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_cases as gc
+import sink_oracle as orc
+from _util import GOLDEN, load_decode, load_prefill, maxdiff
+
+
+@pytest.mark.parametrize("case", gc.PREFILL_CASES, ids=[c[0] for c in gc.PREFILL_CASES])
+def test_oracle_prefill_matches_reference(case):
+    (q, k, v, do, s_aux), z = load_prefill(case)
+    S, W = case[6], case[7]
+    o, lse = orc.sink_attention_fwd(q, k, v, S, W, s_aux)
+    dq, dk, dv, ds = orc.sink_attention_bwd(q, k, v, do, S, W, s_aux)
+    assert maxdiff(o, torch.from_numpy(z["o"])) < 2e-5
+    assert maxdiff(lse, torch.from_numpy(z["lse"])) < 2e-5
+    if z["lse_triton"].size:                                      # LSE the reference kernel saved
+        assert maxdiff(lse, torch.from_numpy(z["lse_triton"])) < 2e-5
+    if z["dq"].size:
+        assert maxdiff(dq, torch.from_numpy(z["dq"])) < 2e-5
+        assert maxdiff(dk, torch.from_numpy(z["dk"])) < 2e-5
+        assert maxdiff(dv, torch.from_numpy(z["dv"])) < 2e-5
+    else:
+        got = gc.checksum(dq, dk, dv)
+        assert abs(got - float(z["grad_checksum"])) < 1e-4 * float(z["grad_checksum"])
+    if s_aux is not None:
+        assert maxdiff(ds, torch.from_numpy(z["ds_aux"])) < 2e-5
+
+
+@pytest.mark.parametrize("case", gc.PREFILL_CASES[:6], ids=[c[0] for c in gc.PREFILL_CASES[:6]])
+def test_eager_restatement_autograd(case):
+    """The eager restatement (what bench.py times as the CPU baseline) reproduces the reference's
+    outputs and, through autograd, its gradients."""
+    (q, k, v, do, s_aux), z = load_prefill(case)
+    S, W = case[6], case[7]
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    sr = s_aux.clone().requires_grad_(True) if s_aux is not None else None
+    o = orc.eager_sink_attention(qr, kr, vr, S, W, sr)
+    o.backward(do)
+    assert maxdiff(o, torch.from_numpy(z["o"])) < 1e-6
+    if z["dq"].size:
+        assert maxdiff(qr.grad, torch.from_numpy(z["dq"])) < 1e-6
+        assert maxdiff(kr.grad, torch.from_numpy(z["dk"])) < 1e-6
+        assert maxdiff(vr.grad, torch.from_numpy(z["dv"])) < 1e-6
+
+
+@pytest.mark.parametrize("case", gc.DECODE_CASES, ids=[c[0] for c in gc.DECODE_CASES])
+def test_oracle_decode_matches_reference(case):
+    (q, k, v, s_aux), z = load_decode(case)
+    o = orc.decode_attention(q, k, v, s_aux)
+    assert maxdiff(o, torch.from_numpy(z["o"])) < 2e-5
+
+
+def test_mask_formula_and_pair_count():
+    for (n, s, w) in [(16, 2, 3), (64, 4, 16), (33, 0, 1), (40, 50, 8), (20, 3, 0), (128, 0, 128)]:
+        m = orc.attended_mask(n, s, w)
+        for i in range(n):
+            for j in range(n):
+                assert bool(m[i, j]) == ((j <= i) and (j < s or j >= i - w + 1))
+        assert int(m.sum()) == orc.attended_pairs(n, s, w)
+    # SURVEY.md 8(d) figures
+    assert orc.attended_pairs(256, 4, 128) == 25146
+    assert orc.attended_pairs(8192, 0, 128) == 1040448
+
+
+def test_degenerate_rows():
+    """window 0 and no sinks: O = 0 and LSE = s_aux; without s_aux LSE = -inf."""
+    g = torch.Generator().manual_seed(1)
+    q, k, v = (torch.randn(1, 2, 9, 16, generator=g) for _ in range(3))
+    s_aux = torch.tensor([0.3, -1.2])
+    o, lse = orc.sink_attention_fwd(q, k, v, 0, 0, s_aux)
+    assert o.abs().max().item() == 0.0
+    assert torch.allclose(lse, s_aux.double()[None, :, None].expand_as(lse))
+    o, lse = orc.sink_attention_fwd(q, k, v, 0, 0, None)
+    assert o.abs().max().item() == 0.0 and bool(torch.isinf(lse).all())
+
+
+def test_ring_cache_model_matches_reference_traces():
+    with open(os.path.join(GOLDEN, "cache_traces.json")) as f:
+        data = json.load(f)
+    for case in data["cases"]:
+        m = orc.RingCacheModel(case["S"], case["W"])
+        m.prefill(case["n_prefill"])
+        for expect in case["trace"]:
+            m.decode()
+            assert m.linear() == expect
