@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sink-attention hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one fwd+bwd pass of `sink_flash_attention` over one synthetic batch.
+  N = 1 : BASELINE.json configs[1] -- gpt-oss-20b attention layer, B=1 N=8192 Hq=64/Hkv=8 D=64
+          window=128 s_aux, bf16.  metric = masked-FLOP TFLOPS (14*D*pairs*B*Hq per step).
+  N > 1 : the same layer under Ulysses sequence parallelism over NVLink (torchrun, one rank per
+          GPU): every rank holds an 8192-token chunk of a (8192*N)-token sequence in HF layout,
+          all-to-all -> full sequence for Hq/N heads -> attention -> all-to-all back (and the
+          mirror image in backward).  Per-GPU work is fixed -> "scaling": "weak".
+One JSON line is printed by rank 0.  Extra objects: roofline (dominant kernel, measured live with
+CUDA events), cpu_baseline (the reference's eager masked-softmax path restated in oracle/, timed
+on the host cores on a bounded sample), e2e (same step through the public API from pinned host
+buffers, H2D/D2H inside the timed region), decode (configs[3] HBM GB/s), clocks.
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port of
+its eager path: the reference is Python/Triton, nothing to compile into oracle/_ref).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "sink-flash-attention-kernel_b200"))
+
+C1 = dict(B=1, N=8192, Hq=64, Hkv=8, D=64, S=0, W=128)            # BASELINE.json configs[1]
+C3 = dict(B=64, Nkv=4100, Hq=64, Hkv=8, D=64)                      # BASELINE.json configs[3]
+METRIC = "fwd+bwd masked-FLOP TFLOPS (gpt-oss-20b attention layer, bf16)"
+UNIT = "TFLOP/s"
+
+
+def attended_pairs(n, s, w):
+    w, s = max(w, 0), max(s, 0)
+    # sum_i [min(i+1, W) + min(S, max(0, i-W+1))] in closed form
+    full = max(0, n - w)
+    win = (min(n, w) * (min(n, w) + 1)) // 2 + full * w
+    sink = 0
+    if s > 0 and n > w:
+        m = n - w                                   # rows i = w .. n-1 see min(s, i-w+1) sinks
+        t = min(s, m)
+        sink = t * (t + 1) // 2 + (m - t) * s
+    return win + sink
+
+
+def masked_flops(cfg, n=None):
+    n = cfg["N"] if n is None else n
+    return 14 * cfg["D"] * attended_pairs(n, cfg["S"], cfg["W"]) * cfg["B"] * cfg["Hq"]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"          # B200_PROFILING.md stated fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's eager masked-softmax path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_eager_sample(n_sample, heads, steps, warmup, threads):
+    """fwd+bwd of the eager path (oracle port of tests/test_s_aux.py:16-72) on a bounded sample of
+    the C1 workload: the first `n_sample` positions of `heads` q heads (eager materialises N x N)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sink_oracle as orc
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(42)
+    hkv = max(1, heads // (C1["Hq"] // C1["Hkv"]))
+    q = torch.randn(1, heads, n_sample, C1["D"], generator=g, requires_grad=True)
+    k = torch.randn(1, hkv, n_sample, C1["D"], generator=g, requires_grad=True)
+    v = torch.randn(1, hkv, n_sample, C1["D"], generator=g, requires_grad=True)
+    s_aux = (torch.randn(heads, generator=g) * 0.5).requires_grad_(True)
+    do = torch.randn(1, heads, n_sample, C1["D"], generator=g)
+    times = []
+    for it in range(warmup + steps):
+        for t in (q, k, v, s_aux):
+            t.grad = None
+        t0 = time.perf_counter()
+        o = orc.eager_sink_attention(q, k, v, C1["S"], C1["W"], s_aux)
+        o.backward(do)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    flops = 14 * C1["D"] * attended_pairs(n_sample, C1["S"], C1["W"]) * heads
+    return flops, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample, heads = 2048, 16
+    flops, times = cpu_eager_sample(n_sample, heads, args.steps, max(args.warmup, 1), threads)
+    ms = 1e3 * sum(times) / len(times)
+    val = flops / (ms * 1e-3) / 1e12
+    sample = (f"first {n_sample} positions x {heads} q heads of the C1 layer (eager path materialises N x N scores; "
+              f"fp32, torch {threads} threads)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "gpt-oss-20b attention layer fwd+bwd (BASELINE configs[1]): B=1 N=8192 Hq=64 Hkv=8 D=64 "
+                               "window=128 s_aux", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sink_attention as sa
+    from sink_attention import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, tf_burst, tf_sust, peak_src = load_peaks()
+    cfg = C1
+    B, N, Hq, Hkv, D, S, W = (cfg[k] for k in ("B", "N", "Hq", "Hkv", "D", "S", "W"))
+    dt = torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(rank + 1)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(steps):
+            flush_l2()
+            a, b = ev(), ev()
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return ts
+
+    s_aux = (torch.randn(Hq, device=dev, generator=g) * 0.5).requires_grad_(True)
+    if world == 1:
+        q = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt).requires_grad_(True)
+        k = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt).requires_grad_(True)
+        v = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt).requires_grad_(True)
+        do = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt)
+
+        def step():
+            for t in (q, k, v, s_aux):
+                t.grad = None
+            o = sa.sink_flash_attention(q, k, v, S, W, s_aux)
+            o.backward(do)
+        n_total = N
+        launches_per_step = 1 + 4           # fwd; bwd = preprocess + ds_aux reduce + dQ + dK/dV
+        workload = ("gpt-oss-20b attention layer fwd+bwd (BASELINE configs[1]): B=1 N=8192 Hq=64 Hkv=8 D=64 window=128 "
+                    "s_aux bf16")
+        parallelism = "single GPU"
+    else:
+        assert Hkv % world == 0, "Ulysses needs the GPU count to divide H_kv=8"
+        n_total = N * world
+        q = torch.randn(B, N, Hq, D, device=dev, generator=g).to(dt).requires_grad_(True)       # HF layout chunk
+        k = torch.randn(B, N, Hkv, D, device=dev, generator=g).to(dt).requires_grad_(True)
+        v = torch.randn(B, N, Hkv, D, device=dev, generator=g).to(dt).requires_grad_(True)
+        do = torch.randn(B, N, Hq, D, device=dev, generator=g).to(dt)
+        uly = sa.UlyssesSinkAttention(num_sink=S, window_size=W, sp_group=None, head_chunks=1)
+
+        def step():
+            for t in (q, k, v, s_aux):
+                t.grad = None
+            o = uly(q, k, v, s_aux)
+            o.backward(do)
+        launches_per_step = 1 + 4
+        workload = (f"gpt-oss-20b attention layer fwd+bwd under Ulysses SP: {N}-token chunk per rank of a {n_total}-token "
+                    f"sequence, Hq=64 Hkv=8 D=64 window=128 s_aux bf16, all-to-all over NVLink each side")
+        parallelism = f"ulysses_sp{world}"
+
+    # ---- the timed region: warm-up, barrier + sync, K steps (per-step CUDA events, L2 flushed between), sync
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    per_step = []
+    for _ in range(args.steps):
+        flush_l2()
+        if world > 1:
+            dist.barrier()
+        a, b = ev(), ev()
+        a.record()
+        step()
+        b.record()
+        b.synchronize()
+        per_step.append(a.elapsed_time(b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(per_step) / len(per_step)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    # masked FLOPs of the whole job: every rank's Hq/world heads over the full n_total sequence
+    job_flops = 14 * D * attended_pairs(n_total, S, W) * B * Hq
+    value = job_flops / (ms * 1e-3) / 1e12
+
+    line = None
+    if rank == 0:
+        fwd_impl = bwd_impl = None
+        roof = None
+        decode = None
+        e2e = None
+        cpu_base = None
+        if world == 1:
+            # ---- per-kernel times (CUDA events on the launching stream) -> dominant kernel roofline
+            qd, kd, vd = q.detach(), k.detach(), v.detach()
+            sd = s_aux.detach()
+            t_fwd = timed(lambda: sa.sink_flash_attention_with_lse(qd, kd, vd, S, W, sd), 10, 3)
+            fwd_impl = _lib.last_impl()
+            o_s, lse_s = sa.sink_flash_attention_with_lse(qd, kd, vd, S, W, sd)
+            stage_ms = {}
+            for name, mask in (("bwd_preprocess(delta,ds_aux)", 1), ("bwd_dq", 2), ("bwd_dkdv", 4)):
+                _lib.load().sfa_set_bwd_stages(mask)
+                try:
+                    ts = timed(lambda: _lib.bwd(qd, kd, vd, o_s, do, lse_s, S, W, sd), 10, 3)
+                finally:
+                    _lib.load().sfa_set_bwd_stages(7)
+                stage_ms[name] = statistics.median(ts)
+            bwd_impl = _lib.last_impl()
+            stage_ms["fwd"] = statistics.median(t_fwd)
+            e = 2
+            bytes_alg = {
+                "fwd": 2 * B * Hq * N * D * e + 2 * B * Hkv * N * D * e + 4 * B * Hq * N,
+                "bwd_preprocess(delta,ds_aux)": 2 * B * Hq * N * D * e + 2 * 4 * B * Hq * N,
+                "bwd_dq": 3 * B * Hq * N * D * e + 2 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
+                "bwd_dkdv": 2 * B * Hq * N * D * e + 4 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
+            }
+            pairs = attended_pairs(N, S, W) * B * Hq
+            flops_alg = {"fwd": 4 * D * pairs, "bwd_preprocess(delta,ds_aux)": 2 * B * Hq * N * D,
+                         "bwd_dq": 6 * D * pairs, "bwd_dkdv": 8 * D * pairs}
+            dom = max(stage_ms, key=stage_ms.get)
+            dur = stage_ms[dom] * 1e-3
+            ach = bytes_alg[dom] / dur / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes": bytes_alg[dom], "avg_launch_ms": stage_ms[dom],
+                    "tensor_tflops": flops_alg[dom] / dur / 1e12, "tensor_frac_of_burst_peak": flops_alg[dom] / dur / 1e12 / tf_burst,
+                    "kernel_ms": stage_ms, "impl": {"fwd": fwd_impl, "bwd": bwd_impl}}
+            roof["whole_step"] = {
+                "algorithmic_bytes": 459.3e6, "hbm_floor_ms": 459.3e6 / (hbm_peak * 1e9) * 1e3,
+                "tensor_floor_ms_at_burst_peak": job_flops / (tf_burst * 1e12) * 1e3,
+                "frac_of_hbm_roofline": (459.3e6 / (hbm_peak * 1e9) * 1e3) / ms,
+                "frac_of_bf16_burst_peak": value / tf_burst,
+            }
+            # ---- decode (BASELINE configs[3]): HBM GB/s, each KV byte counted once
+            Bd, Nkv = C3["B"], C3["Nkv"]
+            qq = torch.randn(Bd, Hq, 1, D, device=dev, generator=g).to(dt)
+            kk = torch.randn(Bd, Hkv, Nkv, D, device=dev, generator=g).to(dt)
+            vv = torch.randn(Bd, Hkv, Nkv, D, device=dev, generator=g).to(dt)
+            td = timed(lambda: sa.sink_decode_attention(qq, kk, vv, sd), 20, 5)
+            dms = statistics.median(td)
+            dbytes = 2 * Bd * Hkv * Nkv * D * 2 + 2 * Bd * Hq * D * 2
+            decode = {"workload": "KV-cache decode (BASELINE configs[3]): batch 64, sink 4 + window 4096, Hq=64 Hkv=8 D=64 "
+                                  "s_aux bf16", "ms_per_step": dms, "hbm_GBps": dbytes / (dms * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": dbytes / (dms * 1e-3) / 1e9 / hbm_peak, "tokens_per_s": Bd / (dms * 1e-3),
+                      "algorithmic_bytes": dbytes, "impl": _lib.last_impl(), "gpu_launches_per_step": 2}
+            del qq, kk, vv
+            # ---- e2e: the public API from pinned HOST buffers, H2D + D2H inside the timed region
+            hq_, hk_, hv_, hdo_ = (t.detach().cpu().pin_memory() for t in (q, k, v, do))
+            hs_ = s_aux.detach().cpu().pin_memory()
+            ho = torch.empty_like(hq_).pin_memory()
+            hdq, hdk, hdv = torch.empty_like(hq_).pin_memory(), torch.empty_like(hk_).pin_memory(), torch.empty_like(hv_).pin_memory()
+            hds = torch.empty_like(hs_).pin_memory()
+
+            def e2e_step():
+                dq_, dk_, dv_, ddo_ = (t.to(dev, non_blocking=True) for t in (hq_, hk_, hv_, hdo_))
+                ds_ = hs_.to(dev, non_blocking=True).requires_grad_(True)
+                dq_.requires_grad_(True); dk_.requires_grad_(True); dv_.requires_grad_(True)
+                o = sa.sink_flash_attention(dq_, dk_, dv_, S, W, ds_)
+                o.backward(ddo_)
+                ho.copy_(o.detach(), non_blocking=True)
+                hdq.copy_(dq_.grad, non_blocking=True); hdk.copy_(dk_.grad, non_blocking=True)
+                hdv.copy_(dv_.grad, non_blocking=True); hds.copy_(ds_.grad, non_blocking=True)
+            te = timed(e2e_step, max(3, min(args.steps, 10)), 2)
+            ems = sum(te) / len(te)
+            h2d = sum(t.numel() * t.element_size() for t in (hq_, hk_, hv_, hdo_, hs_))
+            d2h = sum(t.numel() * t.element_size() for t in (ho, hdq, hdk, hdv, hds))
+            e2e = {"value": job_flops / (ems * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": ems}
+            # ---- CPU baseline beside it (bounded sample, ~10-30 s)
+            threads = os.cpu_count() or 1
+            n_s, h_s = 2048, 16
+            fl, tm = cpu_eager_sample(n_s, h_s, 3, 1, threads)
+            cpu_base = {"value": fl / (sum(tm) / len(tm)) / 1e12, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"first {n_s} positions x {h_s} q heads of the C1 layer, fp32 eager masked-softmax "
+                                  f"fwd+autograd bwd, {len(tm)} timed passes"}
+        else:
+            # multi-GPU e2e: the same Ulysses step fed from pinned host chunks
+            hq_, hk_, hv_, hdo_ = (t.detach().cpu().pin_memory() for t in (q, k, v, do))
+            ho = torch.empty_like(hq_).pin_memory()
+            e2e = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "parallelism": parallelism, "global_tokens": n_total * B,
+                       "masked_flops_per_step": job_flops,
+                       "l2": "256 MiB buffer written between timed steps; per-step CUDA events summed"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if roof is not None:
+            line["roofline"] = roof
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        if decode is not None:
+            line["decode"] = decode
+        if e2e is not None:
+            line["e2e"] = e2e
+    if world > 1:
+        # e2e at N GPUs: every rank feeds its chunk from pinned host memory and reads its O chunk back
+        hq_, hk_, hv_, hdo_ = (t.detach().cpu().pin_memory() for t in (q, k, v, do))
+        hs_ = s_aux.detach().cpu().pin_memory()
+        ho = torch.empty_like(hq_).pin_memory()
+        hdq, hdk, hdv = torch.empty_like(hq_).pin_memory(), torch.empty_like(hk_).pin_memory(), torch.empty_like(hv_).pin_memory()
+
+        def e2e_step():
+            dq_, dk_, dv_, ddo_ = (t.to(dev, non_blocking=True) for t in (hq_, hk_, hv_, hdo_))
+            ds_ = hs_.to(dev, non_blocking=True).requires_grad_(True)
+            dq_.requires_grad_(True); dk_.requires_grad_(True); dv_.requires_grad_(True)
+            o = uly(dq_, dk_, dv_, ds_)
+            o.backward(ddo_)
+            ho.copy_(o.detach(), non_blocking=True)
+            hdq.copy_(dq_.grad, non_blocking=True); hdk.copy_(dk_.grad, non_blocking=True); hdv.copy_(dv_.grad, non_blocking=True)
+        te = timed(e2e_step, max(3, min(args.steps, 10)), 2)
+        t = torch.tensor([sum(te) / len(te)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            h2d = sum(x.numel() * x.element_size() for x in (hq_, hk_, hv_, hdo_, hs_)) * world
+            d2h = sum(x.numel() * x.element_size() for x in (ho, hdq, hdk, hdv)) * world
+            line["e2e"] = {"value": job_flops / (t.item() * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                           "d2h_bytes_per_step": d2h, "ms_per_step": t.item()}
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,9 @@ extern "C" {
 int sfa_version(void);
 const char* sfa_last_error(void);
 int sfa_set_impl(int impl);
+/* timing aid for bench.py: run only the selected backward stages (bit0 = delta/ds_aux preprocess,
+ * bit1 = dQ kernel, bit2 = dK/dV kernel); default 7 = all.  Results are complete only with 7. */
+int sfa_set_bwd_stages(int mask);
 /* name of the kernel family the last call on this thread dispatched to ("tcgen05", "simt", "mma") */
 const char* sfa_last_impl(void);
 

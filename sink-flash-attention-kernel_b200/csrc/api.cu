@@ -11,6 +11,7 @@ namespace sfa {
 static thread_local char g_err[512] = "";
 static thread_local const char* g_impl = "";
 static int g_force_impl = SFA_IMPL_AUTO;
+static int g_bwd_stages = 7;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -70,6 +71,11 @@ int sfa_set_impl(int impl) {
     return -1;
   }
   g_force_impl = impl;
+  return 0;
+}
+
+int sfa_set_bwd_stages(int mask) {
+  g_bwd_stages = mask & 7;
   return 0;
 }
 
@@ -146,13 +152,14 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   p.delta = static_cast<float*>(workspace);
   float* ds_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)B * Hq * N * 4, 256));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
+  if (g_bwd_stages & 1)
+    if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
   if (g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype)) {
     set_impl_name("tcgen05");
-    return cuda_ret(tc_bwd(p, dtype, st), "sfa_bwd(tcgen05)");
+    return cuda_ret(tc_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(tcgen05)");
   }
   set_impl_name("simt");
-  return cuda_ret(simt_bwd(p, dtype, st), "sfa_bwd(simt)");
+  return cuda_ret(simt_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(simt)");
 }
 
 static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {

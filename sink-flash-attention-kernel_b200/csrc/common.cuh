@@ -69,14 +69,14 @@ __host__ __device__ __forceinline__ bool attended(int i, int j, int S, int W) {
 
 // launchers implemented in the .cu files; every one returns a cudaError_t
 cudaError_t simt_fwd(const AttnParams& p, int dtype, cudaStream_t st);
-cudaError_t simt_bwd(const AttnParams& p, int dtype, cudaStream_t st);
+cudaError_t simt_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
 cudaError_t simt_decode(const DecodeParams& p, int dtype, cudaStream_t st);
 cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st);
 
 bool tc_fwd_supported(const AttnParams& p, int dtype);
 cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_bwd_supported(const AttnParams& p, int dtype);
-cudaError_t tc_bwd(const AttnParams& p, int dtype, cudaStream_t st);
+cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
 
 bool mma_decode_supported(const DecodeParams& p, int dtype);
 int mma_decode_splits(int B, int Hkv, int total_len);

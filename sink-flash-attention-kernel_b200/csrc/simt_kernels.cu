@@ -376,16 +376,22 @@ cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cu
   });
 }
 
-cudaError_t simt_bwd(const AttnParams& p, int dtype, cudaStream_t st) {
+cudaError_t simt_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
   return dispatch_dtype(dtype, [&](auto tag) {
     using T = decltype(tag);
-    dim3 gq((p.N + 3) / 4, p.Hq, p.B);
-    simt_dq_kernel<T><<<gq, 128, 0, st>>>(p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    dim3 gk((p.N + 3) / 4, p.Hkv, p.B);
-    simt_dkdv_kernel<T><<<gk, 128, 0, st>>>(p);
-    return cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    if (stages & 2) {
+      dim3 gq((p.N + 3) / 4, p.Hq, p.B);
+      simt_dq_kernel<T><<<gq, 128, 0, st>>>(p);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+    if (stages & 4) {
+      dim3 gk((p.N + 3) / 4, p.Hkv, p.B);
+      simt_dkdv_kernel<T><<<gk, 128, 0, st>>>(p);
+      e = cudaGetLastError();
+    }
+    return e;
   });
 }
 

@@ -19,7 +19,7 @@ OP_FWD, OP_BWD, OP_DECODE = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
-    "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_last_impl", "sfa_workspace_bytes",
+    "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_last_impl", "sfa_workspace_bytes",
     "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma",
 )
 
@@ -51,6 +51,8 @@ def load() -> ctypes.CDLL:
     lib.sfa_last_impl.restype = c.c_char_p
     lib.sfa_set_impl.argtypes = [i]
     lib.sfa_set_impl.restype = i
+    lib.sfa_set_bwd_stages.argtypes = [i]
+    lib.sfa_set_bwd_stages.restype = i
     lib.sfa_workspace_bytes.argtypes = [i] * 7
     lib.sfa_workspace_bytes.restype = c.c_size_t
     lib.sfa_fwd.argtypes = [p, p, p, p, f32p, f32p] + [i] * 8 + [i64p] * 4 + [p, c.c_size_t, p]
