@@ -1,0 +1,91 @@
+// Device helpers shared by the tcgen05 forward and backward kernels: the two-range KV tile plan,
+// 16-bit packing, and TMA tile loads that honour a per-tensor (position, head) dim order.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace sfa {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// KV tiles seen by the packed query tile [q0, q0+P): sink tiles over [0, min(S, q_hi+1)) first,
+// then BN-row tiles over the causal band [max(q0-W+1, S, 0), q_hi].  Same walk as the reference's
+// two ranges (sink_flash_attention.py:151-180) but with run-time, unaligned tile starts.
+struct TilePlan {
+  int n_sink, n_tiles, w_lo, q_hi, s_eff;
+  __device__ __forceinline__ void tile(int t, int BN, int& kstart, int& cols, bool& is_sink) const {
+    if (t < n_sink) {
+      is_sink = true;
+      kstart = t * BN;
+      cols = min(BN, ((s_eff - kstart + 15) >> 4) << 4);
+    } else {
+      is_sink = false;
+      kstart = w_lo + (t - n_sink) * BN;
+      cols = min(BN, ((q_hi + 1 - kstart + 15) >> 4) << 4);
+    }
+  }
+};
+
+__device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W, int BN) {
+  TilePlan pl;
+  pl.q_hi = min(q0 + P, N) - 1;
+  pl.s_eff = min(S, pl.q_hi + 1);
+  pl.n_sink = (pl.s_eff > 0) ? (pl.s_eff + BN - 1) / BN : 0;
+  pl.w_lo = max(max(q0 - W + 1, S), 0);
+  const int n_win = (W > 0 && pl.w_lo <= pl.q_hi) ? (pl.q_hi - pl.w_lo + BN) / BN : 0;
+  pl.n_tiles = pl.n_sink + n_win;
+  return pl;
+}
+
+// attended columns [c_lo, c_hi] of query position i inside a tile that starts at key `kstart`
+__device__ __forceinline__ void row_range(bool is_sink, int i, int kstart, int cols, int S, int W, int& c_lo, int& c_hi) {
+  if (is_sink) {
+    c_lo = 0;
+    c_hi = min(S, i + 1) - kstart - 1;
+  } else {
+    c_lo = max(max(i - W + 1, S) - kstart, 0);
+    c_hi = i - kstart;
+  }
+  c_hi = min(c_hi, cols - 1);
+}
+
+template <typename T> __device__ __forceinline__ uint32_t pack16(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack16<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void tma_tile(void* dst, const CUtensorMap* m, uint64_t* bar, int swap, int d, int n, int h,
+                                         int b) {
+  if (swap) tma_load_4d(dst, m, bar, d, h, n, b);
+  else tma_load_4d(dst, m, bar, d, n, h, b);
+}
+__device__ __forceinline__ void tma_tile_store(const CUtensorMap* m, const void* src, int swap, int d, int n, int h, int b) {
+  if (swap) tma_store_4d(m, src, d, h, n, b);
+  else tma_store_4d(m, src, d, n, h, b);
+}
+
+// GQA packing: G heads x P positions = 128 MMA rows (G = largest power of two dividing the group, <= 16)
+inline void pick_packing(int Hq, int Hkv, int& G, int& P) {
+  const int group = Hq / Hkv;
+  G = 1;
+  while (G < 16 && group % (G * 2) == 0) G *= 2;
+  P = 128 / G;
+}
+
+// KV tile rows: split the widest band (min(W,N) + P - 1 keys) into equal tiles of <= bn_max rows
+inline int pick_bn(int W, int N, int P, int bn_max) {
+  int64_t span = (int64_t)(W < N ? W : N) + P - 1;
+  if (span < 16) span = 16;
+  if (span > (int64_t)N + P) span = (int64_t)N + P;
+  const int nt = (int)((span + bn_max - 1) / bn_max);
+  int bn = (int)(((span + nt - 1) / nt + 15) / 16 * 16);
+  return bn > bn_max ? bn_max : bn;
+}
+
+}  // namespace sfa

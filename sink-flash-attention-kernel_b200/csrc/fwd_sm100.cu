@@ -16,15 +16,11 @@
 // exp2 units with 1/sqrt(D)*log2(e) folded into one FFMA, and rescales O lazily (only when the
 // running max moved by more than 2^8).  Epilogue: O/l -> 16-bit -> swizzled smem -> TMA store;
 // LSE = m*ln2 + log(l) (natural log, sink term included, :192).
-#include "common.cuh"
+#include "attn_common.cuh"
 #include "tmap.cuh"
-#include "umma.cuh"
 
 namespace sfa {
 namespace {
-
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
 
 template <int D> struct FwdCfg {
   static constexpr int kDS = D / 64;                       // 64-channel slabs (one SWIZZLE_128B row each)
@@ -49,48 +45,6 @@ struct FwdArgs {
   const float* s_aux;
   float* lse;
 };
-
-struct TilePlan {
-  int n_sink, n_tiles, w_lo, q_hi, s_eff;
-  __device__ __forceinline__ void tile(int t, int BN, int& kstart, int& cols, bool& is_sink) const {
-    if (t < n_sink) {
-      is_sink = true;
-      kstart = t * BN;
-      cols = min(BN, ((s_eff - kstart + 15) >> 4) << 4);
-    } else {
-      is_sink = false;
-      kstart = w_lo + (t - n_sink) * BN;
-      cols = min(BN, ((q_hi + 1 - kstart + 15) >> 4) << 4);
-    }
-  }
-};
-
-__device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W, int BN) {
-  TilePlan pl;
-  pl.q_hi = min(q0 + P, N) - 1;
-  pl.s_eff = min(S, pl.q_hi + 1);
-  pl.n_sink = (pl.s_eff > 0) ? (pl.s_eff + BN - 1) / BN : 0;
-  pl.w_lo = max(max(q0 - W + 1, S), 0);
-  const int n_win = (W > 0 && pl.w_lo <= pl.q_hi) ? (pl.q_hi - pl.w_lo + BN) / BN : 0;
-  pl.n_tiles = pl.n_sink + n_win;
-  return pl;
-}
-
-template <typename T> __device__ __forceinline__ uint32_t pack16(float a, float b);
-template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-template <> __device__ __forceinline__ uint32_t pack16<__half>(float a, float b) {
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-__device__ __forceinline__ void tma_tile(void* dst, const CUtensorMap* m, uint64_t* bar, int swap, int d, int n, int h,
-                                         int b) {
-  if (swap) tma_load_4d(dst, m, bar, d, h, n, b);
-  else tma_load_4d(dst, m, bar, d, n, h, b);
-}
 
 template <typename T, int D>
 __global__ void __launch_bounds__(192) fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -215,14 +169,7 @@ __global__ void __launch_bounds__(192) fwd_kernel(const __grid_constant__ CUtens
       int kstart, cols; bool is_sink;
       pl.tile(t, a.BN, kstart, cols, is_sink);
       int c_lo, c_hi;   // attended columns of this row inside the tile: [c_lo, c_hi]
-      if (is_sink) {
-        c_lo = 0;
-        c_hi = min(a.S, i + 1) - kstart - 1;
-      } else {
-        c_lo = max(max(i - a.W + 1, a.S) - kstart, 0);
-        c_hi = i - kstart;
-      }
-      c_hi = min(c_hi, cols - 1);
+      row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
       mbar_wait(s_full, t & 1);
       tc_fence_after();
       // pass 1: row max over the attended columns
@@ -348,17 +295,9 @@ cudaError_t launch_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
     attr_done = true;
   }
   const int group = p.Hq / p.Hkv;
-  int G = 1;
-  while (G < 16 && group % (G * 2) == 0) G *= 2;
-  const int P = 128 / G;
-  // KV tile rows: cover the widest band (W + P - 1 keys) in equal tiles of <= kBNMax rows
-  int64_t span = (int64_t)min(p.W, p.N) + P - 1;
-  if (span < 16) span = 16;
-  if (span > p.N + P) span = p.N + P;
-  int nt = (int)((span + C::kBNMax - 1) / C::kBNMax);
-  int BN = (int)(((span + nt - 1) / nt + 15) / 16 * 16);
-  if (BN > C::kBNMax) BN = C::kBNMax;
-  if (p.S > 0 && BN < 16) BN = 16;
+  int G, P;
+  pick_packing(p.Hq, p.Hkv, G, P);
+  const int BN = pick_bn(p.W, p.N, P, C::kBNMax);
 
   TileMap mq, mk, mv, mo;
   if (!make_tile_map(&mq, p.q, dtype, D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
