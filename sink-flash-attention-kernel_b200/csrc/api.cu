@@ -9,7 +9,7 @@
 namespace sfa {
 
 static thread_local char g_err[512] = "";
-static thread_local const char* g_impl = "";
+static const char* volatile g_impl = "";   // process-wide: autograd runs backward on its own thread
 static int g_force_impl = SFA_IMPL_AUTO;
 static int g_bwd_stages = 7;
 

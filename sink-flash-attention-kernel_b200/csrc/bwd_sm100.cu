@@ -1,6 +1,703 @@
-// placeholder until the tcgen05 backward lands (next commit)
-#include "common.cuh"
+// Backward sink attention on the 5th-gen tensor cores (reference kernels being replaced:
+// _sink_flash_attn_bwd_dq_kernel sink_flash_attention.py:371-484 and
+// _sink_flash_attn_bwd_dkdv_kernel :256-364, plus the torch GQA group-sum :648-651).
+//
+// Two persistent kernels share the forward's packed tile (128 MMA rows = G q-heads x P positions
+// of one KV head) and its two-range KV walk:
+//
+//  dq_kernel   (Q-stationary)   per KV tile:  S = Q K^T,  dP = dO V^T      (SS UMMAs, fp32 in TMEM)
+//                                             dS = exp2(S*c - lse) * (dP - delta)  -> 16-bit, written
+//                                             over the already-consumed S/dP columns
+//                                             dQ += dS K                   (TS UMMA, K tile MN-major)
+//              epilogue: dQ * scale -> 16-bit -> swizzled smem -> TMA store.
+//
+//  dkdv_kernel (KV-stationary)  one CTA per 128-key tile; per packed Q chunk that can see it:
+//                                             S^T = K Q^T, dP^T = V dO^T   (keys on the TMEM lanes)
+//                                             P^T, dS^T -> 16-bit in TMEM
+//                                             dV += P^T dO,  dK += dS^T Q  (TS UMMAs)
+//              The q heads of a GQA group are MMA rows of the same chunk, so the group sum of
+//              dK/dV happens inside the fp32 accumulators (no [B,Hq,N,D] temporaries).
+//
+// Warp roles (320 threads): warps 0-7 element-wise math + epilogue (two warps per TMEM lane
+// quarter, each taking half of the columns), warp 8 TMA producer, warp 9 tcgen05.mma issuer.
+#include "attn_common.cuh"
+#include "tmap.cuh"
+
 namespace sfa {
-bool tc_bwd_supported(const AttnParams&, int) { return false; }
-cudaError_t tc_bwd(const AttnParams&, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int kMathWarps = 8;
+constexpr int kMathThreads = kMathWarps * 32;
+constexpr int kThreads = kMathThreads + 64;
+
+struct BwdArgs {
+  int B, N, S, W, Hq, G, P, BN, groups_per_kv, ny, nblk, total_tiles;
+  int q_swap, k_swap, v_swap, dq_swap;
+  int fmt;       // 0 f16, 1 bf16
+  float sl2;     // scale * log2(e)
+  float scale;
+  const float* lse;
+  const float* delta;
+};
+
+__device__ __forceinline__ void decode_tile(const BwdArgs& a, int tile, int& pb, int& y, int& b) {
+  pb = tile % a.nblk;
+  const int r = tile / a.nblk;
+  y = r % a.ny;
+  b = r / a.ny;
+}
+
+// ================================================================================== dQ kernel
+template <int D> struct DqCfg {
+  static constexpr int kDS = D / 64;
+  static constexpr int kBNMax = (D == 64) ? 160 : 128;
+  static constexpr int kStages = (D == 64) ? 2 : 1;     // K and V rings
+  static constexpr int kQStages = 2;                    // Q / dO tiles
+  static constexpr int kQBytes = 128 * D * 2;
+  static constexpr int kKVBytes = kBNMax * D * 2;
+  static constexpr int kSlabQ = 128 * 128;
+  static constexpr int kSlabKV = kBNMax * 128;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kColS = 0;
+  static constexpr uint32_t kColP = kBNMax;             // dP
+  static constexpr uint32_t kColQ = 2 * kBNMax;         // dQ accumulator
+  static constexpr int kSmem = 1024 + 2 * kQStages * kQBytes + 2 * kStages * kKVBytes + 256;
+  static_assert(2 * kBNMax + D <= 512, "TMEM budget");
+  static_assert(kSmem <= 227 * 1024, "smem budget");
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                         const __grid_constant__ CUtensorMap tmdO,
+                                                         const __grid_constant__ CUtensorMap tmK,
+                                                         const __grid_constant__ CUtensorMap tmV,
+                                                         const __grid_constant__ CUtensorMap tmdQ, const BwdArgs a) {
+  using C = DqCfg<D>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* q_s = smem;                                   // [kQStages][kQBytes]
+  unsigned char* do_s = q_s + C::kQStages * C::kQBytes;        // [kQStages][kQBytes]
+  unsigned char* k_s = do_s + C::kQStages * C::kQBytes;        // [kStages][kKVBytes]
+  unsigned char* v_s = k_s + C::kStages * C::kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + C::kStages * C::kKVBytes);
+  uint64_t* qdo_full = bars;                       // [2]
+  uint64_t* qdo_empty = qdo_full + C::kQStages;    // [2]
+  uint64_t* k_full = qdo_empty + C::kQStages;
+  uint64_t* k_empty = k_full + C::kStages;
+  uint64_t* v_full = k_empty + C::kStages;
+  uint64_t* v_empty = v_full + C::kStages;
+  uint64_t* s_full = v_empty + C::kStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* dq_done = p_full + 1;
+  uint64_t* dq_free = dq_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kMathWarps && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdQ);
+    for (int s = 0; s < C::kQStages; ++s) {
+      mbar_init(qdo_full + s, 1);
+      mbar_init(qdo_empty + s, 1);
+    }
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(k_full + s, 1);
+      mbar_init(k_empty + s, 1);
+      mbar_init(v_full + s, 1);
+      mbar_init(v_empty + s, 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, kMathThreads);
+    mbar_init(dq_done, 1);
+    mbar_init(dq_free, kMathThreads);
+    fence_barrier_init();
+  }
+  if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kMathWarps) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int kvc = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        int pb, y, b;
+        decode_tile(a, tile, pb, y, b);
+        const int q0 = pb * a.P, hq0 = y * a.G, kvh = y / a.groups_per_kv;
+        const TilePlan pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN);
+        const int qs = it % C::kQStages;
+        mbar_wait(qdo_empty + qs, ((it / C::kQStages) & 1) ^ 1);
+        mbar_expect_tx(qdo_full + qs, 2 * C::kQBytes);
+        for (int s = 0; s < C::kDS; ++s) {
+          tma_tile(q_s + qs * C::kQBytes + s * C::kSlabQ, &tmQ, qdo_full + qs, a.q_swap, s * 64, q0, hq0, b);
+          tma_tile(do_s + qs * C::kQBytes + s * C::kSlabQ, &tmdO, qdo_full + qs, a.q_swap, s * 64, q0, hq0, b);
+        }
+        for (int t = 0; t < pl.n_tiles; ++t, ++kvc) {
+          int kstart, cols; bool is_sink;
+          pl.tile(t, a.BN, kstart, cols, is_sink);
+          const int st = kvc % C::kStages;
+          const uint32_t ph = (kvc / C::kStages) & 1;
+          mbar_wait(k_empty + st, ph ^ 1);
+          mbar_expect_tx(k_full + st, a.BN * D * 2);
+          for (int s = 0; s < C::kDS; ++s)
+            tma_tile(k_s + st * C::kKVBytes + s * C::kSlabKV, &tmK, k_full + st, a.k_swap, s * 64, kstart, kvh, b);
+          mbar_wait(v_empty + st, ph ^ 1);
+          mbar_expect_tx(v_full + st, a.BN * D * 2);
+          for (int s = 0; s < C::kDS; ++s)
+            tma_tile(v_s + st * C::kKVBytes + s * C::kSlabKV, &tmV, v_full + st, a.v_swap, s * 64, kstart, kvh, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMathWarps + 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_dq = make_idesc(a.fmt, 128, D, 0, 1);
+      int kvc = 0, item = 0, it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        int pb, y, b;
+        decode_tile(a, tile, pb, y, b);
+        const TilePlan pl = make_plan(pb * a.P, a.P, a.N, a.S, a.W, a.BN);
+        const int qs = it % C::kQStages;
+        mbar_wait(qdo_full + qs, (it / C::kQStages) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(q_s + qs * C::kQBytes), doa = smem_u32(do_s + qs * C::kQBytes);
+        for (int t = 0; t < pl.n_tiles; ++t, ++kvc, ++item) {
+          int kstart, cols; bool is_sink;
+          pl.tile(t, a.BN, kstart, cols, is_sink);
+          const int st = kvc % C::kStages;
+          const uint32_t ph = (kvc / C::kStages) & 1;
+          const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
+          const uint32_t ka = smem_u32(k_s + st * C::kKVBytes), va = smem_u32(v_s + st * C::kKVBytes);
+          mbar_wait(k_full + st, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int s = 0; s < C::kDS; ++s)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + C::kColS, make_sdesc(qa + s * C::kSlabQ + kk * 32, 16, 1024),
+                      make_sdesc(ka + s * C::kSlabKV + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
+          mbar_wait(v_full + st, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int s = 0; s < C::kDS; ++s)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + C::kColP, make_sdesc(doa + s * C::kSlabQ + kk * 32, 16, 1024),
+                      make_sdesc(va + s * C::kSlabKV + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
+          umma_commit(v_empty + st);
+          umma_commit(s_full);
+          mbar_wait(p_full, item & 1);
+          tc_fence_after();
+          if (t == 0 && it > 0) {
+            mbar_wait(dq_free, (it - 1) & 1);
+            tc_fence_after();
+          }
+          // dS lives in 16-bit pairs: first half of the key columns over dP, second half over S
+          const int hcol = ((cols / 16 + 1) / 2) * 16;
+          for (int kk = 0; kk < cols / 16; ++kk) {
+            const int c0 = kk * 16;
+            const uint32_t aaddr = (c0 < hcol) ? (tmem + C::kColP + (c0 >> 1)) : (tmem + C::kColS + hcol + ((c0 - hcol) >> 1));
+            umma_ts(tmem + C::kColQ, aaddr, make_sdesc(ka + kk * 2048, C::kSlabKV, 1024), idesc_dq, (t > 0 || kk > 0));
+          }
+          umma_commit(k_empty + st);
+        }
+        umma_commit(dq_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ element-wise math + epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;                  // MMA row == TMEM lane
+    const int pr = a.q_swap ? (r / a.G) : (r % a.P);
+    const int gr = a.q_swap ? (r % a.G) : (r / a.P);
+    const int ro = a.dq_swap ? (pr * a.G + gr) : (gr * a.P + pr);   // row in dQ's box order
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    int item = 0, it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      int pb, y, b;
+      decode_tile(a, tile, pb, y, b);
+      const int q0 = pb * a.P, hq0 = y * a.G;
+      const TilePlan pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN);
+      const int i = q0 + pr, h = hq0 + gr;
+      float neg_l2 = -INFINITY, delta = 0.f;
+      if (i < a.N) {
+        const int64_t row = (static_cast<int64_t>(b) * a.Hq + h) * a.N + i;
+        const float l = a.lse[row];
+        neg_l2 = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+        delta = a.delta[row];
+      }
+      for (int t = 0; t < pl.n_tiles; ++t, ++item) {
+        int kstart, cols; bool is_sink;
+        pl.tile(t, a.BN, kstart, cols, is_sink);
+        int c_lo, c_hi;
+        row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+        if (i >= a.N) c_hi = -1;
+        const int nch = cols / 16;
+        const int hch = (nch + 1) / 2;
+        const int hcol = hch * 16;
+        const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
+        mbar_wait(s_full, item & 1);
+        tc_fence_after();
+        for (int ch = ch0; ch < ch1; ++ch) {
+          const int c0 = ch * 16;
+          uint32_t sv[16], dv[16], pk[8];
+          tmem_ld16(tl + C::kColS + c0, sv);
+          tmem_ld16(tl + C::kColP + c0, dv);
+          tmem_ld_wait();
+          if (c0 + 15 >= c_lo && c0 <= c_hi) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int c = c0 + e;
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2));
+              float d0 = p0 * (__uint_as_float(dv[e]) - delta);
+              float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta);
+              d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
+              d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
+              pk[e >> 1] = pack16<T>(d0, d1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk[e] = 0u;
+          }
+          const uint32_t dst = half ? (tl + C::kColS + hcol + ((c0 - hcol) >> 1)) : (tl + C::kColP + (c0 >> 1));
+          tmem_st8(dst, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full);
+      }
+      // ---------------- epilogue: dQ * scale -> 16-bit -> staging (this tile's Q stage) -> TMA store
+      const int qs = it % C::kQStages;
+      unsigned char* stage = q_s + qs * C::kQBytes;
+      mbar_wait(dq_done, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < D / 2; cc += 16) {
+        const int c0 = half * (D / 2) + cc;
+        uint32_t v[16], pk[8];
+        tmem_ld16(tl + C::kColQ + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2)
+          pk[e >> 1] = pack16<T>(__uint_as_float(v[e]) * a.scale, __uint_as_float(v[e + 1]) * a.scale);
+        unsigned char* slab = stage + (c0 >> 6) * C::kSlabQ;
+        const int chn = (c0 & 63) >> 3;
+        *reinterpret_cast<uint4*>(slab + sw128_off(ro, chn)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(slab + sw128_off(ro, chn + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      tc_fence_before();
+      mbar_arrive(dq_free);
+      fence_proxy_async_smem();
+      named_bar_sync(1, kMathThreads);
+      if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kDS; ++s) tma_tile_store(&tmdQ, stage + s * C::kSlabQ, a.dq_swap, s * 64, q0, hq0, b);
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(qdo_empty + qs);
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
+}
+
+// ================================================================================== dK/dV kernel
+// One CTA per (128-key tile, kv head, batch).  Keys sit on the TMEM lanes; the packed Q chunks that
+// can see the tile stream through a 2-stage Q/dO ring.
+template <int D> struct DkvCfg {
+  static constexpr int kDS = D / 64;
+  static constexpr int kBK = 128;                       // keys per CTA
+  static constexpr int kQStages = 2;
+  static constexpr int kQBytes = 128 * D * 2;
+  static constexpr int kKVBytes = kBK * D * 2;
+  static constexpr int kSlabQ = 128 * 128;
+  static constexpr int kSlabKV = kBK * 128;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kColS = 0;                  // S^T (fp32) -> P^T (16-bit)
+  static constexpr uint32_t kColP = 128;                // dP^T (fp32) -> dS^T (16-bit)
+  static constexpr uint32_t kColK = 256;                // dK accumulator [keys][D]
+  static constexpr uint32_t kColV = 256 + D;            // dV accumulator
+  static constexpr int kSmem = 1024 + 2 * kKVBytes + 2 * kQStages * kQBytes + 2 * 2 * 128 * 4 + 256;
+  static_assert(256 + 2 * D <= 512, "TMEM budget");
+  static_assert(kSmem <= 227 * 1024, "smem budget");
+};
+
+struct DkvArgs {
+  int B, N, S, W, Hq, Hkv, G, P, groups_per_kv;
+  int q_swap, k_swap, v_swap;
+  int fmt;
+  float sl2, scale;
+  const float* lse;
+  const float* delta;
+  void* dk;
+  void* dv;
+  Strides4 sdk, sdv;
+};
+
+// position blocks [pb_lo, pb_hi] (P positions each) whose queries can attend a key in [j0, j0+BK)
+__device__ __forceinline__ void chunk_range(const DkvArgs& a, int j0, int bk, int& pb_lo, int& pb_hi) {
+  const int j1 = min(j0 + bk, a.N) - 1;                 // last key of the tile
+  int i_max = -1;
+  if (j0 < a.S) i_max = a.N - 1;                        // sink keys are seen by every later query
+  if (a.W > 0) i_max = max(i_max, min(a.N - 1, j1 + a.W - 1));
+  pb_lo = j0 / a.P;
+  pb_hi = (i_max >= j0) ? i_max / a.P : pb_lo - 1;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                           const __grid_constant__ CUtensorMap tmdO,
+                                                           const __grid_constant__ CUtensorMap tmK,
+                                                           const __grid_constant__ CUtensorMap tmV, const DkvArgs a) {
+  using C = DkvCfg<D>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* k_s = smem;
+  unsigned char* v_s = k_s + C::kKVBytes;
+  unsigned char* q_s = v_s + C::kKVBytes;                      // [kQStages][kQBytes]
+  unsigned char* do_s = q_s + C::kQStages * C::kQBytes;
+  float* row_l2 = reinterpret_cast<float*>(do_s + C::kQStages * C::kQBytes);   // [2][128]  -lse*log2e per chunk row
+  float* row_dl = row_l2 + 2 * 128;                                            // [2][128]  delta per chunk row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(row_dl + 2 * 128);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = kv_full + 1;             // [2]
+  uint64_t* q_empty = q_full + C::kQStages;   // [2]
+  uint64_t* s_full = q_empty + C::kQStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* acc_done = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * C::kBK;
+  const int kvh = blockIdx.y, b = blockIdx.z;
+  int pb_lo, pb_hi;
+  chunk_range(a, j0, C::kBK, pb_lo, pb_hi);
+  const int npb = max(pb_hi - pb_lo + 1, 0);
+  const int nchunks = npb * a.groups_per_kv;             // chunk c -> (group c % gpk, position block pb_lo + c / gpk)
+
+  if (warp == kMathWarps && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < C::kQStages; ++s) {
+      mbar_init(q_full + s, 1);
+      mbar_init(q_empty + s, 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, kMathThreads);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kMathWarps) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * C::kKVBytes);
+      for (int s = 0; s < C::kDS; ++s) {
+        tma_tile(k_s + s * C::kSlabKV, &tmK, kv_full, a.k_swap, s * 64, j0, kvh, b);
+        tma_tile(v_s + s * C::kSlabKV, &tmV, kv_full, a.v_swap, s * 64, j0, kvh, b);
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        const int grp = c % a.groups_per_kv, pb = pb_lo + c / a.groups_per_kv;
+        const int hq0 = (kvh * a.groups_per_kv + grp) * a.G;
+        const int qs = c % C::kQStages;
+        mbar_wait(q_empty + qs, ((c / C::kQStages) & 1) ^ 1);
+        mbar_expect_tx(q_full + qs, 2 * C::kQBytes);
+        for (int s = 0; s < C::kDS; ++s) {
+          tma_tile(q_s + qs * C::kQBytes + s * C::kSlabQ, &tmQ, q_full + qs, a.q_swap, s * 64, pb * a.P, hq0, b);
+          tma_tile(do_s + qs * C::kQBytes + s * C::kSlabQ, &tmdO, q_full + qs, a.q_swap, s * 64, pb * a.P, hq0, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMathWarps + 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(a.fmt, 128, 128, 0, 0);    // S^T = K Q^T : M = keys, N = chunk rows
+      const uint32_t idesc_acc = make_idesc(a.fmt, 128, D, 0, 1);    // dV += P^T dO : B = dO tile, MN-major
+      const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s);
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      for (int c = 0; c < nchunks; ++c) {
+        const int qs = c % C::kQStages;
+        const uint32_t qa = smem_u32(q_s + qs * C::kQBytes), doa = smem_u32(do_s + qs * C::kQBytes);
+        mbar_wait(q_full + qs, (c / C::kQStages) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < C::kDS; ++s)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem + C::kColS, make_sdesc(ka + s * C::kSlabKV + kk * 32, 16, 1024),
+                    make_sdesc(qa + s * C::kSlabQ + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
+#pragma unroll
+        for (int s = 0; s < C::kDS; ++s)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem + C::kColP, make_sdesc(va + s * C::kSlabKV + kk * 32, 16, 1024),
+                    make_sdesc(doa + s * C::kSlabQ + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, c & 1);
+        tc_fence_after();
+        // contraction over the 128 chunk rows, 16 per UMMA; rows [0,64) were packed into 32-bit columns
+        // [0,32) and rows [64,128) into [64,96) of each region (one range per math-warp half)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem + C::kColV, tmem + C::kColS + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
+                  make_sdesc(doa + kk * 2048, C::kSlabQ, 1024), idesc_acc, (c > 0 || kk > 0));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem + C::kColK, tmem + C::kColP + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
+                  make_sdesc(qa + kk * 2048, C::kSlabQ, 1024), idesc_acc, (c > 0 || kk > 0));
+        umma_commit(q_empty + qs);
+      }
+      umma_commit(acc_done);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ element-wise math + epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const int kr = quarter * 32 + lane;                 // key row == TMEM lane
+    const int j = j0 + kr;
+    const int jw_lo = j0 + quarter * 32, jw_hi = jw_lo + 31;          // this warp's keys
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int tid = threadIdx.x;                        // 0..255
+    const int sh_p = 31 - __clz(a.P), sh_g = 31 - __clz(a.G);          // P and G are powers of two
+    for (int c = 0; c < nchunks; ++c) {
+      const int grp = c % a.groups_per_kv, pb = pb_lo + c / a.groups_per_kv;
+      const int hq0 = (kvh * a.groups_per_kv + grp) * a.G, q0 = pb * a.P;
+      // stage -lse*log2e and delta of the 128 chunk rows (row order = the Q tile's box order)
+      if (tid < 128) {
+        const int pr = a.q_swap ? (tid >> sh_g) : (tid & (a.P - 1));
+        const int gr = a.q_swap ? (tid & (a.G - 1)) : (tid >> sh_p);
+        const int i = q0 + pr;
+        float nl = -INFINITY, dl = 0.f;
+        if (i < a.N) {
+          const int64_t row = (static_cast<int64_t>(b) * a.Hq + hq0 + gr) * a.N + i;
+          const float l = a.lse[row];
+          nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+          dl = a.delta[row];
+        }
+        row_l2[(c & 1) * 128 + tid] = nl;
+        row_dl[(c & 1) * 128 + tid] = dl;
+      }
+      named_bar_sync(1, kMathThreads);
+      const float* rl = row_l2 + (c & 1) * 128;
+      const float* rd = row_dl + (c & 1) * 128;
+      mbar_wait(s_full, c & 1);
+      tc_fence_after();
+      // this thread: columns [half*64, half*64+64) of its key row; 16-bit results go to the low half of the
+      // 32-bit columns it has already consumed: P^T over S^T, dS^T over dP^T
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = half * 64 + cc;
+        uint32_t sv[16], dv[16], pp[8], pd[8];
+        tmem_ld16(tl + C::kColS + c0, sv);
+        tmem_ld16(tl + C::kColP + c0, dv);
+        tmem_ld_wait();
+        // positions covered by these 16 chunk rows
+        int i_lo, i_hi;
+        if (a.q_swap) {
+          i_lo = q0 + (c0 >> sh_g);
+          i_hi = q0 + ((c0 + 15) >> sh_g);
+        } else {
+          i_lo = q0 + (c0 & (a.P - 1));
+          i_hi = (a.P >= 16) ? i_lo + 15 : q0 + a.P - 1;
+          if (a.P < 16) i_lo = q0;
+        }
+        // warp-uniform skip: no key of this warp is attended by any of these rows
+        const bool any = (jw_lo <= i_hi) && ((jw_lo < a.S) || (jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
+        if (any) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const int r0 = c0 + e, r1 = r0 + 1;
+            const int i0 = q0 + (a.q_swap ? (r0 >> sh_g) : (r0 & (a.P - 1)));
+            const int i1 = q0 + (a.q_swap ? (r1 >> sh_g) : (r1 & (a.P - 1)));
+            const float2 l2 = *reinterpret_cast<const float2*>(rl + r0);
+            const float2 dl = *reinterpret_cast<const float2*>(rd + r0);
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, l2.x));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, l2.y));
+            const bool ok0 = attended(i0, j, a.S, a.W) && (j < a.N);
+            const bool ok1 = attended(i1, j, a.S, a.W) && (j < a.N);
+            p0 = ok0 ? p0 : 0.f;
+            p1 = ok1 ? p1 : 0.f;
+            const float d0 = ok0 ? p0 * (__uint_as_float(dv[e]) - dl.x) : 0.f;
+            const float d1 = ok1 ? p1 * (__uint_as_float(dv[e + 1]) - dl.y) : 0.f;
+            pp[e >> 1] = pack16<T>(p0, p1);
+            pd[e >> 1] = pack16<T>(d0, d1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pp[e] = pd[e] = 0u;
+        }
+        // each half packs into the front of its OWN source range (32-bit columns [half*64, half*64+32)),
+        // so it never overwrites fp32 columns the other half has yet to read
+        tmem_st8(tl + C::kColS + half * 64 + (cc >> 1), pp);
+        tmem_st8(tl + C::kColP + half * 64 + (cc >> 1), pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---------------- epilogue: dK * scale, dV -> 16-bit -> global (one key row per thread, half the channels)
+    if (nchunks > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+    }
+    T* dkr = static_cast<T*>(a.dk) + b * a.sdk.b + kvh * a.sdk.h + static_cast<int64_t>(j) * a.sdk.n;
+    T* dvr = static_cast<T*>(a.dv) + b * a.sdv.b + kvh * a.sdv.h + static_cast<int64_t>(j) * a.sdv.n;
+#pragma unroll
+    for (int cc = 0; cc < D / 2; cc += 16) {
+      const int c0 = half * (D / 2) + cc;
+      uint32_t kv_[16], vv_[16], pk[8], pv[8];
+      if (nchunks > 0) {                                  // uniform: the tcgen05.ld stay warp-convergent
+        tmem_ld16(tl + C::kColK + c0, kv_);
+        tmem_ld16(tl + C::kColV + c0, vv_);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) kv_[e] = vv_[e] = 0u;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        pk[e >> 1] = pack16<T>(__uint_as_float(kv_[e]) * a.scale, __uint_as_float(kv_[e + 1]) * a.scale);
+        pv[e >> 1] = pack16<T>(__uint_as_float(vv_[e]), __uint_as_float(vv_[e + 1]));
+      }
+      if (j < a.N) {
+        *reinterpret_cast<uint4*>(dkr + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dkr + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(dvr + c0) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+        *reinterpret_cast<uint4*>(dvr + c0 + 8) = make_uint4(pv[4], pv[5], pv[6], pv[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename T, int D>
+cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
+  const int group = p.Hq / p.Hkv;
+  int G, P;
+  pick_packing(p.Hq, p.Hkv, G, P);
+  const int fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
+  TileMap mq, mdo;
+  if (!make_tile_map(&mq, p.q, dtype, D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mdo, p.dout, dtype, D, p.N, p.Hq, p.B, p.sdo, P, G)) return cudaErrorInvalidValue;
+  if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;   // guarded by tc_bwd_supported
+
+  if (stages & 2) {
+    using C = DqCfg<D>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+      if (e != cudaSuccess) return e;
+      attr_done = true;
+    }
+    const int BN = pick_bn(p.W, p.N, P, C::kBNMax);
+    TileMap mk, mv, mdq;
+    if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mdq, p.dq, dtype, D, p.N, p.Hq, p.B, p.sdq, P, G)) return cudaErrorInvalidValue;
+    BwdArgs a;
+    a.B = p.B; a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.G = G; a.P = P; a.BN = BN;
+    a.groups_per_kv = group / G;
+    a.ny = p.Hq / G;
+    a.nblk = (p.N + P - 1) / P;
+    a.total_tiles = a.nblk * a.ny * p.B;
+    a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh; a.dq_swap = mdq.swap_nh;
+    a.fmt = fmt;
+    a.sl2 = p.scale * kLog2e;
+    a.scale = p.scale;
+    a.lse = p.lse;
+    a.delta = p.delta;
+    const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+    dq_kernel<T, D><<<grid, kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (stages & 4) {
+    using C = DkvCfg<D>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(dkdv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+      if (e != cudaSuccess) return e;
+      attr_done = true;
+    }
+    TileMap mk, mv;
+    if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, C::kBK, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, C::kBK, 1)) return cudaErrorInvalidValue;
+    DkvArgs a;
+    a.B = p.B; a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.Hkv = p.Hkv; a.G = G; a.P = P;
+    a.groups_per_kv = group / G;
+    a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh;
+    a.fmt = fmt;
+    a.sl2 = p.scale * kLog2e;
+    a.scale = p.scale;
+    a.lse = p.lse;
+    a.delta = p.delta;
+    a.dk = p.dk; a.dv = p.dv; a.sdk = p.sdk; a.sdv = p.sdv;
+    dim3 grid((p.N + C::kBK - 1) / C::kBK, p.Hkv, p.B);
+    dkdv_kernel<T, D><<<grid, kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace
+
+bool tc_bwd_supported(const AttnParams& p, int dtype) {
+  if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
+  if (p.D != 64 && p.D != 128) return false;
+  if (p.N < 1) return false;
+  if (p.S <= 0 && p.W <= 0) return false;     // nothing attended: the CUDA-core path writes the zeros
+  if (!(tma_compatible(p.q, p.sq) && tma_compatible(p.k, p.sk) && tma_compatible(p.v, p.sv) &&
+        tma_compatible(p.dout, p.sdo) && tma_compatible(p.dq, p.sdq)))
+    return false;
+  // dK/dV rows are written with 16-byte stores
+  if (reinterpret_cast<uintptr_t>(p.dk) % 16 || reinterpret_cast<uintptr_t>(p.dv) % 16) return false;
+  if (p.sdk.n % 8 || p.sdk.h % 8 || p.sdk.b % 8 || p.sdv.n % 8 || p.sdv.h % 8 || p.sdv.b % 8) return false;
+  // Q and dO tiles must land in shared memory in the same row order
+  const bool q_swap = (p.Hq > 1 && p.N > 1) ? (p.sq.h < p.sq.n) : false;
+  const bool do_swap = (p.Hq > 1 && p.N > 1) ? (p.sdo.h < p.sdo.n) : false;
+  return q_swap == do_swap;
+}
+
+cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
+  if (dtype == SFA_DTYPE_BF16)
+    return p.D == 64 ? launch_bwd<__nv_bfloat16, 64>(p, dtype, stages, st) : launch_bwd<__nv_bfloat16, 128>(p, dtype, stages, st);
+  return p.D == 64 ? launch_bwd<__half, 64>(p, dtype, stages, st) : launch_bwd<__half, 128>(p, dtype, stages, st);
+}
+
 }  // namespace sfa

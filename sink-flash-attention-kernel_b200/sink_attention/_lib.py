@@ -94,6 +94,18 @@ def _unit_last(t: torch.Tensor) -> torch.Tensor:
     return t if t.stride(-1) == 1 else t.contiguous()
 
 
+def _dense_non_overlapping(t: torch.Tensor) -> bool:
+    sizes_strides = sorted(zip(t.stride(), t.shape))
+    expect = 1
+    for st, sz in sizes_strides:
+        if sz == 1:
+            continue
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
 def last_impl() -> str:
     return load().sfa_last_impl().decode()
 
@@ -139,6 +151,10 @@ def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32):
     B, Hq, N, D = q.shape
     Hkv = k.shape[1]
     q, k, v, o, do = (_unit_last(t) for t in (q, k, v, o, do))
+    if do.stride() != q.stride():
+        # the tensor-core kernels load Q and dO tiles with one row order: give dO q's memory layout
+        do = torch.empty_strided(q.shape, q.stride(), device=q.device, dtype=q.dtype).copy_(do) \
+            if _dense_non_overlapping(q) else do.contiguous()
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     ds_aux = torch.empty((Hq,), device=q.device, dtype=torch.float32) if s_aux_f32 is not None else None
     code = DTYPE_CODE[q.dtype]

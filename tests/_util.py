@@ -35,6 +35,15 @@ def maxdiff(a, b):
     return (a[fin] - b[fin]).abs().max().item() if fin.any() else 0.0
 
 
+def excess(a, b, atol, rtol):
+    """max over elements of |a-b| / (atol + rtol*|b|): <= 1 means `a` is close to `b` in the sense of
+    torch.testing.assert_close(atol, rtol), the form the reference's gradient tests use
+    (tests/test_sink_attention.py:94-96 with atol = rtol = 5e-2)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert bool(torch.isfinite(a).all()) and bool(torch.isfinite(b).all()), "non-finite value"
+    return ((a - b).abs() / (atol + rtol * b.abs())).max().item()
+
+
 def to_dev(t, dtype=None, dev="cuda"):
     if t is None:
         return None

@@ -12,7 +12,7 @@ import torch
 
 import golden_cases as gc
 import sink_oracle as orc
-from _util import load_decode, load_prefill, maxdiff, to_dev
+from _util import excess, load_decode, load_prefill, maxdiff, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -132,6 +132,59 @@ def test_fwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     o_ref, lse_ref = orc.sink_attention_fwd(q.cpu(), k.cpu(), v.cpu(), S, W, s_aux.cpu() if use_aux else None)
     assert maxdiff(o_t, o_ref) < 2e-2
     assert maxdiff(lse_t, lse_ref) < 2e-3
+
+
+def _bwd(q, k, v, o, do, lse, S, W, s_aux, impl=None):
+    if impl is not None:
+        _lib.set_impl(impl)
+    try:
+        out = _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
+        torch.cuda.synchronize()
+        name = _lib.last_impl()
+    finally:
+        _lib.set_impl(_lib.IMPL_AUTO)
+    return out, name
+
+
+@pytest.mark.parametrize("dtype", LOW)
+@pytest.mark.parametrize("shape", [
+    # B, Hq, Hkv, N, D, S, W, s_aux
+    (1, 16, 2, 1024, 64, 0, 128, True),      # gpt-oss head ratio 8:1, narrow window (C1 scaled down)
+    (2, 8, 2, 777, 128, 4, 300, False),      # ratio 4:1, D=128, ragged N, sinks: several KV tiles + a sink tile
+    (1, 4, 4, 512, 64, 16, 128, True),       # MHA, sinks + s_aux
+    (1, 32, 2, 300, 64, 3, 50, True),        # group 16 -> 8 positions per tile
+    (1, 6, 2, 260, 64, 2, 70, False),        # group 3 -> unpacked tiles, 3 chunk groups per KV head
+    (1, 4, 2, 1500, 128, 0, 1500, True),     # full causal (window = N): long Q-chunk loops per key tile
+    (1, 8, 1, 200, 64, 150, 8, True),        # sinks spanning more than one key tile
+    (1, 2, 2, 130, 64, 0, 1, False),         # window 1: self only
+    (1, 8, 8, 96, 64, 7, 0, True),           # window 0: sinks (and s_aux) only
+])
+def test_bwd_tcgen05_vs_simt_and_oracle(shape, dtype):
+    """dQ/dK/dV of the tensor-core backward against the CUDA-core backward (same 16-bit inputs, fp32 math)
+    and the CPU oracle.  Tolerance: the reference's own gradient tolerance 5e-2 (test_sink_attention.py:94-96);
+    against the on-device fp32-math path the bar is tighter (16-bit rounding of P/dS only)."""
+    B, Hq, Hkv, N, D, S, W, use_aux = shape
+    g = torch.Generator().manual_seed(N + D + S + 1)
+    q = torch.randn(B, Hq, N, D, generator=g).to("cuda", dtype)
+    k = torch.randn(B, Hkv, N, D, generator=g).to("cuda", dtype)
+    v = torch.randn(B, Hkv, N, D, generator=g).to("cuda", dtype)
+    do = torch.randn(B, Hq, N, D, generator=g).to("cuda", dtype)
+    s_aux = (torch.randn(Hq, generator=g) * 0.5 + 1.0).cuda() if use_aux else None
+    o, lse, _ = _fwd(q, k, v, S, W, s_aux)
+    (dq_t, dk_t, dv_t, ds_t), name_t = _bwd(q, k, v, o, do, lse, S, W, s_aux)
+    (dq_s, dk_s, dv_s, ds_s), name_s = _bwd(q, k, v, o, do, lse, S, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert (name_t, name_s) == ("tcgen05", "simt")
+    # on-device cross-check (same inputs, fp32 CUDA-core math): only the 16-bit rounding of P/dS and of the
+    # outputs separates the two -> 2e-2 absolute + 1e-2 relative (one bf16 ulp of a value near 4 is 3.1e-2)
+    for got, ref in ((dq_t, dq_s), (dk_t, dk_s), (dv_t, dv_s)):
+        assert excess(got, ref, 2e-2, 1e-2) <= 1.0
+    if use_aux:
+        assert maxdiff(ds_t, ds_s) < 1e-4
+    # oracle (fp64 math on the same 16-bit inputs): the reference's own bar, atol = rtol = 5e-2
+    dq_r, dk_r, dv_r, ds_r = orc.sink_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), S, W, s_aux.cpu() if use_aux else None)
+    for got, ref in ((dq_t, dq_r), (dk_t, dk_r), (dv_t, dv_r)):
+        assert excess(got, ref, 5e-2, 5e-2) <= 1.0
+    assert maxdiff(dq_t, dq_r) < 5e-2
 
 
 # ------------------------------------------------------------------------------------------------
