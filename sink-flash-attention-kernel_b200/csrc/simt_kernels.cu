@@ -249,6 +249,59 @@ __global__ void __launch_bounds__(256) preprocess_kernel(AttnParams p, float* ds
   }
 }
 
+// 16-bit fast path of the same: LPR = D/8 lanes per row, one 16-byte load of O and of dO per lane.
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(256) preprocess_vec_kernel(AttnParams p, float* ds_partial) {
+  constexpr int RPB = 256 / LPR;   // rows per block
+  __shared__ float part[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = tid % LPR;
+  const int i = blockIdx.x * RPB + tid / LPR, h = blockIdx.y, b = blockIdx.z;
+  float s = 0.f;
+  if (i < p.N) {
+    const T* o = static_cast<const T*>(p.o) + b * p.so.b + h * p.so.h + (int64_t)i * p.so.n + sub * 8;
+    const T* dO = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h + (int64_t)i * p.sdo.n + sub * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(o);
+    const uint4 c = *reinterpret_cast<const uint4*>(dO);
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, cu[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 x = unpack2<T>(au[t]), y = unpack2<T>(cu[t]);
+      s = fmaf(x.x, y.x, s);
+      s = fmaf(x.y, y.y, s);
+    }
+  }
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  float contrib = 0.f;
+  if (i < p.N && sub == 0) {
+    const int64_t row = ((int64_t)b * p.Hq + h) * p.N + i;
+    p.delta[row] = s;
+    if (p.s_aux) {
+      const float lse = p.lse[row];
+      contrib = (lse == -INFINITY) ? 0.f : -expf(p.s_aux[h] - lse) * s;
+    }
+  }
+  if (ds_partial) {
+    contrib = warp_sum(contrib);
+    if (lane == 0) part[warp] = contrib;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += part[w];
+      ds_partial[((int64_t)b * p.Hq + h) * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) ds_aux_reduce_kernel(const float* __restrict__ ds_partial, float* ds_aux, int B,
                                                             int Hq, int nblk) {
   __shared__ float red[256];
@@ -360,20 +413,48 @@ cudaError_t simt_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
   });
 }
 
+template <typename T>
+cudaError_t launch_preprocess_vec(const AttnParams& p, float* ds_partial, int& nblk, cudaStream_t st) {
+  const int lpr = p.D / 8;
+  nblk = (p.N + 256 / lpr - 1) / (256 / lpr);
+  dim3 grid(nblk, p.Hq, p.B);
+  switch (lpr) {
+    case 4: preprocess_vec_kernel<T, 4><<<grid, 256, 0, st>>>(p, ds_partial); break;
+    case 8: preprocess_vec_kernel<T, 8><<<grid, 256, 0, st>>>(p, ds_partial); break;
+    case 16: preprocess_vec_kernel<T, 16><<<grid, 256, 0, st>>>(p, ds_partial); break;
+    case 32: preprocess_vec_kernel<T, 32><<<grid, 256, 0, st>>>(p, ds_partial); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+static bool vec16_ok(const void* ptr, const Strides4& s) {
+  return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && s.n % 8 == 0 && s.h % 8 == 0 && s.b % 8 == 0;
+}
+
 cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st) {
-  return dispatch_dtype(dtype, [&](auto tag) {
-    using T = decltype(tag);
-    const int nblk = (p.N + 7) / 8;
-    dim3 grid(nblk, p.Hq, p.B);
-    preprocess_kernel<T><<<grid, 256, 0, st>>>(p, p.s_aux ? ds_partial : nullptr);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (p.s_aux && p.ds_aux) {
-      ds_aux_reduce_kernel<<<p.Hq, 256, 0, st>>>(ds_partial, p.ds_aux, p.B, p.Hq, nblk);
-      e = cudaGetLastError();
-    }
-    return e;
-  });
+  float* dsp = p.s_aux ? ds_partial : nullptr;
+  int nblk = (p.N + 7) / 8;
+  cudaError_t e;
+  const bool vec = (dtype != SFA_DTYPE_FP32) && (p.D == 32 || p.D == 64 || p.D == 128 || p.D == 256) &&
+                   vec16_ok(p.o, p.so) && vec16_ok(p.dout, p.sdo);
+  if (vec) {
+    e = (dtype == SFA_DTYPE_BF16) ? launch_preprocess_vec<__nv_bfloat16>(p, dsp, nblk, st)
+                                  : launch_preprocess_vec<__half>(p, dsp, nblk, st);
+  } else {
+    e = dispatch_dtype(dtype, [&](auto tag) {
+      using T = decltype(tag);
+      dim3 grid(nblk, p.Hq, p.B);
+      preprocess_kernel<T><<<grid, 256, 0, st>>>(p, dsp);
+      return cudaGetLastError();
+    });
+  }
+  if (e != cudaSuccess) return e;
+  if (p.s_aux && p.ds_aux) {
+    ds_aux_reduce_kernel<<<p.Hq, 256, 0, st>>>(ds_partial, p.ds_aux, p.B, p.Hq, nblk);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 cudaError_t simt_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {

@@ -234,8 +234,14 @@ def test_strided_hf_layout(dtype):
             assert o.transpose(1, 2).is_contiguous(), "output should come back in HF memory layout"
         o.backward(do.transpose(1, 2))
         outs.append((o, q.grad, k.grad, v.grad))
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
+    (o_a, dq_a, dk_a, dv_a), (o_b, dq_b, dk_b, dv_b) = outs
+    # rows are independent: O and dQ do not depend on how a tile's rows are ordered in shared memory
+    assert torch.equal(o_a, o_b)
+    assert torch.equal(dq_a, dq_b)
+    # dK/dV contract over the tile rows; the two layouts order them differently inside the MMA, so allow the
+    # fp32 summation-order noise (well under one 16-bit ulp of the result)
+    for a, b in ((dk_a, dk_b), (dv_a, dv_b)):
+        assert excess(a, b, 1e-5 if dtype == torch.float32 else 4e-3, 4e-3) <= 1.0
 
 
 # ------------------------------------------------------------------------------------------------
