@@ -55,6 +55,9 @@ int sfa_set_impl(int impl);
 /* timing aid for bench.py: run only the selected backward stages (bit0 = delta/ds_aux preprocess,
  * bit1 = dQ kernel, bit2 = dK/dV kernel); default 7 = all.  Results are complete only with 7. */
 int sfa_set_bwd_stages(int mask);
+/* performance-debug aid: a device buffer of 3*256*2 int64 into which CTA 0 of the dQ kernel appends
+ * (role, event, index, clock64) records; NULL (the default) switches it off. */
+int sfa_set_trace_buffer(void* device_buffer);
 /* name of the kernel family the last call on this thread dispatched to ("tcgen05", "simt", "mma") */
 const char* sfa_last_impl(void);
 
@@ -91,6 +94,12 @@ int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const
 /* tcgen05/TMA self-test: C[M=128,N] = A[128,K] * B^T (+ variants).  Returns 0 and fills c (fp32, device).
  * mode 0: A,B K-major in smem; mode 1: B given as [K,N] (MN-major); mode 2: A through TMEM (TS form). */
 int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream);
+
+/* UMMA issue-rate probe: out2 = device int64[2] <- {cycles to issue, cycles until complete} for reps*ksteps UMMAs */
+int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, void* stream);
+/* load-throughput probe (performance work): streams a bf16 [H,N,64] tensor through shared memory with TMA
+ * boxes of box_n positions x box_h heads (mode 0) or per-thread cp.async (mode 1), `stages` boxes in flight. */
+int sfa_probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,11 @@ int sfa_set_impl(int impl) {
   return 0;
 }
 
+int sfa_set_trace_buffer(void* device_buffer) {
+  set_trace_buffer(static_cast<long long*>(device_buffer));
+  return 0;
+}
+
 int sfa_set_bwd_stages(int mask) {
   g_bwd_stages = mask & 7;
   return 0;
@@ -237,6 +242,16 @@ int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.D = D;
   p.scale = 1.0f / sqrtf((float)D);
   return decode_impl(p, dtype, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int sfa_probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode, void* stream) {
+  return cuda_ret(probe_tma_bw(src, H, N, box_n, box_h, stages, grid, mode, static_cast<cudaStream_t>(stream)),
+                  "sfa_probe_tma_bw");
+}
+
+int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, void* stream) {
+  return cuda_ret(probe_mma_rate(static_cast<long long*>(out2), N, ksteps, reps, uniform, static_cast<cudaStream_t>(stream)),
+                  "sfa_probe_mma_rate");
 }
 
 int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream) {

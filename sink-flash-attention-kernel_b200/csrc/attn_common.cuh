@@ -27,15 +27,27 @@ struct TilePlan {
   }
 };
 
-__device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W, int BN) {
+// x / BN without an integer division (a ~150-cycle dependent chain on the single-thread TMA / MMA roles):
+// q = (x * ceil(2^40 / BN)) >> 40, exact for 0 <= x < 2^24 and BN <= 256.
+__host__ __device__ __forceinline__ unsigned long long bn_magic(int BN) {
+  return ((1ull << 40) + static_cast<unsigned long long>(BN) - 1) / static_cast<unsigned long long>(BN);
+}
+__device__ __forceinline__ int div_bn(int x, unsigned long long magic) {
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(x)) * magic) >> 40);
+}
+
+__device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W, int BN, unsigned long long magic) {
   TilePlan pl;
   pl.q_hi = min(q0 + P, N) - 1;
   pl.s_eff = min(S, pl.q_hi + 1);
-  pl.n_sink = (pl.s_eff > 0) ? (pl.s_eff + BN - 1) / BN : 0;
+  pl.n_sink = (pl.s_eff > 0) ? div_bn(pl.s_eff + BN - 1, magic) : 0;
   pl.w_lo = max(max(q0 - W + 1, S), 0);
-  const int n_win = (W > 0 && pl.w_lo <= pl.q_hi) ? (pl.q_hi - pl.w_lo + BN) / BN : 0;
+  const int n_win = (W > 0 && pl.w_lo <= pl.q_hi) ? div_bn(pl.q_hi - pl.w_lo + BN, magic) : 0;
   pl.n_tiles = pl.n_sink + n_win;
   return pl;
+}
+__device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W, int BN) {
+  return make_plan(q0, P, N, S, W, BN, bn_magic(BN));
 }
 
 // attended columns [c_lo, c_hi] of query position i inside a tile that starts at key `kstart`
@@ -78,14 +90,15 @@ inline void pick_packing(int Hq, int Hkv, int& G, int& P) {
   P = 128 / G;
 }
 
-// KV tile rows: split the widest band (min(W,N) + P - 1 keys) into equal tiles of <= bn_max rows
+// KV tile rows.  A band of min(W,N) + P - 1 keys that fits one tile gets a tile of exactly that size (rounded
+// to the UMMA N granularity of 16); a wider band is cut into full bn_max tiles -- the last, partial tile of a
+// row of tiles only issues UMMAs over its own (16-rounded) column count.
 inline int pick_bn(int W, int N, int P, int bn_max) {
   int64_t span = (int64_t)(W < N ? W : N) + P - 1;
   if (span < 16) span = 16;
   if (span > (int64_t)N + P) span = (int64_t)N + P;
-  const int nt = (int)((span + bn_max - 1) / bn_max);
-  int bn = (int)(((span + nt - 1) / nt + 15) / 16 * 16);
-  return bn > bn_max ? bn_max : bn;
+  if (span > bn_max) return bn_max;
+  return (int)((span + 15) / 16 * 16);
 }
 
 }  // namespace sfa

@@ -20,6 +20,8 @@
 //
 // Warp roles (320 threads): warps 0-7 element-wise math + epilogue (two warps per TMEM lane
 // quarter, each taking half of the columns), warp 8 TMA producer, warp 9 tcgen05.mma issuer.
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 #include "tmap.cuh"
 
@@ -32,13 +34,26 @@ constexpr int kThreads = kMathThreads + 64;
 
 struct BwdArgs {
   int B, N, S, W, Hq, G, P, BN, groups_per_kv, ny, nblk, total_tiles;
+  unsigned long long bn_mul;   // bn_magic(BN)
+  int tiles_per_cta;   // > 0: CTA c owns the contiguous tiles [c*tpc, (c+1)*tpc); 0: tiles c, c+grid, ...
   int q_swap, k_swap, v_swap, dq_swap;
   int fmt;       // 0 f16, 1 bf16
   float sl2;     // scale * log2(e)
   float scale;
   const float* lse;
   const float* delta;
+  long long* trace;   // optional timeline buffer (sfa_set_trace_buffer); nullptr in production
 };
+
+// Timeline probe for performance work: CTA 0 appends (role, code, index, clock64) records.
+// role 0 = TMA producer, 1 = MMA issuer, 2 = math thread 0.  256 records of 2 x int64 per role.
+__device__ __forceinline__ void trace_ev(long long* trace, int role, int& cnt, int code, int idx) {
+  if (trace != nullptr && blockIdx.x == 0 && cnt < 256) {
+    trace[(role * 256 + cnt) * 2] = (static_cast<long long>(code) << 32) | static_cast<unsigned>(idx);
+    trace[(role * 256 + cnt) * 2 + 1] = clock64();
+    ++cnt;
+  }
+}
 
 __device__ __forceinline__ void decode_tile(const BwdArgs& a, int tile, int& pb, int& y, int& b) {
   pb = tile % a.nblk;
@@ -48,22 +63,81 @@ __device__ __forceinline__ void decode_tile(const BwdArgs& a, int tile, int& pb,
 }
 
 // ================================================================================== dQ kernel
+// Work items = (packed Q tile, KV tile) pairs in the order of the two-range walk, two TMEM slots:
+// the UMMAs of item n+1 (S, dP) run while the math warps work on item n, and dQ(n) runs under the
+// math of item n+1.  With D = 64 the dQ accumulator is double-buffered too, so a tile's epilogue is
+// deferred by one item and never waits for its own dQ UMMAs.
 template <int D> struct DqCfg {
   static constexpr int kDS = D / 64;
-  static constexpr int kBNMax = (D == 64) ? 160 : 128;
-  static constexpr int kStages = (D == 64) ? 2 : 1;     // K and V rings
-  static constexpr int kQStages = 2;                    // Q / dO tiles
+  static constexpr int kBNMax = 96;                      // KV rows per item (UMMA N of S and dP)
+  // TMA loads take ~2.4 us under load (measured with the clock64 timeline, tools/trace_dq.py): the rings are
+  // sized so every load is issued two or more items before its first use
+  static constexpr int kKStages = (D == 64) ? 4 : 2;     // K is held from S(n) to dQ(n)
+  static constexpr int kVStages = (D == 64) ? 3 : 2;
+  static constexpr int kQStages = (D == 64) ? 3 : 2;     // Q / dO tiles
+  static constexpr int kDqBufs = (D == 64) ? 2 : 1;
+  static constexpr bool kSepStage = (D == 64);           // own staging buffer for the dQ TMA store
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = kBNMax * D * 2;
   static constexpr int kSlabQ = 128 * 128;
   static constexpr int kSlabKV = kBNMax * 128;
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kColS = 0;
-  static constexpr uint32_t kColP = kBNMax;             // dP
-  static constexpr uint32_t kColQ = 2 * kBNMax;         // dQ accumulator
-  static constexpr int kSmem = 1024 + 2 * kQStages * kQBytes + 2 * kStages * kKVBytes + 256;
-  static_assert(2 * kBNMax + D <= 512, "TMEM budget");
+  static constexpr uint32_t kSlotCols = 2 * kBNMax;      // S then dP
+  static constexpr uint32_t kColQ = 2 * kSlotCols;       // dQ accumulator(s)
+  static constexpr int kSmem = 1024 + (2 * kQStages + (kSepStage ? 1 : 0)) * kQBytes + (kKStages + kVStages) * kKVBytes + 512;
+  static_assert(2 * kSlotCols + kDqBufs * D <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
+};
+
+// Walks this CTA's work items: tiles blockIdx.x, +gridDim.x, ... and the KV tiles of each.
+struct ItemWalk {
+  const BwdArgs& a;
+  int tile, it, t, n;        // tile id, tile iteration, KV tile inside the tile, running item count
+  int step, end;
+  int pb, y, b, q0;          // tile = (b * ny + y) * nblk + pb, kept incrementally (no divisions per tile)
+  TilePlan pl;
+  __device__ __forceinline__ explicit ItemWalk(const BwdArgs& a_) : a(a_), it(-1), t(0), n(-1) {
+    int first;
+    if (a.tiles_per_cta > 0) {
+      step = 1;
+      first = static_cast<int>(blockIdx.x) * a.tiles_per_cta;
+      end = min(first + a.tiles_per_cta, a.total_tiles);
+    } else {
+      step = gridDim.x;
+      first = static_cast<int>(blockIdx.x);
+      end = a.total_tiles;
+    }
+    decode_tile(a, first, pb, y, b);     // the only divisions: once per role
+    tile = first - step;
+    pb -= step;                          // next() adds it back
+    pl.n_tiles = 0;
+    q0 = 0;
+  }
+  __device__ __forceinline__ static void advance(const BwdArgs& a, int step, int& pb, int& y, int& b) {
+    pb += step;
+    while (pb >= a.nblk) {
+      pb -= a.nblk;
+      if (++y == a.ny) {
+        y = 0;
+        ++b;
+      }
+    }
+  }
+  __device__ __forceinline__ bool next() {
+    ++t;
+    while (t >= pl.n_tiles) {
+      tile += step;
+      ++it;
+      if (tile >= end) return false;
+      advance(a, step, pb, y, b);
+      q0 = pb * a.P;
+      pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN, a.bn_mul);
+      t = 0;
+    }
+    ++n;
+    return true;
+  }
+  __device__ __forceinline__ bool last_of_tile() const { return t == pl.n_tiles - 1; }
 };
 
 template <typename T, int D>
@@ -77,20 +151,21 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* q_s = smem;                                   // [kQStages][kQBytes]
   unsigned char* do_s = q_s + C::kQStages * C::kQBytes;        // [kQStages][kQBytes]
-  unsigned char* k_s = do_s + C::kQStages * C::kQBytes;        // [kStages][kKVBytes]
-  unsigned char* v_s = k_s + C::kStages * C::kKVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + C::kStages * C::kKVBytes);
-  uint64_t* qdo_full = bars;                       // [2]
-  uint64_t* qdo_empty = qdo_full + C::kQStages;    // [2]
-  uint64_t* k_full = qdo_empty + C::kQStages;
-  uint64_t* k_empty = k_full + C::kStages;
-  uint64_t* v_full = k_empty + C::kStages;
-  uint64_t* v_empty = v_full + C::kStages;
-  uint64_t* s_full = v_empty + C::kStages;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* dq_done = p_full + 1;
-  uint64_t* dq_free = dq_done + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+  unsigned char* stage_s = do_s + C::kQStages * C::kQBytes;    // [kQBytes] if kSepStage
+  unsigned char* k_s = stage_s + (C::kSepStage ? C::kQBytes : 0);
+  unsigned char* v_s = k_s + C::kKStages * C::kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + C::kVStages * C::kKVBytes);
+  uint64_t* qdo_full = bars;                       // [kQStages]
+  uint64_t* qdo_empty = qdo_full + C::kQStages;    // [kQStages]
+  uint64_t* k_full = qdo_empty + C::kQStages;      // [kKStages]
+  uint64_t* k_empty = k_full + C::kKStages;
+  uint64_t* v_full = k_empty + C::kKStages;        // [kVStages]
+  uint64_t* v_empty = v_full + C::kVStages;
+  uint64_t* s_full = v_empty + C::kVStages;        // [2]
+  uint64_t* p_full = s_full + 2;                   // [2]
+  uint64_t* dq_done = p_full + 2;                  // [kDqBufs]
+  uint64_t* dq_free = dq_done + C::kDqBufs;        // [kDqBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + C::kDqBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -104,16 +179,22 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       mbar_init(qdo_full + s, 1);
       mbar_init(qdo_empty + s, 1);
     }
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < C::kKStages; ++s) {
       mbar_init(k_full + s, 1);
       mbar_init(k_empty + s, 1);
+    }
+    for (int s = 0; s < C::kVStages; ++s) {
       mbar_init(v_full + s, 1);
       mbar_init(v_empty + s, 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, kMathThreads);
-    mbar_init(dq_done, 1);
-    mbar_init(dq_free, kMathThreads);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full + s, 1);
+      mbar_init(p_full + s, kMathThreads);
+    }
+    for (int s = 0; s < C::kDqBufs; ++s) {
+      mbar_init(dq_done + s, 1);
+      mbar_init(dq_free + s, kMathThreads);
+    }
     fence_barrier_init();
   }
   if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -125,34 +206,33 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
   if (warp == kMathWarps) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int kvc = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-        int pb, y, b;
-        decode_tile(a, tile, pb, y, b);
-        const int q0 = pb * a.P, hq0 = y * a.G, kvh = y / a.groups_per_kv;
-        const TilePlan pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN);
-        const int qs = it % C::kQStages;
-        mbar_wait(qdo_empty + qs, ((it / C::kQStages) & 1) ^ 1);
-        mbar_expect_tx(qdo_full + qs, 2 * C::kQBytes);
-        for (int s = 0; s < C::kDS; ++s) {
-          tma_tile(q_s + qs * C::kQBytes + s * C::kSlabQ, &tmQ, qdo_full + qs, a.q_swap, s * 64, q0, hq0, b);
-          tma_tile(do_s + qs * C::kQBytes + s * C::kSlabQ, &tmdO, qdo_full + qs, a.q_swap, s * 64, q0, hq0, b);
+      ItemWalk w(a);
+      int tc = 0;
+      while (w.next()) {
+        const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
+        if (w.t == 0) {
+          const int qs = w.it % C::kQStages;
+          mbar_wait(qdo_empty + qs, ((w.it / C::kQStages) & 1) ^ 1);
+          trace_ev(a.trace, 0, tc, 1, w.it);      // Q/dO stage free -> loads issued
+          mbar_expect_tx(qdo_full + qs, 2 * C::kQBytes);
+          for (int s = 0; s < C::kDS; ++s) {
+            tma_tile(q_s + qs * C::kQBytes + s * C::kSlabQ, &tmQ, qdo_full + qs, a.q_swap, s * 64, w.q0, hq0, w.b);
+            tma_tile(do_s + qs * C::kQBytes + s * C::kSlabQ, &tmdO, qdo_full + qs, a.q_swap, s * 64, w.q0, hq0, w.b);
+          }
         }
-        for (int t = 0; t < pl.n_tiles; ++t, ++kvc) {
-          int kstart, cols; bool is_sink;
-          pl.tile(t, a.BN, kstart, cols, is_sink);
-          const int st = kvc % C::kStages;
-          const uint32_t ph = (kvc / C::kStages) & 1;
-          mbar_wait(k_empty + st, ph ^ 1);
-          mbar_expect_tx(k_full + st, a.BN * D * 2);
-          for (int s = 0; s < C::kDS; ++s)
-            tma_tile(k_s + st * C::kKVBytes + s * C::kSlabKV, &tmK, k_full + st, a.k_swap, s * 64, kstart, kvh, b);
-          mbar_wait(v_empty + st, ph ^ 1);
-          mbar_expect_tx(v_full + st, a.BN * D * 2);
-          for (int s = 0; s < C::kDS; ++s)
-            tma_tile(v_s + st * C::kKVBytes + s * C::kSlabKV, &tmV, v_full + st, a.v_swap, s * 64, kstart, kvh, b);
-        }
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const int kst = w.n % C::kKStages, vst = w.n % C::kVStages;
+        mbar_wait(k_empty + kst, ((w.n / C::kKStages) & 1) ^ 1);
+        trace_ev(a.trace, 0, tc, 2, w.n);        // K stage free
+        mbar_expect_tx(k_full + kst, a.BN * D * 2);
+        for (int s = 0; s < C::kDS; ++s)
+          tma_tile(k_s + kst * C::kKVBytes + s * C::kSlabKV, &tmK, k_full + kst, a.k_swap, s * 64, kstart, kvh, w.b);
+        mbar_wait(v_empty + vst, ((w.n / C::kVStages) & 1) ^ 1);
+        trace_ev(a.trace, 0, tc, 3, w.n);        // V stage free
+        mbar_expect_tx(v_full + vst, a.BN * D * 2);
+        for (int s = 0; s < C::kDS; ++s)
+          tma_tile(v_s + vst * C::kKVBytes + s * C::kSlabKV, &tmV, v_full + vst, a.v_swap, s * 64, kstart, kvh, w.b);
       }
     }
     __syncwarp();
@@ -160,56 +240,81 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc_dq = make_idesc(a.fmt, 128, D, 0, 1);
-      int kvc = 0, item = 0, it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-        int pb, y, b;
-        decode_tile(a, tile, pb, y, b);
-        const TilePlan pl = make_plan(pb * a.P, a.P, a.N, a.S, a.W, a.BN);
-        const int qs = it % C::kQStages;
-        mbar_wait(qdo_full + qs, (it / C::kQStages) & 1);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(q_s + qs * C::kQBytes), doa = smem_u32(do_s + qs * C::kQBytes);
-        for (int t = 0; t < pl.n_tiles; ++t, ++kvc, ++item) {
-          int kstart, cols; bool is_sink;
-          pl.tile(t, a.BN, kstart, cols, is_sink);
-          const int st = kvc % C::kStages;
-          const uint32_t ph = (kvc / C::kStages) & 1;
-          const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
-          const uint32_t ka = smem_u32(k_s + st * C::kKVBytes), va = smem_u32(v_s + st * C::kKVBytes);
-          mbar_wait(k_full + st, ph);
+      int tc = 0;
+      // S = Q K^T and dP = dO V^T of the item `w` points at, into its TMEM slot
+      auto issue_sdp = [&](const ItemWalk& w) {
+        const int slot = w.n & 1, qs = w.it % C::kQStages;
+        if (w.t == 0) {
+          mbar_wait(qdo_full + qs, (w.it / C::kQStages) & 1);
           tc_fence_after();
-#pragma unroll
-          for (int s = 0; s < C::kDS; ++s)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ss(tmem + C::kColS, make_sdesc(qa + s * C::kSlabQ + kk * 32, 16, 1024),
-                      make_sdesc(ka + s * C::kSlabKV + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
-          mbar_wait(v_full + st, ph);
-          tc_fence_after();
-#pragma unroll
-          for (int s = 0; s < C::kDS; ++s)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ss(tmem + C::kColP, make_sdesc(doa + s * C::kSlabQ + kk * 32, 16, 1024),
-                      make_sdesc(va + s * C::kSlabKV + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
-          umma_commit(v_empty + st);
-          umma_commit(s_full);
-          mbar_wait(p_full, item & 1);
-          tc_fence_after();
-          if (t == 0 && it > 0) {
-            mbar_wait(dq_free, (it - 1) & 1);
-            tc_fence_after();
-          }
-          // dS lives in 16-bit pairs: first half of the key columns over dP, second half over S
-          const int hcol = ((cols / 16 + 1) / 2) * 16;
-          for (int kk = 0; kk < cols / 16; ++kk) {
-            const int c0 = kk * 16;
-            const uint32_t aaddr = (c0 < hcol) ? (tmem + C::kColP + (c0 >> 1)) : (tmem + C::kColS + hcol + ((c0 - hcol) >> 1));
-            umma_ts(tmem + C::kColQ, aaddr, make_sdesc(ka + kk * 2048, C::kSlabKV, 1024), idesc_dq, (t > 0 || kk > 0));
-          }
-          umma_commit(k_empty + st);
+          trace_ev(a.trace, 1, tc, 1, w.it);     // Q/dO landed
         }
-        umma_commit(dq_done);
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const int kst = w.n % C::kKStages, vst = w.n % C::kVStages;
+        const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
+        // descriptors of the first K-step; the next ones are +32 B (= +2 in the encoded address field)
+        const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
+        const uint64_t dod = make_sdesc(smem_u32(do_s + qs * C::kQBytes), 16, 1024);
+        const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), 16, 1024);
+        const uint64_t vd = make_sdesc(smem_u32(v_s + vst * C::kKVBytes), 16, 1024);
+        const uint32_t ts = tmem + slot * C::kSlotCols;
+        mbar_wait(k_full + kst, (w.n / C::kKStages) & 1);
+        tc_fence_after();
+        trace_ev(a.trace, 1, tc, 2, w.n);        // K landed
+#pragma unroll
+        for (int s = 0; s < C::kDS; ++s)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(ts, qd + ((s * C::kSlabQ + kk * 32) >> 4), kd + ((s * C::kSlabKV + kk * 32) >> 4), idesc_s, (s | kk) != 0);
+        trace_ev(a.trace, 1, tc, 5, w.n);        // S UMMAs issued
+        mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
+        tc_fence_after();
+        trace_ev(a.trace, 1, tc, 6, w.n);        // V landed
+#pragma unroll
+        for (int s = 0; s < C::kDS; ++s)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(ts + C::kBNMax, dod + ((s * C::kSlabQ + kk * 32) >> 4), vd + ((s * C::kSlabKV + kk * 32) >> 4), idesc_s,
+                    (s | kk) != 0);
+        trace_ev(a.trace, 1, tc, 7, w.n);        // dP UMMAs issued
+        umma_commit(v_empty + vst);
+        umma_commit(s_full + slot);
+        trace_ev(a.trace, 1, tc, 3, w.n);        // S, dP issued
+      };
+      ItemWalk w_sdp(a), w_dq(a);
+      if (w_sdp.next()) issue_sdp(w_sdp);
+      while (w_dq.next()) {
+        if (w_sdp.next()) issue_sdp(w_sdp);          // item n+1 runs under the math of item n
+        const int slot = w_dq.n & 1, qs = w_dq.it % C::kQStages, buf = w_dq.it % C::kDqBufs;
+        const int kst = w_dq.n % C::kKStages;
+        int kstart, cols; bool is_sink;
+        w_dq.pl.tile(w_dq.t, a.BN, kstart, cols, is_sink);
+        mbar_wait(p_full + slot, (w_dq.n >> 1) & 1);
+        tc_fence_after();
+        trace_ev(a.trace, 1, tc, 4, w_dq.n);     // dS ready
+        if (w_dq.t == 0 && w_dq.it >= C::kDqBufs) {
+          mbar_wait(dq_free + buf, ((w_dq.it / C::kDqBufs) - 1) & 1);
+          tc_fence_after();
+        }
+        // dS is held as 16-bit pairs: first half of the key columns over dP, second half over S
+        const uint32_t ts = tmem + slot * C::kSlotCols;
+        const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), C::kSlabKV, 1024);
+        const int hcol = ((cols / 16 + 1) / 2) * 16;
+        const uint32_t dqa = tmem + C::kColQ + buf * D;
+        const uint32_t a_lo = ts + C::kBNMax, a_hi = ts + hcol - (hcol >> 1);   // + c0/2 in both halves
+        const int nk = cols >> 4;
+#pragma unroll
+        for (int kk = 0; kk < C::kBNMax / 16; ++kk)
+          if (kk < nk)
+            umma_ts(dqa, ((kk * 16 < hcol) ? a_lo : a_hi) + kk * 8, kd + kk * (2048 >> 4), idesc_dq, (w_dq.t > 0 || kk > 0));
+        trace_ev(a.trace, 1, tc, 8, w_dq.n);     // dQ UMMAs issued
+        umma_commit(k_empty + kst);
+        if (w_dq.last_of_tile()) {
+          umma_commit(dq_done + buf);
+          if (C::kSepStage) umma_commit(qdo_empty + qs);
+        }
+        trace_ev(a.trace, 1, tc, 9, w_dq.n);     // dQ committed
       }
     }
     __syncwarp();
@@ -221,46 +326,124 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
     const int gr = a.q_swap ? (r % a.G) : (r / a.P);
     const int ro = a.dq_swap ? (pr * a.G + gr) : (gr * a.P + pr);   // row in dQ's box order
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    int item = 0, it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      int pb, y, b;
-      decode_tile(a, tile, pb, y, b);
-      const int q0 = pb * a.P, hq0 = y * a.G;
-      const TilePlan pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN);
-      const int i = q0 + pr, h = hq0 + gr;
-      float neg_l2 = -INFINITY, delta = 0.f;
-      if (i < a.N) {
-        const int64_t row = (static_cast<int64_t>(b) * a.Hq + h) * a.N + i;
-        const float l = a.lse[row];
-        neg_l2 = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
-        delta = a.delta[row];
+
+    // lse and delta of this thread's row in the tile (pb, y, b): loaded one tile ahead, consumed (and only then
+    // waited for) when that tile starts
+    auto load_row = [&](bool valid, int pb, int y, int b, float& l, float& dl) {
+      l = INFINITY;                      // rows past N: P = exp2(s - inf) = 0
+      dl = 0.f;
+      const int i = pb * a.P + pr;
+      if (valid && i < a.N) {
+        const int64_t row = (static_cast<int64_t>(b) * a.Hq + y * a.G + gr) * a.N + i;
+        // volatile: the loads must be issued here (a tile ahead of their use), not sunk to the use
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l) : "l"(a.lse + row));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dl) : "l"(a.delta + row));
       }
-      for (int t = 0; t < pl.n_tiles; ++t, ++item) {
-        int kstart, cols; bool is_sink;
-        pl.tile(t, a.BN, kstart, cols, is_sink);
-        int c_lo, c_hi;
-        row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
-        if (i >= a.N) c_hi = -1;
-        const int nch = cols / 16;
-        const int hch = (nch + 1) / 2;
-        const int hcol = hch * 16;
-        const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
-        mbar_wait(s_full, item & 1);
-        tc_fence_after();
-        for (int ch = ch0; ch < ch1; ++ch) {
-          const int c0 = ch * 16;
-          uint32_t sv[16], dv[16], pk[8];
-          tmem_ld16(tl + C::kColS + c0, sv);
-          tmem_ld16(tl + C::kColP + c0, dv);
-          tmem_ld_wait();
-          if (c0 + 15 >= c_lo && c0 <= c_hi) {
+    };
+    struct Pending { int valid, it, q0, hq0, b; } pend = {0, 0, 0, 0, 0};
+    auto epilogue = [&](const Pending& e) {
+      const int qs = e.it % C::kQStages, buf = e.it % C::kDqBufs;
+      unsigned char* stage = C::kSepStage ? stage_s : (q_s + qs * C::kQBytes);
+      if (C::kSepStage) {
+        // the previous tile's TMA store must have finished reading the staging buffer
+        if (threadIdx.x == 0) tma_store_wait_read0();
+        named_bar_sync(2, kMathThreads);
+      }
+      mbar_wait(dq_done + buf, (e.it / C::kDqBufs) & 1);
+      tc_fence_after();
+      uint32_t v[D / 32][16];
+#pragma unroll
+      for (int cc = 0; cc < D / 32; ++cc) tmem_ld16(tl + C::kColQ + buf * D + half * (D / 2) + cc * 16, v[cc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_free + buf);
+#pragma unroll
+      for (int cc = 0; cc < D / 32; ++cc) {
+        const int c0 = half * (D / 2) + cc * 16;
+        uint32_t pk[8];
+#pragma unroll
+        for (int e2 = 0; e2 < 16; e2 += 2)
+          pk[e2 >> 1] = pack16<T>(__uint_as_float(v[cc][e2]) * a.scale, __uint_as_float(v[cc][e2 + 1]) * a.scale);
+        unsigned char* slab = stage + (c0 >> 6) * C::kSlabQ;
+        const int chn = (c0 & 63) >> 3;
+        *reinterpret_cast<uint4*>(slab + sw128_off(ro, chn)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(slab + sw128_off(ro, chn + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, kMathThreads);
+      if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kDS; ++s) tma_tile_store(&tmdQ, stage + s * C::kSlabQ, a.dq_swap, s * 64, e.q0, e.hq0, e.b);
+        tma_store_commit();
+        if (!C::kSepStage) {
+          tma_store_wait_read0();
+          mbar_arrive(qdo_empty + qs);
+        }
+      }
+    };
+
+    float l_next, dl_next, neg_l2 = -INFINITY, delta = 0.f;
+    int i = 0, mtc = 0;
+    ItemWalk w(a);
+    {
+      int pb = w.pb, y = w.y, b = w.b;
+      ItemWalk::advance(a, w.step, pb, y, b);
+      load_row(w.tile + w.step < w.end, pb, y, b, l_next, dl_next);
+    }
+    while (w.next()) {
+      if (w.t == 0) {
+        neg_l2 = (l_next == -INFINITY) ? -INFINITY : -l_next * kLog2e;   // lse = -inf: nothing attended, P = 0
+        delta = dl_next;
+        i = w.q0 + pr;
+        int pb = w.pb, y = w.y, b = w.b;
+        ItemWalk::advance(a, w.step, pb, y, b);
+        load_row(w.tile + w.step < w.end, pb, y, b, l_next, dl_next);
+      }
+      const int slot = w.n & 1;
+      const uint32_t ts = tl + slot * C::kSlotCols;
+      int kstart, cols; bool is_sink;
+      w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+      int c_lo, c_hi;
+      row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+      if (i >= a.N) c_hi = -1;
+      const int nch = cols / 16;
+      const int hch = (nch + 1) / 2;
+      const int hcol = hch * 16;
+      const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 1, w.n);     // waiting for S, dP
+      mbar_wait(s_full + slot, (w.n >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 2, w.n);     // S, dP complete
+      // all of this thread's S and dP columns are fetched before the first use: one exposed TMEM latency per item
+      constexpr int kMaxCh = (C::kBNMax / 16 + 1) / 2;
+      uint32_t sv[kMaxCh][16], dv[kMaxCh][16];
+#pragma unroll
+      for (int jj = 0; jj < kMaxCh; ++jj)
+        if (ch0 + jj < ch1) {
+          tmem_ld16(ts + (ch0 + jj) * 16, sv[jj]);
+          tmem_ld16(ts + C::kBNMax + (ch0 + jj) * 16, dv[jj]);
+        }
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < kMaxCh; ++jj)
+        if (ch0 + jj < ch1) {
+          const int c0 = (ch0 + jj) * 16;
+          uint32_t pk[8];
+          const bool full = (c0 >= c_lo) && (c0 + 15 <= c_hi);
+          if (__all_sync(0xffffffffu, full)) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[jj][e]), a.sl2, neg_l2));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[jj][e + 1]), a.sl2, neg_l2));
+              pk[e >> 1] = pack16<T>(p0 * (__uint_as_float(dv[jj][e]) - delta), p1 * (__uint_as_float(dv[jj][e + 1]) - delta));
+            }
+          } else if (c0 + 15 >= c_lo && c0 <= c_hi) {
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
               const int c = c0 + e;
-              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2));
-              float d0 = p0 * (__uint_as_float(dv[e]) - delta);
-              float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta);
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[jj][e]), a.sl2, neg_l2));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[jj][e + 1]), a.sl2, neg_l2));
+              float d0 = p0 * (__uint_as_float(dv[jj][e]) - delta);
+              float d1 = p1 * (__uint_as_float(dv[jj][e + 1]) - delta);
               d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
               d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
               pk[e >> 1] = pack16<T>(d0, d1);
@@ -269,43 +452,22 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 8; ++e) pk[e] = 0u;
           }
-          const uint32_t dst = half ? (tl + C::kColS + hcol + ((c0 - hcol) >> 1)) : (tl + C::kColP + (c0 >> 1));
+          __syncwarp();
+          const uint32_t dst = half ? (ts + hcol + ((c0 - hcol) >> 1)) : (ts + C::kBNMax + (c0 >> 1));
           tmem_st8(dst, pk);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(p_full);
-      }
-      // ---------------- epilogue: dQ * scale -> 16-bit -> staging (this tile's Q stage) -> TMA store
-      const int qs = it % C::kQStages;
-      unsigned char* stage = q_s + qs * C::kQBytes;
-      mbar_wait(dq_done, it & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < D / 2; cc += 16) {
-        const int c0 = half * (D / 2) + cc;
-        uint32_t v[16], pk[8];
-        tmem_ld16(tl + C::kColQ + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; e += 2)
-          pk[e >> 1] = pack16<T>(__uint_as_float(v[e]) * a.scale, __uint_as_float(v[e + 1]) * a.scale);
-        unsigned char* slab = stage + (c0 >> 6) * C::kSlabQ;
-        const int chn = (c0 & 63) >> 3;
-        *reinterpret_cast<uint4*>(slab + sw128_off(ro, chn)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(slab + sw128_off(ro, chn + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(dq_free);
-      fence_proxy_async_smem();
-      named_bar_sync(1, kMathThreads);
-      if (threadIdx.x == 0) {
-        for (int s = 0; s < C::kDS; ++s) tma_tile_store(&tmdQ, stage + s * C::kSlabQ, a.dq_swap, s * 64, q0, hq0, b);
-        tma_store_commit();
-        tma_store_wait_read0();
-        mbar_arrive(qdo_empty + qs);
+      mbar_arrive(p_full + slot);
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 3, w.n);     // dS written
+      if (pend.valid) {
+        epilogue(pend);
+        pend.valid = 0;
+        if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 4, w.n);   // deferred epilogue done
       }
+      if (w.last_of_tile()) pend = Pending{1, w.it, w.q0, w.y * a.G, w.b};
     }
+    if (pend.valid) epilogue(pend);
     if (threadIdx.x == 0) tma_store_wait_all0();
   }
   tc_fence_before();
@@ -594,6 +756,12 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
   if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
 }
 
+}  // namespace
+static long long* g_trace = nullptr;
+void set_trace_buffer(long long* p) { g_trace = p; }
+long long* trace_buffer() { return g_trace; }
+namespace {
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -641,7 +809,11 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.scale = p.scale;
     a.lse = p.lse;
     a.delta = p.delta;
+    a.trace = trace_buffer();
+    a.bn_mul = bn_magic(BN);
     const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+    static const int contig = getenv("SFA_CONTIG") ? atoi(getenv("SFA_CONTIG")) : 0;
+    a.tiles_per_cta = contig ? (a.total_tiles + grid - 1) / grid : 0;
     dq_kernel<T, D><<<grid, kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -91,7 +91,169 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// UMMA issue-rate probe: one thread issues `reps` x (K/16) SS-form UMMAs (M = 128, N, K from zero-filled
+// shared memory) and records clock64 after the issue loop and after the commit has landed.
+__global__ void __launch_bounds__(128) mma_rate_kernel(long long* out, int N, int ksteps, int reps, int fmt, int uniform) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  const uint32_t idesc = make_idesc(fmt, 128, N, 0, 0);
+  const uint64_t ad = make_sdesc(smem_u32(smem), 16, 1024), bd = make_sdesc(smem_u32(smem + 16384), 16, 1024);
+  if (uniform) {
+    if (warp == 1) {                       // whole warp runs the loop; one elected lane issues
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r)
+        for (int kk = 0; kk < ksteps; ++kk)
+          if (elect_one()) umma_ss(tmem + (r & 1) * 256, ad + (kk & 3) * 2, bd + (kk & 3) * 2, idesc, kk > 0);
+      const long long t1 = clock64();
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+      mbar_wait(bar, 0);
+      const long long t2 = clock64();
+      if (threadIdx.x == 32) {
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    const long long t0 = clock64();
+    if (uniform == 0) {
+      for (int r = 0; r < reps; ++r)
+        for (int kk = 0; kk < ksteps; ++kk) umma_ss(tmem + (r & 1) * 256, ad + (kk & 3) * 2, bd + (kk & 3) * 2, idesc, kk > 0);
+    } else if (uniform == 2) {      // two interleaved accumulation chains
+      for (int r = 0; r < reps; ++r)
+        for (int kk = 0; kk < ksteps; ++kk) umma_ss(tmem + (kk & 1) * 256, ad + (kk & 3) * 2, bd + (kk & 3) * 2, idesc, kk > 1);
+    } else if (uniform == 3) {      // four interleaved chains
+      for (int r = 0; r < reps; ++r)
+        for (int kk = 0; kk < ksteps; ++kk) umma_ss(tmem + (kk & 3) * 128, ad + (kk & 3) * 2, bd + (kk & 3) * 2, idesc, kk > 3);
+    } else {                        // fully unrolled issue, no loop arithmetic
+      for (int r = 0; r < reps; ++r) {
+        umma_ss(tmem, ad, bd, idesc, 0);
+        umma_ss(tmem, ad + 2, bd + 2, idesc, 1);
+        umma_ss(tmem, ad + 4, bd + 4, idesc, 1);
+        umma_ss(tmem, ad + 6, bd + 6, idesc, 1);
+      }
+    }
+    const long long t1 = clock64();
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// TMA load-throughput probe (performance work, tools/probe_tma.py): every CTA streams boxes of
+// box_n positions x box_h heads x 64 channels (16-bit) through a ring of `stages` shared-memory
+// buffers; nothing consumes the data.  mode 1 replaces TMA by per-thread cp.async (16 B each).
+__global__ void __launch_bounds__(160) tma_bw_kernel(const __grid_constant__ CUtensorMap tm, const unsigned char* src,
+                                                     int swap, int nblk, int nboxes, int box_n, int box_h,
+                                                     int stages, int mode, long long head_stride_bytes) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int box_bytes = box_n * box_h * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * box_bytes);
+  uint64_t* empty = full + stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full + s, mode == 0 ? 1 : 128);
+      mbar_init(empty + s, 1);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (mode == 0) {
+    if (warp == 0 && lane == 0) {
+      int k = 0;
+      for (int bx = blockIdx.x; bx < nboxes; bx += gridDim.x, ++k) {
+        const int st = k % stages;
+        mbar_wait(empty + st, ((k / stages) & 1) ^ 1);
+        mbar_expect_tx(full + st, box_bytes);
+        const int pb = bx % nblk, hg = bx / nblk;
+        if (swap) tma_load_4d(smem + st * box_bytes, &tm, full + st, 0, hg * box_h, pb * box_n, 0);
+        else tma_load_4d(smem + st * box_bytes, &tm, full + st, 0, pb * box_n, hg * box_h, 0);
+      }
+    } else if (warp == 1 && lane == 0) {
+      int k = 0;
+      for (int bx = blockIdx.x; bx < nboxes; bx += gridDim.x, ++k) {
+        const int st = k % stages;
+        mbar_wait(full + st, (k / stages) & 1);
+        mbar_arrive(empty + st);
+      }
+    }
+  } else {
+    // warps 0-3: cp.async producers (16 B per thread per request, rows of 128 B, swizzled like the TMA box);
+    // warp 4 lane 0: consumer
+    if (warp < 4) {
+      int k = 0;
+      const int t = threadIdx.x;
+      for (int bx = blockIdx.x; bx < nboxes; bx += gridDim.x, ++k) {
+        const int st = k % stages;
+        if (lane == 0) mbar_wait(empty + st, ((k / stages) & 1) ^ 1);
+        __syncwarp();
+        const int pb = bx % nblk, hg = bx / nblk;
+        for (int idx = t; idx < box_n * box_h * 8; idx += 128) {
+          const int row = idx >> 3, ch = idx & 7;
+          const int hh = row / box_n, nn = row % box_n;
+          const unsigned char* g = src + (long long)(hg * box_h + hh) * head_stride_bytes + (long long)(pb * box_n + nn) * 128 + ch * 16;
+          const uint32_t d = smem_u32(smem + st * box_bytes + sw128_off(row, ch));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full + st)) : "memory");
+      }
+    } else if (lane == 0) {
+      int k = 0;
+      for (int bx = blockIdx.x; bx < nboxes; bx += gridDim.x, ++k) {
+        const int st = k % stages;
+        mbar_wait(full + st, (k / stages) & 1);
+        mbar_arrive(empty + st);
+      }
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode,
+                         cudaStream_t st) {
+  TileMap m;
+  Strides4 sa{(int64_t)H * N * 64, (int64_t)N * 64, 64};
+  if (!make_tile_map(&m, src, SFA_DTYPE_BF16, 64, N, H, 1, sa, box_n, box_h)) return cudaErrorInvalidValue;
+  const int box_bytes = box_n * box_h * 128;
+  const int smem = 1024 + stages * box_bytes + 2 * stages * 8 + 64;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(tma_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const int nblk = N / box_n, nboxes = nblk * (H / box_h);
+  tma_bw_kernel<<<grid, 160, smem, st>>>(m.map, static_cast<const unsigned char*>(src), m.swap_nh, nblk, nboxes, box_n,
+                                         box_h, stages, mode, (long long)N * 128);
+  return cudaGetLastError();
+}
+
+cudaError_t probe_mma_rate(long long* out, int N, int ksteps, int reps, int uniform, cudaStream_t st) {
+  const int smem = 1024 + 16384 + 32768 + 64;
+  cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  mma_rate_kernel<<<1, 128, smem, st>>>(out, N, ksteps, reps, 1, uniform);
+  return cudaGetLastError();
+}
 
 cudaError_t probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, cudaStream_t st) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return cudaErrorInvalidValue;

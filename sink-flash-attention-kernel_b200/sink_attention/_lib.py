@@ -19,8 +19,8 @@ OP_FWD, OP_BWD, OP_DECODE = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
-    "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma",
+    "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate",
 )
 
 _lib = None
@@ -53,6 +53,8 @@ def load() -> ctypes.CDLL:
     lib.sfa_set_impl.restype = i
     lib.sfa_set_bwd_stages.argtypes = [i]
     lib.sfa_set_bwd_stages.restype = i
+    lib.sfa_set_trace_buffer.argtypes = [p]
+    lib.sfa_set_trace_buffer.restype = i
     lib.sfa_workspace_bytes.argtypes = [i] * 7
     lib.sfa_workspace_bytes.restype = c.c_size_t
     lib.sfa_fwd.argtypes = [p, p, p, p, f32p, f32p] + [i] * 8 + [i64p] * 4 + [p, c.c_size_t, p]
@@ -63,6 +65,10 @@ def load() -> ctypes.CDLL:
     lib.sfa_decode.restype = i
     lib.sfa_decode_ring.argtypes = [p] * 6 + [f32p] + [i] * 7 + [i64p] * 4 + [p, c.c_size_t, p]
     lib.sfa_decode_ring.restype = i
+    lib.sfa_probe_mma_rate.argtypes = [p, i, i, i, i, p]
+    lib.sfa_probe_mma_rate.restype = i
+    lib.sfa_probe_tma_bw.argtypes = [p, i, i, i, i, i, i, i, p]
+    lib.sfa_probe_tma_bw.restype = i
     lib.sfa_probe_umma.argtypes = [p, p, f32p, i, i, i, i, p]
     lib.sfa_probe_umma.restype = i
     _lib = lib

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Timeline of CTA 0 of the dQ kernel (clock64 stamps per role) at the C1 shape: where the time per tile goes."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "sink-flash-attention-kernel_b200"))
+import sink_attention as sa  # noqa: E402
+from sink_attention import _lib  # noqa: E402
+
+B, N, Hq, Hkv, D, S, W = 1, 8192, 64, 8, 64, 0, 128
+dev = "cuda"
+g = torch.Generator(device=dev).manual_seed(1)
+dt = torch.bfloat16
+q = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt)
+k = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt)
+v = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt)
+do = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt)
+s_aux = torch.randn(Hq, device=dev, generator=g)
+o, lse = sa.sink_flash_attention_with_lse(q, k, v, S, W, s_aux)
+lib = _lib.load()
+for _ in range(3):
+    _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
+torch.cuda.synchronize()
+buf = torch.zeros(3 * 256 * 2, dtype=torch.int64, device=dev)
+lib.sfa_set_trace_buffer(buf.data_ptr())
+lib.sfa_set_bwd_stages(2)
+_lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
+torch.cuda.synchronize()
+lib.sfa_set_trace_buffer(None)
+lib.sfa_set_bwd_stages(7)
+t = buf.cpu().view(3, 256, 2)
+names = {0: {1: "Q/dO stage free, load issued", 2: "K stage free", 3: "V stage free"},
+         1: {1: "Q/dO landed", 2: "K landed", 3: "S,dP issued", 4: "dS ready", 5: "S mma issued", 6: "V landed", 7: "dP mma issued", 8: "dQ mma issued", 9: "dQ committed"},
+         2: {1: "wait S,dP", 2: "S,dP complete", 3: "dS written", 4: "epilogue done"}}
+ev = []
+for role in range(3):
+    for j in range(256):
+        tag, clk = int(t[role, j, 0]), int(t[role, j, 1])
+        if clk == 0:
+            break
+        ev.append((clk, role, tag >> 32, tag & 0xffffffff))
+ev.sort()
+t0 = ev[0][0]
+for clk, role, code, idx in ev[:260]:
+    print(f"{clk - t0:8d}  {'PROD MMA  MATH'.split()[role]:5s} {names[role][code]:30s} #{idx}")
