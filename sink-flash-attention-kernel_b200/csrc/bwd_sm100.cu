@@ -47,8 +47,11 @@ struct BwdArgs {
 
 // Timeline probe for performance work: CTA 0 appends (role, code, index, clock64) records.
 // role 0 = TMA producer, 1 = MMA issuer, 2 = math thread 0.  256 records of 2 x int64 per role.
+#ifndef SFA_TRACE
+#define SFA_TRACE 0      // build with -DSFA_TRACE=1 to compile the timeline probe in
+#endif
 __device__ __forceinline__ void trace_ev(long long* trace, int role, int& cnt, int code, int idx) {
-  if (trace != nullptr && blockIdx.x == 0 && cnt < 256) {
+  if (SFA_TRACE && trace != nullptr && blockIdx.x == 0 && cnt < 256) {
     trace[(role * 256 + cnt) * 2] = (static_cast<long long>(code) << 32) | static_cast<unsigned>(idx);
     trace[(role * 256 + cnt) * 2 + 1] = clock64();
     ++cnt;
@@ -475,6 +478,373 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
   if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
 }
 
+// ================================================================================== dQ kernel, head_dim 64
+// Measured on B200 (tools/probe_mma.py, tools/trace_dq.py): one tcgen05.mma costs the issuing thread
+// ~70-90 cycles whatever its N up to 144, and every mbarrier round trip on the single-thread roles
+// ~200-300 cycles -- so the schedule below minimises UMMA instructions and barrier hops per tile:
+// KV items of up to 144 columns (one item per tile at window 128), S issued TWO items ahead into a
+// double-buffered region, dP one item ahead into a single region, and the math split in two phases:
+//   phase 1 (needs S only):   P = exp2(S*c - lse)                 -- the MUFU-bound part
+//   phase 2 (needs dP):       dS = P * (dP - delta) -> 16-bit over the consumed S columns
+// so the UMMA burst of item n (dQ(n), dP(n+1), S(n+2)) runs under phase 1 of item n+1.
+struct Dq64Cfg {
+  static constexpr int D = 64;
+  static constexpr int kBNMax = 144;
+  static constexpr int kKStages = 4;      // K(n) is held from S(n) (issued at item n-2) to dQ(n)
+  static constexpr int kVStages = 2;
+  static constexpr int kQStages = 3;      // Q tiles (needed by S, two items ahead)
+  static constexpr int kOStages = 3;      // dO tiles (needed by dP, one item ahead)
+  static constexpr int kQBytes = 128 * D * 2;
+  static constexpr int kKVBytes = kBNMax * D * 2;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kColS = 0;               // S buffers at 0 and kBNMax
+  static constexpr uint32_t kColP = 2 * kBNMax;      // dP
+  static constexpr uint32_t kColQ = 3 * kBNMax;      // dQ accumulator
+  static constexpr int kMaxCh = (kBNMax / 16 + 1) / 2;   // 16-column chunks per math thread
+  static constexpr int kSmem = 1024 + (kQStages + kOStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + 512;
+  static_assert(3 * kBNMax + D <= 512, "TMEM budget");
+  static_assert(kSmem <= 227 * 1024, "smem budget");
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) dq64_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                           const __grid_constant__ CUtensorMap tmdO,
+                                                           const __grid_constant__ CUtensorMap tmK,
+                                                           const __grid_constant__ CUtensorMap tmV,
+                                                           const __grid_constant__ CUtensorMap tmdQ, const BwdArgs a) {
+  using C = Dq64Cfg;
+  constexpr int D = C::D;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* q_s = smem;                                   // [kQStages][kQBytes]
+  unsigned char* do_s = q_s + C::kQStages * C::kQBytes;        // [kOStages][kQBytes]
+  unsigned char* stage_s = do_s + C::kOStages * C::kQBytes;    // dQ staging
+  unsigned char* k_s = stage_s + C::kQBytes;                   // [kKStages][kKVBytes]
+  unsigned char* v_s = k_s + C::kKStages * C::kKVBytes;        // [kVStages][kKVBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + C::kVStages * C::kKVBytes);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = q_full + C::kQStages;
+  uint64_t* do_full = q_empty + C::kQStages;
+  uint64_t* do_empty = do_full + C::kOStages;
+  uint64_t* k_full = do_empty + C::kOStages;
+  uint64_t* k_empty = k_full + C::kKStages;
+  uint64_t* v_full = k_empty + C::kKStages;
+  uint64_t* v_empty = v_full + C::kVStages;
+  uint64_t* s_full = v_empty + C::kVStages;        // [2]
+  uint64_t* dp_full = s_full + 2;
+  uint64_t* p_full = dp_full + 1;
+  uint64_t* dq_done = p_full + 1;
+  uint64_t* dq_free = dq_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kMathWarps && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdQ);
+    for (int s = 0; s < C::kQStages; ++s) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
+    for (int s = 0; s < C::kOStages; ++s) { mbar_init(do_full + s, 1); mbar_init(do_empty + s, 1); }
+    for (int s = 0; s < C::kKStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+    for (int s = 0; s < C::kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_full + 1, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(p_full, kMathThreads);
+    mbar_init(dq_done, 1);
+    mbar_init(dq_free, kMathThreads);
+    fence_barrier_init();
+  }
+  if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kMathWarps) {
+    // ------------------------------------------------------------------ TMA producer
+    // issue order = consumption order of the UMMA thread: {Q, K} of item m, then {dO, V} of item m-1
+    if (lane == 0) {
+      ItemWalk wk(a), wv(a);
+      int tc = 0;
+      auto load_k = [&](const ItemWalk& w) {
+        const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
+        if (w.t == 0) {
+          const int qs = w.it % C::kQStages;
+          mbar_wait(q_empty + qs, ((w.it / C::kQStages) & 1) ^ 1);
+          mbar_expect_tx(q_full + qs, C::kQBytes);
+          tma_tile(q_s + qs * C::kQBytes, &tmQ, q_full + qs, a.q_swap, 0, w.q0, hq0, w.b);
+        }
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const int kst = w.n % C::kKStages;
+        mbar_wait(k_empty + kst, ((w.n / C::kKStages) & 1) ^ 1);
+        mbar_expect_tx(k_full + kst, a.BN * D * 2);
+        tma_tile(k_s + kst * C::kKVBytes, &tmK, k_full + kst, a.k_swap, 0, kstart, kvh, w.b);
+        trace_ev(a.trace, 0, tc, 2, w.n);
+      };
+      auto load_v = [&](const ItemWalk& w) {
+        const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
+        if (w.t == 0) {
+          const int os = w.it % C::kOStages;
+          mbar_wait(do_empty + os, ((w.it / C::kOStages) & 1) ^ 1);
+          mbar_expect_tx(do_full + os, C::kQBytes);
+          tma_tile(do_s + os * C::kQBytes, &tmdO, do_full + os, a.q_swap, 0, w.q0, hq0, w.b);
+        }
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const int vst = w.n % C::kVStages;
+        mbar_wait(v_empty + vst, ((w.n / C::kVStages) & 1) ^ 1);
+        mbar_expect_tx(v_full + vst, a.BN * D * 2);
+        tma_tile(v_s + vst * C::kKVBytes, &tmV, v_full + vst, a.v_swap, 0, kstart, kvh, w.b);
+        trace_ev(a.trace, 0, tc, 3, w.n);
+      };
+      bool more_k = wk.next();
+      if (more_k) load_k(wk);
+      while (wv.next()) {
+        if (more_k) {
+          more_k = wk.next();
+          if (more_k) load_k(wk);
+        }
+        load_v(wv);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMathWarps + 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_dq = make_idesc(a.fmt, 128, D, 0, 1);
+      int tc = 0;
+      auto issue_s = [&](const ItemWalk& w) {       // S(n) = Q K^T into S buffer n & 1
+        const int qs = w.it % C::kQStages, kst = w.n % C::kKStages;
+        if (w.t == 0) {
+          mbar_wait(q_full + qs, (w.it / C::kQStages) & 1);
+          tc_fence_after();
+        }
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
+        const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
+        const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), 16, 1024);
+        mbar_wait(k_full + kst, (w.n / C::kKStages) & 1);
+        tc_fence_after();
+        const uint32_t ts = tmem + C::kColS + (w.n & 1) * C::kBNMax;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss(ts, qd + kk * 2, kd + kk * 2, idesc_s, kk != 0);
+        umma_commit(s_full + (w.n & 1));
+        if (w.last_of_tile()) umma_commit(q_empty + qs);
+        trace_ev(a.trace, 1, tc, 5, w.n);
+      };
+      auto issue_dp = [&](const ItemWalk& w) {      // dP(n) = dO V^T into the single dP region
+        const int os = w.it % C::kOStages, vst = w.n % C::kVStages;
+        if (w.t == 0) {
+          mbar_wait(do_full + os, (w.it / C::kOStages) & 1);
+          tc_fence_after();
+        }
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
+        const uint64_t dod = make_sdesc(smem_u32(do_s + os * C::kQBytes), 16, 1024);
+        const uint64_t vd = make_sdesc(smem_u32(v_s + vst * C::kKVBytes), 16, 1024);
+        mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + C::kColP, dod + kk * 2, vd + kk * 2, idesc_s, kk != 0);
+        umma_commit(dp_full);
+        umma_commit(v_empty + vst);
+        if (w.last_of_tile()) umma_commit(do_empty + os);
+        trace_ev(a.trace, 1, tc, 7, w.n);
+      };
+      ItemWalk w_s(a), w_p(a), w_q(a);
+      bool more_s = w_s.next();
+      if (more_s) issue_s(w_s);                      // S(0)
+      if (more_s && (more_s = w_s.next())) issue_s(w_s);   // S(1)
+      bool more_p = w_p.next();
+      if (more_p) issue_dp(w_p);                     // dP(0)
+      while (w_q.next()) {                           // item n: dQ(n), dP(n+1), S(n+2)
+        const int kst = w_q.n % C::kKStages;
+        int kstart, cols; bool is_sink;
+        w_q.pl.tile(w_q.t, a.BN, kstart, cols, is_sink);
+        mbar_wait(p_full, w_q.n & 1);
+        tc_fence_after();
+        trace_ev(a.trace, 1, tc, 4, w_q.n);
+        if (w_q.t == 0 && w_q.it > 0) {
+          mbar_wait(dq_free, (w_q.it - 1) & 1);
+          tc_fence_after();
+        }
+        // dS(n): 16-bit pairs over the S buffer -- columns [0,hcol) at [0,hcol/2), columns [hcol,cols) from hcol on
+        const uint32_t ts = tmem + C::kColS + (w_q.n & 1) * C::kBNMax;
+        const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), C::kKVBytes, 1024);
+        const int hcol = ((cols / 16 + 1) / 2) * 16;
+        const uint32_t a_lo = ts, a_hi = ts + hcol - (hcol >> 1);
+        const int nk = cols >> 4;
+#pragma unroll
+        for (int kk = 0; kk < C::kBNMax / 16; ++kk)
+          if (kk < nk)
+            umma_ts(tmem + C::kColQ, ((kk * 16 < hcol) ? a_lo : a_hi) + kk * 8, kd + kk * (2048 >> 4), idesc_dq,
+                    (w_q.t > 0 || kk > 0));
+        umma_commit(k_empty + kst);
+        if (w_q.last_of_tile()) umma_commit(dq_done);
+        trace_ev(a.trace, 1, tc, 8, w_q.n);
+        if (more_p && (more_p = w_p.next())) issue_dp(w_p);
+        if (more_s && (more_s = w_s.next())) issue_s(w_s);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ element-wise math + epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;                  // MMA row == TMEM lane
+    const int pr = a.q_swap ? (r / a.G) : (r % a.P);
+    const int gr = a.q_swap ? (r % a.G) : (r / a.P);
+    const int ro = a.dq_swap ? (pr * a.G + gr) : (gr * a.P + pr);   // row in dQ's box order
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+
+    auto load_row = [&](bool valid, int pb, int y, int b, float& l, float& dl) {
+      l = INFINITY;                      // rows past N: P = exp2(s - inf) = 0
+      dl = 0.f;
+      const int i = pb * a.P + pr;
+      if (valid && i < a.N) {
+        const int64_t row = (static_cast<int64_t>(b) * a.Hq + y * a.G + gr) * a.N + i;
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l) : "l"(a.lse + row));      // issued a tile ahead of use
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dl) : "l"(a.delta + row));
+      }
+    };
+    struct Pending { int valid, it, q0, hq0, b; } pend = {0, 0, 0, 0, 0};
+    auto epilogue = [&](const Pending& e) {
+      if (threadIdx.x == 0) tma_store_wait_read0();     // previous store has finished reading the staging buffer
+      named_bar_sync(2, kMathThreads);
+      mbar_wait(dq_done, e.it & 1);
+      tc_fence_after();
+      uint32_t v[2][16];
+      tmem_ld16(tl + C::kColQ + half * 32, v[0]);
+      tmem_ld16(tl + C::kColQ + half * 32 + 16, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_free);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int e2 = 0; e2 < 16; e2 += 2)
+          pk[e2 >> 1] = pack16<T>(__uint_as_float(v[cc][e2]) * a.scale, __uint_as_float(v[cc][e2 + 1]) * a.scale);
+        const int chn = half * 4 + cc * 2;
+        *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, chn)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, chn + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, kMathThreads);
+      if (threadIdx.x == 0) {
+        tma_tile_store(&tmdQ, stage_s, a.dq_swap, 0, e.q0, e.hq0, e.b);
+        tma_store_commit();
+      }
+    };
+
+    float l_next, dl_next, neg_l2 = -INFINITY, delta = 0.f;
+    int i = 0, mtc = 0;
+    ItemWalk w(a);
+    {
+      int pb = w.pb, y = w.y, b = w.b;
+      ItemWalk::advance(a, w.step, pb, y, b);
+      load_row(w.tile + w.step < w.end, pb, y, b, l_next, dl_next);
+    }
+    while (w.next()) {
+      if (w.t == 0) {
+        neg_l2 = (l_next == -INFINITY) ? -INFINITY : -l_next * kLog2e;   // lse = -inf: nothing attended, P = 0
+        delta = dl_next;
+        i = w.q0 + pr;
+        int pb = w.pb, y = w.y, b = w.b;
+        ItemWalk::advance(a, w.step, pb, y, b);
+        load_row(w.tile + w.step < w.end, pb, y, b, l_next, dl_next);
+      }
+      const uint32_t ts = tl + C::kColS + (w.n & 1) * C::kBNMax;
+      int kstart, cols; bool is_sink;
+      w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+      int c_lo, c_hi;
+      row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+      if (i >= a.N) c_hi = -1;
+      const int nch = cols / 16;
+      const int hch = (nch + 1) / 2;
+      const int hcol = hch * 16;
+      const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
+
+      // ---- phase 1: P = exp2(S*c - lse) for this thread's columns (kept in registers)
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 1, w.n);
+      mbar_wait(s_full + (w.n & 1), (w.n >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 2, w.n);
+      uint32_t pv[C::kMaxCh][16];
+#pragma unroll
+      for (int jj = 0; jj < C::kMaxCh; ++jj)
+        if (ch0 + jj < ch1) tmem_ld16(ts + (ch0 + jj) * 16, pv[jj]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < C::kMaxCh; ++jj)
+        if (ch0 + jj < ch1) {
+          const int c0 = (ch0 + jj) * 16;
+          if (__any_sync(0xffffffffu, c0 + 15 >= c_lo && c0 <= c_hi)) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              pv[jj][e] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e]), a.sl2, neg_l2)));
+          }
+        }
+      // ---- the previous tile's dQ is complete by now: write it out while dP(n) finishes
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 5, w.n);
+      if (pend.valid) {
+        epilogue(pend);
+        pend.valid = 0;
+        if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 4, w.n);
+      }
+      // ---- phase 2: dS = P * (dP - delta), masked, 16-bit, over the consumed S columns
+      mbar_wait(dp_full, w.n & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 6, w.n);
+#pragma unroll
+      for (int jj = 0; jj < C::kMaxCh; ++jj)
+        if (ch0 + jj < ch1) {
+          const int c0 = (ch0 + jj) * 16;
+          uint32_t dv[16], pk[8];
+          tmem_ld16(tl + C::kColP + c0, dv);
+          tmem_ld_wait();
+          const bool full = (c0 >= c_lo) && (c0 + 15 <= c_hi);
+          if (__all_sync(0xffffffffu, full)) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2)
+              pk[e >> 1] = pack16<T>(__uint_as_float(pv[jj][e]) * (__uint_as_float(dv[e]) - delta),
+                                     __uint_as_float(pv[jj][e + 1]) * (__uint_as_float(dv[e + 1]) - delta));
+          } else if (c0 + 15 >= c_lo && c0 <= c_hi) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int c = c0 + e;
+              float d0 = __uint_as_float(pv[jj][e]) * (__uint_as_float(dv[e]) - delta);
+              float d1 = __uint_as_float(pv[jj][e + 1]) * (__uint_as_float(dv[e + 1]) - delta);
+              d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
+              d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
+              pk[e >> 1] = pack16<T>(d0, d1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk[e] = 0u;
+          }
+          __syncwarp();
+          tmem_st8(half ? (ts + hcol + ((c0 - hcol) >> 1)) : (ts + (c0 >> 1)), pk);
+        }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 3, w.n);
+      if (w.last_of_tile()) pend = Pending{1, w.it, w.q0, w.y * a.G, w.b};
+    }
+    if (pend.valid) epilogue(pend);
+    if (threadIdx.x == 0) tma_store_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
+}
+
 // ================================================================================== dK/dV kernel
 // One CTA per (128-key tile, kv head, batch).  Keys sit on the TMEM lanes; the packed Q chunks that
 // can see the tile stream through a 2-stage Q/dO ring.
@@ -756,6 +1126,363 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
   if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
 }
 
+// ================================================================================== dK/dV kernel, head_dim 64
+// Same schedule idea as dq64_kernel, KV-stationary: S^T two chunks ahead into a double-buffered
+// region, dP^T one chunk ahead into a single region, two-phase math (exp first), and BOTH 16-bit
+// operands of the accumulating UMMAs (P^T for dV, dS^T for dK) packed into the consumed S^T
+// buffer, which frees the dP^T region as soon as the math has read it.  Two issuer warps share the
+// UMMA work (a tcgen05.mma costs its issuing thread ~80 cycles): B issues S^T / dP^T, A issues dV / dK.
+struct Dkv64Cfg {
+  static constexpr int D = 64;
+  static constexpr int kBK = 128;
+  static constexpr int kQStages = 4;      // Q(c): S^T(c) is issued at chunk c-2, dK(c) at chunk c
+  static constexpr int kOStages = 3;      // dO(c): dP^T(c) at chunk c-1, dV(c) at chunk c
+  static constexpr int kQBytes = 128 * D * 2;
+  static constexpr int kKVBytes = kBK * D * 2;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kColS = 0;      // S^T buffers at 0 and 128
+  static constexpr uint32_t kColP = 256;    // dP^T
+  static constexpr uint32_t kColK = 384;    // dK accumulator [keys][64]
+  static constexpr uint32_t kColV = 448;    // dV accumulator
+  static constexpr int kThreads = kMathThreads + 96;     // + TMA producer, issuer B, issuer A
+  static constexpr int kSmem = 1024 + 2 * kKVBytes + (kQStages + kOStages) * kQBytes + 2 * 2 * 128 * 4 + 512;
+  static_assert(kSmem <= 227 * 1024, "smem budget");
+};
+
+template <typename T>
+__global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                       const __grid_constant__ CUtensorMap tmdO,
+                                                                       const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmV,
+                                                                       const DkvArgs a) {
+  using C = Dkv64Cfg;
+  constexpr int D = C::D;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* k_s = smem;
+  unsigned char* v_s = k_s + C::kKVBytes;
+  unsigned char* q_s = v_s + C::kKVBytes;                      // [kQStages][kQBytes]
+  unsigned char* do_s = q_s + C::kQStages * C::kQBytes;        // [kOStages][kQBytes]
+  float* row_l2 = reinterpret_cast<float*>(do_s + C::kOStages * C::kQBytes);   // [2][128]  -lse*log2e per chunk row
+  float* row_dl = row_l2 + 2 * 128;                                            // [2][128]  delta per chunk row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(row_dl + 2 * 128);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = kv_full + 1;              // [kQStages]
+  uint64_t* do_full = q_full + C::kQStages;    // [kOStages]
+  uint64_t* chunk_done = do_full + C::kOStages;   // [4]  dV(c), dK(c) complete: frees Q(c), dO(c) and S^T buffer c & 1
+  uint64_t* s_full = chunk_done + 4;           // [2]
+  uint64_t* dp_full = s_full + 2;
+  uint64_t* p_full = dp_full + 1;              // [2]: both issuer warps wait on it, alternating barriers rule out a missed phase
+  uint64_t* acc_done = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * C::kBK;
+  const int kvh = blockIdx.y, b = blockIdx.z;
+  int pb_lo, pb_hi;
+  chunk_range(a, j0, C::kBK, pb_lo, pb_hi);
+  const int npb = max(pb_hi - pb_lo + 1, 0);
+  const int gpk = a.groups_per_kv;
+  const int nchunks = npb * gpk;        // chunk c -> (position block pb_lo + c / gpk, group c % gpk); walked with counters
+
+  if (warp == kMathWarps && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < C::kQStages; ++s) mbar_init(q_full + s, 1);
+    for (int s = 0; s < C::kOStages; ++s) mbar_init(do_full + s, 1);
+    for (int s = 0; s < 4; ++s) mbar_init(chunk_done + s, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_full + 1, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(p_full, kMathThreads);
+    mbar_init(p_full + 1, kMathThreads);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kMathWarps) {
+    // ------------------------------------------------------------------ TMA producer: Q(c+1) then dO(c), c = -1, 0, ...
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * C::kKVBytes);
+      tma_tile(k_s, &tmK, kv_full, a.k_swap, 0, j0, kvh, b);
+      tma_tile(v_s, &tmV, kv_full, a.v_swap, 0, j0, kvh, b);
+      int pbq = pb_lo, gq = 0, pbo = pb_lo, go = 0;
+      for (int c = -1; c < nchunks; ++c) {
+        const int cq = c + 1;
+        if (cq < nchunks) {
+          const int qs = cq % C::kQStages;
+          if (cq >= C::kQStages) mbar_wait(chunk_done + ((cq - C::kQStages) & 3), ((cq - C::kQStages) >> 2) & 1);
+          mbar_expect_tx(q_full + qs, C::kQBytes);
+          tma_tile(q_s + qs * C::kQBytes, &tmQ, q_full + qs, a.q_swap, 0, pbq * a.P, (kvh * gpk + gq) * a.G, b);
+          if (++gq == gpk) { gq = 0; ++pbq; }
+        }
+        if (c >= 0) {
+          const int os = c % C::kOStages;
+          if (c >= C::kOStages) mbar_wait(chunk_done + ((c - C::kOStages) & 3), ((c - C::kOStages) >> 2) & 1);
+          mbar_expect_tx(do_full + os, C::kQBytes);
+          tma_tile(do_s + os * C::kQBytes, &tmdO, do_full + os, a.q_swap, 0, pbo * a.P, (kvh * gpk + go) * a.G, b);
+          if (++go == gpk) { go = 0; ++pbo; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMathWarps + 1) {
+    // ------------------------------------------------------------------ issuer B: S^T(c) = K Q(c)^T, dP^T(c) = V dO(c)^T
+    if (lane == 0 && nchunks > 0) {
+      const uint32_t idesc_s = make_idesc(a.fmt, 128, 128, 0, 0);
+      const uint64_t kd = make_sdesc(smem_u32(k_s), 16, 1024), vd = make_sdesc(smem_u32(v_s), 16, 1024);
+      auto issue_s = [&](int c) {
+        const int qs = c % C::kQStages;
+        mbar_wait(q_full + qs, (c / C::kQStages) & 1);
+        tc_fence_after();
+        const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
+        const uint32_t ts = tmem + C::kColS + (c & 1) * 128;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss(ts, kd + kk * 2, qd + kk * 2, idesc_s, kk != 0);
+        umma_commit(s_full + (c & 1));
+      };
+      auto issue_dp = [&](int c) {
+        const int os = c % C::kOStages;
+        mbar_wait(do_full + os, (c / C::kOStages) & 1);
+        tc_fence_after();
+        const uint64_t dod = make_sdesc(smem_u32(do_s + os * C::kQBytes), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + C::kColP, vd + kk * 2, dod + kk * 2, idesc_s, kk != 0);
+        umma_commit(dp_full);
+      };
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      if (nchunks > 1) issue_s(1);
+      issue_dp(0);
+      for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+          mbar_wait(p_full + (c & 1), (c >> 1) & 1);   // the math has read dP^T(c)
+          tc_fence_after();
+          issue_dp(c + 1);
+        }
+        if (c + 2 < nchunks) {
+          mbar_wait(chunk_done + (c & 3), (c >> 2) & 1);   // dV(c), dK(c) have consumed S^T buffer c & 1
+          tc_fence_after();
+          issue_s(c + 2);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMathWarps + 2) {
+    // ------------------------------------------------------------------ issuer A: dV += P^T dO, dK += dS^T Q
+    if (lane == 0) {
+      const uint32_t idesc_acc = make_idesc(a.fmt, 128, D, 0, 1);
+      for (int c = 0; c < nchunks; ++c) {
+        const int qs = c % C::kQStages, os = c % C::kOStages;
+        const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), C::kQBytes, 1024);
+        const uint64_t dod = make_sdesc(smem_u32(do_s + os * C::kQBytes), C::kQBytes, 1024);
+        const uint32_t ts = tmem + C::kColS + (c & 1) * 128;
+        mbar_wait(p_full + (c & 1), (c >> 1) & 1);
+        tc_fence_after();
+        // packed operands inside the S^T buffer: P^T rows [0,64) at +0, dS^T rows [0,64) at +32,
+        // P^T rows [64,128) at +64, dS^T rows [64,128) at +96 (8 columns per 16 rows)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem + C::kColV, ts + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8), dod + kk * (2048 >> 4), idesc_acc,
+                  (c > 0 || kk > 0));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem + C::kColK, ts + 32 + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8), qd + kk * (2048 >> 4), idesc_acc,
+                  (c > 0 || kk > 0));
+        umma_commit(chunk_done + (c & 3));
+      }
+      umma_commit(acc_done);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ element-wise math + epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const int kr = quarter * 32 + lane;                 // key row == TMEM lane
+    const int j = j0 + kr;
+    const int jw_lo = j0 + quarter * 32, jw_hi = jw_lo + 31;          // this warp's keys
+    // queries that attend key j: i in [j, i_hi]
+    const int i_hi = (j >= a.N) ? -1 : ((j < a.S) ? 0x7fffffff : ((a.W > 0) ? j + a.W - 1 : -1));
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int tid = threadIdx.x;                        // 0..255
+    const int sh_p = 31 - __clz(a.P), sh_g = 31 - __clz(a.G);          // P and G are powers of two
+
+    // -lse*log2e and delta of chunk row `tid` (threads 0..127), loaded one chunk ahead
+    auto load_row = [&](int pb, int grp, float& nl, float& dl) {
+      nl = -INFINITY;
+      dl = 0.f;
+      if (tid < 128) {
+        const int pr = a.q_swap ? (tid >> sh_g) : (tid & (a.P - 1));
+        const int gr = a.q_swap ? (tid & (a.G - 1)) : (tid >> sh_p);
+        const int i = pb * a.P + pr;
+        if (i < a.N) {
+          const int64_t row = (static_cast<int64_t>(b) * a.Hq + (kvh * gpk + grp) * a.G + gr) * a.N + i;
+          float l;
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l) : "l"(a.lse + row));
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dl) : "l"(a.delta + row));
+          nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+        }
+      }
+    };
+    int pb = pb_lo, grp = 0;
+    float nl_n, dl_n;
+    if (nchunks > 0) {
+      load_row(pb, grp, nl_n, dl_n);
+      if (tid < 128) {
+        row_l2[tid] = nl_n;
+        row_dl[tid] = dl_n;
+      }
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int q0 = pb * a.P;
+      int pbn = pb, gn = grp;
+      if (++gn == gpk) { gn = 0; ++pbn; }
+      named_bar_sync(1, kMathThreads);                  // rows of chunk c are in row_*[c & 1]
+      if (c + 1 < nchunks) load_row(pbn, gn, nl_n, dl_n);   // in flight during this chunk's math
+      const float* rl = row_l2 + (c & 1) * 128;
+      const float* rd = row_dl + (c & 1) * 128;
+      const uint32_t ts = tl + C::kColS + (c & 1) * 128;
+
+      // per 16-column block: attended positions [i_lo, i_hi_b]; any / all lanes of the warp attended
+      uint32_t pv[4][16];
+      bool any_b[4];
+      mbar_wait(s_full + (c & 1), (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) tmem_ld16(ts + half * 64 + jj * 16, pv[jj]);
+      tmem_ld_wait();
+      // ---- phase 1: P^T = exp2(S^T * c - lse[row])
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int c0 = half * 64 + jj * 16;
+        int i_lo, i_up;
+        if (a.q_swap) {
+          i_lo = q0 + (c0 >> sh_g);
+          i_up = q0 + ((c0 + 15) >> sh_g);
+        } else if (a.P >= 16) {
+          i_lo = q0 + (c0 & (a.P - 1));
+          i_up = i_lo + 15;
+        } else {
+          i_lo = q0;
+          i_up = q0 + a.P - 1;
+        }
+        any_b[jj] = (jw_lo <= i_up) && ((jw_lo < a.S) || (a.W > 0 && jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
+        if (any_b[jj]) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(rl + c0 + e);
+            pv[jj][e] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e]), a.sl2, l4.x)));
+            pv[jj][e + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e + 1]), a.sl2, l4.y)));
+            pv[jj][e + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e + 2]), a.sl2, l4.z)));
+            pv[jj][e + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e + 3]), a.sl2, l4.w)));
+          }
+        }
+      }
+      // ---- phase 2: mask, dS^T = P^T * (dP^T - delta[row]); both packed into this half's consumed S^T columns
+      mbar_wait(dp_full, c & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int c0 = half * 64 + jj * 16;
+        uint32_t dv[16], pp[8], pd[8];
+        tmem_ld16(tl + C::kColP + c0, dv);
+        tmem_ld_wait();
+        if (any_b[jj]) {
+          // position of chunk row r: i = q0 + (r & (P-1))  or  q0 + (r >> log2 G)
+          const int r_lo = a.q_swap ? (c0 >> sh_g) : (c0 & (a.P - 1));
+          const int r_up = a.q_swap ? ((c0 + 15) >> sh_g) : ((a.P >= 16) ? r_lo + 15 : a.P - 1);
+          const bool full = (q0 + (a.q_swap || a.P >= 16 ? r_lo : 0) >= j) && (q0 + r_up <= i_hi);
+          if (__all_sync(0xffffffffu, full)) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(rd + c0 + e);
+              const float p0 = __uint_as_float(pv[jj][e]), p1 = __uint_as_float(pv[jj][e + 1]);
+              const float p2 = __uint_as_float(pv[jj][e + 2]), p3 = __uint_as_float(pv[jj][e + 3]);
+              pp[e >> 1] = pack16<T>(p0, p1);
+              pp[(e >> 1) + 1] = pack16<T>(p2, p3);
+              pd[e >> 1] = pack16<T>(p0 * (__uint_as_float(dv[e]) - d4.x), p1 * (__uint_as_float(dv[e + 1]) - d4.y));
+              pd[(e >> 1) + 1] = pack16<T>(p2 * (__uint_as_float(dv[e + 2]) - d4.z), p3 * (__uint_as_float(dv[e + 3]) - d4.w));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int r0 = c0 + e, r1 = r0 + 1;
+              const int i0 = q0 + (a.q_swap ? (r0 >> sh_g) : (r0 & (a.P - 1)));
+              const int i1 = q0 + (a.q_swap ? (r1 >> sh_g) : (r1 & (a.P - 1)));
+              const float2 dl = *reinterpret_cast<const float2*>(rd + r0);
+              const bool ok0 = (i0 >= j) && (i0 <= i_hi);
+              const bool ok1 = (i1 >= j) && (i1 <= i_hi);
+              const float p0 = ok0 ? __uint_as_float(pv[jj][e]) : 0.f;
+              const float p1 = ok1 ? __uint_as_float(pv[jj][e + 1]) : 0.f;
+              const float d0 = ok0 ? p0 * (__uint_as_float(dv[e]) - dl.x) : 0.f;
+              const float d1 = ok1 ? p1 * (__uint_as_float(dv[e + 1]) - dl.y) : 0.f;
+              pp[e >> 1] = pack16<T>(p0, p1);
+              pd[e >> 1] = pack16<T>(d0, d1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pp[e] = pd[e] = 0u;
+        }
+        __syncwarp();
+        tmem_st8(ts + half * 64 + jj * 8, pp);
+        tmem_st8(ts + half * 64 + 32 + jj * 8, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full + (c & 1));
+      if (c + 1 < nchunks && tid < 128) {
+        row_l2[((c + 1) & 1) * 128 + tid] = nl_n;
+        row_dl[((c + 1) & 1) * 128 + tid] = dl_n;
+      }
+      pb = pbn;
+      grp = gn;
+    }
+    // ---- epilogue: dK * scale, dV -> 16-bit -> global (one key row per thread, half the channels)
+    if (nchunks > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+    }
+    T* dkr = static_cast<T*>(a.dk) + b * a.sdk.b + kvh * a.sdk.h + static_cast<int64_t>(j) * a.sdk.n;
+    T* dvr = static_cast<T*>(a.dv) + b * a.sdv.b + kvh * a.sdv.h + static_cast<int64_t>(j) * a.sdv.n;
+#pragma unroll
+    for (int cc = 0; cc < D / 2; cc += 16) {
+      const int c0 = half * (D / 2) + cc;
+      uint32_t kv_[16], vv_[16], pk[8], pv2[8];
+      if (nchunks > 0) {                                  // uniform: the tcgen05.ld stay warp-convergent
+        tmem_ld16(tl + C::kColK + c0, kv_);
+        tmem_ld16(tl + C::kColV + c0, vv_);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) kv_[e] = vv_[e] = 0u;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        pk[e >> 1] = pack16<T>(__uint_as_float(kv_[e]) * a.scale, __uint_as_float(kv_[e + 1]) * a.scale);
+        pv2[e >> 1] = pack16<T>(__uint_as_float(vv_[e]), __uint_as_float(vv_[e + 1]));
+      }
+      if (j < a.N) {
+        *reinterpret_cast<uint4*>(dkr + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dkr + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(dvr + c0) = make_uint4(pv2[0], pv2[1], pv2[2], pv2[3]);
+        *reinterpret_cast<uint4*>(dvr + c0 + 8) = make_uint4(pv2[4], pv2[5], pv2[6], pv2[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
+}
+
 }  // namespace
 static long long* g_trace = nullptr;
 void set_trace_buffer(long long* p) { g_trace = p; }
@@ -785,14 +1512,17 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
   if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;   // guarded by tc_bwd_supported
 
   if (stages & 2) {
-    using C = DqCfg<D>;
+    constexpr int kBNMax = (D == 64) ? Dq64Cfg::kBNMax : DqCfg<D>::kBNMax;
+    constexpr int kSmemDq = (D == 64) ? Dq64Cfg::kSmem : DqCfg<D>::kSmem;
     static bool attr_done = false;
     if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+      cudaError_t e;
+      if constexpr (D == 64) e = cudaFuncSetAttribute(dq64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDq);
+      else e = cudaFuncSetAttribute(dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDq);
       if (e != cudaSuccess) return e;
       attr_done = true;
     }
-    const int BN = pick_bn(p.W, p.N, P, C::kBNMax);
+    const int BN = pick_bn(p.W, p.N, P, kBNMax);
     TileMap mk, mv, mdq;
     if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
     if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
@@ -812,23 +1542,26 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.trace = trace_buffer();
     a.bn_mul = bn_magic(BN);
     const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
-    static const int contig = getenv("SFA_CONTIG") ? atoi(getenv("SFA_CONTIG")) : 0;
-    a.tiles_per_cta = contig ? (a.total_tiles + grid - 1) / grid : 0;
-    dq_kernel<T, D><<<grid, kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
+    a.tiles_per_cta = 0;
+    if constexpr (D == 64) dq64_kernel<T><<<grid, kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
+    else dq_kernel<T, D><<<grid, kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   if (stages & 4) {
-    using C = DkvCfg<D>;
+    constexpr int kBK = 128;
+    constexpr int kSmemKv = (D == 64) ? Dkv64Cfg::kSmem : DkvCfg<D>::kSmem;
     static bool attr_done = false;
     if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(dkdv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+      cudaError_t e;
+      if constexpr (D == 64) e = cudaFuncSetAttribute(dkdv64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemKv);
+      else e = cudaFuncSetAttribute(dkdv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemKv);
       if (e != cudaSuccess) return e;
       attr_done = true;
     }
     TileMap mk, mv;
-    if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, C::kBK, 1)) return cudaErrorInvalidValue;
-    if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, C::kBK, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, kBK, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, kBK, 1)) return cudaErrorInvalidValue;
     DkvArgs a;
     a.B = p.B; a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.Hkv = p.Hkv; a.G = G; a.P = P;
     a.groups_per_kv = group / G;
@@ -839,8 +1572,9 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.lse = p.lse;
     a.delta = p.delta;
     a.dk = p.dk; a.dv = p.dv; a.sdk = p.sdk; a.sdv = p.sdv;
-    dim3 grid((p.N + C::kBK - 1) / C::kBK, p.Hkv, p.B);
-    dkdv_kernel<T, D><<<grid, kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
+    if constexpr (D == 64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    else dkdv_kernel<T, D><<<grid, kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

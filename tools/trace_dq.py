@@ -32,9 +32,9 @@ torch.cuda.synchronize()
 lib.sfa_set_trace_buffer(None)
 lib.sfa_set_bwd_stages(7)
 t = buf.cpu().view(3, 256, 2)
-names = {0: {1: "Q/dO stage free, load issued", 2: "K stage free", 3: "V stage free"},
+names = {0: {1: "Q/dO stage free, load issued", 2: "K load issued", 3: "V load issued"},
          1: {1: "Q/dO landed", 2: "K landed", 3: "S,dP issued", 4: "dS ready", 5: "S mma issued", 6: "V landed", 7: "dP mma issued", 8: "dQ mma issued", 9: "dQ committed"},
-         2: {1: "wait S,dP", 2: "S,dP complete", 3: "dS written", 4: "epilogue done"}}
+         2: {1: "wait S", 2: "S complete", 3: "dS written", 4: "epilogue done", 5: "phase 1 done", 6: "dP complete"}}
 ev = []
 for role in range(3):
     for j in range(256):
