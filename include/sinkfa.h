@@ -97,6 +97,10 @@ int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mod
 
 /* UMMA issue-rate probe: out2 = device int64[2] <- {cycles to issue, cycles until complete} for reps*ksteps UMMAs */
 int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, void* stream);
+/* math-pipe probe: out1 = device int64[1] <- cycles for `iters` 16-element softmax steps of one warp (see probe_sm100.cu) */
+int sfa_probe_math_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream);
+/* TMEM read-throughput probe: out1 <- cycles for `iters` tcgen05.ld round trips per warp (mode 0: x16, 1: x32, 2: 2 x x32) */
+int sfa_probe_tmem_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream);
 /* load-throughput probe (performance work): streams a bf16 [H,N,64] tensor through shared memory with TMA
  * boxes of box_n positions x box_h heads (mode 0) or per-thread cp.async (mode 1), `stages` boxes in flight. */
 int sfa_probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode, void* stream);

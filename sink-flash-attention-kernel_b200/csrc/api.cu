@@ -254,6 +254,16 @@ int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, voi
                   "sfa_probe_mma_rate");
 }
 
+int sfa_probe_math_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream) {
+  return cuda_ret(probe_math_rate(static_cast<long long*>(out1), static_cast<float*>(sink), mode, iters, threads,
+                                  static_cast<cudaStream_t>(stream)), "sfa_probe_math_rate");
+}
+
+int sfa_probe_tmem_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream) {
+  return cuda_ret(probe_tmem_rate(static_cast<long long*>(out1), static_cast<float*>(sink), mode, iters, threads,
+                                  static_cast<cudaStream_t>(stream)), "sfa_probe_tmem_rate");
+}
+
 int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream) {
   return cuda_ret(probe_umma(a, b, c, N, K, mode, dtype, static_cast<cudaStream_t>(stream)), "sfa_probe_umma");
 }

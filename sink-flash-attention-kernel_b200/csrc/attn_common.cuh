@@ -62,6 +62,7 @@ __device__ __forceinline__ void row_range(bool is_sink, int i, int kstart, int c
   c_hi = min(c_hi, cols - 1);
 }
 
+// fp32 pair -> packed 16-bit pair (round to nearest even)
 template <typename T> __device__ __forceinline__ uint32_t pack16(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -71,6 +72,9 @@ template <> __device__ __forceinline__ uint32_t pack16<__half>(float a, float b)
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Measured (tools/time_graph.py): replacing the cvt by integer rounding (IADD + PRMT) made every kernel SLOWER
+// (dQ 94 -> 112 us): the math warps are bound by TMEM round-trip latency and issue slots, not by the XU pipe.
+template <typename T> __device__ __forceinline__ uint32_t pack16_fast(float a, float b) { return pack16<T>(a, b); }
 
 __device__ __forceinline__ void tma_tile(void* dst, const CUtensorMap* m, uint64_t* bar, int swap, int d, int n, int h,
                                          int b) {

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
             for (int e = 0; e < 16; e += 2) {
               const float p0 = fast_exp2(fmaf(__uint_as_float(sv[jj][e]), a.sl2, neg_l2));
               const float p1 = fast_exp2(fmaf(__uint_as_float(sv[jj][e + 1]), a.sl2, neg_l2));
-              pk[e >> 1] = pack16<T>(p0 * (__uint_as_float(dv[jj][e]) - delta), p1 * (__uint_as_float(dv[jj][e + 1]) - delta));
+              pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[jj][e]) - delta), p1 * (__uint_as_float(dv[jj][e + 1]) - delta));
             }
           } else if (c0 + 15 >= c_lo && c0 <= c_hi) {
 #pragma unroll
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
               float d1 = p1 * (__uint_as_float(dv[jj][e + 1]) - delta);
               d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
               d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
-              pk[e >> 1] = pack16<T>(d0, d1);
+              pk[e >> 1] = pack16_fast<T>(d0, d1);
             }
           } else {
 #pragma unroll
@@ -479,39 +479,57 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
 }
 
 // ================================================================================== dQ kernel, head_dim 64
-// Measured on B200 (tools/probe_mma.py, tools/trace_dq.py): one tcgen05.mma costs the issuing thread
-// ~70-90 cycles whatever its N up to 144, and every mbarrier round trip on the single-thread roles
-// ~200-300 cycles -- so the schedule below minimises UMMA instructions and barrier hops per tile:
-// KV items of up to 144 columns (one item per tile at window 128), S issued TWO items ahead into a
-// double-buffered region, dP one item ahead into a single region, and the math split in two phases:
-//   phase 1 (needs S only):   P = exp2(S*c - lse)                 -- the MUFU-bound part
-//   phase 2 (needs dP):       dS = P * (dP - delta) -> 16-bit over the consumed S columns
-// so the UMMA burst of item n (dQ(n), dP(n+1), S(n+2)) runs under phase 1 of item n+1.
+// Measured on B200 (tools/probe_mma.py, tools/trace_dq.py): one tcgen05.mma costs its issuing thread
+// ~70-90 cycles whatever its N up to 144, every mbarrier round trip on a single-thread role ~200-300
+// cycles, MUFU.EX2 runs at 16/clk/SM (a 128 x 144 tile of exps is >= 1152 cycles) and a TMA load
+// takes 1-2.5 us under load.  Hence a deep, warp-specialised pipeline in which no role does two jobs:
+//
+//   warp 12      TMA producer          Q/K rings (S side), dO/V rings (dP side)
+//   warp 13      UMMA issuer S         S(n)  = Q K^T   -> S buffer n & 1 (two items ahead of dQ)
+//   warp 14      UMMA issuer dP        dP(n) = dO V^T  -> the single dP region
+//   warp 15      UMMA issuer dQ        dQ   += dS(n) K (TS form, dS read from the S buffer)
+//   warps 0-3    exp                   P  = exp2(S*c - lse)           -> 16-bit over S columns [0, 72)
+//   warps 4-7    dS                    dS = P * (dP - delta), masked  -> 16-bit over S columns [72, 144)
+//   warps 8-11   epilogue              dQ * scale -> 16-bit -> swizzled smem -> TMA store
+//
+// KV items are up to 144 columns (one item per tile at window 128).
 struct Dq64Cfg {
   static constexpr int D = 64;
   static constexpr int kBNMax = 144;
-  static constexpr int kKStages = 4;      // K(n) is held from S(n) (issued at item n-2) to dQ(n)
+  static constexpr int kKStages = 4;      // K(n) is held from S(n) (two items ahead) to dQ(n)
   static constexpr int kVStages = 2;
-  static constexpr int kQStages = 3;      // Q tiles (needed by S, two items ahead)
-  static constexpr int kOStages = 3;      // dO tiles (needed by dP, one item ahead)
+  static constexpr int kQStages = 3;      // Q tiles (S side)
+  static constexpr int kOStages = 3;      // dO tiles (dP side)
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = kBNMax * D * 2;
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kColS = 0;               // S buffers at 0 and kBNMax
+  static constexpr uint32_t kColS = 0;               // S buffers at 0 and kBNMax; P at +0, dS at +kBNMax/2
   static constexpr uint32_t kColP = 2 * kBNMax;      // dP
   static constexpr uint32_t kColQ = 3 * kBNMax;      // dQ accumulator
-  static constexpr int kMaxCh = (kBNMax / 16 + 1) / 2;   // 16-column chunks per math thread
+  static constexpr int kThreads = 16 * 32;
   static constexpr int kSmem = 1024 + (kQStages + kOStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + 512;
   static_assert(3 * kBNMax + D <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
 
+template <typename T> __device__ __forceinline__ void unpack16(uint32_t u, float& a, float& b);
+template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(uint32_t u, float& a, float& b) {
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack16<__half>(uint32_t u, float& a, float& b) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+  a = f.x;
+  b = f.y;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) dq64_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                           const __grid_constant__ CUtensorMap tmdO,
-                                                           const __grid_constant__ CUtensorMap tmK,
-                                                           const __grid_constant__ CUtensorMap tmV,
-                                                           const __grid_constant__ CUtensorMap tmdQ, const BwdArgs a) {
+__global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                    const __grid_constant__ CUtensorMap tmdO,
+                                                                    const __grid_constant__ CUtensorMap tmK,
+                                                                    const __grid_constant__ CUtensorMap tmV,
+                                                                    const __grid_constant__ CUtensorMap tmdQ,
+                                                                    const BwdArgs a) {
   using C = Dq64Cfg;
   constexpr int D = C::D;
   extern __shared__ unsigned char smem_raw[];
@@ -530,16 +548,18 @@ __global__ void __launch_bounds__(kThreads, 1) dq64_kernel(const __grid_constant
   uint64_t* k_empty = k_full + C::kKStages;
   uint64_t* v_full = k_empty + C::kKStages;
   uint64_t* v_empty = v_full + C::kVStages;
-  uint64_t* s_full = v_empty + C::kVStages;        // [2]
-  uint64_t* dp_full = s_full + 2;
-  uint64_t* p_full = dp_full + 1;
-  uint64_t* dq_done = p_full + 1;
-  uint64_t* dq_free = dq_done + 1;
+  uint64_t* s_full = v_empty + C::kVStages;        // [2]  S(n) complete                       (issuer S -> exp)
+  uint64_t* p1_done = s_full + 2;                  // [2]  P(n) written                        (exp -> dS warps)
+  uint64_t* dp_full = p1_done + 2;                 //      dP(n) complete                      (issuer dP -> dS warps)
+  uint64_t* p_full = dp_full + 1;                  // [2]  dS(n) written, dP(n) consumed       (dS warps -> issuers dQ, dP)
+  uint64_t* sbuf_free = p_full + 2;                // [2]  dQ(n) complete: S buffer n & 1 free (issuer dQ -> issuer S)
+  uint64_t* dq_done = sbuf_free + 2;               //      tile's dQ complete                  (issuer dQ -> epilogue)
+  uint64_t* dq_free = dq_done + 1;                 //      dQ accumulator read                 (epilogue -> issuer dQ)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == kMathWarps && lane == 0) {
+  if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmK);
@@ -549,300 +569,344 @@ __global__ void __launch_bounds__(kThreads, 1) dq64_kernel(const __grid_constant
     for (int s = 0; s < C::kOStages; ++s) { mbar_init(do_full + s, 1); mbar_init(do_empty + s, 1); }
     for (int s = 0; s < C::kKStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
     for (int s = 0; s < C::kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
-    mbar_init(s_full, 1);
-    mbar_init(s_full + 1, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full + s, 1);
+      mbar_init(p1_done + s, 128);
+      mbar_init(p_full + s, 128);
+      mbar_init(sbuf_free + s, 1);
+    }
     mbar_init(dp_full, 1);
-    mbar_init(p_full, kMathThreads);
     mbar_init(dq_done, 1);
-    mbar_init(dq_free, kMathThreads);
+    mbar_init(dq_free, 128);
     fence_barrier_init();
   }
-  if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == 13) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kMathWarps) {
+  if (warp == 12) {
     // ------------------------------------------------------------------ TMA producer
-    // issue order = consumption order of the UMMA thread: {Q, K} of item m, then {dO, V} of item m-1
     if (lane == 0) {
-      ItemWalk wk(a), wv(a);
-      int tc = 0;
-      auto load_k = [&](const ItemWalk& w) {
+      ItemWalk w(a);
+      while (w.next()) {
         const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const int kst = w.n % C::kKStages, vst = w.n % C::kVStages;
         if (w.t == 0) {
           const int qs = w.it % C::kQStages;
           mbar_wait(q_empty + qs, ((w.it / C::kQStages) & 1) ^ 1);
           mbar_expect_tx(q_full + qs, C::kQBytes);
           tma_tile(q_s + qs * C::kQBytes, &tmQ, q_full + qs, a.q_swap, 0, w.q0, hq0, w.b);
         }
-        int kstart, cols; bool is_sink;
-        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
-        const int kst = w.n % C::kKStages;
         mbar_wait(k_empty + kst, ((w.n / C::kKStages) & 1) ^ 1);
         mbar_expect_tx(k_full + kst, a.BN * D * 2);
         tma_tile(k_s + kst * C::kKVBytes, &tmK, k_full + kst, a.k_swap, 0, kstart, kvh, w.b);
-        trace_ev(a.trace, 0, tc, 2, w.n);
-      };
-      auto load_v = [&](const ItemWalk& w) {
-        const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
         if (w.t == 0) {
           const int os = w.it % C::kOStages;
           mbar_wait(do_empty + os, ((w.it / C::kOStages) & 1) ^ 1);
           mbar_expect_tx(do_full + os, C::kQBytes);
           tma_tile(do_s + os * C::kQBytes, &tmdO, do_full + os, a.q_swap, 0, w.q0, hq0, w.b);
         }
-        int kstart, cols; bool is_sink;
-        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
-        const int vst = w.n % C::kVStages;
         mbar_wait(v_empty + vst, ((w.n / C::kVStages) & 1) ^ 1);
         mbar_expect_tx(v_full + vst, a.BN * D * 2);
         tma_tile(v_s + vst * C::kKVBytes, &tmV, v_full + vst, a.v_swap, 0, kstart, kvh, w.b);
-        trace_ev(a.trace, 0, tc, 3, w.n);
-      };
-      bool more_k = wk.next();
-      if (more_k) load_k(wk);
-      while (wv.next()) {
-        if (more_k) {
-          more_k = wk.next();
-          if (more_k) load_k(wk);
-        }
-        load_v(wv);
       }
     }
     __syncwarp();
-  } else if (warp == kMathWarps + 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ UMMA issuer S
     if (lane == 0) {
-      const uint32_t idesc_dq = make_idesc(a.fmt, 128, D, 0, 1);
+      ItemWalk w(a);
       int tc = 0;
-      auto issue_s = [&](const ItemWalk& w) {       // S(n) = Q K^T into S buffer n & 1
-        const int qs = w.it % C::kQStages, kst = w.n % C::kKStages;
-        if (w.t == 0) {
-          mbar_wait(q_full + qs, (w.it / C::kQStages) & 1);
-          tc_fence_after();
-        }
+      while (w.next()) {
+        trace_ev(a.trace, 1, tc, 1, w.n);
+        const int qs = w.it % C::kQStages, kst = w.n % C::kKStages, sb = w.n & 1;
         int kstart, cols; bool is_sink;
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
         const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
         const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), 16, 1024);
+        if (w.t == 0) mbar_wait(q_full + qs, (w.it / C::kQStages) & 1);
         mbar_wait(k_full + kst, (w.n / C::kKStages) & 1);
+        if (w.n >= 2) mbar_wait(sbuf_free + sb, ((w.n - 2) >> 1) & 1);     // dQ(n-2) has consumed dS(n-2)
         tc_fence_after();
-        const uint32_t ts = tmem + C::kColS + (w.n & 1) * C::kBNMax;
+        trace_ev(a.trace, 1, tc, 2, w.n);
+        const uint32_t ts = tmem + C::kColS + sb * C::kBNMax;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_ss(ts, qd + kk * 2, kd + kk * 2, idesc_s, kk != 0);
-        umma_commit(s_full + (w.n & 1));
+        umma_commit(s_full + sb);
         if (w.last_of_tile()) umma_commit(q_empty + qs);
-        trace_ev(a.trace, 1, tc, 5, w.n);
-      };
-      auto issue_dp = [&](const ItemWalk& w) {      // dP(n) = dO V^T into the single dP region
+        trace_ev(a.trace, 1, tc, 3, w.n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ UMMA issuer dP
+    if (lane == 0) {
+      ItemWalk w(a);
+      int tc = 0;
+      while (w.next()) {
+        trace_ev(a.trace, 2, tc, 1, w.n);
         const int os = w.it % C::kOStages, vst = w.n % C::kVStages;
-        if (w.t == 0) {
-          mbar_wait(do_full + os, (w.it / C::kOStages) & 1);
-          tc_fence_after();
-        }
         int kstart, cols; bool is_sink;
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
         const uint64_t dod = make_sdesc(smem_u32(do_s + os * C::kQBytes), 16, 1024);
         const uint64_t vd = make_sdesc(smem_u32(v_s + vst * C::kKVBytes), 16, 1024);
+        if (w.t == 0) mbar_wait(do_full + os, (w.it / C::kOStages) & 1);
         mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
+        if (w.n >= 1) mbar_wait(p_full + ((w.n - 1) & 1), ((w.n - 1) >> 1) & 1);   // dP(n-1) has been read
         tc_fence_after();
+        trace_ev(a.trace, 2, tc, 2, w.n);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + C::kColP, dod + kk * 2, vd + kk * 2, idesc_s, kk != 0);
         umma_commit(dp_full);
         umma_commit(v_empty + vst);
         if (w.last_of_tile()) umma_commit(do_empty + os);
-        trace_ev(a.trace, 1, tc, 7, w.n);
-      };
-      ItemWalk w_s(a), w_p(a), w_q(a);
-      bool more_s = w_s.next();
-      if (more_s) issue_s(w_s);                      // S(0)
-      if (more_s && (more_s = w_s.next())) issue_s(w_s);   // S(1)
-      bool more_p = w_p.next();
-      if (more_p) issue_dp(w_p);                     // dP(0)
-      while (w_q.next()) {                           // item n: dQ(n), dP(n+1), S(n+2)
-        const int kst = w_q.n % C::kKStages;
+        trace_ev(a.trace, 2, tc, 3, w.n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 15) {
+    // ------------------------------------------------------------------ UMMA issuer dQ
+    if (lane == 0) {
+      const uint32_t idesc_dq = make_idesc(a.fmt, 128, D, 0, 1);
+      ItemWalk w(a);
+      int tc = 0;
+      while (w.next()) {
+        trace_ev(a.trace, 3, tc, 1, w.n);
+        const int kst = w.n % C::kKStages, sb = w.n & 1;
         int kstart, cols; bool is_sink;
-        w_q.pl.tile(w_q.t, a.BN, kstart, cols, is_sink);
-        mbar_wait(p_full, w_q.n & 1);
-        tc_fence_after();
-        trace_ev(a.trace, 1, tc, 4, w_q.n);
-        if (w_q.t == 0 && w_q.it > 0) {
-          mbar_wait(dq_free, (w_q.it - 1) & 1);
-          tc_fence_after();
-        }
-        // dS(n): 16-bit pairs over the S buffer -- columns [0,hcol) at [0,hcol/2), columns [hcol,cols) from hcol on
-        const uint32_t ts = tmem + C::kColS + (w_q.n & 1) * C::kBNMax;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), C::kKVBytes, 1024);
-        const int hcol = ((cols / 16 + 1) / 2) * 16;
-        const uint32_t a_lo = ts, a_hi = ts + hcol - (hcol >> 1);
+        const uint32_t ads = tmem + C::kColS + sb * C::kBNMax + C::kBNMax / 2;    // dS(n), 8 columns per 16 keys
         const int nk = cols >> 4;
+        mbar_wait(p_full + sb, (w.n >> 1) & 1);
+        if (w.t == 0 && w.it > 0) mbar_wait(dq_free, (w.it - 1) & 1);
+        tc_fence_after();
+        trace_ev(a.trace, 3, tc, 2, w.n);
 #pragma unroll
         for (int kk = 0; kk < C::kBNMax / 16; ++kk)
-          if (kk < nk)
-            umma_ts(tmem + C::kColQ, ((kk * 16 < hcol) ? a_lo : a_hi) + kk * 8, kd + kk * (2048 >> 4), idesc_dq,
-                    (w_q.t > 0 || kk > 0));
+          if (kk < nk) umma_ts(tmem + C::kColQ, ads + kk * 8, kd + kk * (2048 >> 4), idesc_dq, (w.t > 0 || kk > 0));
+        umma_commit(sbuf_free + sb);
         umma_commit(k_empty + kst);
-        if (w_q.last_of_tile()) umma_commit(dq_done);
-        trace_ev(a.trace, 1, tc, 8, w_q.n);
-        if (more_p && (more_p = w_p.next())) issue_dp(w_p);
-        if (more_s && (more_s = w_s.next())) issue_s(w_s);
+        if (w.last_of_tile()) umma_commit(dq_done);
+        trace_ev(a.trace, 3, tc, 3, w.n);
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ element-wise math + epilogue
-    const int quarter = warp & 3, half = warp >> 2;
-    const int r = quarter * 32 + lane;                  // MMA row == TMEM lane
+    // ------------------------------------------------------------------ math roles: TMEM lane == MMA row
+    const int role = warp >> 2;                          // 0 exp, 1 dS, 2 epilogue
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
     const int pr = a.q_swap ? (r / a.G) : (r % a.P);
     const int gr = a.q_swap ? (r % a.G) : (r / a.P);
-    const int ro = a.dq_swap ? (pr * a.G + gr) : (gr * a.P + pr);   // row in dQ's box order
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
 
-    auto load_row = [&](bool valid, int pb, int y, int b, float& l, float& dl) {
-      l = INFINITY;                      // rows past N: P = exp2(s - inf) = 0
-      dl = 0.f;
+    // one fp32 per (tile, row) from a [B,Hq,N] array, loaded one tile ahead of its use
+    auto load_row = [&](const float* src, bool valid, int pb, int y, int b, float dflt) {
+      float v = dflt;
       const int i = pb * a.P + pr;
       if (valid && i < a.N) {
         const int64_t row = (static_cast<int64_t>(b) * a.Hq + y * a.G + gr) * a.N + i;
-        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l) : "l"(a.lse + row));      // issued a tile ahead of use
-        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dl) : "l"(a.delta + row));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(src + row));
       }
-    };
-    struct Pending { int valid, it, q0, hq0, b; } pend = {0, 0, 0, 0, 0};
-    auto epilogue = [&](const Pending& e) {
-      if (threadIdx.x == 0) tma_store_wait_read0();     // previous store has finished reading the staging buffer
-      named_bar_sync(2, kMathThreads);
-      mbar_wait(dq_done, e.it & 1);
-      tc_fence_after();
-      uint32_t v[2][16];
-      tmem_ld16(tl + C::kColQ + half * 32, v[0]);
-      tmem_ld16(tl + C::kColQ + half * 32 + 16, v[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_free);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int e2 = 0; e2 < 16; e2 += 2)
-          pk[e2 >> 1] = pack16<T>(__uint_as_float(v[cc][e2]) * a.scale, __uint_as_float(v[cc][e2 + 1]) * a.scale);
-        const int chn = half * 4 + cc * 2;
-        *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, chn)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, chn + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, kMathThreads);
-      if (threadIdx.x == 0) {
-        tma_tile_store(&tmdQ, stage_s, a.dq_swap, 0, e.q0, e.hq0, e.b);
-        tma_store_commit();
-      }
+      return v;
     };
 
-    float l_next, dl_next, neg_l2 = -INFINITY, delta = 0.f;
-    int i = 0, mtc = 0;
-    ItemWalk w(a);
-    {
-      int pb = w.pb, y = w.y, b = w.b;
-      ItemWalk::advance(a, w.step, pb, y, b);
-      load_row(w.tile + w.step < w.end, pb, y, b, l_next, dl_next);
-    }
-    while (w.next()) {
-      if (w.t == 0) {
-        neg_l2 = (l_next == -INFINITY) ? -INFINITY : -l_next * kLog2e;   // lse = -inf: nothing attended, P = 0
-        delta = dl_next;
-        i = w.q0 + pr;
+    if (role == 0) {
+      // ---------------------------------------------------------------- exp warps
+      ItemWalk w(a);
+      float l_next, neg_l2 = -INFINITY;
+      int i = 0, mtc = 0;
+      {
         int pb = w.pb, y = w.y, b = w.b;
         ItemWalk::advance(a, w.step, pb, y, b);
-        load_row(w.tile + w.step < w.end, pb, y, b, l_next, dl_next);
+        l_next = load_row(a.lse, w.tile + w.step < w.end, pb, y, b, INFINITY);
       }
-      const uint32_t ts = tl + C::kColS + (w.n & 1) * C::kBNMax;
-      int kstart, cols; bool is_sink;
-      w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
-      int c_lo, c_hi;
-      row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
-      if (i >= a.N) c_hi = -1;
-      const int nch = cols / 16;
-      const int hch = (nch + 1) / 2;
-      const int hcol = hch * 16;
-      const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
-
-      // ---- phase 1: P = exp2(S*c - lse) for this thread's columns (kept in registers)
-      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 1, w.n);
-      mbar_wait(s_full + (w.n & 1), (w.n >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 2, w.n);
-      uint32_t pv[C::kMaxCh][16];
-#pragma unroll
-      for (int jj = 0; jj < C::kMaxCh; ++jj)
-        if (ch0 + jj < ch1) tmem_ld16(ts + (ch0 + jj) * 16, pv[jj]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int jj = 0; jj < C::kMaxCh; ++jj)
-        if (ch0 + jj < ch1) {
-          const int c0 = (ch0 + jj) * 16;
-          if (__any_sync(0xffffffffu, c0 + 15 >= c_lo && c0 <= c_hi)) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              pv[jj][e] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e]), a.sl2, neg_l2)));
-          }
+      while (w.next()) {
+        if (w.t == 0) {
+          neg_l2 = (l_next == -INFINITY) ? -INFINITY : -l_next * kLog2e;   // lse = +-inf (no row / nothing attended): P = 0
+          i = w.q0 + pr;
+          int pb = w.pb, y = w.y, b = w.b;
+          ItemWalk::advance(a, w.step, pb, y, b);
+          l_next = load_row(a.lse, w.tile + w.step < w.end, pb, y, b, INFINITY);
         }
-      // ---- the previous tile's dQ is complete by now: write it out while dP(n) finishes
-      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 5, w.n);
-      if (pend.valid) {
-        epilogue(pend);
-        pend.valid = 0;
-        if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 4, w.n);
-      }
-      // ---- phase 2: dS = P * (dP - delta), masked, 16-bit, over the consumed S columns
-      mbar_wait(dp_full, w.n & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 6, w.n);
+        const int sb = w.n & 1;
+        const uint32_t ts = tl + C::kColS + sb * C::kBNMax;
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        int c_lo, c_hi;
+        row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+        if (i >= a.N) c_hi = -1;
+        const int nch = cols >> 4;
+        if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 1, w.n);
+        mbar_wait(s_full + sb, (w.n >> 1) & 1);
+        tc_fence_after();
+        if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 2, w.n);
+        // in place, three 16-column chunks at a time: P (16-bit pairs) lands on S columns already consumed
+        // (issuing the next batch's tcgen05.ld ahead of the compute was measured slower: 94 -> 121 us)
+#pragma unroll 1
+        for (int cb = 0; cb < nch; cb += 3) {
+          uint32_t sv[3][16];
 #pragma unroll
-      for (int jj = 0; jj < C::kMaxCh; ++jj)
-        if (ch0 + jj < ch1) {
-          const int c0 = (ch0 + jj) * 16;
-          uint32_t dv[16], pk[8];
-          tmem_ld16(tl + C::kColP + c0, dv);
+          for (int jj = 0; jj < 3; ++jj)
+            if (cb + jj < nch) tmem_ld16(ts + (cb + jj) * 16, sv[jj]);
           tmem_ld_wait();
-          const bool full = (c0 >= c_lo) && (c0 + 15 <= c_hi);
-          if (__all_sync(0xffffffffu, full)) {
+          if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 5, w.n);
 #pragma unroll
-            for (int e = 0; e < 16; e += 2)
-              pk[e >> 1] = pack16<T>(__uint_as_float(pv[jj][e]) * (__uint_as_float(dv[e]) - delta),
-                                     __uint_as_float(pv[jj][e + 1]) * (__uint_as_float(dv[e + 1]) - delta));
-          } else if (c0 + 15 >= c_lo && c0 <= c_hi) {
+          for (int jj = 0; jj < 3; ++jj)
+            if (cb + jj < nch) {
+              const int c0 = (cb + jj) * 16;
+              uint32_t pk[8];
+              if (__any_sync(0xffffffffu, c0 + 15 >= c_lo && c0 <= c_hi)) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const int c = c0 + e;
-              float d0 = __uint_as_float(pv[jj][e]) * (__uint_as_float(dv[e]) - delta);
-              float d1 = __uint_as_float(pv[jj][e + 1]) * (__uint_as_float(dv[e + 1]) - delta);
-              d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
-              d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
-              pk[e >> 1] = pack16<T>(d0, d1);
+                for (int e = 0; e < 16; e += 2)
+                  pk[e >> 1] = pack16_fast<T>(fast_exp2(fmaf(__uint_as_float(sv[jj][e]), a.sl2, neg_l2)),
+                                              fast_exp2(fmaf(__uint_as_float(sv[jj][e + 1]), a.sl2, neg_l2)));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = 0u;
+              }
+              tmem_st8(ts + (c0 >> 1), pk);
             }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pk[e] = 0u;
-          }
-          __syncwarp();
-          tmem_st8(half ? (ts + hcol + ((c0 - hcol) >> 1)) : (ts + (c0 >> 1)), pk);
+          if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 6, w.n);
         }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_full);
-      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 3, w.n);
-      if (w.last_of_tile()) pend = Pending{1, w.it, w.q0, w.y * a.G, w.b};
+        tmem_st_wait();
+        if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 7, w.n);
+        tc_fence_before();
+        mbar_arrive(p1_done + sb);
+        if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 3, w.n);
+      }
+    } else if (role == 1) {
+      // ---------------------------------------------------------------- dS warps
+      ItemWalk w(a);
+      float dl_next, delta = 0.f;
+      int i = 0, mtc = 0;
+      {
+        int pb = w.pb, y = w.y, b = w.b;
+        ItemWalk::advance(a, w.step, pb, y, b);
+        dl_next = load_row(a.delta, w.tile + w.step < w.end, pb, y, b, 0.f);
+      }
+      while (w.next()) {
+        if (w.t == 0) {
+          delta = dl_next;
+          i = w.q0 + pr;
+          int pb = w.pb, y = w.y, b = w.b;
+          ItemWalk::advance(a, w.step, pb, y, b);
+          dl_next = load_row(a.delta, w.tile + w.step < w.end, pb, y, b, 0.f);
+        }
+        const int sb = w.n & 1;
+        const uint32_t ts = tl + C::kColS + sb * C::kBNMax;
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        int c_lo, c_hi;
+        row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+        if (i >= a.N) c_hi = -1;
+        const int nch = cols >> 4;
+        if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 1, w.n);
+        mbar_wait(p1_done + sb, (w.n >> 1) & 1);
+        if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 4, w.n);
+        mbar_wait(dp_full, w.n & 1);
+        tc_fence_after();
+        if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 2, w.n);
+        // two 16-column chunks per TMEM round trip.  (Measured alternatives, all slower at the C1 shape: one chunk
+        // per trip with a single masked code path 94 -> 164 us; issuing the next batch's loads ahead of the compute
+        // 94 -> 121 us; integer bf16 packing instead of cvt 94 -> 112 us.)
+#pragma unroll 1
+        for (int cb = 0; cb < nch; cb += 2) {
+          uint32_t pv[2][8], dv[2][16];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+            if (cb + jj < nch) {
+              tmem_ld8(ts + ((cb + jj) * 8), pv[jj]);
+              tmem_ld16(tl + C::kColP + (cb + jj) * 16, dv[jj]);
+            }
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+            if (cb + jj < nch) {
+              const int c0 = (cb + jj) * 16;
+              uint32_t pk[8];
+              const bool full = (c0 >= c_lo) && (c0 + 15 <= c_hi);
+              if (__all_sync(0xffffffffu, full)) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                  float p0, p1;
+                  unpack16<T>(pv[jj][e >> 1], p0, p1);
+                  pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[jj][e]) - delta), p1 * (__uint_as_float(dv[jj][e + 1]) - delta));
+                }
+              } else if (__any_sync(0xffffffffu, c0 + 15 >= c_lo && c0 <= c_hi)) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                  const int c = c0 + e;
+                  float p0, p1;
+                  unpack16<T>(pv[jj][e >> 1], p0, p1);
+                  float d0 = p0 * (__uint_as_float(dv[jj][e]) - delta);
+                  float d1 = p1 * (__uint_as_float(dv[jj][e + 1]) - delta);
+                  d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
+                  d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
+                  pk[e >> 1] = pack16_fast<T>(d0, d1);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = 0u;
+              }
+              tmem_st8(ts + C::kBNMax / 2 + (c0 >> 1), pk);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full + sb);
+        if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 3, w.n);
+      }
+    } else {
+      // ---------------------------------------------------------------- epilogue warps
+      const int ro = a.dq_swap ? (pr * a.G + gr) : (gr * a.P + pr);   // row in dQ's box order
+      const int et = threadIdx.x - 256;                                 // 0..127
+      ItemWalk w(a);
+      int mtc = 0;
+      while (w.next()) {
+        if (!w.last_of_tile()) continue;
+        if (et == 0) trace_ev(a.trace, 6, mtc, 1, w.n);
+        if (et == 0) tma_store_wait_read0();     // previous store has finished reading the staging buffer
+        named_bar_sync(2, 128);
+        mbar_wait(dq_done, w.it & 1);
+        tc_fence_after();
+        if (et == 0) trace_ev(a.trace, 6, mtc, 2, w.n);
+        uint32_t v[4][16];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld16(tl + C::kColQ + cc * 16, v[cc]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_free);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e2 = 0; e2 < 16; e2 += 2)
+            pk[e2 >> 1] = pack16<T>(__uint_as_float(v[cc][e2]) * a.scale, __uint_as_float(v[cc][e2 + 1]) * a.scale);
+          *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, cc * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, cc * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          tma_tile_store(&tmdQ, stage_s, a.dq_swap, 0, w.q0, w.y * a.G, w.b);
+          tma_store_commit();
+          trace_ev(a.trace, 6, mtc, 3, w.n);
+        }
+      }
+      if (et == 0) tma_store_wait_all0();
     }
-    if (pend.valid) epilogue(pend);
-    if (threadIdx.x == 0) tma_store_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
+  if (warp == 13) tmem_dealloc(tmem, C::kTmemCols);
 }
 
 // ================================================================================== dK/dV kernel
@@ -1073,8 +1137,8 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
             p1 = ok1 ? p1 : 0.f;
             const float d0 = ok0 ? p0 * (__uint_as_float(dv[e]) - dl.x) : 0.f;
             const float d1 = ok1 ? p1 * (__uint_as_float(dv[e + 1]) - dl.y) : 0.f;
-            pp[e >> 1] = pack16<T>(p0, p1);
-            pd[e >> 1] = pack16<T>(d0, d1);
+            pp[e >> 1] = pack16_fast<T>(p0, p1);
+            pd[e >> 1] = pack16_fast<T>(d0, d1);
           }
         } else {
 #pragma unroll
@@ -1543,7 +1607,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.bn_mul = bn_magic(BN);
     const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
     a.tiles_per_cta = 0;
-    if constexpr (D == 64) dq64_kernel<T><<<grid, kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
+    if constexpr (D == 64) dq64_kernel<T><<<grid, Dq64Cfg::kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
     else dq_kernel<T, D><<<grid, kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

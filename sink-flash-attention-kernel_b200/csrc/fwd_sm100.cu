@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(192) fwd_kernel(const __grid_constant__ CUtens
             p0 = (c >= c_lo && c <= c_hi) ? p0 : 0.f;
             p1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? p1 : 0.f;
             lsum += p0 + p1;
-            pk[e >> 1] = pack16<T>(p0, p1);
+            pk[e >> 1] = pack16_fast<T>(p0, p1);
           }
         } else {
 #pragma unroll

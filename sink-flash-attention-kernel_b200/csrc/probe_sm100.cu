@@ -159,6 +159,86 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(long long* out, int N, in
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// TMEM read-throughput probe: every warp loops over tcgen05.ld (32x32b, x16 / x32 / 2 x x32 per wait) on its lane quarter.
+__global__ void tmem_rate_kernel(long long* out, float* sink, int mode, int iters) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tl = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const uint32_t col = (it * 64) & 255;
+    if (mode == 0) {
+      uint32_t v[16];
+      tmem_ld16(tl + col, v);
+      tmem_ld_wait();
+      acc ^= v[0] ^ v[15];
+    } else if (mode == 1) {
+      uint32_t v[32];
+      tmem_ld32(tl + col, v);
+      tmem_ld_wait();
+      acc ^= v[0] ^ v[31];
+    } else {
+      uint32_t v[32], w[32];
+      tmem_ld32(tl + col, v);
+      tmem_ld32(tl + col + 32, w);
+      tmem_ld_wait();
+      acc ^= v[0] ^ w[31];
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  if (acc == 0x12345u) sink[threadIdx.x] = 1.f;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+
+// Math-pipe probe: cycles per 16-element step of the softmax inner loop on registers only.
+//   mode 0: 16 FFMA + 16 MUFU.EX2          mode 1: + 8 cvt.rn.bf16x2 (F2FP)      mode 2: + integer bf16 packing
+//   mode 3: 16 FFMA + 8 F2FP (no MUFU)     mode 4: 16 FFMA only
+__global__ void math_rate_kernel(long long* out, float* sink, int mode, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) x[e] = static_cast<float>(threadIdx.x + e) * 1e-3f;
+  uint32_t acc = 0;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      x[e] = fmaf(x[e], a, b);
+      if (mode <= 2) x[e] = fast_exp2(x[e]);
+    }
+    if (mode == 1 || mode == 3) {
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(x[e], x[e + 1]);
+        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&v);
+      }
+    } else if (mode == 2) {
+#pragma unroll
+      for (int e = 0; e < 16; e += 2)
+        pk[e >> 1] = __byte_perm(__float_as_uint(x[e]) + 0x8000u, __float_as_uint(x[e + 1]) + 0x8000u, 0x7632);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pk[e] = 0;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc ^= pk[e];
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  float ssum = 0.f;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) ssum += x[e];
+  if (ssum == 123.456f || acc == 0x12345u) sink[threadIdx.x] = ssum;
+}
+
 // TMA load-throughput probe (performance work, tools/probe_tma.py): every CTA streams boxes of
 // box_n positions x box_h heads x 64 channels (16-bit) through a ring of `stages` shared-memory
 // buffers; nothing consumes the data.  mode 1 replaces TMA by per-thread cp.async (16 B each).
@@ -244,6 +324,16 @@ cudaError_t probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, in
   const int nblk = N / box_n, nboxes = nblk * (H / box_h);
   tma_bw_kernel<<<grid, 160, smem, st>>>(m.map, static_cast<const unsigned char*>(src), m.swap_nh, nblk, nboxes, box_n,
                                          box_h, stages, mode, (long long)N * 128);
+  return cudaGetLastError();
+}
+
+cudaError_t probe_tmem_rate(long long* out, float* sink, int mode, int iters, int threads, cudaStream_t st) {
+  tmem_rate_kernel<<<148, threads, 0, st>>>(out, sink, mode, iters);
+  return cudaGetLastError();
+}
+
+cudaError_t probe_math_rate(long long* out, float* sink, int mode, int iters, int threads, cudaStream_t st) {
+  math_rate_kernel<<<148, threads, 0, st>>>(out, sink, mode, iters, 0.999f, -0.001f);
   return cudaGetLastError();
 }
 

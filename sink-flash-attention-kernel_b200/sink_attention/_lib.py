@@ -20,7 +20,7 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
 )
 
 _lib = None
@@ -65,6 +65,10 @@ def load() -> ctypes.CDLL:
     lib.sfa_decode.restype = i
     lib.sfa_decode_ring.argtypes = [p] * 6 + [f32p] + [i] * 7 + [i64p] * 4 + [p, c.c_size_t, p]
     lib.sfa_decode_ring.restype = i
+    lib.sfa_probe_math_rate.argtypes = [p, p, i, i, i, p]
+    lib.sfa_probe_math_rate.restype = i
+    lib.sfa_probe_tmem_rate.argtypes = [p, p, i, i, i, p]
+    lib.sfa_probe_tmem_rate.restype = i
     lib.sfa_probe_mma_rate.argtypes = [p, i, i, i, i, p]
     lib.sfa_probe_mma_rate.restype = i
     lib.sfa_probe_tma_bw.argtypes = [p, i, i, i, i, i, i, i, p]

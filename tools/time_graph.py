@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""GPU-side times of the C1 kernels with the CPU launch path taken out: each stage is captured in a CUDA graph
+and replayed (L2 flushed before every replay, CUDA events around the replay)."""
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "sink-flash-attention-kernel_b200"))
+import sink_attention as sa  # noqa: E402
+from sink_attention import _lib  # noqa: E402
+
+B, N, Hq, Hkv, D, S, W = 1, 8192, 64, 8, 64, 0, 128
+if len(sys.argv) > 1 and sys.argv[1] == "c2s":
+    B, N, Hq, Hkv, D, S, W = 1, 8192, 32, 8, 128, 4, 4096
+dev = "cuda"
+g = torch.Generator(device=dev).manual_seed(1)
+dt = torch.bfloat16
+q = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt)
+k = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt)
+v = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt)
+do = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt)
+s_aux = torch.randn(Hq, device=dev, generator=g)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+lib = _lib.load()
+o, lse = sa.sink_flash_attention_with_lse(q, k, v, S, W, s_aux)
+
+
+def graph_time(fn, reps=15):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fn()
+    ts = []
+    for it in range(reps):
+        flush.fill_(it)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        gr.replay()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return statistics.median(ts), min(ts)
+
+
+def stage(mask):
+    def fn():
+        lib.sfa_set_bwd_stages(mask)
+        _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
+        lib.sfa_set_bwd_stages(7)
+    return fn
+
+
+print("fwd            us (median, min):", graph_time(lambda: sa.sink_flash_attention_with_lse(q, k, v, S, W, s_aux)))
+print("bwd preprocess us:", graph_time(stage(1)))
+print("bwd dq         us:", graph_time(stage(2)))
+print("bwd dkdv       us:", graph_time(stage(4)))
+print("bwd all        us:", graph_time(stage(7)))
+
+
+def full():
+    o2, lse2 = sa.sink_flash_attention_with_lse(q, k, v, S, W, s_aux)
+    _lib.bwd(q, k, v, o2, do, lse2, S, W, s_aux)
+
+
+print("fwd+bwd        us:", graph_time(full))

@@ -24,19 +24,18 @@ lib = _lib.load()
 for _ in range(3):
     _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
 torch.cuda.synchronize()
-buf = torch.zeros(3 * 256 * 2, dtype=torch.int64, device=dev)
+buf = torch.zeros(8 * 256 * 2, dtype=torch.int64, device=dev)
 lib.sfa_set_trace_buffer(buf.data_ptr())
 lib.sfa_set_bwd_stages(2)
 _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
 torch.cuda.synchronize()
 lib.sfa_set_trace_buffer(None)
 lib.sfa_set_bwd_stages(7)
-t = buf.cpu().view(3, 256, 2)
-names = {0: {1: "Q/dO stage free, load issued", 2: "K load issued", 3: "V load issued"},
-         1: {1: "Q/dO landed", 2: "K landed", 3: "S,dP issued", 4: "dS ready", 5: "S mma issued", 6: "V landed", 7: "dP mma issued", 8: "dQ mma issued", 9: "dQ committed"},
-         2: {1: "wait S", 2: "S complete", 3: "dS written", 4: "epilogue done", 5: "phase 1 done", 6: "dP complete"}}
+t = buf.cpu().view(8, 256, 2)
+ROLES = ["PROD", "I_S", "I_dP", "I_dQ", "EXP", "DS", "EPI", "-"]
+CODES = {1: "begin / wait", 2: "inputs ready", 3: "done", 4: "P ready", 5: "batch loaded", 6: "batch computed", 7: "st waited"}
 ev = []
-for role in range(3):
+for role in range(8):
     for j in range(256):
         tag, clk = int(t[role, j, 0]), int(t[role, j, 1])
         if clk == 0:
@@ -44,5 +43,7 @@ for role in range(3):
         ev.append((clk, role, tag >> 32, tag & 0xffffffff))
 ev.sort()
 t0 = ev[0][0]
-for clk, role, code, idx in ev[:260]:
-    print(f"{clk - t0:8d}  {'PROD MMA  MATH'.split()[role]:5s} {names[role][code]:30s} #{idx}")
+lo = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+for clk, role, code, idx in ev:
+    if lo <= idx < lo + 2 and role == (int(sys.argv[2]) if len(sys.argv) > 2 else role):
+        print(f"{clk - t0:8d}  {ROLES[role]:5s} {CODES[code]:14s} #{idx}")
