@@ -198,19 +198,39 @@ def run_ours(args):
         return ts
 
     s_aux = (torch.randn(Hq, device=dev, generator=g) * 0.5).requires_grad_(True)
+    step_graph = None
     if world == 1:
         q = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt).requires_grad_(True)
         k = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt).requires_grad_(True)
         v = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dt).requires_grad_(True)
         do = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dt)
 
-        def step():
+        def eager_step():
             for t in (q, k, v, s_aux):
                 t.grad = None
             o = sa.sink_flash_attention(q, k, v, S, W, s_aux)
             o.backward(do)
+
+        # The timed step is a CUDA-graph replay of exactly the launches the autograd Function makes (sfa_fwd,
+        # then sfa_bwd: delta/ds_aux preprocess, ds_aux reduce, dQ kernel, dK/dV kernel): the five kernels take
+        # ~0.45 ms, less than the Python/ctypes launch path around them, so the eager number measures the host.
+        qd_, kd_, vd_, sd_ = q.detach(), k.detach(), v.detach(), s_aux.detach()
+
+        def c_abi_step():
+            o_, lse_ = _lib.fwd(qd_, kd_, vd_, S, W, sd_)
+            return _lib.bwd(qd_, kd_, vd_, o_, do, lse_, S, W, sd_)
+
+        for _ in range(3):
+            c_abi_step()
+        torch.cuda.synchronize()
+        step_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(step_graph):
+            graph_out = c_abi_step()
+
+        def step():
+            step_graph.replay()
         n_total = N
-        launches_per_step = 1 + 4           # fwd; bwd = preprocess + ds_aux reduce + dQ + dK/dV
+        launches_per_step = 5               # fwd; bwd = delta/ds_aux preprocess + ds_aux reduce + dQ + dK/dV
         workload = ("gpt-oss-20b attention layer fwd+bwd (BASELINE configs[1]): B=1 N=8192 Hq=64 Hkv=8 D=64 window=128 "
                     "s_aux bf16")
         parallelism = "single GPU"
@@ -275,22 +295,36 @@ def run_ours(args):
         e2e = None
         cpu_base = None
         if world == 1:
-            # ---- per-kernel times (CUDA events on the launching stream) -> dominant kernel roofline
+            # ---- per-kernel times: each stage captured in its own CUDA graph, replayed with the L2 flushed,
+            # CUDA events around the replay (on the launching stream) -> dominant kernel roofline
             qd, kd, vd = q.detach(), k.detach(), v.detach()
             sd = s_aux.detach()
-            t_fwd = timed(lambda: sa.sink_flash_attention_with_lse(qd, kd, vd, S, W, sd), 10, 3)
+
+            def graph_timed(fn, steps=10):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    keep = fn()
+                ts = timed(gr.replay, steps, 2)
+                del keep
+                return statistics.median(ts)
+
+            t_eager = timed(eager_step, 5, 3)
+            stage_ms = {}
+            stage_ms["fwd"] = graph_timed(lambda: sa.sink_flash_attention_with_lse(qd, kd, vd, S, W, sd))
             fwd_impl = _lib.last_impl()
             o_s, lse_s = sa.sink_flash_attention_with_lse(qd, kd, vd, S, W, sd)
-            stage_ms = {}
             for name, mask in (("bwd_preprocess(delta,ds_aux)", 1), ("bwd_dq", 2), ("bwd_dkdv", 4)):
-                _lib.load().sfa_set_bwd_stages(mask)
-                try:
-                    ts = timed(lambda: _lib.bwd(qd, kd, vd, o_s, do, lse_s, S, W, sd), 10, 3)
-                finally:
-                    _lib.load().sfa_set_bwd_stages(7)
-                stage_ms[name] = statistics.median(ts)
+                def one_stage(mask=mask):
+                    _lib.load().sfa_set_bwd_stages(mask)
+                    try:
+                        return _lib.bwd(qd, kd, vd, o_s, do, lse_s, S, W, sd)
+                    finally:
+                        _lib.load().sfa_set_bwd_stages(7)
+                stage_ms[name] = graph_timed(one_stage)
             bwd_impl = _lib.last_impl()
-            stage_ms["fwd"] = statistics.median(t_fwd)
             e = 2
             bytes_alg = {
                 "fwd": 2 * B * Hq * N * D * e + 2 * B * Hkv * N * D * e + 4 * B * Hq * N,
@@ -309,6 +343,13 @@ def run_ours(args):
                     "algorithmic_bytes": bytes_alg[dom], "avg_launch_ms": stage_ms[dom],
                     "tensor_tflops": flops_alg[dom] / dur / 1e12, "tensor_frac_of_burst_peak": flops_alg[dom] / dur / 1e12 / tf_burst,
                     "kernel_ms": stage_ms, "impl": {"fwd": fwd_impl, "bwd": bwd_impl}}
+            traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(traffic_path):       # dram__bytes_read+write per launch from the committed ncu --set full capture
+                with open(traffic_path) as f:
+                    tr = json.load(f)
+                roof["traffic"] = tr.get(dom)
+                roof["traffic_source"] = tr.get("source")
+            roof["eager_api_ms_per_step"] = sum(t_eager) / len(t_eager)
             roof["whole_step"] = {
                 "algorithmic_bytes": 459.3e6, "hbm_floor_ms": 459.3e6 / (hbm_peak * 1e9) * 1e3,
                 "tensor_floor_ms_at_burst_peak": job_flops / (tf_burst * 1e12) * 1e3,
@@ -368,7 +409,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "parallelism": parallelism, "global_tokens": n_total * B,
                        "masked_flops_per_step": job_flops,
-                       "l2": "256 MiB buffer written between timed steps; per-step CUDA events summed"},
+                       "l2": "256 MiB buffer written between timed steps; per-step CUDA events summed",
+                       "step": ("CUDA-graph replay of the C-ABI launches of one fwd+bwd (sfa_fwd + sfa_bwd)" if step_graph is not None
+                                else "eager autograd step with NCCL all-to-all each side")},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
