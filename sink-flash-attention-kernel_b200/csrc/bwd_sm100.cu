@@ -931,6 +931,7 @@ template <int D> struct DkvCfg {
 };
 
 struct DkvArgs {
+  long long* trace;
   int B, N, S, W, Hq, Hkv, G, P, groups_per_kv;
   int q_swap, k_swap, v_swap;
   int fmt;
@@ -1208,7 +1209,9 @@ struct Dkv64Cfg {
   static constexpr uint32_t kColP = 256;    // dP^T
   static constexpr uint32_t kColK = 384;    // dK accumulator [keys][64]
   static constexpr uint32_t kColV = 448;    // dV accumulator
-  static constexpr int kThreads = kMathThreads + 96;     // + TMA producer, issuer B, issuer A
+  static constexpr int kMathW = 16;                      // 4 per scheduler: each thread owns one key row x 32 chunk rows
+  static constexpr int kMathT = kMathW * 32;
+  static constexpr int kThreads = kMathT + 96;           // + TMA producer, issuer B, issuer A
   static constexpr int kSmem = 1024 + 2 * kKVBytes + (kQStages + kOStages) * kQBytes + 2 * 2 * 128 * 4 + 512;
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
@@ -1241,6 +1244,14 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const trc = (SFA_TRACE && blockIdx.x == 20 && blockIdx.y == 0 && blockIdx.z == 0) ? a.trace : nullptr;
+  auto tev = [&](int role, int& cnt, int code, int idx) {
+    if (SFA_TRACE && trc != nullptr && cnt < 256) {
+      trc[(role * 256 + cnt) * 2] = (static_cast<long long>(code) << 32) | static_cast<unsigned>(idx);
+      trc[(role * 256 + cnt) * 2 + 1] = clock64();
+      ++cnt;
+    }
+  };
   const int j0 = blockIdx.x * C::kBK;
   const int kvh = blockIdx.y, b = blockIdx.z;
   int pb_lo, pb_hi;
@@ -1249,7 +1260,7 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
   const int gpk = a.groups_per_kv;
   const int nchunks = npb * gpk;        // chunk c -> (position block pb_lo + c / gpk, group c % gpk); walked with counters
 
-  if (warp == kMathWarps && lane == 0) {
+  if (warp == C::kMathW && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmK);
@@ -1261,18 +1272,18 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
     mbar_init(s_full, 1);
     mbar_init(s_full + 1, 1);
     mbar_init(dp_full, 1);
-    mbar_init(p_full, kMathThreads);
-    mbar_init(p_full + 1, kMathThreads);
+    mbar_init(p_full, C::kMathT);
+    mbar_init(p_full + 1, C::kMathT);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == C::kMathW + 1) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kMathWarps) {
+  if (warp == C::kMathW) {
     // ------------------------------------------------------------------ TMA producer: Q(c+1) then dO(c), c = -1, 0, ...
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * C::kKVBytes);
@@ -1298,29 +1309,36 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
       }
     }
     __syncwarp();
-  } else if (warp == kMathWarps + 1) {
+  } else if (warp == C::kMathW + 1) {
     // ------------------------------------------------------------------ issuer B: S^T(c) = K Q(c)^T, dP^T(c) = V dO(c)^T
     if (lane == 0 && nchunks > 0) {
       const uint32_t idesc_s = make_idesc(a.fmt, 128, 128, 0, 0);
       const uint64_t kd = make_sdesc(smem_u32(k_s), 16, 1024), vd = make_sdesc(smem_u32(v_s), 16, 1024);
+      int tc = 0;
       auto issue_s = [&](int c) {
         const int qs = c % C::kQStages;
+        tev(1, tc, 1, c);
         mbar_wait(q_full + qs, (c / C::kQStages) & 1);
         tc_fence_after();
+        tev(1, tc, 2, c);
         const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
         const uint32_t ts = tmem + C::kColS + (c & 1) * 128;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_ss(ts, kd + kk * 2, qd + kk * 2, idesc_s, kk != 0);
         umma_commit(s_full + (c & 1));
+        tev(1, tc, 3, c);
       };
       auto issue_dp = [&](int c) {
         const int os = c % C::kOStages;
+        tev(2, tc, 1, c);
         mbar_wait(do_full + os, (c / C::kOStages) & 1);
         tc_fence_after();
+        tev(2, tc, 2, c);
         const uint64_t dod = make_sdesc(smem_u32(do_s + os * C::kQBytes), 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + C::kColP, vd + kk * 2, dod + kk * 2, idesc_s, kk != 0);
         umma_commit(dp_full);
+        tev(2, tc, 3, c);
       };
       mbar_wait(kv_full, 0);
       tc_fence_after();
@@ -1329,11 +1347,13 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
       issue_dp(0);
       for (int c = 0; c < nchunks; ++c) {
         if (c + 1 < nchunks) {
+          tev(2, tc, 4, c);
           mbar_wait(p_full + (c & 1), (c >> 1) & 1);   // the math has read dP^T(c)
           tc_fence_after();
           issue_dp(c + 1);
         }
         if (c + 2 < nchunks) {
+          tev(1, tc, 4, c);
           mbar_wait(chunk_done + (c & 3), (c >> 2) & 1);   // dV(c), dK(c) have consumed S^T buffer c & 1
           tc_fence_after();
           issue_s(c + 2);
@@ -1341,47 +1361,51 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
       }
     }
     __syncwarp();
-  } else if (warp == kMathWarps + 2) {
+  } else if (warp == C::kMathW + 2) {
     // ------------------------------------------------------------------ issuer A: dV += P^T dO, dK += dS^T Q
     if (lane == 0) {
       const uint32_t idesc_acc = make_idesc(a.fmt, 128, D, 0, 1);
+      int tc = 0;
       for (int c = 0; c < nchunks; ++c) {
+        tev(3, tc, 1, c);
         const int qs = c % C::kQStages, os = c % C::kOStages;
         const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), C::kQBytes, 1024);
         const uint64_t dod = make_sdesc(smem_u32(do_s + os * C::kQBytes), C::kQBytes, 1024);
         const uint32_t ts = tmem + C::kColS + (c & 1) * 128;
         mbar_wait(p_full + (c & 1), (c >> 1) & 1);
         tc_fence_after();
-        // packed operands inside the S^T buffer: P^T rows [0,64) at +0, dS^T rows [0,64) at +32,
-        // P^T rows [64,128) at +64, dS^T rows [64,128) at +96 (8 columns per 16 rows)
+        tev(3, tc, 2, c);
+        // packed operands inside the S^T buffer, per 32-row part p: P^T rows [32p, 32p+32) at columns 32p + [0,16),
+        // dS^T rows of the same part at columns 32p + [16,32)  (8 columns per 16 rows)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem + C::kColV, ts + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8), dod + kk * (2048 >> 4), idesc_acc,
-                  (c > 0 || kk > 0));
+          umma_ts(tmem + C::kColV, ts + (kk >> 1) * 32 + (kk & 1) * 8, dod + kk * (2048 >> 4), idesc_acc, (c > 0 || kk > 0));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem + C::kColK, ts + 32 + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8), qd + kk * (2048 >> 4), idesc_acc,
+          umma_ts(tmem + C::kColK, ts + (kk >> 1) * 32 + 16 + (kk & 1) * 8, qd + kk * (2048 >> 4), idesc_acc,
                   (c > 0 || kk > 0));
         umma_commit(chunk_done + (c & 3));
+        tev(3, tc, 3, c);
       }
       umma_commit(acc_done);
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ element-wise math + epilogue
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, part = warp >> 2;     // part: which 32 of the 128 chunk rows
     const int kr = quarter * 32 + lane;                 // key row == TMEM lane
     const int j = j0 + kr;
     const int jw_lo = j0 + quarter * 32, jw_hi = jw_lo + 31;          // this warp's keys
     // queries that attend key j: i in [j, i_hi]
     const int i_hi = (j >= a.N) ? -1 : ((j < a.S) ? 0x7fffffff : ((a.W > 0) ? j + a.W - 1 : -1));
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int tid = threadIdx.x;                        // 0..255
+    const int tid = threadIdx.x;                        // 0..511
     const int sh_p = 31 - __clz(a.P), sh_g = 31 - __clz(a.G);          // P and G are powers of two
 
-    // -lse*log2e and delta of chunk row `tid` (threads 0..127), loaded one chunk ahead
-    auto load_row = [&](int pb, int grp, float& nl, float& dl) {
-      nl = -INFINITY;
+    // lse and delta of chunk row `tid` (threads 0..127): issued one chunk ahead and only consumed (converted to
+    // -lse*log2e and stored to shared memory) at the end of the current chunk, so the load latency is hidden
+    auto load_row = [&](int pb, int grp, float& l, float& dl) {
+      l = INFINITY;                      // rows past N: P = exp2(s - inf) = 0
       dl = 0.f;
       if (tid < 128) {
         const int pr = a.q_swap ? (tid >> sh_g) : (tid & (a.P - 1));
@@ -1389,19 +1413,18 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
         const int i = pb * a.P + pr;
         if (i < a.N) {
           const int64_t row = (static_cast<int64_t>(b) * a.Hq + (kvh * gpk + grp) * a.G + gr) * a.N + i;
-          float l;
           asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l) : "l"(a.lse + row));
           asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dl) : "l"(a.delta + row));
-          nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
         }
       }
     };
-    int pb = pb_lo, grp = 0;
+    auto neg_l2_of = [](float l) { return (l == -INFINITY) ? -INFINITY : -l * kLog2e; };   // lse = -inf: nothing attended
+    int pb = pb_lo, grp = 0, mtc = 0;
     float nl_n, dl_n;
     if (nchunks > 0) {
       load_row(pb, grp, nl_n, dl_n);
       if (tid < 128) {
-        row_l2[tid] = nl_n;
+        row_l2[tid] = neg_l2_of(nl_n);
         row_dl[tid] = dl_n;
       }
     }
@@ -1409,24 +1432,27 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
       const int q0 = pb * a.P;
       int pbn = pb, gn = grp;
       if (++gn == gpk) { gn = 0; ++pbn; }
-      named_bar_sync(1, kMathThreads);                  // rows of chunk c are in row_*[c & 1]
+      if (tid == 0) tev(4, mtc, 1, c);
+      named_bar_sync(1, C::kMathT);                     // rows of chunk c are in row_*[c & 1]
+      if (tid == 0) tev(4, mtc, 5, c);
       if (c + 1 < nchunks) load_row(pbn, gn, nl_n, dl_n);   // in flight during this chunk's math
       const float* rl = row_l2 + (c & 1) * 128;
       const float* rd = row_dl + (c & 1) * 128;
       const uint32_t ts = tl + C::kColS + (c & 1) * 128;
 
       // per 16-column block: attended positions [i_lo, i_hi_b]; any / all lanes of the warp attended
-      uint32_t pv[4][16];
-      bool any_b[4];
+      uint32_t pv[2][16];
+      bool any_b[2];
       mbar_wait(s_full + (c & 1), (c >> 1) & 1);
       tc_fence_after();
+      if (tid == 0) tev(4, mtc, 2, c);
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) tmem_ld16(ts + half * 64 + jj * 16, pv[jj]);
+      for (int jj = 0; jj < 2; ++jj) tmem_ld16(ts + part * 32 + jj * 16, pv[jj]);
       tmem_ld_wait();
       // ---- phase 1: P^T = exp2(S^T * c - lse[row])
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int c0 = half * 64 + jj * 16;
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c0 = part * 32 + jj * 16;
         int i_lo, i_up;
         if (a.q_swap) {
           i_lo = q0 + (c0 >> sh_g);
@@ -1450,15 +1476,20 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
           }
         }
       }
-      // ---- phase 2: mask, dS^T = P^T * (dP^T - delta[row]); both packed into this half's consumed S^T columns
+      // ---- phase 2: mask, dS^T = P^T * (dP^T - delta[row]); both packed into this part's consumed S^T columns
+      if (tid == 0) tev(4, mtc, 6, c);
       mbar_wait(dp_full, c & 1);
       tc_fence_after();
+      if (tid == 0) tev(4, mtc, 4, c);
+      uint32_t dvv[2][16];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int c0 = half * 64 + jj * 16;
-        uint32_t dv[16], pp[8], pd[8];
-        tmem_ld16(tl + C::kColP + c0, dv);
-        tmem_ld_wait();
+      for (int jj = 0; jj < 2; ++jj) tmem_ld16(tl + C::kColP + part * 32 + jj * 16, dvv[jj]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c0 = part * 32 + jj * 16;
+        uint32_t pp[8], pd[8];
+        uint32_t (&dv)[16] = dvv[jj];
         if (any_b[jj]) {
           // position of chunk row r: i = q0 + (r & (P-1))  or  q0 + (r >> log2 G)
           const int r_lo = a.q_swap ? (c0 >> sh_g) : (c0 & (a.P - 1));
@@ -1475,6 +1506,26 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
               pd[e >> 1] = pack16<T>(p0 * (__uint_as_float(dv[e]) - d4.x), p1 * (__uint_as_float(dv[e + 1]) - d4.y));
               pd[(e >> 1) + 1] = pack16<T>(p2 * (__uint_as_float(dv[e + 2]) - d4.z), p3 * (__uint_as_float(dv[e + 3]) - d4.w));
             }
+          } else if (!a.q_swap && a.P >= 16) {
+            // head-major rows: the 16 rows of the block are 16 consecutive positions i_lo + e, so the attended
+            // elements of key j form one run [lo, hi] -> a 16-bit mask, one predicate per element
+            const int lo = max(j - (q0 + r_lo), 0), hi = min(i_hi - (q0 + r_lo), 15);
+            const uint32_t mask = (hi >= lo) ? ((0xffffu >> (15 - hi)) & (0xffffu << lo)) : 0u;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(rd + c0 + e);
+              const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+              float pe[4], de[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                pe[u] = (mask & (1u << (e + u))) ? __uint_as_float(pv[jj][e + u]) : 0.f;   // dP, delta are finite: P = 0 => dS = 0
+                de[u] = pe[u] * (__uint_as_float(dv[e + u]) - dl[u]);
+              }
+              pp[e >> 1] = pack16_fast<T>(pe[0], pe[1]);
+              pp[(e >> 1) + 1] = pack16_fast<T>(pe[2], pe[3]);
+              pd[e >> 1] = pack16_fast<T>(de[0], de[1]);
+              pd[(e >> 1) + 1] = pack16_fast<T>(de[2], de[3]);
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
@@ -1488,8 +1539,8 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
               const float p1 = ok1 ? __uint_as_float(pv[jj][e + 1]) : 0.f;
               const float d0 = ok0 ? p0 * (__uint_as_float(dv[e]) - dl.x) : 0.f;
               const float d1 = ok1 ? p1 * (__uint_as_float(dv[e + 1]) - dl.y) : 0.f;
-              pp[e >> 1] = pack16<T>(p0, p1);
-              pd[e >> 1] = pack16<T>(d0, d1);
+              pp[e >> 1] = pack16_fast<T>(p0, p1);
+              pd[e >> 1] = pack16_fast<T>(d0, d1);
             }
           }
         } else {
@@ -1497,14 +1548,15 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
           for (int e = 0; e < 8; ++e) pp[e] = pd[e] = 0u;
         }
         __syncwarp();
-        tmem_st8(ts + half * 64 + jj * 8, pp);
-        tmem_st8(ts + half * 64 + 32 + jj * 8, pd);
+        tmem_st8(ts + part * 32 + jj * 8, pp);
+        tmem_st8(ts + part * 32 + 16 + jj * 8, pd);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full + (c & 1));
+      if (tid == 0) tev(4, mtc, 3, c);
       if (c + 1 < nchunks && tid < 128) {
-        row_l2[((c + 1) & 1) * 128 + tid] = nl_n;
+        row_l2[((c + 1) & 1) * 128 + tid] = neg_l2_of(nl_n);
         row_dl[((c + 1) & 1) * 128 + tid] = dl_n;
       }
       pb = pbn;
@@ -1517,9 +1569,8 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
     }
     T* dkr = static_cast<T*>(a.dk) + b * a.sdk.b + kvh * a.sdk.h + static_cast<int64_t>(j) * a.sdk.n;
     T* dvr = static_cast<T*>(a.dv) + b * a.sdv.b + kvh * a.sdv.h + static_cast<int64_t>(j) * a.sdv.n;
-#pragma unroll
-    for (int cc = 0; cc < D / 2; cc += 16) {
-      const int c0 = half * (D / 2) + cc;
+    {
+      const int c0 = part * 16;                           // 16 of the 64 channels per thread
       uint32_t kv_[16], vv_[16], pk[8], pv2[8];
       if (nchunks > 0) {                                  // uniform: the tcgen05.ld stay warp-convergent
         tmem_ld16(tl + C::kColK + c0, kv_);
@@ -1544,7 +1595,7 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMathWarps + 1) tmem_dealloc(tmem, C::kTmemCols);
+  if (warp == C::kMathW + 1) tmem_dealloc(tmem, C::kTmemCols);
 }
 
 }  // namespace
@@ -1636,6 +1687,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.lse = p.lse;
     a.delta = p.delta;
     a.dk = p.dk; a.dv = p.dv; a.sdk = p.sdk; a.sdv = p.sdv;
+    a.trace = trace_buffer();
     dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
     if constexpr (D == 64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
     else dkdv_kernel<T, D><<<grid, kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);

@@ -26,20 +26,22 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = torch.zeros(8 * 256 * 2, dtype=torch.int64, device=dev)
 lib.sfa_set_trace_buffer(buf.data_ptr())
-lib.sfa_set_bwd_stages(2)
+lib.sfa_set_bwd_stages(int(os.environ.get('TRACE_STAGE', '2')))
 _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
 torch.cuda.synchronize()
 lib.sfa_set_trace_buffer(None)
 lib.sfa_set_bwd_stages(7)
 t = buf.cpu().view(8, 256, 2)
 ROLES = ["PROD", "I_S", "I_dP", "I_dQ", "EXP", "DS", "EPI", "-"]
-CODES = {1: "begin / wait", 2: "inputs ready", 3: "done", 4: "P ready", 5: "batch loaded", 6: "batch computed", 7: "st waited"}
+if os.environ.get("TRACE_STAGE") == "4":
+    ROLES = ["PROD", "B:S^T", "B:dP^T", "A:dVdK", "MATH", "-", "-", "-"]
+CODES = {1: "begin / wait", 2: "inputs ready", 3: "done", 4: "P ready / dep ok", 5: "batch loaded / bar", 6: "batch computed / ph1 done", 7: "st waited"}
 ev = []
 for role in range(8):
     for j in range(256):
         tag, clk = int(t[role, j, 0]), int(t[role, j, 1])
         if clk == 0:
-            break
+            continue
         ev.append((clk, role, tag >> 32, tag & 0xffffffff))
 ev.sort()
 t0 = ev[0][0]
