@@ -1,6 +1,7 @@
 // extern "C" surface of libsinkfa (declared in include/sinkfa.h): argument validation,
 // workspace carving and dispatch to the kernel families.  No device allocation, no stream sync.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -121,6 +122,7 @@ int sfa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (g_force_impl != SFA_IMPL_SIMT && tc_fwd_supported(p, dtype)) {
     set_impl_name("tcgen05");
+    if (tc_fwd64_supported(p, dtype) && !getenv("SFA_FWD_V1")) return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
     return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");
   }
   set_impl_name("simt");

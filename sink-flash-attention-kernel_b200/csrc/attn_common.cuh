@@ -50,6 +50,70 @@ __device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W
   return make_plan(q0, P, N, S, W, BN, bn_magic(BN));
 }
 
+// Persistent-kernel work walker.  Args type A provides N, S, W, P, BN, ny, nblk, total_tiles, tiles_per_cta,
+// bn_mul.  Tile id = (b * ny + y) * nblk + pb (pb: position block of P positions, y: packed head group).
+template <class A>
+__device__ __forceinline__ void decode_tile(const A& a, int tile, int& pb, int& y, int& b) {
+  pb = tile % a.nblk;
+  const int r = tile / a.nblk;
+  y = r % a.ny;
+  b = r / a.ny;
+}
+
+// Walks this CTA's work items: tiles blockIdx.x, +gridDim.x, ... (or a contiguous range) and the KV tiles of
+// each, with the tile coordinates kept incrementally (no integer divisions per tile: a division is a
+// ~150-cycle dependent chain on the single-thread TMA / UMMA roles).
+template <class A>
+struct ItemWalkT {
+  const A& a;
+  int tile, it, t, n;        // tile id, tile iteration, KV tile inside the tile, running item count
+  int step, end;
+  int pb, y, b, q0;
+  TilePlan pl;
+  __device__ __forceinline__ explicit ItemWalkT(const A& a_) : a(a_), it(-1), t(0), n(-1) {
+    int first;
+    if (a.tiles_per_cta > 0) {
+      step = 1;
+      first = static_cast<int>(blockIdx.x) * a.tiles_per_cta;
+      end = min(first + a.tiles_per_cta, a.total_tiles);
+    } else {
+      step = gridDim.x;
+      first = static_cast<int>(blockIdx.x);
+      end = a.total_tiles;
+    }
+    decode_tile(a, first, pb, y, b);     // the only divisions: once per role
+    tile = first - step;
+    pb -= step;                          // next() adds it back
+    pl.n_tiles = 0;
+    q0 = 0;
+  }
+  __device__ __forceinline__ static void advance(const A& a, int step, int& pb, int& y, int& b) {
+    pb += step;
+    while (pb >= a.nblk) {
+      pb -= a.nblk;
+      if (++y == a.ny) {
+        y = 0;
+        ++b;
+      }
+    }
+  }
+  __device__ __forceinline__ bool next() {
+    ++t;
+    while (t >= pl.n_tiles) {
+      tile += step;
+      ++it;
+      if (tile >= end) return false;
+      advance(a, step, pb, y, b);
+      q0 = pb * a.P;
+      pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN, a.bn_mul);
+      t = 0;
+    }
+    ++n;
+    return true;
+  }
+  __device__ __forceinline__ bool last_of_tile() const { return t == pl.n_tiles - 1; }
+};
+
 // attended columns [c_lo, c_hi] of query position i inside a tile that starts at key `kstart`
 __device__ __forceinline__ void row_range(bool is_sink, int i, int kstart, int cols, int S, int W, int& c_lo, int& c_hi) {
   if (is_sink) {

@@ -58,13 +58,6 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int& cnt, i
   }
 }
 
-__device__ __forceinline__ void decode_tile(const BwdArgs& a, int tile, int& pb, int& y, int& b) {
-  pb = tile % a.nblk;
-  const int r = tile / a.nblk;
-  y = r % a.ny;
-  b = r / a.ny;
-}
-
 // ================================================================================== dQ kernel
 // Work items = (packed Q tile, KV tile) pairs in the order of the two-range walk, two TMEM slots:
 // the UMMAs of item n+1 (S, dP) run while the math warps work on item n, and dQ(n) runs under the
@@ -92,56 +85,7 @@ template <int D> struct DqCfg {
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
 
-// Walks this CTA's work items: tiles blockIdx.x, +gridDim.x, ... and the KV tiles of each.
-struct ItemWalk {
-  const BwdArgs& a;
-  int tile, it, t, n;        // tile id, tile iteration, KV tile inside the tile, running item count
-  int step, end;
-  int pb, y, b, q0;          // tile = (b * ny + y) * nblk + pb, kept incrementally (no divisions per tile)
-  TilePlan pl;
-  __device__ __forceinline__ explicit ItemWalk(const BwdArgs& a_) : a(a_), it(-1), t(0), n(-1) {
-    int first;
-    if (a.tiles_per_cta > 0) {
-      step = 1;
-      first = static_cast<int>(blockIdx.x) * a.tiles_per_cta;
-      end = min(first + a.tiles_per_cta, a.total_tiles);
-    } else {
-      step = gridDim.x;
-      first = static_cast<int>(blockIdx.x);
-      end = a.total_tiles;
-    }
-    decode_tile(a, first, pb, y, b);     // the only divisions: once per role
-    tile = first - step;
-    pb -= step;                          // next() adds it back
-    pl.n_tiles = 0;
-    q0 = 0;
-  }
-  __device__ __forceinline__ static void advance(const BwdArgs& a, int step, int& pb, int& y, int& b) {
-    pb += step;
-    while (pb >= a.nblk) {
-      pb -= a.nblk;
-      if (++y == a.ny) {
-        y = 0;
-        ++b;
-      }
-    }
-  }
-  __device__ __forceinline__ bool next() {
-    ++t;
-    while (t >= pl.n_tiles) {
-      tile += step;
-      ++it;
-      if (tile >= end) return false;
-      advance(a, step, pb, y, b);
-      q0 = pb * a.P;
-      pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN, a.bn_mul);
-      t = 0;
-    }
-    ++n;
-    return true;
-  }
-  __device__ __forceinline__ bool last_of_tile() const { return t == pl.n_tiles - 1; }
-};
+using ItemWalk = ItemWalkT<BwdArgs>;
 
 template <typename T, int D>
 __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -748,33 +692,19 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
         mbar_wait(s_full + sb, (w.n >> 1) & 1);
         tc_fence_after();
         if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 2, w.n);
-        // in place, three 16-column chunks at a time: P (16-bit pairs) lands on S columns already consumed
-        // (issuing the next batch's tcgen05.ld ahead of the compute was measured slower: 94 -> 121 us)
+        // In place, one 16-column chunk per trip, ONE code path (masked elements are zeroed later by the dS warps):
+        // ncu showed the math warps starved for instructions (stall_no_inst 50-80 % in unrolled multi-variant
+        // bodies), so the loop body is kept small enough to stay resident in the instruction cache.
 #pragma unroll 1
-        for (int cb = 0; cb < nch; cb += 3) {
-          uint32_t sv[3][16];
-#pragma unroll
-          for (int jj = 0; jj < 3; ++jj)
-            if (cb + jj < nch) tmem_ld16(ts + (cb + jj) * 16, sv[jj]);
+        for (int cb = 0; cb < nch; ++cb) {
+          uint32_t sv[16], pk[8];
+          tmem_ld16(ts + cb * 16, sv);
           tmem_ld_wait();
-          if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 5, w.n);
 #pragma unroll
-          for (int jj = 0; jj < 3; ++jj)
-            if (cb + jj < nch) {
-              const int c0 = (cb + jj) * 16;
-              uint32_t pk[8];
-              if (__any_sync(0xffffffffu, c0 + 15 >= c_lo && c0 <= c_hi)) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 2)
-                  pk[e >> 1] = pack16_fast<T>(fast_exp2(fmaf(__uint_as_float(sv[jj][e]), a.sl2, neg_l2)),
-                                              fast_exp2(fmaf(__uint_as_float(sv[jj][e + 1]), a.sl2, neg_l2)));
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pk[e] = 0u;
-              }
-              tmem_st8(ts + (c0 >> 1), pk);
-            }
-          if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 6, w.n);
+          for (int e = 0; e < 16; e += 2)
+            pk[e >> 1] = pack16_fast<T>(fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2)),
+                                        fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2)));
+          tmem_st8(ts + cb * 8, pk);
         }
         tmem_st_wait();
         if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 7, w.n);
@@ -814,50 +744,24 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
         mbar_wait(dp_full, w.n & 1);
         tc_fence_after();
         if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 2, w.n);
-        // two 16-column chunks per TMEM round trip.  (Measured alternatives, all slower at the C1 shape: one chunk
-        // per trip with a single masked code path 94 -> 164 us; issuing the next batch's loads ahead of the compute
-        // 94 -> 121 us; integer bf16 packing instead of cvt 94 -> 112 us.)
+        // one 16-column chunk per trip, one (always masked) code path -- see the exp warps
 #pragma unroll 1
-        for (int cb = 0; cb < nch; cb += 2) {
-          uint32_t pv[2][8], dv[2][16];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
-            if (cb + jj < nch) {
-              tmem_ld8(ts + ((cb + jj) * 8), pv[jj]);
-              tmem_ld16(tl + C::kColP + (cb + jj) * 16, dv[jj]);
-            }
+        for (int cb = 0; cb < nch; ++cb) {
+          uint32_t pv[8], dv[16], pk[8];
+          const int c0 = cb * 16;
+          tmem_ld8(ts + cb * 8, pv);
+          tmem_ld16(tl + C::kColP + c0, dv);
           tmem_ld_wait();
+          const int lo = c_lo - c0, hi = c_hi - c0;       // attended elements of this chunk: [lo, hi]
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
-            if (cb + jj < nch) {
-              const int c0 = (cb + jj) * 16;
-              uint32_t pk[8];
-              const bool full = (c0 >= c_lo) && (c0 + 15 <= c_hi);
-              if (__all_sync(0xffffffffu, full)) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                  float p0, p1;
-                  unpack16<T>(pv[jj][e >> 1], p0, p1);
-                  pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[jj][e]) - delta), p1 * (__uint_as_float(dv[jj][e + 1]) - delta));
-                }
-              } else if (__any_sync(0xffffffffu, c0 + 15 >= c_lo && c0 <= c_hi)) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                  const int c = c0 + e;
-                  float p0, p1;
-                  unpack16<T>(pv[jj][e >> 1], p0, p1);
-                  float d0 = p0 * (__uint_as_float(dv[jj][e]) - delta);
-                  float d1 = p1 * (__uint_as_float(dv[jj][e + 1]) - delta);
-                  d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
-                  d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
-                  pk[e >> 1] = pack16_fast<T>(d0, d1);
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pk[e] = 0u;
-              }
-              tmem_st8(ts + C::kBNMax / 2 + (c0 >> 1), pk);
-            }
+          for (int e = 0; e < 16; e += 2) {
+            float p0, p1;
+            unpack16<T>(pv[e >> 1], p0, p1);
+            p0 = (e >= lo && e <= hi) ? p0 : 0.f;         // dP and delta are finite: P = 0 => dS = 0
+            p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
+            pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[e]) - delta), p1 * (__uint_as_float(dv[e + 1]) - delta));
+          }
+          tmem_st8(ts + C::kBNMax / 2 + (c0 >> 1), pk);
         }
         tmem_st_wait();
         tc_fence_before();

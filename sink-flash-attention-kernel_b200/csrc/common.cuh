@@ -75,6 +75,8 @@ cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cu
 
 bool tc_fwd_supported(const AttnParams& p, int dtype);
 cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st);
+bool tc_fwd64_supported(const AttnParams& p, int dtype);   // persistent warp-specialised forward, head_dim 64
+cudaError_t tc_fwd64(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_bwd_supported(const AttnParams& p, int dtype);
 cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
 

@@ -1,0 +1,435 @@
+// Persistent, warp-specialised forward for head_dim 64 (reference kernel being replaced:
+// _sink_flash_attn_fwd_kernel, sink_flash_attention.py:93-194).  Same packed tile (128 MMA rows = G q-heads x
+// P positions of one KV head) and two-range KV walk as fwd_sm100.cu, restructured around what the
+// round-1 probes measured on B200: a tcgen05.mma costs its issuing thread ~80 cycles, an mbarrier hop on a
+// single-thread role 200-300 cycles, MUFU.EX2 runs at 16/clk/SM, and the old kernel paid ~18 TMEM round trips
+// plus a full prologue per tile.  Here:
+//
+//   warp 12      TMA producer      Q ring (3 tiles), K and V rings (3 items of up to 144 keys each)
+//   warp 13      UMMA issuer S     S(n) = Q K^T -> S buffer n & 1, two items ahead of the softmax
+//   warp 14      UMMA issuer PV    O(tile & 1) += P(n) V(n)   (TS form, P read from the S buffer)
+//   warps 0-7    softmax           two warps per TMEM lane quarter, each owning half of the key columns of its
+//                                  rows: ONE tcgen05.ld round trip per item, S kept in registers for the max
+//                                  and the exp pass, P written as 16-bit over the consumed S columns
+//   warps 8-11   epilogue          O / l -> 16-bit -> swizzled smem -> TMA store, LSE = m ln2 + log l
+//
+// Online softmax in exp2 units seeded with (m, l) = (s_aux, 1) (:139-146); O is rescaled lazily (only when a
+// row max moves by more than 2^8), which never happens for single-item tiles such as window 128.
+#include "attn_common.cuh"
+#include "tmap.cuh"
+
+namespace sfa {
+namespace {
+
+struct Fwd64Args {
+  int B, N, S, W, Hq, G, P, BN, groups_per_kv, ny, nblk, total_tiles, tiles_per_cta;
+  unsigned long long bn_mul;
+  int q_swap, k_swap, v_swap, o_swap;
+  int fmt;
+  float sl2;
+  const float* s_aux;
+  float* lse;
+  long long* trace;
+};
+#ifndef SFA_TRACE
+#define SFA_TRACE 0
+#endif
+__device__ __forceinline__ void tev(long long* trace, int role, int& cnt, int code, int idx) {
+  if (SFA_TRACE && trace != nullptr && blockIdx.x == 0 && cnt < 256) {
+    trace[(role * 256 + cnt) * 2] = (static_cast<long long>(code) << 32) | static_cast<unsigned>(idx);
+    trace[(role * 256 + cnt) * 2 + 1] = clock64();
+    ++cnt;
+  }
+}
+using Walk = ItemWalkT<Fwd64Args>;
+
+struct Fwd64Cfg {
+  static constexpr int D = 64;
+  static constexpr int kBNMax = 144;
+  static constexpr int kQStages = 3, kKStages = 3, kVStages = 3;
+  static constexpr int kQBytes = 128 * D * 2;
+  static constexpr int kKVBytes = kBNMax * D * 2;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kColS = 0;               // S buffers at 0 and kBNMax
+  static constexpr uint32_t kColO = 2 * kBNMax;      // O accumulators at +0 and +D
+  static constexpr int kMaxCh = (kBNMax / 16 + 1) / 2;
+  static constexpr int kThreads = 15 * 32;
+  static constexpr int kStatFloats = 2 * 128 + 2 * 2 * 128 + 2 * 2 * 128;   // row_m[2][128], row_l[2][2][128], xch[2][2][128]
+  static constexpr int kSmem = 1024 + (kQStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + kStatFloats * 4 + 512;
+  static_assert(2 * kBNMax + 2 * D <= 512, "TMEM budget");
+  static_assert(kSmem <= 227 * 1024, "smem budget");
+};
+
+template <typename T>
+__global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                      const __grid_constant__ CUtensorMap tmK,
+                                                                      const __grid_constant__ CUtensorMap tmV,
+                                                                      const __grid_constant__ CUtensorMap tmO,
+                                                                      const Fwd64Args a) {
+  using C = Fwd64Cfg;
+  constexpr int D = C::D;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* q_s = smem;                                   // [kQStages][kQBytes]
+  unsigned char* stage_s = q_s + C::kQStages * C::kQBytes;     // O staging
+  unsigned char* k_s = stage_s + C::kQBytes;                   // [kKStages][kKVBytes]
+  unsigned char* v_s = k_s + C::kKStages * C::kKVBytes;        // [kVStages][kKVBytes]
+  float* row_m = reinterpret_cast<float*>(v_s + C::kVStages * C::kKVBytes);   // [2][128]     final running max (log2 units) per tile parity
+  float* row_l = row_m + 2 * 128;                                             // [2][2][128]  partial row sums of the two column halves
+  float* xch = row_l + 2 * 2 * 128;                                           // [2][2][128]  per-item row-max exchange between the halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 128);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = q_full + C::kQStages;
+  uint64_t* k_full = q_empty + C::kQStages;
+  uint64_t* k_empty = k_full + C::kKStages;
+  uint64_t* v_full = k_empty + C::kKStages;
+  uint64_t* v_empty = v_full + C::kVStages;
+  uint64_t* s_full = v_empty + C::kVStages;        // [2]  S(n) complete                      (issuer S -> softmax)
+  uint64_t* p_full = s_full + 2;                   // [2]  P(n) written                       (softmax -> issuer PV)
+  uint64_t* sbuf_free = p_full + 2;                // [2]  PV(n) complete: S buffer n & 1 free (issuer PV -> issuer S, softmax rescale)
+  uint64_t* o_done = sbuf_free + 2;                // [2]  tile's O complete                  (issuer PV -> epilogue)
+  uint64_t* o_free = o_done + 2;                   // [2]  O accumulator + row stats read     (epilogue -> issuer PV, softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < C::kQStages; ++s) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
+    for (int s = 0; s < C::kKStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+    for (int s = 0; s < C::kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full + s, 1);
+      mbar_init(p_full + s, 256);
+      mbar_init(sbuf_free + s, 1);
+      mbar_init(o_done + s, 1);
+      mbar_init(o_free + s, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 13) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 12) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      Walk w(a);
+      while (w.next()) {
+        const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const int kst = w.n % C::kKStages, vst = w.n % C::kVStages;
+        if (w.t == 0) {
+          const int qs = w.it % C::kQStages;
+          mbar_wait(q_empty + qs, ((w.it / C::kQStages) & 1) ^ 1);
+          mbar_expect_tx(q_full + qs, C::kQBytes);
+          tma_tile(q_s + qs * C::kQBytes, &tmQ, q_full + qs, a.q_swap, 0, w.q0, hq0, w.b);
+        }
+        mbar_wait(k_empty + kst, ((w.n / C::kKStages) & 1) ^ 1);
+        mbar_expect_tx(k_full + kst, a.BN * D * 2);
+        tma_tile(k_s + kst * C::kKVBytes, &tmK, k_full + kst, a.k_swap, 0, kstart, kvh, w.b);
+        mbar_wait(v_empty + vst, ((w.n / C::kVStages) & 1) ^ 1);
+        mbar_expect_tx(v_full + vst, a.BN * D * 2);
+        tma_tile(v_s + vst * C::kKVBytes, &tmV, v_full + vst, a.v_swap, 0, kstart, kvh, w.b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ UMMA issuer S
+    if (lane == 0) {
+      Walk w(a);
+      int tc = 0;
+      while (w.next()) {
+        tev(a.trace, 1, tc, 1, w.n);
+        const int qs = w.it % C::kQStages, kst = w.n % C::kKStages, sb = w.n & 1;
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
+        const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
+        const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), 16, 1024);
+        if (w.t == 0) mbar_wait(q_full + qs, (w.it / C::kQStages) & 1);
+        mbar_wait(k_full + kst, (w.n / C::kKStages) & 1);
+        if (w.n >= 2) mbar_wait(sbuf_free + sb, ((w.n - 2) >> 1) & 1);     // PV(n-2) has consumed P(n-2)
+        tc_fence_after();
+        tev(a.trace, 1, tc, 2, w.n);
+        const uint32_t ts = tmem + C::kColS + sb * C::kBNMax;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss(ts, qd + kk * 2, kd + kk * 2, idesc_s, kk != 0);
+        umma_commit(s_full + sb);
+        umma_commit(k_empty + kst);
+        if (w.last_of_tile()) umma_commit(q_empty + qs);
+        tev(a.trace, 1, tc, 3, w.n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ UMMA issuer PV
+    if (lane == 0) {
+      const uint32_t idesc_pv = make_idesc(a.fmt, 128, D, 0, 1);
+      Walk w(a);
+      int tc = 0;
+      while (w.next()) {
+        tev(a.trace, 3, tc, 1, w.n);
+        const int vst = w.n % C::kVStages, sb = w.n & 1, tb = w.it & 1;
+        int kstart, cols; bool is_sink;
+        w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+        const uint64_t vd = make_sdesc(smem_u32(v_s + vst * C::kKVBytes), C::kKVBytes, 1024);
+        const uint32_t ts = tmem + C::kColS + sb * C::kBNMax;
+        const int nk = cols >> 4;
+        const int hcol = ((nk + 1) / 2) * 16;
+        const uint32_t a_lo = ts, a_hi = ts + hcol - (hcol >> 1);     // P: first column half packed at +0, second at +hcol
+        mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
+        mbar_wait(p_full + sb, (w.n >> 1) & 1);
+        if (w.t == 0 && w.it >= 2) mbar_wait(o_free + tb, ((w.it - 2) >> 1) & 1);
+        tc_fence_after();
+        tev(a.trace, 3, tc, 2, w.n);
+#pragma unroll
+        for (int kk = 0; kk < C::kBNMax / 16; ++kk)
+          if (kk < nk)
+            umma_ts(tmem + C::kColO + tb * D, ((kk * 16 < hcol) ? a_lo : a_hi) + kk * 8, vd + kk * (2048 >> 4), idesc_pv,
+                    (w.t > 0 || kk > 0));
+        umma_commit(sbuf_free + sb);
+        umma_commit(v_empty + vst);
+        if (w.last_of_tile()) umma_commit(o_done + tb);
+        tev(a.trace, 3, tc, 3, w.n);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ softmax: row == TMEM lane, half of the columns
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const int pr = a.q_swap ? (r / a.G) : (r % a.P);
+    const int gr = a.q_swap ? (r % a.G) : (r / a.P);
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    float m_used = -INFINITY, l = 0.f;
+    int i = 0, mtc = 0;
+    Walk w(a);
+    while (w.next()) {
+      const int sb = w.n & 1, tb = w.it & 1;
+      if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
+      if (w.t == 0) {
+        i = w.q0 + pr;
+        const int h = w.y * a.G + gr;
+        m_used = a.s_aux ? __ldg(a.s_aux + h) * kLog2e : -INFINITY;
+        l = (a.s_aux && half == 0) ? 1.f : 0.f;
+      }
+      const uint32_t ts = tl + C::kColS + sb * C::kBNMax;
+      int kstart, cols; bool is_sink;
+      w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
+      int c_lo, c_hi;
+      row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+      if (i >= a.N) c_hi = -1;
+      const int nch = cols >> 4;
+      const int hch = (nch + 1) / 2;
+      const int hcol = hch * 16;
+      const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
+
+      mbar_wait(s_full + sb, (w.n >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) tev(a.trace, 4, mtc, 2, w.n);
+      // Two rolled passes over this half's 16-column chunks (max, then exp), one code path with the mask always on.
+      // ncu showed the unrolled three-variant version starved for instructions (stall_no_inst 50-80 % of the
+      // samples in the max / exp code): the hot loops must stay resident in the instruction cache that the
+      // softmax, epilogue and issuer warps of a scheduler share.  S is re-read from TMEM in the second pass
+      // (a tcgen05.ld round trip is ~60 cycles, probe_tmem).
+      // ---- pass 1: row max over the attended columns of this half
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};    // four independent chains
+#pragma unroll 1
+      for (int cb = ch0; cb < ch1; ++cb) {
+        uint32_t sv[16];
+        tmem_ld16(ts + cb * 16, sv);
+        tmem_ld_wait();
+        const int lo = c_lo - cb * 16, hi = c_hi - cb * 16;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          mxa[e & 3] = fmaxf(mxa[e & 3], (e >= lo && e <= hi) ? __uint_as_float(sv[e]) : -INFINITY);
+      }
+      if (threadIdx.x == 0) tev(a.trace, 4, mtc, 5, w.n);
+      float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+      // ---- the two halves of a row agree on its max through shared memory
+      float* xb = xch + (w.n & 1) * 256;
+      xb[half * 128 + r] = mx;
+      if (threadIdx.x == 0) tev(a.trace, 4, mtc, 6, w.n);
+      named_bar_sync(1 + quarter, 64);
+      mx = fmaxf(mx, xb[(half ^ 1) * 128 + r]);
+      if (threadIdx.x == 0) tev(a.trace, 4, mtc, 4, w.n);
+      const float m_new = fmaxf(m_used, mx * a.sl2);
+      const bool need = (m_new - m_used) > 8.0f;        // also -inf -> finite; false for NaN (-inf - -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? exp2f(m_used - m_new) : 1.f;
+        if (need) {
+          l *= alpha;
+          m_used = m_new;
+        }
+        if (w.t > 0) {
+          // lazy rescale of this half's O columns: PV(n-1) must have completed
+          mbar_wait(sbuf_free + ((w.n - 1) & 1), ((w.n - 1) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t v[16];
+            const uint32_t oa = tl + C::kColO + tb * D + half * 32 + cc * 16;
+            tmem_ld16(oa, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st16(oa, v);
+          }
+        }
+      }
+      // ---- pass 2: P = exp2(s*c - m) -> 16-bit over the consumed S columns of this half, partial row sum
+      const float neg_m = -m_used;
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int cb = ch0; cb < ch1; ++cb) {
+        uint32_t sv[16], pk[8];
+        const int c0 = cb * 16;
+        tmem_ld16(ts + c0, sv);
+        tmem_ld_wait();
+        const int lo = c_lo - c0, hi = c_hi - c0;
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_m));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_m));
+          p0 = (e >= lo && e <= hi) ? p0 : 0.f;
+          p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
+          lsum += p0 + p1;
+          pk[e >> 1] = pack16_fast<T>(p0, p1);
+        }
+        tmem_st8(half ? (ts + hcol + ((c0 - hcol) >> 1)) : (ts + (c0 >> 1)), pk);
+      }
+      l += lsum;
+      if (threadIdx.x == 0) tev(a.trace, 4, mtc, 7, w.n);
+      tmem_st_wait();
+      if (w.last_of_tile()) {
+        // hand the row statistics to the epilogue warps (ordered by the p_full -> PV -> o_done chain)
+        if (w.it >= 2) mbar_wait(o_free + tb, ((w.it - 2) >> 1) & 1);
+        if (half == 0) row_m[tb * 128 + r] = m_used;
+        row_l[(tb * 2 + half) * 128 + r] = l;
+      }
+      tc_fence_before();
+      mbar_arrive(p_full + sb);
+      if (threadIdx.x == 0) tev(a.trace, 4, mtc, 3, w.n);
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int pr = a.q_swap ? (r / a.G) : (r % a.P);
+    const int gr = a.q_swap ? (r % a.G) : (r / a.P);
+    const int ro = a.o_swap ? (pr * a.G + gr) : (gr * a.P + pr);      // row in O's box order
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int et = threadIdx.x - 256;
+    Walk w(a);
+    int mtc = 0;
+    while (w.next()) {
+      if (!w.last_of_tile()) continue;
+      const int tb = w.it & 1;
+      if (et == 0) tev(a.trace, 6, mtc, 1, w.n);
+      if (et == 0) tma_store_wait_read0();     // the previous store has finished reading the staging buffer
+      named_bar_sync(6, 128);
+      mbar_wait(o_done + tb, (w.it >> 1) & 1);
+      tc_fence_after();
+      if (et == 0) tev(a.trace, 6, mtc, 2, w.n);
+      const float m_fin = row_m[tb * 128 + r];
+      const float l_fin = row_l[(tb * 2) * 128 + r] + row_l[(tb * 2 + 1) * 128 + r];
+      const float inv = (l_fin > 0.f) ? 1.f / l_fin : 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[16], pk[8];
+        tmem_ld16(tl + C::kColO + tb * D + cc * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2)
+          pk[e >> 1] = pack16<T>(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv);
+        *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, cc * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(stage_s + sw128_off(ro, cc * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      tc_fence_before();
+      mbar_arrive(o_free + tb);
+      const int i = w.q0 + pr;
+      if (i < a.N)
+        a.lse[(static_cast<int64_t>(w.b) * a.Hq + w.y * a.G + gr) * a.N + i] =
+            (l_fin > 0.f) ? m_fin * kLn2 + logf(l_fin) : -INFINITY;
+      fence_proxy_async_smem();
+      named_bar_sync(5, 128);
+      if (et == 0) {
+        tma_tile_store(&tmO, stage_s, a.o_swap, 0, w.q0, w.y * a.G, w.b);
+        tma_store_commit();
+        tev(a.trace, 6, mtc, 3, w.n);
+      }
+    }
+    if (et == 0) tma_store_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc(tmem, C::kTmemCols);
+}
+
+int sm_count_fwd() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename T>
+cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
+  using C = Fwd64Cfg;
+  constexpr int D = 64;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(fwd64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int group = p.Hq / p.Hkv;
+  int G, P;
+  pick_packing(p.Hq, p.Hkv, G, P);
+  const int BN = pick_bn(p.W, p.N, P, C::kBNMax);
+  TileMap mq, mk, mv, mo;
+  if (!make_tile_map(&mq, p.q, dtype, D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mo, p.o, dtype, D, p.N, p.Hq, p.B, p.so, P, G)) return cudaErrorInvalidValue;
+  Fwd64Args a;
+  a.B = p.B; a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.G = G; a.P = P; a.BN = BN;
+  a.groups_per_kv = group / G;
+  a.ny = p.Hq / G;
+  a.nblk = (p.N + P - 1) / P;
+  a.total_tiles = a.nblk * a.ny * p.B;
+  a.tiles_per_cta = 0;
+  a.bn_mul = bn_magic(BN);
+  a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh; a.o_swap = mo.swap_nh;
+  a.fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
+  a.sl2 = p.scale * kLog2e;
+  a.s_aux = p.s_aux;
+  a.lse = p.lse;
+  a.trace = trace_buffer();
+  const int grid = a.total_tiles < sm_count_fwd() ? a.total_tiles : sm_count_fwd();
+  fwd64_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tc_fwd64_supported(const AttnParams& p, int dtype) {
+  return p.D == 64 && (p.S > 0 || p.W > 0);     // nothing attended at all: the one-tile-per-CTA kernel writes the O = 0 rows
+}
+
+cudaError_t tc_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
+  return dtype == SFA_DTYPE_BF16 ? launch_fwd64<__nv_bfloat16>(p, dtype, st) : launch_fwd64<__half>(p, dtype, st);
+}
+
+}  // namespace sfa

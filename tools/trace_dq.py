@@ -26,13 +26,19 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = torch.zeros(8 * 256 * 2, dtype=torch.int64, device=dev)
 lib.sfa_set_trace_buffer(buf.data_ptr())
-lib.sfa_set_bwd_stages(int(os.environ.get('TRACE_STAGE', '2')))
-_lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
+stage = int(os.environ.get('TRACE_STAGE', '2'))
+if stage == 0:
+    sa.sink_flash_attention_with_lse(q, k, v, S, W, s_aux)
+else:
+    lib.sfa_set_bwd_stages(stage)
+    _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
 torch.cuda.synchronize()
 lib.sfa_set_trace_buffer(None)
 lib.sfa_set_bwd_stages(7)
 t = buf.cpu().view(8, 256, 2)
 ROLES = ["PROD", "I_S", "I_dP", "I_dQ", "EXP", "DS", "EPI", "-"]
+if os.environ.get("TRACE_STAGE") == "0":
+    ROLES = ["PROD", "I_S", "-", "I_PV", "SOFTMAX", "-", "EPI", "-"]
 if os.environ.get("TRACE_STAGE") == "4":
     ROLES = ["PROD", "B:S^T", "B:dP^T", "A:dVdK", "MATH", "-", "-", "-"]
 CODES = {1: "begin / wait", 2: "inputs ready", 3: "done", 4: "P ready / dep ok", 5: "batch loaded / bar", 6: "batch computed / ph1 done", 7: "st waited"}
