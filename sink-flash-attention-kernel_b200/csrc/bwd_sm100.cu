@@ -1345,18 +1345,12 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
       const uint32_t ts = tl + C::kColS + (c & 1) * 128;
 
       // per 16-column block: attended positions [i_lo, i_hi_b]; any / all lanes of the warp attended
-      uint32_t pv[2][16];
-      bool any_b[2];
-      mbar_wait(s_full + (c & 1), (c >> 1) & 1);
-      tc_fence_after();
-      if (tid == 0) tev(4, mtc, 2, c);
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) tmem_ld16(ts + part * 32 + jj * 16, pv[jj]);
-      tmem_ld_wait();
-      // ---- phase 1: P^T = exp2(S^T * c - lse[row])
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int c0 = part * 32 + jj * 16;
+      // Both phases are rolled loops over this thread's two 16-row blocks with ONE code path each, so the hot code
+      // of the 16 math warps stays resident in the instruction cache (ncu: stall_no_inst dominated the unrolled
+      // multi-variant version).  P^T goes to TMEM as 16-bit in phase 1 (its final place, already masked) and is
+      // read back in phase 2, so nothing has to live in registers across the dP^T wait.
+      // attended rows of key j inside block [c0, c0+16): bit e of the mask
+      auto block_mask = [&](int c0, bool& any) -> uint32_t {
         int i_lo, i_up;
         if (a.q_swap) {
           i_lo = q0 + (c0 >> sh_g);
@@ -1368,91 +1362,86 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
           i_lo = q0;
           i_up = q0 + a.P - 1;
         }
-        any_b[jj] = (jw_lo <= i_up) && ((jw_lo < a.S) || (a.W > 0 && jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
-        if (any_b[jj]) {
+        // warp-uniform: does any key of this warp see any row of the block?
+        any = (jw_lo <= i_up) && ((jw_lo < a.S) || (a.W > 0 && jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
+        if (!any) return 0u;
+        if (!a.q_swap && a.P >= 16) {       // 16 consecutive positions: one run [lo, hi]
+          const int lo = max(j - i_lo, 0), hi = min(i_hi - i_lo, 15);
+          return (hi >= lo) ? ((0xffffu >> (15 - hi)) & (0xffffu << lo)) : 0u;
+        }
+        uint32_t m = 0;
+#pragma unroll 1
+        for (int e = 0; e < 16; ++e) {
+          const int rr = c0 + e;
+          const int i = q0 + (a.q_swap ? (rr >> sh_g) : (rr & (a.P - 1)));
+          m |= ((i >= j) && (i <= i_hi)) ? (1u << e) : 0u;
+        }
+        return m;
+      };
+      mbar_wait(s_full + (c & 1), (c >> 1) & 1);
+      tc_fence_after();
+      if (tid == 0) tev(4, mtc, 2, c);
+      // ---- phase 1: P^T = mask * exp2(S^T * c - lse[row]) -> 16-bit at S^T columns part*32 + [0,16)
+#pragma unroll 1
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c0 = part * 32 + jj * 16;
+        bool any;
+        const uint32_t mask = block_mask(c0, any);
+        uint32_t pp[8];
+        if (any) {
+          uint32_t sv[16];
+          tmem_ld16(ts + c0, sv);
+          tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
             const float4 l4 = *reinterpret_cast<const float4*>(rl + c0 + e);
-            pv[jj][e] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e]), a.sl2, l4.x)));
-            pv[jj][e + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e + 1]), a.sl2, l4.y)));
-            pv[jj][e + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e + 2]), a.sl2, l4.z)));
-            pv[jj][e + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(pv[jj][e + 3]), a.sl2, l4.w)));
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, l4.x));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, l4.y));
+            float p2 = fast_exp2(fmaf(__uint_as_float(sv[e + 2]), a.sl2, l4.z));
+            float p3 = fast_exp2(fmaf(__uint_as_float(sv[e + 3]), a.sl2, l4.w));
+            p0 = (mask & (1u << e)) ? p0 : 0.f;
+            p1 = (mask & (2u << e)) ? p1 : 0.f;
+            p2 = (mask & (4u << e)) ? p2 : 0.f;
+            p3 = (mask & (8u << e)) ? p3 : 0.f;
+            pp[e >> 1] = pack16_fast<T>(p0, p1);
+            pp[(e >> 1) + 1] = pack16_fast<T>(p2, p3);
           }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pp[e] = 0u;
         }
+        tmem_st8(ts + part * 32 + jj * 8, pp);
       }
-      // ---- phase 2: mask, dS^T = P^T * (dP^T - delta[row]); both packed into this part's consumed S^T columns
+      tmem_st_wait();
+      // ---- phase 2: dS^T = P^T * (dP^T - delta[row]) -> 16-bit at S^T columns part*32 + [16,32)
       if (tid == 0) tev(4, mtc, 6, c);
       mbar_wait(dp_full, c & 1);
       tc_fence_after();
       if (tid == 0) tev(4, mtc, 4, c);
-      uint32_t dvv[2][16];
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) tmem_ld16(tl + C::kColP + part * 32 + jj * 16, dvv[jj]);
-      tmem_ld_wait();
-#pragma unroll
+#pragma unroll 1
       for (int jj = 0; jj < 2; ++jj) {
         const int c0 = part * 32 + jj * 16;
-        uint32_t pp[8], pd[8];
-        uint32_t (&dv)[16] = dvv[jj];
-        if (any_b[jj]) {
-          // position of chunk row r: i = q0 + (r & (P-1))  or  q0 + (r >> log2 G)
-          const int r_lo = a.q_swap ? (c0 >> sh_g) : (c0 & (a.P - 1));
-          const int r_up = a.q_swap ? ((c0 + 15) >> sh_g) : ((a.P >= 16) ? r_lo + 15 : a.P - 1);
-          const bool full = (q0 + (a.q_swap || a.P >= 16 ? r_lo : 0) >= j) && (q0 + r_up <= i_hi);
-          if (__all_sync(0xffffffffu, full)) {
+        bool any;
+        (void)block_mask(c0, any);
+        uint32_t pd[8];
+        if (any) {
+          uint32_t pq[8], dv[16];
+          tmem_ld8(ts + part * 32 + jj * 8, pq);
+          tmem_ld16(tl + C::kColP + c0, dv);
+          tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 d4 = *reinterpret_cast<const float4*>(rd + c0 + e);
-              const float p0 = __uint_as_float(pv[jj][e]), p1 = __uint_as_float(pv[jj][e + 1]);
-              const float p2 = __uint_as_float(pv[jj][e + 2]), p3 = __uint_as_float(pv[jj][e + 3]);
-              pp[e >> 1] = pack16<T>(p0, p1);
-              pp[(e >> 1) + 1] = pack16<T>(p2, p3);
-              pd[e >> 1] = pack16<T>(p0 * (__uint_as_float(dv[e]) - d4.x), p1 * (__uint_as_float(dv[e + 1]) - d4.y));
-              pd[(e >> 1) + 1] = pack16<T>(p2 * (__uint_as_float(dv[e + 2]) - d4.z), p3 * (__uint_as_float(dv[e + 3]) - d4.w));
-            }
-          } else if (!a.q_swap && a.P >= 16) {
-            // head-major rows: the 16 rows of the block are 16 consecutive positions i_lo + e, so the attended
-            // elements of key j form one run [lo, hi] -> a 16-bit mask, one predicate per element
-            const int lo = max(j - (q0 + r_lo), 0), hi = min(i_hi - (q0 + r_lo), 15);
-            const uint32_t mask = (hi >= lo) ? ((0xffffu >> (15 - hi)) & (0xffffu << lo)) : 0u;
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 d4 = *reinterpret_cast<const float4*>(rd + c0 + e);
-              const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-              float pe[4], de[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                pe[u] = (mask & (1u << (e + u))) ? __uint_as_float(pv[jj][e + u]) : 0.f;   // dP, delta are finite: P = 0 => dS = 0
-                de[u] = pe[u] * (__uint_as_float(dv[e + u]) - dl[u]);
-              }
-              pp[e >> 1] = pack16_fast<T>(pe[0], pe[1]);
-              pp[(e >> 1) + 1] = pack16_fast<T>(pe[2], pe[3]);
-              pd[e >> 1] = pack16_fast<T>(de[0], de[1]);
-              pd[(e >> 1) + 1] = pack16_fast<T>(de[2], de[3]);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const int r0 = c0 + e, r1 = r0 + 1;
-              const int i0 = q0 + (a.q_swap ? (r0 >> sh_g) : (r0 & (a.P - 1)));
-              const int i1 = q0 + (a.q_swap ? (r1 >> sh_g) : (r1 & (a.P - 1)));
-              const float2 dl = *reinterpret_cast<const float2*>(rd + r0);
-              const bool ok0 = (i0 >= j) && (i0 <= i_hi);
-              const bool ok1 = (i1 >= j) && (i1 <= i_hi);
-              const float p0 = ok0 ? __uint_as_float(pv[jj][e]) : 0.f;
-              const float p1 = ok1 ? __uint_as_float(pv[jj][e + 1]) : 0.f;
-              const float d0 = ok0 ? p0 * (__uint_as_float(dv[e]) - dl.x) : 0.f;
-              const float d1 = ok1 ? p1 * (__uint_as_float(dv[e + 1]) - dl.y) : 0.f;
-              pp[e >> 1] = pack16_fast<T>(p0, p1);
-              pd[e >> 1] = pack16_fast<T>(d0, d1);
-            }
+          for (int e = 0; e < 16; e += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(rd + c0 + e);
+            float p0, p1, p2, p3;
+            unpack16<T>(pq[e >> 1], p0, p1);
+            unpack16<T>(pq[(e >> 1) + 1], p2, p3);
+            pd[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[e]) - d4.x), p1 * (__uint_as_float(dv[e + 1]) - d4.y));
+            pd[(e >> 1) + 1] = pack16_fast<T>(p2 * (__uint_as_float(dv[e + 2]) - d4.z), p3 * (__uint_as_float(dv[e + 3]) - d4.w));
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) pp[e] = pd[e] = 0u;
+          for (int e = 0; e < 8; ++e) pd[e] = 0u;
         }
-        __syncwarp();
-        tmem_st8(ts + part * 32 + jj * 8, pp);
         tmem_st8(ts + part * 32 + 16 + jj * 8, pd);
       }
       tmem_st_wait();
