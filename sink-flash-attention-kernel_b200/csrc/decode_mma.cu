@@ -9,6 +9,8 @@
 // two segments (sink buffer + ring window buffer, cache.py:185-216): softmax is order-invariant so
 // the ring is read in place.  Partials (m, l, o) go to a workspace when splits > 1 and a small
 // combine kernel folds in s_aux as the reference's virtual split (decode_kernel.py:205-224).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sfa {
@@ -59,15 +61,24 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi
 }
 
 template <int D> struct DecodeCfg {
-  static constexpr int kStages = (D <= 64) ? 6 : (D <= 128 ? 3 : 2);
+  // keys per pipeline block: at D = 64 a 16-key block is only 4 KB of K+V and the per-block fixed work (softmax
+  // update, shuffles, loop, cp.async wait) dominated (66 % of HBM peak vs 81 % at D = 128), so D = 64 uses 32 keys
+  static constexpr int kKB = (D <= 64) ? 32 : 16;
+  static constexpr int kStages = 3 - (D > 128 ? 1 : 0);     // x 4 warps x 2 x kBlkBytes: 96 KB -> 2 CTAs per SM
   static constexpr int kRowBytes = D * 2;
-  static constexpr int kBlkBytes = 16 * kRowBytes;            // one 16-key block of K (or V)
+  static constexpr int kBlkBytes = kKB * kRowBytes;           // one block of K (or V)
   static constexpr int kWarpBytes = kStages * 2 * kBlkBytes;  // K+V ring of one warp
   static constexpr int kQBytes = 16 * kRowBytes;
   static constexpr int kMergeBytes = 4 * 16 * D * 4 + 4 * 16 * 2 * 4;
   static constexpr int kPipeBytes = 4 * kWarpBytes + kQBytes;
   static constexpr int kSmem = kPipeBytes > kMergeBytes ? kPipeBytes : kMergeBytes;
 };
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // byte offset of 16-B chunk `c` of row `r` in a [16][D] 16-bit tile, XOR-swizzled for ldmatrix
 template <int D> __device__ __forceinline__ int tile_off(int r, int c) { return r * (D * 2) + ((c ^ (r & 7)) << 4); }
@@ -114,16 +125,17 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
   }
   const int len0 = p.len[0];
 
-  // blocks of 16 keys; warp w owns blocks w, w+4, ... of this split
-  const int nblk_total = (k_end - k_begin + 15) / 16;
+  // blocks of kKB keys; warp w owns blocks w, w+4, ... of this split
+  constexpr int KB = C::kKB;
+  const int nblk_total = (k_end - k_begin + KB - 1) / KB;
   const int nblk = (nblk_total > warp) ? (nblk_total - warp + 3) / 4 : 0;
 
   auto load_block = [&](int it) {
-    const int key0 = k_begin + (warp + 4 * it) * 16;
+    const int key0 = k_begin + (warp + 4 * it) * KB;
     unsigned char* ks_ = ring + (it % C::kStages) * 2 * C::kBlkBytes;
     unsigned char* vs_ = ks_ + C::kBlkBytes;
 #pragma unroll
-    for (int c = lane; c < 16 * (D / 8); c += 32) {
+    for (int c = lane; c < KB * (D / 8); c += 32) {
       const int r = c / (D / 8), ch = c % (D / 8);
       const int key = key0 + r;
       const bool valid = key < k_end;
@@ -155,24 +167,27 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
     __syncwarp();
     const unsigned char* ks_ = ring + (it % C::kStages) * 2 * C::kBlkBytes;
     const unsigned char* vs_ = ks_ + C::kBlkBytes;
-    const int key0 = k_begin + (warp + 4 * it) * 16;
+    const int key0 = k_begin + (warp + 4 * it) * KB;
 
-    // S[16 heads x 16 keys] = Q K^T
-    float sc[2][4];
+    // S[16 heads x KB keys] = Q K^T   (KB/8 n-tiles of 8 keys)
+    float sc[KB / 8][4];
 #pragma unroll
-    for (int n = 0; n < 2; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+    for (int n = 0; n < KB / 8; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < D / 16; ++ks) {
-      uint32_t bf[4];
-      const int mat = lane >> 3, r = (lane & 7) + 8 * (mat >> 1), ch = ks * 2 + (mat & 1);
-      ldsm_x4(bf, ks_ + tile_off<D>(r, ch));
-      mma16816<T>(sc[0], qf[ks], bf[0], bf[1]);
-      mma16816<T>(sc[1], qf[ks], bf[2], bf[3]);
+#pragma unroll
+      for (int kb16 = 0; kb16 < KB / 16; ++kb16) {
+        uint32_t bf[4];
+        const int mat = lane >> 3, r = kb16 * 16 + (lane & 7) + 8 * (mat >> 1), ch = ks * 2 + (mat & 1);
+        ldsm_x4(bf, ks_ + tile_off<D>(r, ch));
+        mma16816<T>(sc[kb16 * 2], qf[ks], bf[0], bf[1]);
+        mma16816<T>(sc[kb16 * 2 + 1], qf[ks], bf[2], bf[3]);
+      }
     }
     // mask keys past the split end, move to log2 units
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int n = 0; n < 2; ++n)
+    for (int n = 0; n < KB / 8; ++n)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = key0 + n * 8 + 2 * (lane & 3) + (e & 1);
@@ -181,44 +196,54 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
         mx[e >> 1] = fmaxf(mx[e >> 1], s2);
       }
     float alpha[2];
+    bool moved = false;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_row[r], mx[r]);     // finite: every block holds >= 1 valid key
-      alpha[r] = exp2f(m_row[r] - m_new);
+      moved |= (m_new != m_row[r]);
+      alpha[r] = ex2_fast(m_row[r] - m_new);
       m_row[r] = m_new;
       l_row[r] *= alpha[r];
     }
-    uint32_t pf[4];
-    {
+    const bool rescale = __any_sync(0xffffffffu, moved);    // the running max rarely moves after the first blocks
+    uint32_t pf[KB / 16][4];
+#pragma unroll
+    for (int kb16 = 0; kb16 < KB / 16; ++kb16) {
       float pv[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          pv[n][e] = exp2f(sc[n][e] - m_row[e >> 1]);
+          pv[n][e] = ex2_fast(sc[kb16 * 2 + n][e] - m_row[e >> 1]);
           l_row[e >> 1] += pv[n][e];
         }
-      pf[0] = pack2<T>(pv[0][0], pv[0][1]);
-      pf[1] = pack2<T>(pv[0][2], pv[0][3]);
-      pf[2] = pack2<T>(pv[1][0], pv[1][1]);
-      pf[3] = pack2<T>(pv[1][2], pv[1][3]);
+      pf[kb16][0] = pack2<T>(pv[0][0], pv[0][1]);
+      pf[kb16][1] = pack2<T>(pv[0][2], pv[0][3]);
+      pf[kb16][2] = pack2<T>(pv[1][0], pv[1][1]);
+      pf[kb16][3] = pack2<T>(pv[1][2], pv[1][3]);
     }
     // O[16 x D] = O*alpha + P V
 #pragma unroll
     for (int n2 = 0; n2 < D / 16; ++n2) {
-      uint32_t vf[4];
-      const int mat = lane >> 3, r = (lane & 7) + 8 * (mat & 1), ch = n2 * 2 + (mat >> 1);
-      ldsm_x4_t(vf, vs_ + tile_off<D>(r, ch));
+      if (rescale) {
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        float(&acc)[4] = o[n2 * 2 + hlf];
-        acc[0] *= alpha[0];
-        acc[1] *= alpha[0];
-        acc[2] *= alpha[1];
-        acc[3] *= alpha[1];
-        mma16816<T>(acc, pf, vf[hlf * 2], vf[hlf * 2 + 1]);
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          float(&acc)[4] = o[n2 * 2 + hlf];
+          acc[0] *= alpha[0];
+          acc[1] *= alpha[0];
+          acc[2] *= alpha[1];
+          acc[3] *= alpha[1];
+        }
+      }
+#pragma unroll
+      for (int kb16 = 0; kb16 < KB / 16; ++kb16) {
+        uint32_t vf[4];
+        const int mat = lane >> 3, r = kb16 * 16 + (lane & 7) + 8 * (mat & 1), ch = n2 * 2 + (mat >> 1);
+        ldsm_x4_t(vf, vs_ + tile_off<D>(r, ch));
+        mma16816<T>(o[n2 * 2], pf[kb16], vf[0], vf[1]);
+        mma16816<T>(o[n2 * 2 + 1], pf[kb16], vf[2], vf[3]);
       }
     }
     __syncwarp();
@@ -347,15 +372,32 @@ bool mma_decode_supported(const DecodeParams& p, int dtype) {
   return true;
 }
 
-// Enough CTAs for >= ~3 waves of 148 SMs x 2 resident CTAs, but at least 256 keys per split.
+// Split count.  The kernel runs 2 CTAs per SM; B*Hkv*splits CTAs execute in ceil(ctas / 296) rounds and a partly
+// filled last round wastes bandwidth, but every extra split costs a pipeline fill plus partial (m, l, o) traffic
+// and any split > 1 costs the combine launch.  Measured at BASELINE configs[3] (B*Hkv = 512, 4100 keys, D = 64):
+// splits 1 / 2 / 3 / 4 / 6 / 8 -> 112.6 / 118.8 / 120.8 / 118.8 / 127.0 / 133.1 us.  The cost model below
+// (round efficiency x 4 % per extra split + 6 % for the second kernel) reproduces that ordering and still
+// splits small batches enough to fill the machine.
 int mma_decode_splits(int B, int Hkv, int total_len) {
-  const int base = B * Hkv;
-  int splits = (148 * 6 + base - 1) / base;
-  const int max_by_len = (total_len + 255) / 256;
-  if (splits > max_by_len) splits = max_by_len;
-  if (splits < 1) splits = 1;
-  if (splits > 64) splits = 64;
-  return splits;
+  static const int forced = getenv("SFA_DECODE_SPLITS") ? atoi(getenv("SFA_DECODE_SPLITS")) : 0;   // experiments only
+  if (forced > 0) return forced;
+  const long long base = (long long)B * Hkv;
+  int max_s = (total_len + 255) / 256;
+  if (max_s > 64) max_s = 64;
+  if (max_s < 1) max_s = 1;
+  const double slots = 148.0 * 2.0;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= max_s; ++s) {
+    const double rounds = (double)(base * s) / slots;
+    const double eff = rounds / (double)(long long)(rounds + 0.999999);     // filled fraction of the rounds
+    const double cost = (1.0 / eff) * (1.0 + 0.04 * (s - 1)) + (s > 1 ? 0.06 : 0.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
 }
 
 cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st) {
