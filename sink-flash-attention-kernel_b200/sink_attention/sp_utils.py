@@ -87,6 +87,54 @@ class _HeadToSeq(torch.autograd.Function):
         return _a2a_seq_to_head(g.contiguous(), ctx.group), None
 
 
+class _QKVSeqToHead(torch.autograd.Function):
+    """q, k, v in ONE all-to-all each way: ``[B, n, H, D]`` chunks -> ``[B, n*P, H/P, D]`` views of one receive
+    buffer (heads of this rank: its q heads, then its k heads, then its v heads).  The views have a position
+    stride of (hq_l + 2*hkv_l)*D -- the kernels take arbitrary (batch, head, position) strides, so nothing is
+    copied after the exchange.  Backward packs dq/dk/dv the same way and sends them home in one all-to-all."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, group):
+        P, _ = _group_size_rank(group)
+        B, n, Hq, D = q.shape
+        Hkv = k.shape[2]
+        hq_l, hkv_l = Hq // P, Hkv // P
+        tot = hq_l + 2 * hkv_l
+        send = torch.empty(P, B, n, tot, D, device=q.device, dtype=q.dtype)
+        send[:, :, :, :hq_l].copy_(q.reshape(B, n, P, hq_l, D).permute(2, 0, 1, 3, 4))
+        send[:, :, :, hq_l:hq_l + hkv_l].copy_(k.reshape(B, n, P, hkv_l, D).permute(2, 0, 1, 3, 4))
+        send[:, :, :, hq_l + hkv_l:].copy_(v.reshape(B, n, P, hkv_l, D).permute(2, 0, 1, 3, 4))
+        recv = torch.empty_like(send)                       # recv[s] = sequence chunk s, this rank's heads
+        dist.all_to_all_single(recv, send, group=group)
+        full = recv.view(1, P * n, tot, D) if B == 1 else recv.permute(1, 0, 2, 3, 4).reshape(B, P * n, tot, D)
+        ctx.group, ctx.dims = group, (P, B, n, Hq, Hkv, D)
+        return full[:, :, :hq_l], full[:, :, hq_l:hq_l + hkv_l], full[:, :, hq_l + hkv_l:]
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        P, B, n, Hq, Hkv, D = ctx.dims
+        hq_l, hkv_l = Hq // P, Hkv // P
+        tot = hq_l + 2 * hkv_l
+        send = torch.empty(P, B, n, tot, D, device=dq.device, dtype=dq.dtype)     # send[s] = chunk s, my heads
+        send[:, :, :, :hq_l].copy_(dq.reshape(B, P, n, hq_l, D).permute(1, 0, 2, 3, 4))
+        send[:, :, :, hq_l:hq_l + hkv_l].copy_(dk.reshape(B, P, n, hkv_l, D).permute(1, 0, 2, 3, 4))
+        send[:, :, :, hq_l + hkv_l:].copy_(dv.reshape(B, P, n, hkv_l, D).permute(1, 0, 2, 3, 4))
+        recv = torch.empty_like(send)                                             # recv[r] = heads of rank r
+        dist.all_to_all_single(recv, send, group=ctx.group)
+        gq = recv[:, :, :, :hq_l].permute(1, 2, 0, 3, 4).reshape(B, n, Hq, D)
+        gk = recv[:, :, :, hq_l:hq_l + hkv_l].permute(1, 2, 0, 3, 4).reshape(B, n, Hkv, D)
+        gv = recv[:, :, :, hq_l + hkv_l:].permute(1, 2, 0, 3, 4).reshape(B, n, Hkv, D)
+        return gq, gk, gv, None
+
+
+def ulysses_qkv_seq_to_head(q, k, v, group=None):
+    """Differentiable fused exchange of q, k and v (one NCCL all-to-all each direction)."""
+    P, _ = _group_size_rank(group)
+    if P == 1:
+        return q, k, v
+    return _QKVSeqToHead.apply(q, k, v, group)
+
+
 def ulysses_seq_to_head(x: torch.Tensor, group=None) -> torch.Tensor:
     """Differentiable all-to-all ``[B, N/P, H, D] -> [B, N, H/P, D]`` (HF layout)."""
     return _SeqToHead.apply(x, group)
@@ -131,9 +179,7 @@ class UlyssesSinkAttention(torch.nn.Module):
         while hkv_l % nchunk:
             nchunk -= 1
         if nchunk == 1:
-            qh = ulysses_seq_to_head(q, self.sp_group)
-            kh = ulysses_seq_to_head(k, self.sp_group)
-            vh = ulysses_seq_to_head(v, self.sp_group)
+            qh, kh, vh = ulysses_qkv_seq_to_head(q, k, v, self.sp_group)
             oh = sink_flash_attention(qh.transpose(1, 2), kh.transpose(1, 2), vh.transpose(1, 2),
                                       self.num_sink, self.window_size, s_loc).transpose(1, 2)
             return ulysses_head_to_seq(oh, self.sp_group)
