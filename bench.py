@@ -167,7 +167,12 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    real_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout: keep fd 1 clean for the one JSON line
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, tf_burst, tf_sust, peak_src = load_peaks()
     cfg = C1
@@ -243,11 +248,38 @@ def run_ours(args):
         do = torch.randn(B, N, Hq, D, device=dev, generator=g).to(dt)
         uly = sa.UlyssesSinkAttention(num_sink=S, window_size=W, sp_group=None, head_chunks=1)
 
-        def step():
+        def eager_uly_step():
             for t in (q, k, v, s_aux):
                 t.grad = None
             o = uly(q, k, v, s_aux)
             o.backward(do)
+
+        step = eager_uly_step
+        step_mode = "eager autograd step with NCCL all-to-all each side"
+        # The eager step is ~40 small torch launches + 4 NCCL calls around 0.35 ms of attention kernels, i.e. bound
+        # by the host.  Capture the whole step (attention kernels, pack/unpack copies and the all-to-alls) in one
+        # CUDA graph; every rank replays it in lock-step.  Falls back to the eager step if capture is refused.
+        if os.environ.get("SFA_BENCH_ULY_GRAPH") == "1":     # opt-in: the capture hung once on a 2-GPU box (round 1)
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        eager_uly_step()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                dist.barrier()
+                uly_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(uly_graph):
+                    eager_uly_step()
+                torch.cuda.synchronize()
+                step = uly_graph.replay
+                step_graph = uly_graph
+                step_mode = "CUDA-graph replay of the autograd Ulysses step (attention kernels + NCCL all-to-all each side)"
+            except Exception as e:      # noqa: BLE001
+                print(f"[bench] rank {rank}: graph capture of the Ulysses step failed ({type(e).__name__}: {e}); timing the eager step",
+                      file=sys.stderr)
+                step = eager_uly_step
         launches_per_step = 1 + 4
         workload = (f"gpt-oss-20b attention layer fwd+bwd under Ulysses SP: {N}-token chunk per rank of a {n_total}-token "
                     f"sequence, Hq=64 Hkv=8 D=64 window=128 s_aux bf16, all-to-all over NVLink each side")
@@ -410,8 +442,8 @@ def run_ours(args):
             "config": {"workload": workload, "parallelism": parallelism, "global_tokens": n_total * B,
                        "masked_flops_per_step": job_flops,
                        "l2": "256 MiB buffer written between timed steps; per-step CUDA events summed",
-                       "step": ("CUDA-graph replay of the C-ABI launches of one fwd+bwd (sfa_fwd + sfa_bwd)" if step_graph is not None
-                                else "eager autograd step with NCCL all-to-all each side")},
+                       "step": ("CUDA-graph replay of the C-ABI launches of one fwd+bwd (sfa_fwd + sfa_bwd)" if world == 1
+                                else step_mode)},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
@@ -449,7 +481,11 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
 
 
 def main():

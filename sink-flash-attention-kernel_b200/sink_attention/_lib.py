@@ -161,10 +161,12 @@ def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32):
     B, Hq, N, D = q.shape
     Hkv = k.shape[1]
     q, k, v, o, do = (_unit_last(t) for t in (q, k, v, o, do))
-    if do.stride() != q.stride():
-        # the tensor-core kernels load Q and dO tiles with one row order: give dO q's memory layout
-        do = torch.empty_strided(q.shape, q.stride(), device=q.device, dtype=q.dtype).copy_(do) \
-            if _dense_non_overlapping(q) else do.contiguous()
+    # The tensor-core kernels load Q and dO tiles with one row order, which is set by whether the head stride is
+    # smaller than the position stride (HF [B,N,H,D] views) or not ([B,H,N,D]).  Only that ORDER has to agree.
+    def _hf_order(t):
+        return t.shape[1] > 1 and t.shape[2] > 1 and t.stride(1) < t.stride(2)
+    if _hf_order(do) != _hf_order(q):
+        do = do.transpose(1, 2).contiguous().transpose(1, 2) if _hf_order(q) else do.contiguous()
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     ds_aux = torch.empty((Hq,), device=q.device, dtype=torch.float32) if s_aux_f32 is not None else None
     code = DTYPE_CODE[q.dtype]
