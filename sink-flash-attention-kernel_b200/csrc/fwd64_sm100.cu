@@ -5,13 +5,14 @@
 // single-thread role 200-300 cycles, MUFU.EX2 runs at 16/clk/SM, and the old kernel paid ~18 TMEM round trips
 // plus a full prologue per tile.  Here:
 //
-//   warp 12      TMA producer      Q ring (3 tiles), K and V rings (3 items of up to 144 keys each)
-//   warp 13      UMMA issuer S     S(n) = Q K^T -> S buffer n & 1, two items ahead of the softmax
-//   warp 14      UMMA issuer PV    O(tile & 1) += P(n) V(n)   (TS form, P read from the S buffer)
-//   warps 0-7    softmax           two warps per TMEM lane quarter, each owning half of the key columns of its
-//                                  rows: ONE tcgen05.ld round trip per item, S kept in registers for the max
-//                                  and the exp pass, P written as 16-bit over the consumed S columns
-//   warps 8-11   epilogue          O / l -> 16-bit -> swizzled smem -> TMA store, LSE = m ln2 + log l
+//   warp 20      TMA producer      Q ring (3 tiles), K and V rings (3 items of up to 144 keys each)
+//   warp 21      UMMA issuer S     S(n) = Q K^T -> S buffer n & 1, two items ahead of the softmax
+//   warp 22      UMMA issuer PV    O(tile & 1) += P(n) V(n)   (TS form, P read from the S buffer)
+//   warps 0-15   softmax           four warps per TMEM lane quarter, each owning a quarter of the key columns of
+//                                  its rows; two rolled passes (max, exp) with one masked code path -- small loop
+//                                  bodies, the kernels are instruction-cache bound otherwise; P written as 16-bit
+//                                  over the consumed S columns
+//   warps 16-19  epilogue          O / l -> 16-bit -> swizzled smem -> TMA store, LSE = m ln2 + log l
 //
 // Online softmax in exp2 units seeded with (m, l) = (s_aux, 1) (:139-146); O is rescaled lazily (only when a
 // row max moves by more than 2^8), which never happens for single-item tiles such as window 128.
@@ -53,12 +54,22 @@ struct Fwd64Cfg {
   static constexpr uint32_t kColS = 0;               // S buffers at 0 and kBNMax
   static constexpr uint32_t kColO = 2 * kBNMax;      // O accumulators at +0 and +D
   static constexpr int kMaxCh = (kBNMax / 16 + 1) / 2;
-  static constexpr int kThreads = 15 * 32;
-  static constexpr int kStatFloats = 2 * 128 + 2 * 2 * 128 + 2 * 2 * 128;   // row_m[2][128], row_l[2][2][128], xch[2][2][128]
+  static constexpr int kSoftWarps = 12;              // three warps per TMEM lane quarter, each a third of the key columns (144 = 3 x 48)
+  static constexpr int kParts = kSoftWarps / 4;
+  static constexpr int kThreads = (kSoftWarps + 4 + 3) * 32;
+  static constexpr int kStatFloats = 2 * 128 + 2 * kParts * 128 + 2 * kParts * 128 + 64;   // row_m, row_l, xch, s_aux (<= 64 heads cached)
   static constexpr int kSmem = 1024 + (kQStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + kStatFloats * 4 + 512;
   static_assert(2 * kBNMax + 2 * D <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
+
+// chunk ranges of the column parts: nch 16-column chunks split as evenly as possible
+__device__ __forceinline__ void part_starts(int nch, int (&cs)[Fwd64Cfg::kParts + 1]) {
+  const int base = nch / Fwd64Cfg::kParts, rem = nch % Fwd64Cfg::kParts;
+  cs[0] = 0;
+#pragma unroll
+  for (int p = 0; p < Fwd64Cfg::kParts; ++p) cs[p + 1] = cs[p] + base + (p < rem ? 1 : 0);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -75,9 +86,9 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   unsigned char* k_s = stage_s + C::kQBytes;                   // [kKStages][kKVBytes]
   unsigned char* v_s = k_s + C::kKStages * C::kKVBytes;        // [kVStages][kKVBytes]
   float* row_m = reinterpret_cast<float*>(v_s + C::kVStages * C::kKVBytes);   // [2][128]     final running max (log2 units) per tile parity
-  float* row_l = row_m + 2 * 128;                                             // [2][2][128]  partial row sums of the two column halves
-  float* xch = row_l + 2 * 2 * 128;                                           // [2][2][128]  per-item row-max exchange between the halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 128);
+  float* row_l = row_m + 2 * 128;                                             // [2][kParts][128]  partial row sums of the column parts
+  float* xch = row_l + 2 * C::kParts * 128;                                   // [2][kParts][128]  per-item row-max exchange between the parts
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * C::kParts * 128 + 64);
   uint64_t* q_full = bars;
   uint64_t* q_empty = q_full + C::kQStages;
   uint64_t* k_full = q_empty + C::kQStages;
@@ -93,7 +104,8 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 12 && lane == 0) {
+  constexpr int kWEpi = C::kSoftWarps, kWProd = kWEpi + 4, kWIssS = kWProd + 1, kWIssPV = kWProd + 2;
+  if (warp == kWProd && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -103,20 +115,20 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     for (int s = 0; s < C::kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full + s, 1);
-      mbar_init(p_full + s, 256);
+      mbar_init(p_full + s, C::kSoftWarps * 32);
       mbar_init(sbuf_free + s, 1);
       mbar_init(o_done + s, 1);
       mbar_init(o_free + s, 128);
     }
     fence_barrier_init();
   }
-  if (warp == 13) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == kWIssS) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 12) {
+  if (warp == kWProd) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       Walk w(a);
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       }
     }
     __syncwarp();
-  } else if (warp == 13) {
+  } else if (warp == kWIssS) {
     // ------------------------------------------------------------------ UMMA issuer S
     if (lane == 0) {
       Walk w(a);
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       }
     }
     __syncwarp();
-  } else if (warp == 14) {
+  } else if (warp == kWIssPV) {
     // ------------------------------------------------------------------ UMMA issuer PV
     if (lane == 0) {
       const uint32_t idesc_pv = make_idesc(a.fmt, 128, D, 0, 1);
@@ -182,8 +194,9 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         const uint64_t vd = make_sdesc(smem_u32(v_s + vst * C::kKVBytes), C::kKVBytes, 1024);
         const uint32_t ts = tmem + C::kColS + sb * C::kBNMax;
         const int nk = cols >> 4;
-        const int hcol = ((nk + 1) / 2) * 16;
-        const uint32_t a_lo = ts, a_hi = ts + hcol - (hcol >> 1);     // P: first column half packed at +0, second at +hcol
+        // P of column part p (chunks [cs_p, cs_{p+1})) is packed from S column 16*cs_p on: 8 columns per chunk
+        int cs[C::kParts + 1];
+        part_starts(nk, cs);
         mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
         mbar_wait(p_full + sb, (w.n >> 1) & 1);
         if (w.t == 0 && w.it >= 2) mbar_wait(o_free + tb, ((w.it - 2) >> 1) & 1);
@@ -191,9 +204,13 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         tev(a.trace, 3, tc, 2, w.n);
 #pragma unroll
         for (int kk = 0; kk < C::kBNMax / 16; ++kk)
-          if (kk < nk)
-            umma_ts(tmem + C::kColO + tb * D, ((kk * 16 < hcol) ? a_lo : a_hi) + kk * 8, vd + kk * (2048 >> 4), idesc_pv,
+          if (kk < nk) {
+            int pstart = 0;
+#pragma unroll
+            for (int pp = 1; pp < C::kParts; ++pp) pstart = (kk >= cs[pp]) ? cs[pp] : pstart;
+            umma_ts(tmem + C::kColO + tb * D, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv,
                     (w.t > 0 || kk > 0));
+          }
         umma_commit(sbuf_free + sb);
         umma_commit(v_empty + vst);
         if (w.last_of_tile()) umma_commit(o_done + tb);
@@ -201,9 +218,12 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------ softmax: row == TMEM lane, half of the columns
-    const int quarter = warp & 3, half = warp >> 2;
+  } else if (warp < C::kSoftWarps) {
+    // ------------------------------------------------------------------ softmax: row == TMEM lane, one part of the columns
+    const int quarter = warp & 3, part = warp >> 2;
+    float* saux_s = xch + 2 * C::kParts * 128;          // s_aux * log2e of the first 64 heads (a global load per tile cost ~400 cycles)
+    if (a.s_aux != nullptr && threadIdx.x < 64 && threadIdx.x < a.Hq) saux_s[threadIdx.x] = a.s_aux[threadIdx.x] * kLog2e;
+    named_bar_sync(7, C::kSoftWarps * 32);
     const int r = quarter * 32 + lane;
     const int pr = a.q_swap ? (r / a.G) : (r % a.P);
     const int gr = a.q_swap ? (r % a.G) : (r / a.P);
@@ -217,8 +237,8 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       if (w.t == 0) {
         i = w.q0 + pr;
         const int h = w.y * a.G + gr;
-        m_used = a.s_aux ? __ldg(a.s_aux + h) * kLog2e : -INFINITY;
-        l = (a.s_aux && half == 0) ? 1.f : 0.f;
+        m_used = a.s_aux ? (h < 64 ? saux_s[h] : __ldg(a.s_aux + h) * kLog2e) : -INFINITY;
+        l = (a.s_aux && part == 0) ? 1.f : 0.f;
       }
       const uint32_t ts = tl + C::kColS + sb * C::kBNMax;
       int kstart, cols; bool is_sink;
@@ -227,13 +247,20 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
       if (i >= a.N) c_hi = -1;
       const int nch = cols >> 4;
-      const int hch = (nch + 1) / 2;
-      const int hcol = hch * 16;
-      const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
+      const int pbase = nch / C::kParts, prem = nch % C::kParts;       // same split as part_starts()
+      const int ch0 = part * pbase + min(part, prem), ch1 = ch0 + pbase + (part < prem ? 1 : 0);
 
       mbar_wait(s_full + sb, (w.n >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 2, w.n);
+      auto wtrace = [&](int code) {
+        if (SFA_TRACE && a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (w.n == 14 || w.n == 15)) {
+          const int slot = 5 * 256 + warp * 8 + (w.n - 14) * 4 + code;
+          a.trace[slot * 2] = (static_cast<long long>(code + 1) << 32) | static_cast<unsigned>(w.n * 100 + warp);
+          a.trace[slot * 2 + 1] = clock64();
+        }
+      };
+      wtrace(0);
       // Two rolled passes over this half's 16-column chunks (max, then exp), one code path with the mask always on.
       // ncu showed the unrolled three-variant version starved for instructions (stall_no_inst 50-80 % of the
       // samples in the max / exp code): the hot loops must stay resident in the instruction cache that the
@@ -247,19 +274,27 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         tmem_ld16(ts + cb * 16, sv);
         tmem_ld_wait();
         const int lo = c_lo - cb * 16, hi = c_hi - cb * 16;
+        if (__all_sync(0xffffffffu, lo <= 0 && hi >= 15)) {      // interior chunk: no mask (most chunks of a band)
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          mxa[e & 3] = fmaxf(mxa[e & 3], (e >= lo && e <= hi) ? __uint_as_float(sv[e]) : -INFINITY);
+          for (int e = 0; e < 16; ++e) mxa[e & 3] = fmaxf(mxa[e & 3], __uint_as_float(sv[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            mxa[e & 3] = fmaxf(mxa[e & 3], (e >= lo && e <= hi) ? __uint_as_float(sv[e]) : -INFINITY);
+        }
       }
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 5, w.n);
+      wtrace(1);
       float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-      // ---- the two halves of a row agree on its max through shared memory
-      float* xb = xch + (w.n & 1) * 256;
-      xb[half * 128 + r] = mx;
+      // ---- the parts of a row agree on its max through shared memory
+      float* xb = xch + (w.n & 1) * (C::kParts * 128);
+      xb[part * 128 + r] = mx;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 6, w.n);
-      named_bar_sync(1 + quarter, 64);
-      mx = fmaxf(mx, xb[(half ^ 1) * 128 + r]);
+      named_bar_sync(1 + quarter, C::kParts * 32);
+#pragma unroll
+      for (int pp = 0; pp < C::kParts; ++pp) mx = fmaxf(mx, xb[pp * 128 + r]);
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 4, w.n);
+      wtrace(2);
       const float m_new = fmaxf(m_used, mx * a.sl2);
       const bool need = (m_new - m_used) > 8.0f;        // also -inf -> finite; false for NaN (-inf - -inf)
       if (__any_sync(0xffffffffu, need)) {
@@ -272,15 +307,17 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
           // lazy rescale of this half's O columns: PV(n-1) must have completed
           mbar_wait(sbuf_free + ((w.n - 1) & 1), ((w.n - 1) >> 1) & 1);
           tc_fence_after();
+          if (part < 2) {        // warp-uniform: parts 0 and 1 rescale 32 of the 64 O columns each
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t v[16];
+              const uint32_t oa = tl + C::kColO + tb * D + part * 32 + cc * 16;
+              tmem_ld16(oa, v);
+              tmem_ld_wait();
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            uint32_t v[16];
-            const uint32_t oa = tl + C::kColO + tb * D + half * 32 + cc * 16;
-            tmem_ld16(oa, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-            tmem_st16(oa, v);
+              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+              tmem_st16(oa, v);
+            }
           }
         }
       }
@@ -294,16 +331,26 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         tmem_ld16(ts + c0, sv);
         tmem_ld_wait();
         const int lo = c_lo - c0, hi = c_hi - c0;
+        if (__all_sync(0xffffffffu, lo <= 0 && hi >= 15)) {      // interior chunk: no mask
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_m));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_m));
-          p0 = (e >= lo && e <= hi) ? p0 : 0.f;
-          p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
-          lsum += p0 + p1;
-          pk[e >> 1] = pack16_fast<T>(p0, p1);
+          for (int e = 0; e < 16; e += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_m));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_m));
+            lsum += p0 + p1;
+            pk[e >> 1] = pack16_fast<T>(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_m));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_m));
+            p0 = (e >= lo && e <= hi) ? p0 : 0.f;
+            p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
+            lsum += p0 + p1;
+            pk[e >> 1] = pack16_fast<T>(p0, p1);
+          }
         }
-        tmem_st8(half ? (ts + hcol + ((c0 - hcol) >> 1)) : (ts + (c0 >> 1)), pk);
+        tmem_st8(ts + ch0 * 16 + ((c0 - ch0 * 16) >> 1), pk);
       }
       l += lsum;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 7, w.n);
@@ -311,14 +358,15 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       if (w.last_of_tile()) {
         // hand the row statistics to the epilogue warps (ordered by the p_full -> PV -> o_done chain)
         if (w.it >= 2) mbar_wait(o_free + tb, ((w.it - 2) >> 1) & 1);
-        if (half == 0) row_m[tb * 128 + r] = m_used;
-        row_l[(tb * 2 + half) * 128 + r] = l;
+        if (part == 0) row_m[tb * 128 + r] = m_used;
+        row_l[(tb * C::kParts + part) * 128 + r] = l;
       }
       tc_fence_before();
       mbar_arrive(p_full + sb);
+      wtrace(3);
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 3, w.n);
     }
-  } else if (warp < 12) {
+  } else if (warp < kWProd) {
     // ------------------------------------------------------------------ epilogue
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -326,7 +374,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     const int gr = a.q_swap ? (r % a.G) : (r / a.P);
     const int ro = a.o_swap ? (pr * a.G + gr) : (gr * a.P + pr);      // row in O's box order
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int et = threadIdx.x - 256;
+    const int et = threadIdx.x - kWEpi * 32;
     Walk w(a);
     int mtc = 0;
     while (w.next()) {
@@ -339,7 +387,9 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       tc_fence_after();
       if (et == 0) tev(a.trace, 6, mtc, 2, w.n);
       const float m_fin = row_m[tb * 128 + r];
-      const float l_fin = row_l[(tb * 2) * 128 + r] + row_l[(tb * 2 + 1) * 128 + r];
+      float l_fin = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < C::kParts; ++pp) l_fin += row_l[(tb * C::kParts + pp) * 128 + r];
       const float inv = (l_fin > 0.f) ? 1.f / l_fin : 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
@@ -370,7 +420,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) tmem_dealloc(tmem, C::kTmemCols);
+  if (warp == kWIssS) tmem_dealloc(tmem, C::kTmemCols);
 }
 
 int sm_count_fwd() {

@@ -51,6 +51,11 @@ for role in range(8):
         ev.append((clk, role, tag >> 32, tag & 0xffffffff))
 ev.sort()
 t0 = ev[0][0]
+if os.environ.get('TRACE_WARPS'):
+    for clk, role, code, idx in ev:
+        if role == 5:
+            print(f"{clk - t0:8d}  warp {idx % 100:2d} item {idx // 100}  {['S ready', 'pass1 done', 'max exchanged', 'arrived'][code - 1]}")
+    sys.exit(0)
 lo = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 for clk, role, code, idx in ev:
     if lo <= idx < lo + 2 and role == (int(sys.argv[2]) if len(sys.argv) > 2 else role):
