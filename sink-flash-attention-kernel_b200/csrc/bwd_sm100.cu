@@ -753,13 +753,22 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
           tmem_ld16(tl + C::kColP + c0, dv);
           tmem_ld_wait();
           const int lo = c_lo - c0, hi = c_hi - c0;       // attended elements of this chunk: [lo, hi]
+          if (__all_sync(0xffffffffu, lo <= 0 && hi >= 15)) {     // interior chunk of the band: no mask
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float p0, p1;
-            unpack16<T>(pv[e >> 1], p0, p1);
-            p0 = (e >= lo && e <= hi) ? p0 : 0.f;         // dP and delta are finite: P = 0 => dS = 0
-            p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
-            pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[e]) - delta), p1 * (__uint_as_float(dv[e + 1]) - delta));
+            for (int e = 0; e < 16; e += 2) {
+              float p0, p1;
+              unpack16<T>(pv[e >> 1], p0, p1);
+              pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[e]) - delta), p1 * (__uint_as_float(dv[e + 1]) - delta));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              float p0, p1;
+              unpack16<T>(pv[e >> 1], p0, p1);
+              p0 = (e >= lo && e <= hi) ? p0 : 0.f;         // dP and delta are finite: P = 0 => dS = 0
+              p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
+              pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[e]) - delta), p1 * (__uint_as_float(dv[e + 1]) - delta));
+            }
           }
           tmem_st8(ts + C::kBNMax / 2 + (c0 >> 1), pk);
         }
@@ -1392,19 +1401,32 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
           uint32_t sv[16];
           tmem_ld16(ts + c0, sv);
           tmem_ld_wait();
+          if (__all_sync(0xffffffffu, mask == 0xffffu)) {      // block fully inside the band for every key of the warp
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(rl + c0 + e);
-            float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, l4.x));
-            float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, l4.y));
-            float p2 = fast_exp2(fmaf(__uint_as_float(sv[e + 2]), a.sl2, l4.z));
-            float p3 = fast_exp2(fmaf(__uint_as_float(sv[e + 3]), a.sl2, l4.w));
-            p0 = (mask & (1u << e)) ? p0 : 0.f;
-            p1 = (mask & (2u << e)) ? p1 : 0.f;
-            p2 = (mask & (4u << e)) ? p2 : 0.f;
-            p3 = (mask & (8u << e)) ? p3 : 0.f;
-            pp[e >> 1] = pack16_fast<T>(p0, p1);
-            pp[(e >> 1) + 1] = pack16_fast<T>(p2, p3);
+            for (int e = 0; e < 16; e += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(rl + c0 + e);
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, l4.x));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, l4.y));
+              const float p2 = fast_exp2(fmaf(__uint_as_float(sv[e + 2]), a.sl2, l4.z));
+              const float p3 = fast_exp2(fmaf(__uint_as_float(sv[e + 3]), a.sl2, l4.w));
+              pp[e >> 1] = pack16_fast<T>(p0, p1);
+              pp[(e >> 1) + 1] = pack16_fast<T>(p2, p3);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(rl + c0 + e);
+              float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, l4.x));
+              float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, l4.y));
+              float p2 = fast_exp2(fmaf(__uint_as_float(sv[e + 2]), a.sl2, l4.z));
+              float p3 = fast_exp2(fmaf(__uint_as_float(sv[e + 3]), a.sl2, l4.w));
+              p0 = (mask & (1u << e)) ? p0 : 0.f;
+              p1 = (mask & (2u << e)) ? p1 : 0.f;
+              p2 = (mask & (4u << e)) ? p2 : 0.f;
+              p3 = (mask & (8u << e)) ? p3 : 0.f;
+              pp[e >> 1] = pack16_fast<T>(p0, p1);
+              pp[(e >> 1) + 1] = pack16_fast<T>(p2, p3);
+            }
           }
         } else {
 #pragma unroll
