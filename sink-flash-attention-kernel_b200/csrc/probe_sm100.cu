@@ -36,9 +36,10 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
   const uint32_t kColA = 256;  // TMEM columns used for the A operand in mode 2
 
   if (threadIdx.x == 0) {
-    const uint32_t bytes = (mode != 2 ? 128 * K * 2 : 0) + N * K * 2;
+    const uint32_t bytes = (mode == 3 ? 64 * K * 2 : (mode != 2 ? 128 * K * 2 : 0)) + N * K * 2;
     mbar_expect_tx(bars, bytes);
-    if (mode != 2)
+    if (mode == 3) tma_load_4d(a_s, &tmA, bars, 0, 0, 0, 0);
+    else if (mode != 2)
       for (int s = 0; s < K / 64; ++s) tma_load_4d(a_s + s * 16384, &tmA, bars, s * 64, 0, 0, 0);
     const int nslab_b = (mode == 0) ? K / 64 : N / 64;
     for (int s = 0; s < nslab_b; ++s) tma_load_4d(b_s + s * 32768, &tmB, bars, s * 64, 0, 0, 0);
@@ -70,10 +71,15 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
       for (int kk = 0; kk < K / 16; ++kk)
         umma_ss(tmem, make_sdesc(aa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                 make_sdesc(ba + kk * 2048, 32768, 1024), idesc, kk > 0);
-    } else {
+    } else if (mode == 2) {
       const uint32_t idesc = make_idesc(fmt, 128, N, 0, 1);
       for (int kk = 0; kk < K / 16; ++kk)
         umma_ts(tmem, tmem + kColA + kk * 8, make_sdesc(ba + kk * 2048, 32768, 1024), idesc, kk > 0);
+    } else {
+      // mode 3: M = 64, A MN-major (tile stored [K rows][64 M-elements]), B MN-major ([K rows][N], 64-wide slabs)
+      const uint32_t idesc = make_idesc(fmt, 64, N, 1, 1);
+      for (int kk = 0; kk < K / 16; ++kk)
+        umma_ss(tmem, make_sdesc(aa + kk * 2048, 16384, 1024), make_sdesc(ba + kk * 2048, 32768, 1024), idesc, kk > 0);
     }
     umma_commit(bars + 1);
   }
@@ -83,8 +89,14 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     uint32_t v[16];
     tmem_ld16(tl + c0, v);
     tmem_ld_wait();
+    if (mode == 3) {      // M = 64: row r lives in lane (r % 16) + 32 * (r / 16); rows 64..127 of c receive the other lanes
+      const int row = (lane < 16) ? warp * 16 + lane : 64 + warp * 16 + (lane - 16);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) c[static_cast<int64_t>(threadIdx.x) * N + c0 + e] = __uint_as_float(v[e]);
+      for (int e = 0; e < 16; ++e) c[static_cast<int64_t>(row) * N + c0 + e] = __uint_as_float(v[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) c[static_cast<int64_t>(threadIdx.x) * N + c0 + e] = __uint_as_float(v[e]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -408,9 +420,13 @@ cudaError_t probe_umma(const void* a, const void* b, float* c, int N, int K, int
   if (mode == 0 && K % 64) return cudaErrorInvalidValue;
   if (mode != 0 && (N % 64 || N > 256)) return cudaErrorInvalidValue;
   if (mode == 1 && K % 64) return cudaErrorInvalidValue;
+  if (mode == 3 && K > 128) return cudaErrorInvalidValue;
   TileMap ma, mb;
   Strides4 sa{(int64_t)128 * K, (int64_t)128 * K, K};
-  if (!make_tile_map(&ma, a, dtype, K, 128, 1, 1, sa, 128, 1)) return cudaErrorInvalidValue;
+  if (mode == 3) {        // A given as [K][64]
+    Strides4 s3{(int64_t)K * 64, (int64_t)K * 64, 64};
+    if (!make_tile_map(&ma, a, dtype, 64, K, 1, 1, s3, K, 1)) return cudaErrorInvalidValue;
+  } else if (!make_tile_map(&ma, a, dtype, K, 128, 1, 1, sa, 128, 1)) return cudaErrorInvalidValue;
   if (mode == 0) {
     Strides4 sb{(int64_t)N * K, (int64_t)N * K, K};
     if (!make_tile_map(&mb, b, dtype, K, N, 1, 1, sb, N, 1)) return cudaErrorInvalidValue;
