@@ -89,8 +89,8 @@ size_t sfa_workspace_bytes(int op, int B, int Hq, int Hkv, int N, int D, int dty
   (void)dtype;
   if (op == SFA_OP_FWD) return 0;
   if (op == SFA_OP_BWD) {
-    // delta [B,Hq,N] + ds_aux partials [B,Hq,ceil(N/8)]
-    return align_up((size_t)B * Hq * N * 4, 256) + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256);
+    // delta [B,Hq,N] + ds_aux partials [B,Hq,ceil(N/8)] + per-row ds_aux contributions [B,Hq,N]
+    return 2 * align_up((size_t)B * Hq * N * 4, 256) + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256);
   }
   if (op == SFA_OP_DECODE) {
     const int splits = mma_decode_splits(B, Hkv, N);
@@ -157,13 +157,22 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   p.W = window < 0 ? 0 : window;
   p.scale = 1.0f / sqrtf((float)D);
   p.delta = static_cast<float*>(workspace);
-  float* ds_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)B * Hq * N * 4, 256));
+  const size_t rows_bytes = align_up((size_t)B * Hq * N * 4, 256);
+  float* ds_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes);
+  p.dsrow = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g_bwd_stages & 1)
+  const bool use_tc = g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype);
+  // narrow windows (one KV item per tile): the dQ kernel computes delta = rowsum(P o dP) and the ds_aux rows
+  // itself -- no preprocess pass over O and dO
+  const bool fused = use_tc && tc_bwd_fuses_delta(p, dtype);
+  if ((g_bwd_stages & 1) && !fused)
     if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
-  if (g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype)) {
+  if (use_tc) {
     set_impl_name("tcgen05");
-    return cuda_ret(tc_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(tcgen05)");
+    if (int r = cuda_ret(tc_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(tcgen05)")) return r;
+    if (fused && (g_bwd_stages & 2) && p.s_aux && p.ds_aux)
+      return cuda_ret(ds_aux_reduce(p.dsrow, p.ds_aux, B, Hq, N, st), "sfa_bwd(ds_aux reduce)");
+    return 0;
   }
   set_impl_name("simt");
   return cuda_ret(simt_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(simt)");

@@ -43,6 +43,12 @@ struct BwdArgs {
   const float* lse;
   const float* delta;
   long long* trace;   // optional timeline buffer (sfa_set_trace_buffer); nullptr in production
+  // fused delta (dq64 only, launches in which every tile has exactly one KV item): the dS warps compute
+  // delta = rowsum(P o dP) (== rowsum(dO o O): the s_aux column has V = 0) and write it for the dK/dV kernel
+  int fuse_delta;
+  float* delta_out;
+  float* dsrow;        // -exp(s_aux - lse) * delta per row, or nullptr
+  const float* s_aux;
 };
 
 // Timeline probe for performance work: CTA 0 appends (role, code, index, clock64) records.
@@ -715,20 +721,24 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
     } else if (role == 1) {
       // ---------------------------------------------------------------- dS warps
       ItemWalk w(a);
-      float dl_next, delta = 0.f;
+      // prefetched per tile: delta of this row (preprocessed), or -- with fused delta -- its lse (for ds_aux)
+      const float* pre_src = a.fuse_delta ? a.lse : a.delta;
+      const bool pre_on = !a.fuse_delta || a.dsrow != nullptr;
+      float pre_next, pre_cur = 0.f, delta = 0.f;
       int i = 0, mtc = 0;
       {
         int pb = w.pb, y = w.y, b = w.b;
         ItemWalk::advance(a, w.step, pb, y, b);
-        dl_next = load_row(a.delta, w.tile + w.step < w.end, pb, y, b, 0.f);
+        pre_next = load_row(pre_src, pre_on && (w.tile + w.step < w.end), pb, y, b, 0.f);
       }
       while (w.next()) {
         if (w.t == 0) {
-          delta = dl_next;
+          pre_cur = pre_next;
+          delta = pre_cur;
           i = w.q0 + pr;
           int pb = w.pb, y = w.y, b = w.b;
           ItemWalk::advance(a, w.step, pb, y, b);
-          dl_next = load_row(a.delta, w.tile + w.step < w.end, pb, y, b, 0.f);
+          pre_next = load_row(pre_src, pre_on && (w.tile + w.step < w.end), pb, y, b, 0.f);
         }
         const int sb = w.n & 1;
         const uint32_t ts = tl + C::kColS + sb * C::kBNMax;
@@ -744,6 +754,35 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
         mbar_wait(dp_full, w.n & 1);
         tc_fence_after();
         if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 2, w.n);
+        if (a.fuse_delta) {
+          // delta = sum over the attended columns of P * dP (one extra sweep over this tile's single KV item)
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int cb = 0; cb < nch; ++cb) {
+            uint32_t pv[8], dv[16];
+            tmem_ld8(ts + cb * 8, pv);
+            tmem_ld16(tl + C::kColP + cb * 16, dv);
+            tmem_ld_wait();
+            const int lo = c_lo - cb * 16, hi = c_hi - cb * 16;
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              float p0, p1;
+              unpack16<T>(pv[e >> 1], p0, p1);
+              p0 = (e >= lo && e <= hi) ? p0 : 0.f;
+              p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
+              d4[e & 3] = fmaf(p0, __uint_as_float(dv[e]), d4[e & 3]);
+              d4[(e + 1) & 3] = fmaf(p1, __uint_as_float(dv[e + 1]), d4[(e + 1) & 3]);
+            }
+          }
+          delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          if (i < a.N) {
+            const int h = w.y * a.G + gr;
+            const int64_t row = (static_cast<int64_t>(w.b) * a.Hq + h) * a.N + i;
+            a.delta_out[row] = delta;
+            if (a.dsrow != nullptr)      // pre_cur = lse of this row; ds_aux[h] = -sum exp(s_aux - lse) * delta  (:653-665)
+              a.dsrow[row] = (pre_cur == -INFINITY) ? 0.f : -__expf(__ldg(a.s_aux + h) - pre_cur) * delta;
+          }
+        }
         // one 16-column chunk per trip, one (always masked) code path -- see the exp warps
 #pragma unroll 1
         for (int cb = 0; cb < nch; ++cb) {
@@ -1530,6 +1569,16 @@ int sm_count() {
   return n;
 }
 
+// Fused delta: possible when every packed tile has exactly one KV item (no sinks, the band of a tile fits one
+// item).  OFF by default -- measured at the C1 shape it saves the 43 us preprocess pass but costs the dS warps
+// (which sit on the dS -> dP -> dS critical chain) 35 us, and delta from 16-bit P puts ds_aux 1.4e-2 away from
+// the fp32 path (the bar is 2e-3).  SFA_FUSE_DELTA=1 enables it for experiments.
+inline bool fuses_delta(const AttnParams& p, int P, int BN) {
+  static const bool enabled = getenv("SFA_FUSE_DELTA") != nullptr;
+  const int64_t span = (int64_t)(p.W < p.N ? p.W : p.N) + P - 1;
+  return enabled && p.S == 0 && p.W > 0 && span <= BN;
+}
+
 template <typename T, int D>
 cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
   const int group = p.Hq / p.Hkv;
@@ -1571,6 +1620,10 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.delta = p.delta;
     a.trace = trace_buffer();
     a.bn_mul = bn_magic(BN);
+    a.fuse_delta = (D == 64 && fuses_delta(p, P, BN)) ? 1 : 0;
+    a.delta_out = p.delta;
+    a.dsrow = (p.s_aux != nullptr && p.ds_aux != nullptr) ? p.dsrow : nullptr;
+    a.s_aux = p.s_aux;
     const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
     a.tiles_per_cta = 0;
     if constexpr (D == 64) dq64_kernel<T><<<grid, Dq64Cfg::kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
@@ -1613,6 +1666,14 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
 }
 
 }  // namespace
+
+bool tc_bwd_fuses_delta(const AttnParams& p, int dtype) {
+  (void)dtype;
+  if (p.D != 64) return false;
+  int G, P;
+  pick_packing(p.Hq, p.Hkv, G, P);
+  return fuses_delta(p, P, pick_bn(p.W, p.N, P, Dq64Cfg::kBNMax));
+}
 
 bool tc_bwd_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;

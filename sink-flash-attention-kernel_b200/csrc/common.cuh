@@ -28,6 +28,7 @@ struct AttnParams {
   void* dv;
   float* ds_aux;
   float* delta;     // workspace [B,Hq,N]
+  float* dsrow;     // workspace [B,Hq,N]: per-row ds_aux contributions when the dQ kernel computes delta itself
   Strides4 sq, sk, sv, so, sdo, sdq, sdk, sdv;
   int B, Hq, Hkv, N, D, S, W;
   float scale;
@@ -78,6 +79,8 @@ cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_fwd64_supported(const AttnParams& p, int dtype);   // persistent warp-specialised forward, head_dim 64
 cudaError_t tc_fwd64(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_bwd_supported(const AttnParams& p, int dtype);
+bool tc_bwd_fuses_delta(const AttnParams& p, int dtype);   // the dQ kernel derives delta (and ds_aux rows) itself: no preprocess pass
+cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st);
 cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
 
 bool mma_decode_supported(const DecodeParams& p, int dtype);

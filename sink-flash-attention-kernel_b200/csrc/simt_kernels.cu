@@ -457,6 +457,11 @@ cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cu
   return e;
 }
 
+cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st) {
+  ds_aux_reduce_kernel<<<Hq, 256, 0, st>>>(partial, ds_aux, B, Hq, nblk);
+  return cudaGetLastError();
+}
+
 cudaError_t simt_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
   return dispatch_dtype(dtype, [&](auto tag) {
     using T = decltype(tag);
