@@ -90,7 +90,9 @@ size_t sfa_workspace_bytes(int op, int B, int Hq, int Hkv, int N, int D, int dty
   if (op == SFA_OP_FWD) return 0;
   if (op == SFA_OP_BWD) {
     // delta [B,Hq,N] + ds_aux partials [B,Hq,ceil(N/8)] + per-row ds_aux contributions [B,Hq,N]
-    return 2 * align_up((size_t)B * Hq * N * 4, 256) + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256);
+    // + fp32 dK/dV partials of the key blocks shared by neighbouring CTAs of the fused backward kernel
+    return 2 * align_up((size_t)B * Hq * N * 4, 256) + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256) +
+           align_up(tc_bwd_fused_workspace_bytes(), 256);
   }
   if (op == SFA_OP_DECODE) {
     const int splits = mma_decode_splits(B, Hkv, N);
@@ -160,6 +162,7 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   const size_t rows_bytes = align_up((size_t)B * Hq * N * 4, 256);
   float* ds_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes);
   p.dsrow = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256));
+  float* fused_part = reinterpret_cast<float*>(reinterpret_cast<char*>(p.dsrow) + rows_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool use_tc = g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype);
   // narrow windows (one KV item per tile): the dQ kernel computes delta = rowsum(P o dP) and the ds_aux rows
@@ -167,6 +170,11 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   const bool fused = use_tc && tc_bwd_fuses_delta(p, dtype);
   if ((g_bwd_stages & 1) && !fused)
     if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
+  if (use_tc && (g_bwd_stages & 6) == 6 && tc_bwd_fused_supported(p, dtype)) {
+    // narrow window, no sinks, head_dim 64: one kernel for dQ, dK and dV
+    set_impl_name("tcgen05-fused");
+    return cuda_ret(tc_bwd_fused(p, dtype, fused_part, st), "sfa_bwd(tcgen05 fused)");
+  }
   if (use_tc) {
     set_impl_name("tcgen05");
     if (int r = cuda_ret(tc_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(tcgen05)")) return r;

@@ -82,6 +82,10 @@ bool tc_bwd_supported(const AttnParams& p, int dtype);
 bool tc_bwd_fuses_delta(const AttnParams& p, int dtype);   // the dQ kernel derives delta (and ds_aux rows) itself: no preprocess pass
 cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st);
 cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
+// fused dQ + dK + dV kernel for narrow windows without sink tokens (bwdf_sm100.cu); `part` = fp32 partials workspace
+bool tc_bwd_fused_supported(const AttnParams& p, int dtype);
+size_t tc_bwd_fused_workspace_bytes();
+cudaError_t tc_bwd_fused(const AttnParams& p, int dtype, float* part, cudaStream_t st);
 
 bool mma_decode_supported(const DecodeParams& p, int dtype);
 int mma_decode_splits(int B, int Hkv, int total_len);

@@ -4,6 +4,10 @@
 //   mode 0: C = A[128,K] * B[N,K]^T      both operands K-major (S = Q K^T, dP = dO V^T)
 //   mode 1: C = A[128,K] * B[K,N]        B MN-major           (dQ = dS K with smem A)
 //   mode 2: as mode 1 with A fed from TMEM                    (O += P V, dV += P^T dO, ...)
+//   mode 3: M = 64, A [K,64] and B [K,N] both MN-major (SWIZZLE_128B, TMA-written)   (dV^T = dO^T P)
+//   mode 4: mode 3 plus a second M = 64 accumulator in the same columns at lane offset 16
+//   mode 5: mode 3 with B written by the threads in the un-swizzled core-matrix layout
+//   mode 6: M = 128, A [128,K] K-major written by the threads un-swizzled, B [K,N] MN-major SWIZZLE_128B
 #include "common.cuh"
 #include "tmap.cuh"
 #include "umma.cuh"
@@ -14,7 +18,7 @@ namespace {
 template <typename T>
 __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUtensorMap tmA,
                                                     const __grid_constant__ CUtensorMap tmB, const T* __restrict__ a_gmem,
-                                                    float* __restrict__ c, int N, int K, int mode, int fmt) {
+                                                    const T* __restrict__ b_gmem, float* __restrict__ c, int N, int K, int mode, int fmt) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* a_s = smem;                 // K/64 slabs of [128][64]
@@ -36,13 +40,32 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
   const uint32_t kColA = 256;  // TMEM columns used for the A operand in mode 2
 
   if (threadIdx.x == 0) {
-    const uint32_t bytes = (mode == 3 ? 64 * K * 2 : (mode != 2 ? 128 * K * 2 : 0)) + N * K * 2;
+    const int nslab_mn = (N + 63) / 64;
+    const bool a_tma = (mode != 2 && mode != 6), b_tma = (mode != 5);
+    const uint32_t bytes = (!a_tma ? 0 : (mode >= 3 ? 64 * K * 2 : 128 * K * 2)) +
+                           (!b_tma ? 0 : (mode >= 3 ? nslab_mn * 64 * K * 2 : N * K * 2));
     mbar_expect_tx(bars, bytes);
-    if (mode == 3) tma_load_4d(a_s, &tmA, bars, 0, 0, 0, 0);
+    if (mode == 6) {
+    } else if (mode >= 3) tma_load_4d(a_s, &tmA, bars, 0, 0, 0, 0);
     else if (mode != 2)
       for (int s = 0; s < K / 64; ++s) tma_load_4d(a_s + s * 16384, &tmA, bars, s * 64, 0, 0, 0);
-    const int nslab_b = (mode == 0) ? K / 64 : N / 64;
-    for (int s = 0; s < nslab_b; ++s) tma_load_4d(b_s + s * 32768, &tmB, bars, s * 64, 0, 0, 0);
+    const int nslab_b = (mode == 0) ? K / 64 : (N + 63) / 64;
+    if (b_tma)
+      for (int s = 0; s < nslab_b; ++s) tma_load_4d(b_s + s * 32768, &tmB, bars, s * 64, 0, 0, 0);
+  }
+  if (mode == 5 && static_cast<int>(threadIdx.x) < K) {   // B row k -> [n / 8][k / 8][k % 8][n % 8]
+    const int k = threadIdx.x;
+    for (int n0 = 0; n0 < N; n0 += 8)
+      *reinterpret_cast<uint4*>(b_s + (n0 >> 3) * 2048 + (k >> 3) * 128 + (k & 7) * 16) =
+          *reinterpret_cast<const uint4*>(b_gmem + static_cast<int64_t>(k) * N + n0);
+    fence_proxy_async_smem();
+  }
+  if (mode == 6) {                                          // A row r -> [k / 8][r / 8][r % 8][k % 8]
+    const int r = threadIdx.x;
+    for (int k0 = 0; k0 < K; k0 += 8)
+      *reinterpret_cast<uint4*>(a_s + (k0 >> 3) * 2048 + (r >> 3) * 128 + (r & 7) * 16) =
+          *reinterpret_cast<const uint4*>(a_gmem + static_cast<int64_t>(r) * K + k0);
+    fence_proxy_async_smem();
   }
   if (mode == 2) {  // A row per thread -> packed 16-bit pairs -> TMEM
     const T* row = a_gmem + static_cast<int64_t>(threadIdx.x) * K;
@@ -78,8 +101,22 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     } else {
       // mode 3: M = 64, A MN-major (tile stored [K rows][64 M-elements]), B MN-major ([K rows][N], 64-wide slabs)
       const uint32_t idesc = make_idesc(fmt, 64, N, 1, 1);
+      if (mode < 5)
       for (int kk = 0; kk < K / 16; ++kk)
         umma_ss(tmem, make_sdesc(aa + kk * 2048, 16384, 1024), make_sdesc(ba + kk * 2048, 32768, 1024), idesc, kk > 0);
+      if (mode == 5) {
+        for (int kk = 0; kk < K / 16; ++kk)
+          umma_ss(tmem, make_sdesc(aa + kk * 2048, 16384, 1024), make_sdesc_ns(ba + kk * 256, 128, 2048), idesc, kk > 0);
+      } else if (mode == 6) {
+        const uint32_t idesc6 = make_idesc(fmt, 128, N, 0, 1);
+        for (int kk = 0; kk < K / 16; ++kk)
+          umma_ss(tmem, make_sdesc_ns(aa + kk * 4096, 2048, 128), make_sdesc(ba + kk * 2048, 32768, 1024), idesc6, kk > 0);
+      } else
+      // mode 4: a second, independent M = 64 accumulator in the SAME columns at lane offset 16 (first half of K only)
+      if (mode == 4)
+        for (int kk = 0; kk < K / 32; ++kk)
+          umma_ss(tmem + (16u << 16), make_sdesc(aa + kk * 2048, 16384, 1024), make_sdesc(ba + kk * 2048, 32768, 1024),
+                  idesc, kk > 0);
     }
     umma_commit(bars + 1);
   }
@@ -89,7 +126,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     uint32_t v[16];
     tmem_ld16(tl + c0, v);
     tmem_ld_wait();
-    if (mode == 3) {      // M = 64: row r lives in lane (r % 16) + 32 * (r / 16); rows 64..127 of c receive the other lanes
+    if (mode >= 3 && mode != 6) {      // M = 64: row r lives in lane (r % 16) + 32 * (r / 16); rows 64..127 of c receive the other lanes
       const int row = (lane < 16) ? warp * 16 + lane : 64 + warp * 16 + (lane - 16);
 #pragma unroll
       for (int e = 0; e < 16; ++e) c[static_cast<int64_t>(row) * N + c0 + e] = __uint_as_float(v[e]);
@@ -418,12 +455,15 @@ cudaError_t probe_umma(const void* a, const void* b, float* c, int N, int K, int
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return cudaErrorInvalidValue;
   if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 256) return cudaErrorInvalidValue;
   if (mode == 0 && K % 64) return cudaErrorInvalidValue;
-  if (mode != 0 && (N % 64 || N > 256)) return cudaErrorInvalidValue;
+  if (mode != 0 && mode < 3 && (N % 64 || N > 256)) return cudaErrorInvalidValue;
   if (mode == 1 && K % 64) return cudaErrorInvalidValue;
-  if (mode == 3 && K > 128) return cudaErrorInvalidValue;
+  if (mode >= 3 && K > 128) return cudaErrorInvalidValue;
   TileMap ma, mb;
   Strides4 sa{(int64_t)128 * K, (int64_t)128 * K, K};
-  if (mode == 3) {        // A given as [K][64]
+  if (mode == 6) {
+    Strides4 s3{(int64_t)K * 64, (int64_t)K * 64, 64};   // unused placeholder map
+    if (!make_tile_map(&ma, b, dtype, 64, K, 1, 1, s3, K, 1)) return cudaErrorInvalidValue;
+  } else if (mode >= 3) {        // A given as [K][64]
     Strides4 s3{(int64_t)K * 64, (int64_t)K * 64, 64};
     if (!make_tile_map(&ma, a, dtype, 64, K, 1, 1, s3, K, 1)) return cudaErrorInvalidValue;
   } else if (!make_tile_map(&ma, a, dtype, K, 128, 1, 1, sa, 128, 1)) return cudaErrorInvalidValue;
@@ -440,11 +480,11 @@ cudaError_t probe_umma(const void* a, const void* b, float* c, int N, int K, int
   if (dtype == SFA_DTYPE_BF16) {
     e = cudaFuncSetAttribute(probe_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    probe_kernel<__nv_bfloat16><<<1, 128, smem, st>>>(ma.map, mb.map, static_cast<const __nv_bfloat16*>(a), c, N, K, mode, fmt);
+    probe_kernel<__nv_bfloat16><<<1, 128, smem, st>>>(ma.map, mb.map, static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), c, N, K, mode, fmt);
   } else {
     e = cudaFuncSetAttribute(probe_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    probe_kernel<__half><<<1, 128, smem, st>>>(ma.map, mb.map, static_cast<const __half*>(a), c, N, K, mode, fmt);
+    probe_kernel<__half><<<1, 128, smem, st>>>(ma.map, mb.map, static_cast<const __half*>(a), static_cast<const __half*>(b), c, N, K, mode, fmt);
   }
   return cudaGetLastError();
 }

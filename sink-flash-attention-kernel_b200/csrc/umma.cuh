@@ -142,6 +142,20 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
   return d;
 }
 
+// Shared-memory matrix descriptor WITHOUT swizzle ("interleaved" canonical layout): 8 x 16-byte core matrices
+// (8 rows of 8 16-bit elements, 128 contiguous bytes).  Used for operands the math warps write themselves
+// as [col / 8][row / 8][row % 8][col % 8]:
+//   K-major use  (rows = M/N index, cols = K):  SBO = bytes between 8-row groups, LBO = bytes between 8-col groups
+//   MN-major use (rows = K index, cols = M/N):  LBO = bytes between 8-row (K) groups, SBO = bytes between 8-col groups
+__device__ __forceinline__ uint64_t make_sdesc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version (sm_100)
+  return d;
+}
+
 // ---- TMEM <-> registers, 32 lanes x 32-bit, N consecutive columns (warp w touches lanes 32*(w%4)..+31)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
