@@ -97,6 +97,9 @@ int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mod
 
 /* UMMA issue-rate probe: out2 = device int64[2] <- {cycles to issue, cycles until complete} for reps*ksteps UMMAs */
 int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, void* stream);
+/* UMMA operand-layout timing probe: prm16 = {M, N, a_mn_major, b_mn_major, a_swizzle128, a_lbo, a_sbo, a_kstep_bytes,
+   b_swizzle128, b_lbo, b_sbo, b_kstep_bytes, n_mmas, ksteps, d_lane_offset, 0}; out2 as sfa_probe_mma_rate */
+int sfa_probe_mma_desc(void* out2, const int* prm16, void* stream);
 /* math-pipe probe: out1 = device int64[1] <- cycles for `iters` 16-element softmax steps of one warp (see probe_sm100.cu) */
 int sfa_probe_math_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream);
 /* TMEM read-throughput probe: out1 <- cycles for `iters` tcgen05.ld round trips per warp (mode 0: x16, 1: x32, 2: 2 x x32) */

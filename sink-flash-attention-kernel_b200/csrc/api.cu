@@ -273,6 +273,10 @@ int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, voi
                   "sfa_probe_mma_rate");
 }
 
+int sfa_probe_mma_desc(void* out2, const int* prm16, void* stream) {
+  return cuda_ret(probe_mma_desc(static_cast<long long*>(out2), prm16, static_cast<cudaStream_t>(stream)), "sfa_probe_mma_desc");
+}
+
 int sfa_probe_math_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream) {
   return cuda_ret(probe_math_rate(static_cast<long long*>(out1), static_cast<float*>(sink), mode, iters, threads,
                                   static_cast<cudaStream_t>(stream)), "sfa_probe_math_rate");

@@ -19,16 +19,22 @@
 // dK^T / dV^T live in a RING of R = nb + 1 key-block slots of P TMEM columns (block j -> slot j mod R); an M = 64
 // accumulator only occupies lanes 0-15 of every lane quarter, so dV^T sits at lane offset 0 and dK^T at lane
 // offset 16 of the SAME columns (validated by sfa_probe_umma mode 4).  P and dS are stored in ring-column
-// order, so each k-step of dV^T / dK^T is at most two UMMAs (the ring minus the one slot that is being
-// drained).  After the tile that last touches a block, the epilogue warps read its slot (dV^T and dK^T with
-// one tcgen05.ld), zero it and write dK/dV -- the GQA group sum happened inside the contraction over the rows.
+// order, so each k-step of dV^T / dK^T is ONE UMMA over the whole ring (every UMMA costs >= 55 cycles whatever
+// its N, tools/probe_mma_desc.py); the image columns of the one slot outside the window are zero.  After the
+// tile that last touches a block, the epilogue warps read its slot (dV^T and dK^T with one tcgen05.ld) and write
+// dK/dV -- the GQA group sum happened inside the contraction over the rows.  The slot is cleared for its next
+// block by a UMMA against a zero operand, i.e. in tensor-pipe order (a tcgen05.st would race the read-modify-
+// write of the in-flight ring UMMAs).
 //
 // A CTA owns a contiguous run of tiles.  Key blocks shared with the neighbouring CTA (the nb - 1 blocks before
 // its first tile and the last nb - 1 blocks of its run) are written as fp32 partials and summed by a small
 // fix-up kernel: no atomics, no inter-CTA waits, deterministic.
 //
-// Warp roles (19 warps): 0-11 math (lane quarter = warp & 3, a third of the 16-column chunks each), 12-15
-// epilogue (dQ store, ring drain), 16 TMA producer, 17 UMMA issuer S / dP, 18 UMMA issuer dV^T / dK^T / dQ.
+// Warp roles (24 warps): 0-11 math (lane quarter = warp & 3, a third of the 16-column chunks each), 12-15 and
+// 16-19 two epilogue groups taking alternate tiles (dQ store, ring drain), 20 TMA producer, 21 UMMA issuer
+// S / dP, 22 UMMA issuer dV^T, 23 UMMA issuer dK^T, 24 UMMA issuer dQ.  An issuing thread spends 100-150 cycles
+// per tcgen05.mma here (9 instructions on the uniform datapath, competing with six busy warps per scheduler)
+// while the tensor pipe needs 55-80: one issuer for all five products ran at ~8000 cycles per tile.
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -50,8 +56,10 @@ struct FusedCfg {
   static constexpr uint32_t kColQ = 2 * kColsMax;      // dQ
   static constexpr uint32_t kColR = 2 * kColsMax + D;  // ring
   static constexpr int kMathWarps = 12;
-  static constexpr int kThreads = 19 * 32;
-  static constexpr int kSmem = 1024 + 4 * kQBytes + 4 * kKVBytes + 2 * kPBytes + 512;
+  static constexpr int kThreads = 25 * 32;
+  static constexpr int kStageBytes = 8 * 1024;         // dQ store transpose, [32 rows][32 B] per epilogue warp
+  static constexpr int kZeroBytes = 1024;              // zero B operand of the slot-clearing UMMAs (P <= 32 columns)
+  static constexpr int kSmem = 1024 + 4 * kQBytes + 4 * kKVBytes + 2 * kPBytes + kStageBytes + kZeroBytes + 512;
   static constexpr int kPartKeys = 128;                // keys per side of a CTA's fp32 partials
   static constexpr int kMaxCtas = 160;
   static_assert(kColR + kRingCols <= 512, "TMEM budget");
@@ -71,7 +79,20 @@ struct FusedArgs {
   void* dv;
   Strides4 sdq, sdk, sdv;
   float* part;   // [grid][2 sides][kPartKeys][2 (dV, dK)][64] fp32
+  long long* trace;   // optional timeline buffer (sfa_set_trace_buffer, -DSFA_TRACE=1 builds); nullptr in production
 };
+
+// Timeline probe for performance work (tools/trace_fused.py): CTA 0 appends (role, code, tile, clock64) records.
+#ifndef SFA_TRACE
+#define SFA_TRACE 0
+#endif
+__device__ __forceinline__ void ftrace(long long* trace, int role, int& cnt, int code, int idx) {
+  if (SFA_TRACE && trace != nullptr && blockIdx.x == 0 && cnt < 256) {
+    trace[(role * 256 + cnt) * 2] = (static_cast<long long>(code) << 32) | static_cast<unsigned>(idx);
+    trace[(role * 256 + cnt) * 2 + 1] = clock64();
+    ++cnt;
+  }
+}
 
 template <typename T> __device__ __forceinline__ void unpack16f(uint32_t u, float& a, float& b);
 template <> __device__ __forceinline__ void unpack16f<__nv_bfloat16>(uint32_t u, float& a, float& b) {
@@ -147,7 +168,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   unsigned char* v_s = k_s + 2 * C::kKVBytes;         // [2][kKVBytes]
   unsigned char* p_s = v_s + 2 * C::kKVBytes;         // P image
   unsigned char* ds_s = p_s + C::kPBytes;             // dS image
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + C::kPBytes);
+  unsigned char* stage_s = ds_s + C::kPBytes;         // [8 warps][32 rows][32 B]: dQ store transpose
+  unsigned char* z_s = stage_s + C::kStageBytes;      // zeros: B operand of the slot-clearing UMMAs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(z_s + C::kZeroBytes);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = q_full + 2;     // [2]  dK^T(n) complete
   uint64_t* k_full = q_empty + 2;
@@ -160,18 +183,18 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   uint64_t* s_free = s_full + 1;      // S(n) read                              (math -> issuer A)
   uint64_t* dp_full = s_free + 1;     // dP(n) complete                         (issuer A -> math)
   uint64_t* dp_free = dp_full + 1;    // dP(n) read                             (math -> issuer A)
-  uint64_t* p_ready = dp_free + 1;    // P(n) in shared memory                  (math -> issuer B)
-  uint64_t* p_free = p_ready + 1;     // dV^T(n) complete: P image reusable     (issuer B -> math)
-  uint64_t* ds_ready = p_free + 1;    // dS(n) in shared memory                 (math -> issuer B)
-  uint64_t* ds_free = ds_ready + 1;   // dK^T(n), dQ(n) complete                (issuer B -> math)
-  uint64_t* dq_done = ds_free + 1;    // all UMMAs of tile n complete           (issuer B -> epilogue)
-  uint64_t* dq_free = dq_done + 1;    // dQ(n) read                             (epilogue -> issuer B)
-  uint64_t* drain_done = dq_free + 1; // [2] ring drains of tile n finished     (epilogue -> issuer B), by n & 1
+  uint64_t* p_ready = dp_free + 1;    // P(n) in shared memory                  (math -> issuer V)
+  uint64_t* p_free = p_ready + 1;     // dV^T(n) complete: P image reusable     (issuer V -> math)
+  uint64_t* ds_ready = p_free + 1;    // dS(n) in shared memory                 (math -> issuer K)
+  uint64_t* ds_free = ds_ready + 1;   // dK^T(n), dQ(n) complete                (issuer K -> math)
+  uint64_t* dq_done = ds_free + 1;    // [2] all UMMAs of tile n complete       (issuers V + K -> epilogue group n & 1)
+  uint64_t* dq_free = dq_done + 2;    // [2] dQ(n) read                         (epilogue group n & 1 -> issuer K)
+  uint64_t* drain_done = dq_free + 2; // [2] ring drain of tile n finished      (epilogue group n & 1 -> issuers V, K)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drain_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 16 && lane == 0) {
+  if (warp == 20 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmK);
@@ -184,14 +207,17 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
     mbar_init(p_ready, C::kMathWarps);
     mbar_init(p_free, 1);
     mbar_init(ds_ready, C::kMathWarps);
-    mbar_init(ds_free, 1);
-    mbar_init(dq_done, 1);
-    mbar_init(dq_free, 4);
-    mbar_init(drain_done + 0, 4);
-    mbar_init(drain_done + 1, 4);
+    mbar_init(ds_free, 2);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(dq_done + g, 3);
+      mbar_init(dq_free + g, 4);
+      mbar_init(drain_done + g, 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 17) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == 21) tmem_alloc(tmem_slot, C::kTmemCols);
+  for (int i = threadIdx.x; i < C::kZeroBytes / 4; i += C::kThreads) reinterpret_cast<uint32_t*>(z_s)[i] = 0u;
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -210,12 +236,15 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
 
   const int P = a.P, nb = a.nb, R = a.R;
 
-  if (warp == 16) {
+  if (warp >= 20) {
+  if (warp == 20) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       FusedWalk w(a);
       const uint32_t kv_bytes = a.cols * C::D * 2;
+      int tc = 0;
       while (w.next()) {
+        ftrace(a.trace, 0, tc, 1, w.it);
         const int s = w.it & 1;
         const uint32_t eph = ((w.it >> 1) & 1) ^ 1;
         const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb - nb + 1) * P;
@@ -231,109 +260,132 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         mbar_wait(v_empty + s, eph);
         mbar_expect_tx(v_full + s, kv_bytes);
         tma_tile(v_s + s * C::kKVBytes, &tmV, v_full + s, a.v_swap, 0, kstart, w.y, w.b);
+        ftrace(a.trace, 0, tc, 3, w.it);
       }
     }
     __syncwarp();
-  } else if (warp == 17) {
+  } else if (warp == 21) {
     // ------------------------------------------------------------------ UMMA issuer A: S = Q K^T, dP = dO V^T
     if (lane == 0) {
       const uint32_t idesc = make_idesc(a.fmt, 128, a.cols, 0, 0);
+      const uint64_t qd0 = make_sdesc(smem_u32(q_s), 16, 1024), kd0 = make_sdesc(smem_u32(k_s), 16, 1024);
+      const uint64_t dod0 = make_sdesc(smem_u32(do_s), 16, 1024), vd0 = make_sdesc(smem_u32(v_s), 16, 1024);
       FusedWalk w(a);
+      int tc = 0;
       while (w.next()) {
+        ftrace(a.trace, 1, tc, 1, w.it);
         const int s = w.it & 1;
         const uint32_t fph = (w.it >> 1) & 1;
-        const uint64_t qd = make_sdesc(smem_u32(q_s + s * C::kQBytes), 16, 1024);
-        const uint64_t kd = make_sdesc(smem_u32(k_s + s * C::kKVBytes), 16, 1024);
-        const uint64_t dod = make_sdesc(smem_u32(do_s + s * C::kQBytes), 16, 1024);
-        const uint64_t vd = make_sdesc(smem_u32(v_s + s * C::kKVBytes), 16, 1024);
+        const uint64_t qd = qd0 + s * (C::kQBytes >> 4), kd = kd0 + s * (C::kKVBytes >> 4);
+        const uint64_t dod = dod0 + s * (C::kQBytes >> 4), vd = vd0 + s * (C::kKVBytes >> 4);
         mbar_wait(q_full + s, fph);
         mbar_wait(k_full + s, fph);
         if (w.it >= 1) mbar_wait(s_free, (w.it - 1) & 1);
         tc_fence_after();
+        ftrace(a.trace, 1, tc, 2, w.it);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + C::kColS, qd + kk * 2, kd + kk * 2, idesc, kk != 0);
         umma_commit(s_full);
+        ftrace(a.trace, 1, tc, 3, w.it);
         mbar_wait(do_full + s, fph);
         mbar_wait(v_full + s, fph);
         if (w.it >= 1) mbar_wait(dp_free, (w.it - 1) & 1);
         tc_fence_after();
+        ftrace(a.trace, 1, tc, 4, w.it);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + C::kColP, dod + kk * 2, vd + kk * 2, idesc, kk != 0);
         umma_commit(dp_full);
         umma_commit(v_empty + s);
+        ftrace(a.trace, 1, tc, 5, w.it);
       }
     }
     __syncwarp();
-  } else if (warp == 18) {
-    // ------------------------------------------------------------------ UMMA issuer B: dV^T, dK^T, dQ
-    if (lane == 0) {
+  } else {
+    // ------------------------------------------------------------------ UMMA issuers V (dV^T), K (dK^T), Q (dQ)
+    // Each k-step covers the WHOLE ring with one UMMA: the image columns of the slot whose block left the window
+    // with the previous tile are zero (written by the math warps), so that slot -- possibly being drained right
+    // now -- only gets +0.  The slot the tile's newest block enters is cleared first by a one-k-step UMMA against
+    // a zero B operand (accumulate off): the clearing is ordered with the other UMMAs, not with the drain.
+    if (lane == 0 && warp == 24) {
+      // dQ = dS K: A = dS image (K-major, un-swizzled), B = K tile (MN-major)
       const uint32_t idesc_dq = make_idesc(a.fmt, 128, C::D, 0, 1);
-      const uint32_t p_a = smem_u32(p_s), ds_a = smem_u32(ds_s);
-      const int sh = a.lgP - 4;                 // 16-column chunks per key block = 1 << sh
+      const uint64_t dsa0 = make_sdesc_ns(smem_u32(ds_s), 2048, 128);
+      const uint64_t kb0 = make_sdesc(smem_u32(k_s), C::kKVBytes, 1024);
+      const uint32_t wrap16 = static_cast<uint32_t>(R * P) * 16u;
       FusedWalk w(a);
       SlotTrack st;
       st.slot0 = 0;
+      int tc = 0;
       while (w.next()) {
+        ftrace(a.trace, 7, tc, 1, w.it);
         st.step(w, R);
         const int s = w.it & 1;
         const uint32_t fph = (w.it >> 1) & 1;
-        // active ring columns: everything but the slot of the block that left the window with the previous tile
-        int x = st.slot0 + nb;
-        if (x >= R) x -= R;
-        const int n_lo = x * P, c_hi0 = (x + 1) * P, n_hi = (R - 1 - x) * P;
-        const uint32_t idesc_lo = make_idesc(a.fmt, 64, n_lo, 1, 1), idesc_hi = make_idesc(a.fmt, 64, n_hi, 1, 1);
-        const uint32_t do_a = smem_u32(do_s + s * C::kQBytes), q_a = smem_u32(q_s + s * C::kQBytes);
-        const uint32_t k_a = smem_u32(k_s + s * C::kKVBytes);
-
-        mbar_wait(p_ready, w.it & 1);
-        mbar_wait(do_full + s, fph);
-        // the slot the tile's newest block enters must have been drained (and zeroed)
+        const uint64_t kb = kb0 + s * (C::kKVBytes >> 4);
+        mbar_wait(ds_ready, w.it & 1);
+        mbar_wait(k_full + s, fph);
+        if (w.it >= 1) mbar_wait(dq_free + ((w.it - 1) & 1), ((w.it - 1) >> 1) & 1);
+        tc_fence_after();
+        ftrace(a.trace, 7, tc, 2, w.it);
+        // natural chunk kk of the tile sits at ring column (slot0 * P + 16 kk) mod (R * P); one image column
+        // group of 8 is 2048 B = 128 descriptor units, i.e. 16 units per column
+        uint32_t rc16 = static_cast<uint32_t>(st.slot0 * P) * 16u;
+#pragma unroll 1
+        for (int kk = 0; kk < a.nch; ++kk) {
+          umma_ss(tmem + C::kColQ, dsa0 + rc16, kb + kk * (2048 >> 4), idesc_dq, kk > 0);
+          rc16 += 256u;
+          if (rc16 >= wrap16) rc16 -= wrap16;
+        }
+        umma_commit(ds_free);
+        umma_commit(k_empty + s);
+        umma_commit(dq_done + s);
+        ftrace(a.trace, 7, tc, 3, w.it);
+      }
+    } else if (lane == 0) {
+      const bool isK = (warp == 23);
+      const uint32_t idesc_ring = make_idesc(a.fmt, 64, R * P, 1, 1);
+      const uint32_t idesc_zero = make_idesc(a.fmt, 64, P, 1, 1);
+      const uint64_t img = make_sdesc_ns(smem_u32(isK ? ds_s : p_s), 128, 2048);          // MN-major B: ring columns
+      const uint64_t zero_b = make_sdesc_ns(smem_u32(z_s), 128, 256);
+      const uint64_t a0 = make_sdesc(smem_u32(isK ? q_s : do_s), 16384, 1024);            // MN-major A: Q^T / dO^T
+      const uint32_t ring = tmem + C::kColR + (isK ? (16u << 16) : 0u);
+      uint64_t* const in_ready = isK ? ds_ready : p_ready;
+      uint64_t* const a_full = isK ? q_full : do_full;
+      uint64_t* const a_empty = isK ? q_empty : do_empty;
+      const int role = isK ? 5 : 2;
+      FusedWalk w(a);
+      SlotTrack st;
+      st.slot0 = 0;
+      int tc = 0;
+      while (w.next()) {
+        ftrace(a.trace, role, tc, 1, w.it);
+        st.step(w, R);
+        const int s = w.it & 1;
+        const uint32_t fph = (w.it >> 1) & 1;
+        int newest = st.slot0 + nb - 1;
+        if (newest >= R) newest -= R;
+        const uint64_t ad = a0 + s * (C::kQBytes >> 4);
+        mbar_wait(in_ready, w.it & 1);
+        mbar_wait(a_full + s, fph);
+        // the slot the tile's newest block enters must have been drained
         if (w.seg_first) {
           if (w.it >= 1) mbar_wait(drain_done + ((w.it - 1) & 1), ((w.it - 1) >> 1) & 1);
         } else if (w.it >= 2) {
           mbar_wait(drain_done + (w.it & 1), ((w.it - 2) >> 1) & 1);
         }
         tc_fence_after();
-#pragma unroll 1
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t ad = make_sdesc(do_a + kk * 2048, 16384, 1024);
-          if (n_lo > 0) umma_ss(tmem + C::kColR, ad, make_sdesc_ns(p_a + kk * 256, 128, 2048), idesc_lo, 1);
-          if (n_hi > 0)
-            umma_ss(tmem + C::kColR + c_hi0, ad, make_sdesc_ns(p_a + (c_hi0 >> 3) * 2048 + kk * 256, 128, 2048), idesc_hi, 1);
-        }
-        umma_commit(p_free);
-        umma_commit(do_empty + s);
-
-        mbar_wait(ds_ready, w.it & 1);
-        mbar_wait(q_full + s, fph);
-        tc_fence_after();
-        const uint32_t ring_k = tmem + C::kColR + (16u << 16);
-#pragma unroll 1
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t ad = make_sdesc(q_a + kk * 2048, 16384, 1024);
-          if (n_lo > 0) umma_ss(ring_k, ad, make_sdesc_ns(ds_a + kk * 256, 128, 2048), idesc_lo, 1);
-          if (n_hi > 0)
-            umma_ss(ring_k + c_hi0, ad, make_sdesc_ns(ds_a + (c_hi0 >> 3) * 2048 + kk * 256, 128, 2048), idesc_hi, 1);
-        }
-        umma_commit(q_empty + s);
-
-        mbar_wait(k_full + s, fph);
-        if (w.it >= 1) mbar_wait(dq_free, (w.it - 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int kk = 0; kk < a.nch; ++kk) {
-          int slot = st.slot0 + (kk >> sh);
-          if (slot >= R) slot -= R;
-          const int rc = slot * P + ((kk & ((1 << sh) - 1)) << 4);
-          umma_ss(tmem + C::kColQ, make_sdesc_ns(ds_a + (rc >> 3) * 2048, 2048, 128),
-                  make_sdesc(k_a + kk * 2048, C::kKVBytes, 1024), idesc_dq, kk > 0);
-        }
-        umma_commit(ds_free);
-        umma_commit(k_empty + s);
-        umma_commit(dq_done);
+        ftrace(a.trace, role, tc, 2, w.it);
+        umma_ss(ring + newest * P, ad, zero_b, idesc_zero, 0);
+#pragma unroll 2
+        for (int kk = 0; kk < 8; ++kk) umma_ss(ring, ad + kk * (2048 >> 4), img + kk * (256 >> 4), idesc_ring, 1);
+        umma_commit(a_empty + s);
+        umma_commit(isK ? ds_free : p_free);
+        umma_commit(dq_done + s);
+        ftrace(a.trace, role, tc, 3, w.it);
       }
     }
     __syncwarp();
+  }
   } else {
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                     // TMEM lane == MMA row
@@ -344,9 +396,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
     if (warp < C::kMathWarps) {
       // ---------------------------------------------------------------- math warps
       const int part = warp >> 2;                          // chunks part, part + 3, part + 6
-      const int sh = a.lgP - 4;
       const uint32_t rowoff = static_cast<uint32_t>((r >> 3) * 128 + (r & 7) * 16);
       const uint32_t p_a = smem_u32(p_s) + rowoff, ds_a = smem_u32(ds_s) + rowoff;
+      const int RP = R * P;
       auto load_row = [&](const float* src, const FusedWalk& t, bool valid, float dflt) {
         float v = dflt;
         const int i = t.pb * P + pr;
@@ -361,9 +413,12 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       st.slot0 = 0;
       bool has_next = wn.next();
       float l_next = load_row(a.lse, wn, has_next, INFINITY), d_next = load_row(a.delta, wn, has_next, 0.f);
+      int tc = 0;
+      const bool tr = SFA_TRACE && (threadIdx.x == 0);
       while (w.next()) {
+        if (tr) ftrace(a.trace, 3, tc, 1, w.it);
         st.step(w, R);
-        const float lse_i = l_next, delta = d_next;
+        const float lse_i = l_next, dsc = d_next * a.scale;
         has_next = wn.next();
         l_next = load_row(a.lse, wn, has_next, INFINITY);
         d_next = load_row(a.delta, wn, has_next, 0.f);
@@ -372,43 +427,45 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         const int kstart = (w.pb - nb + 1) * P;
         const int c_lo = max(i - a.W + 1, 0) - kstart;
         const int c_hi = (i < a.N) ? (i - kstart) : -1;
-
-        uint32_t pk[3][8];
-        uint32_t off[3];
-        // ---- pass 1: P = exp2(S * c - lse), masked, 16-bit -> P image (ring-column order)
+        int xs = st.slot0 + nb;                            // slot whose block left the window: zero image columns
+        if (xs >= R) xs -= R;
+        const uint32_t zoff = static_cast<uint32_t>(xs * P) * 256u;
+        // ---- pass 1: P = exp2(S * c - lse), masked, 16-bit -> P image (ring-column order).  The loops over this
+        // warp's chunks are ROLLED: the kernel's roles run concurrently and share a ~32 KB instruction cache (the
+        // fully unrolled version, 73 KB of code, ran 2x slower in every role).
         mbar_wait_warp(s_full, w.it & 1);
-        if (w.it >= 1) mbar_wait_warp(p_free, (w.it - 1) & 1);
         tc_fence_after();
+        if (w.it >= 1) mbar_wait_warp(p_free, (w.it - 1) & 1);
+        if (tr) ftrace(a.trace, 3, tc, 2, w.it);
+        if (part == 1)
+          for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(p_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
+        const int rc0 = st.slot0 * P;
+#pragma unroll 1
+        for (int cb = part; cb < a.nch; cb += 3) {
+          uint32_t sv[16], pk[8];
+          tmem_ld16(tl + C::kColS + cb * 16, sv);
+          tmem_ld_wait();
+          int rc = rc0 + cb * 16;                          // ring column of natural chunk cb, 256 B per column
+          if (rc >= RP) rc -= RP;
+          const uint32_t off = static_cast<uint32_t>(rc) * 256u;
+          const int lo = c_lo - cb * 16, hi = c_hi - cb * 16;      // attended elements of this chunk: [lo, hi]
+          if (__all_sync(0xffffffffu, lo <= 0 && hi >= 15)) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int cb = part + 3 * k;
-          if (cb < a.nch) {
-            uint32_t sv[16];
-            tmem_ld16(tl + C::kColS + cb * 16, sv);
-            tmem_ld_wait();
-            int slot = st.slot0 + (cb >> sh);
-            if (slot >= R) slot -= R;
-            const int rc = slot * P + ((cb & ((1 << sh) - 1)) << 4);
-            off[k] = static_cast<uint32_t>(rc >> 3) * 2048u;
-            const int lo = c_lo - cb * 16, hi = c_hi - cb * 16;      // attended elements of this chunk: [lo, hi]
-            if (__all_sync(0xffffffffu, lo <= 0 && hi >= 15)) {
+            for (int e = 0; e < 16; e += 2)
+              pk[e >> 1] = pack16<T>(fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2)),
+                                     fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2)));
+          } else {
 #pragma unroll
-              for (int e = 0; e < 16; e += 2)
-                pk[k][e >> 1] = pack16<T>(fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2)),
-                                          fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2)));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; e += 2) {
-                float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2));
-                float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2));
-                p0 = (e >= lo && e <= hi) ? p0 : 0.f;
-                p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
-                pk[k][e >> 1] = pack16<T>(p0, p1);
-              }
+            for (int e = 0; e < 16; e += 2) {
+              float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2));
+              float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2));
+              p0 = (e >= lo && e <= hi) ? p0 : 0.f;
+              p1 = (e + 1 >= lo && e + 1 <= hi) ? p1 : 0.f;
+              pk[e >> 1] = pack16<T>(p0, p1);
             }
-            st_shared_v4(p_a + off[k], pk[k][0], pk[k][1], pk[k][2], pk[k][3]);
-            st_shared_v4(p_a + off[k] + 2048u, pk[k][4], pk[k][5], pk[k][6], pk[k][7]);
           }
+          st_shared_v4(p_a + off, pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(p_a + off + 2048u, pk[4], pk[5], pk[6], pk[7]);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -417,26 +474,36 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           mbar_arrive(s_free);
           mbar_arrive(p_ready);
         }
-        // ---- pass 2: dS = P o (dP - delta), 16-bit -> dS image
+        if (tr) ftrace(a.trace, 3, tc, 3, w.it);
+        // ---- pass 2: dS = scale * P o (dP - delta), 16-bit -> dS image (dQ and dK both carry the scale); P comes
+        // back from the image (this thread's own row)
         mbar_wait_warp(dp_full, w.it & 1);
-        if (w.it >= 1) mbar_wait_warp(ds_free, (w.it - 1) & 1);
         tc_fence_after();
+        if (w.it >= 1) mbar_wait_warp(ds_free, (w.it - 1) & 1);
+        if (tr) ftrace(a.trace, 3, tc, 4, w.it);
+        if (part == 1)
+          for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(ds_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
+#pragma unroll 1
+        for (int cb = part; cb < a.nch; cb += 3) {
+          uint32_t dv[16], pk[8], dk[8];
+          tmem_ld16(tl + C::kColP + cb * 16, dv);
+          int rc = rc0 + cb * 16;
+          if (rc >= RP) rc -= RP;
+          const uint32_t off = static_cast<uint32_t>(rc) * 256u;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]) : "r"(p_a + off) : "memory");
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(pk[4]), "=r"(pk[5]), "=r"(pk[6]), "=r"(pk[7]) : "r"(p_a + off + 2048u) : "memory");
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int cb = part + 3 * k;
-          if (cb < a.nch) {
-            uint32_t dv[16], dk[8];
-            tmem_ld16(tl + C::kColP + cb * 16, dv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              float p0, p1;
-              unpack16f<T>(pk[k][e >> 1], p0, p1);          // masked P is exactly 0 and dP is finite: dS = 0 there
-              dk[e >> 1] = pack16<T>(p0 * (__uint_as_float(dv[e]) - delta), p1 * (__uint_as_float(dv[e + 1]) - delta));
-            }
-            st_shared_v4(ds_a + off[k], dk[0], dk[1], dk[2], dk[3]);
-            st_shared_v4(ds_a + off[k] + 2048u, dk[4], dk[5], dk[6], dk[7]);
+          for (int e = 0; e < 16; e += 2) {
+            float p0, p1;
+            unpack16f<T>(pk[e >> 1], p0, p1);              // masked P is exactly 0 and dP is finite: dS = 0 there
+            dk[e >> 1] = pack16<T>(p0 * fmaf(__uint_as_float(dv[e]), a.scale, -dsc),
+                                   p1 * fmaf(__uint_as_float(dv[e + 1]), a.scale, -dsc));
           }
+          st_shared_v4(ds_a + off, dk[0], dk[1], dk[2], dk[3]);
+          st_shared_v4(ds_a + off + 2048u, dk[4], dk[5], dk[6], dk[7]);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -445,48 +512,84 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           mbar_arrive(dp_free);
           mbar_arrive(ds_ready);
         }
+        if (tr) ftrace(a.trace, 3, tc, 5, w.it);
       }
     } else {
       // ---------------------------------------------------------------- epilogue warps: dQ store, ring drain
+      // two groups of four warps (one per lane quarter); group g takes the tiles with (it & 1) == g
+      const int grp = (warp - C::kMathWarps) >> 2;
       const int which = lane >> 4;                          // 0: dV^T (lanes 0-15), 1: dK^T (lanes 16-31)
       const int dch = quarter * 16 + (lane & 15);           // channel of this lane's ring row
-      const float osc = which ? a.scale : 1.f;
       T* const okv = static_cast<T*>(which ? a.dk : a.dv);
       const Strides4 skv = which ? a.sdk : a.sdv;
       float* const part_cta = a.part + static_cast<size_t>(blockIdx.x) * 2 * C::kPartKeys * 128 + which * 64 + dch;
+      // dQ rows go through a per-warp [32 rows][32 B] transpose buffer: 2 lanes write 32 contiguous bytes of a row
+      const uint32_t stg = smem_u32(stage_s) + (warp - C::kMathWarps) * 1024;
+      const uint32_t st_wr = stg + lane * 32, st_key = (lane >> 2) & 1;
+      int64_t row_off[2];                                   // this lane stores chunk (lane & 1) of rows 16 t + lane / 2
+      int row_pr[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int r2 = quarter * 32 + 16 * t + (lane >> 1);
+        const int pr2 = a.q_swap ? (r2 / a.G) : (r2 & (P - 1));
+        const int gr2 = a.q_swap ? (r2 & (a.G - 1)) : (r2 >> a.lgP);
+        row_pr[t] = pr2;
+        row_off[t] = static_cast<int64_t>(gr2) * a.sdq.h + static_cast<int64_t>(pr2) * a.sdq.n + (lane & 1) * 8;
+      }
       FusedWalk w(a);
       SlotTrack st;
       st.slot0 = 0;
       int pa = 0;
+      int tc = 0;
+      const bool tr = SFA_TRACE && (lane == 0) && (quarter == 0);
+      const int trole = grp ? 6 : 4;
       while (w.next()) {
         st.step(w, R);
         if (w.seg_first) pa = w.pb;
-        mbar_wait_warp(dq_done, w.it & 1);
+        if ((w.it & 1) != grp) continue;
+        if (tr) ftrace(a.trace, trole, tc, 1, w.it);
+        mbar_wait_warp(dq_done + grp, (w.it >> 1) & 1);
         tc_fence_after();
+        if (tr) ftrace(a.trace, trole, tc, 2, w.it);
         {
-          uint32_t v[4][16];
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) tmem_ld16(tl + C::kColQ + cc * 16, v[cc]);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dq_free);
-          const int i = w.pb * P + pr;
-          if (i < a.N) {
-            T* dst = static_cast<T*>(a.dq) + static_cast<int64_t>(w.b) * a.sdq.b +
-                     static_cast<int64_t>(w.y * a.G + gr) * a.sdq.h + static_cast<int64_t>(i) * a.sdq.n;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int e2 = 0; e2 < 16; e2 += 2)
-                pk[e2 >> 1] = pack16<T>(__uint_as_float(v[cc][e2]) * a.scale, __uint_as_float(v[cc][e2 + 1]) * a.scale);
-              *reinterpret_cast<uint4*>(dst + cc * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(dst + cc * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          T* const tile_dq = static_cast<T*>(a.dq) + static_cast<int64_t>(w.b) * a.sdq.b +
+                             static_cast<int64_t>(w.y * a.G) * a.sdq.h + static_cast<int64_t>(w.pb * P) * a.sdq.n;
+          const bool ok0 = w.pb * P + row_pr[0] < a.N, ok1 = w.pb * P + row_pr[1] < a.N;
+#pragma unroll 1
+          for (int hq = 0; hq < 4; ++hq) {                  // channels 16 hq .. 16 hq + 15
+            uint32_t x[16];
+            tmem_ld16(tl + C::kColQ + hq * 16, x);
+            tmem_ld_wait();
+            if (hq == 3) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(dq_free + grp);
+              if (tr) ftrace(a.trace, trole, tc, 3, w.it);
             }
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              st_shared_v4(st_wr + ((c ^ st_key) << 4),
+                           pack16<T>(__uint_as_float(x[8 * c + 0]), __uint_as_float(x[8 * c + 1])),
+                           pack16<T>(__uint_as_float(x[8 * c + 2]), __uint_as_float(x[8 * c + 3])),
+                           pack16<T>(__uint_as_float(x[8 * c + 4]), __uint_as_float(x[8 * c + 5])),
+                           pack16<T>(__uint_as_float(x[8 * c + 6]), __uint_as_float(x[8 * c + 7])));
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int rr = 16 * t + (lane >> 1);
+              uint4 val;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                           : "r"(stg + rr * 32 + (((lane & 1) ^ ((rr >> 2) & 1)) << 4))
+                           : "memory");
+              if (t == 0 ? ok0 : ok1) *reinterpret_cast<uint4*>(tile_dq + row_off[t] + hq * 16) = val;
+            }
+            __syncwarp();
           }
         }
-        // ring drain: the block this tile touched last -- or every live block at the end of a segment
+        if (tr) ftrace(a.trace, trole, tc, 4, w.it);
+        // ring drain: the block this tile touched last -- or, at the end of a segment, every live block (then
+        // the whole ring is cleared with tcgen05.st: no ring UMMA is in flight until this drain is signalled)
         const bool last = w.seg_last();
         const bool tails = last && !w.seq_end();            // the run ends inside a sequence: blocks jb >= 1 are partial
         const int nd = last ? nb : 1;
@@ -499,39 +602,45 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           if (slot >= R) slot -= R;
 #pragma unroll 1
           for (int h = 0; h < nh; ++h) {
-            uint32_t x[16], z[16];
-            const uint32_t col = tl + C::kColR + slot * P + h * 16;
-            tmem_ld16(col, x);
+            uint32_t x[16];
+            tmem_ld16(tl + C::kColR + slot * P + h * 16, x);
             tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) z[e] = 0u;
-            tmem_st16(col, z);
             const bool head = j < pa, tail = tails && jb >= 1;
             if (head || tail) {
               const int idx = head ? (j - (pa - nb + 1)) : (jb - 1);
               float* dst = part_cta + (static_cast<size_t>(tail ? 1 : 0) * C::kPartKeys + idx * P + h * 16) * 128;
 #pragma unroll
-              for (int e = 0; e < 16; ++e) dst[e * 128] = __uint_as_float(x[e]) * osc;
+              for (int e = 0; e < 16; ++e) dst[e * 128] = __uint_as_float(x[e]);
             } else {
               const int key0 = j * P + h * 16;
               T* dst = okv + static_cast<int64_t>(w.b) * skv.b + static_cast<int64_t>(w.y) * skv.h +
                        static_cast<int64_t>(key0) * skv.n + dch;
+              const int nv = a.N - key0;
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (key0 + e < a.N) dst[static_cast<int64_t>(e) * skv.n] = from_f<T>(__uint_as_float(x[e]) * osc);
+              for (int e = 0; e < 16; ++e) {
+                if (e < nv) *dst = from_f<T>(__uint_as_float(x[e]));
+                dst += skv.n;
+              }
             }
           }
         }
-        tmem_st_wait();
+        if (last) {
+          uint32_t z[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) z[e] = 0u;
+          for (int c = 0; c < R * P; c += 16) tmem_st16(tl + C::kColR + c, z);
+          tmem_st_wait();
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(drain_done + (w.it & 1));
+        if (lane == 0) mbar_arrive(drain_done + grp);
+        if (tr) ftrace(a.trace, trole, tc, 5, w.it);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) tmem_dealloc(tmem, C::kTmemCols);
+  if (warp == 21) tmem_dealloc(tmem, C::kTmemCols);
 }
 
 // Sums the fp32 partials of the key blocks shared by two neighbouring CTAs (tail of c - 1, head of c).
@@ -615,6 +724,7 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, cudaStream
   a.dq = p.dq; a.dk = p.dk; a.dv = p.dv;
   a.sdq = p.sdq; a.sdk = p.sdk; a.sdv = p.sdv;
   a.part = part;
+  a.trace = trace_buffer();
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(bwd_fused64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);

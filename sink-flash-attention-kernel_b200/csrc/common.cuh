@@ -94,6 +94,7 @@ cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st);
 cudaError_t probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode,
                          cudaStream_t st);
 cudaError_t probe_mma_rate(long long* out, int N, int ksteps, int reps, int uniform, cudaStream_t st);
+cudaError_t probe_mma_desc(long long* out, const int* prm16, cudaStream_t st);
 cudaError_t probe_math_rate(long long* out, float* sink, int mode, int iters, int threads, cudaStream_t st);
 cudaError_t probe_tmem_rate(long long* out, float* sink, int mode, int iters, int threads, cudaStream_t st);
 void set_trace_buffer(long long* p);   // performance-debug timeline (device buffer, 3*256*2 int64) or nullptr

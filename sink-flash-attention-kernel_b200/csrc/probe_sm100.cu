@@ -208,6 +208,143 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(long long* out, int N, in
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// UMMA operand-layout timing probe: one thread issues n UMMAs whose descriptors are built from raw numbers
+// (prm[]: M, N, a_mn, b_mn, a_swz, a_lbo, a_sbo, a_kstep, b_swz, b_lbo, b_sbo, b_kstep, n, ksteps, d_lane), shared
+// memory zero-filled: cycles per instruction for each layout the kernels consider.
+struct DescPrm { int v[16]; };
+__global__ void __launch_bounds__(512) mma_desc_kernel(long long* out, DescPrm p, int fmt) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBytes = 160 * 1024;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kBytes);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  // p.v[15] bit 3: pseudo-random bf16 operands (|x| < 2) instead of zeros; bit 4: alternate with S-form UMMAs
+  for (int i = threadIdx.x; i < kBytes / 4; i += blockDim.x) {
+    uint32_t h = static_cast<uint32_t>(i) * 2654435761u;
+    h ^= h >> 13;
+    reinterpret_cast<uint32_t*>(smem)[i] = (p.v[15] & 8) ? ((h & 0x807f807fu) | 0x3f003f00u) : 0u;
+  }
+  const int warp = threadIdx.x >> 5;
+  volatile uint32_t* done_flag = slot + 1;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 2, 1);
+    mbar_init(bar + 3, 1);
+    fence_barrier_init();
+    *done_flag = 0u;
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  const int M = p.v[0], N = p.v[1], n = p.v[12], ksteps = p.v[13];
+  // background load (p.v[15]): bit 0 = warps 4-15 stream st.shared.v4 into a scratch region, bit 1 = they stream
+  // tcgen05.ld of 16 columns, bit 2 = they stream ld.shared.v4 -- while thread 32 issues the UMMAs
+  if (warp >= 4) {
+    const int bg = p.v[15] & 7;
+    const uint32_t scratch = smem_u32(smem + 128 * 1024) + (threadIdx.x - 128) * 16;
+    const uint32_t tl = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 256;
+    uint32_t acc = 0;
+    while (*done_flag == 0u && bg != 0) {
+      if (bg & 1)
+        for (int i = 0; i < 4; ++i)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(scratch + i * 6144), "r"(acc) : "memory");
+      if (bg & 2) {
+        uint32_t x[16];
+        tmem_ld16(tl, x);
+        tmem_ld_wait();
+        acc += x[3];
+      }
+      if (bg & 4)
+        for (int i = 0; i < 4; ++i) {
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(scratch + i * 6144) : "memory");
+          acc += a0 + a3;
+        }
+    }
+    if (acc == 0x12345678u) out[2] = acc;
+  }
+  const uint32_t idesc = make_idesc(fmt, M, N, p.v[2], p.v[3]);
+  const uint32_t aa = smem_u32(smem), ba = smem_u32(smem + 64 * 1024);
+  const int extra = (p.v[15] >> 8) & 3;     // extra issuing threads (lane 0 of warps 2, 3): same UMMAs, own accumulators
+  if ((threadIdx.x == 64 && extra >= 1) || (threadIdx.x == 96 && extra >= 2)) {
+    uint64_t ad[8], bd[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k2 = kk % ksteps;
+      ad[kk] = p.v[4] ? make_sdesc(aa + k2 * p.v[7], p.v[5], p.v[6]) : make_sdesc_ns(aa + k2 * p.v[7], p.v[5], p.v[6]);
+      bd[kk] = p.v[8] ? make_sdesc(ba + k2 * p.v[11], p.v[9], p.v[10]) : make_sdesc_ns(ba + k2 * p.v[11], p.v[9], p.v[10]);
+    }
+    const uint32_t d = tmem + (warp - 1) * 160;
+    for (int i = 0; i < n; i += 8) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) umma_ss(d, ad[kk], bd[kk], idesc, kk > 0);
+    }
+    umma_commit(bar + 2 + (warp - 2));
+    mbar_wait(bar + 2 + (warp - 2), 0);
+  }
+  if (threadIdx.x == 32) {
+    uint64_t ad[8], bd[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k2 = kk % ksteps;
+      ad[kk] = p.v[4] ? make_sdesc(aa + k2 * p.v[7], p.v[5], p.v[6]) : make_sdesc_ns(aa + k2 * p.v[7], p.v[5], p.v[6]);
+      bd[kk] = p.v[8] ? make_sdesc(ba + k2 * p.v[11], p.v[9], p.v[10]) : make_sdesc_ns(ba + k2 * p.v[11], p.v[9], p.v[10]);
+    }
+    const uint32_t d = tmem + (static_cast<uint32_t>(p.v[14]) << 16);
+    const uint32_t idesc_s = make_idesc(fmt, 128, 144, 0, 0);
+    const uint64_t sa = make_sdesc(aa + 32768, 16, 1024), sb = make_sdesc(ba + 49152, 16, 1024);
+    const int alt = p.v[15] >> 4;   // 0: one chain; 1: alternate with S-form UMMAs; 2: same shape, alternate accumulators;
+                                    // 3: same shape, two accumulators in blocks of 8
+    long long t0;
+    if (alt == 0) {
+      t0 = clock64();
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_ss(d, ad[kk], bd[kk], idesc, kk > 0);
+      }
+    } else if (alt == 1) {
+      t0 = clock64();
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int kk = 0; kk < 8; kk += 2) {
+          umma_ss(d, ad[kk], bd[kk], idesc, kk > 0);
+          umma_ss(tmem + 288, sa + (kk >> 1) * 2, sb + (kk >> 1) * 2, idesc_s, kk > 0);
+        }
+      }
+    } else if (alt == 2) {
+      t0 = clock64();
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int kk = 0; kk < 8; kk += 2) {
+          umma_ss(d, ad[kk], bd[kk], idesc, kk > 0);
+          umma_ss(d + 256, ad[kk + 1], bd[kk + 1], idesc, kk > 0);
+        }
+      }
+    } else {
+      t0 = clock64();
+      for (int i = 0; i < n; i += 16) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_ss(d, ad[kk], bd[kk], idesc, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_ss(d + 256, ad[kk], bd[kk], idesc, kk > 0);
+      }
+    }
+    const long long t1 = clock64();
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+    *done_flag = 1u;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // TMEM read-throughput probe: every warp loops over tcgen05.ld (32x32b, x16 / x32 / 2 x x32 per wait) on its lane quarter.
 __global__ void tmem_rate_kernel(long long* out, float* sink, int mode, int iters) {
   __shared__ uint32_t slot;
@@ -448,6 +585,16 @@ cudaError_t probe_mma_rate(long long* out, int N, int ksteps, int reps, int unif
   cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   mma_rate_kernel<<<1, 128, smem, st>>>(out, N, ksteps, reps, 1, uniform);
+  return cudaGetLastError();
+}
+
+cudaError_t probe_mma_desc(long long* out, const int* prm16, cudaStream_t st) {
+  const int smem = 1024 + 160 * 1024 + 64;
+  cudaError_t e = cudaFuncSetAttribute(mma_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  DescPrm p;
+  for (int i = 0; i < 16; ++i) p.v[i] = prm16[i];
+  mma_desc_kernel<<<1, 512, smem, st>>>(out, p, 1);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_mma_desc", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
 )
 
 _lib = None
@@ -71,6 +71,8 @@ def load() -> ctypes.CDLL:
     lib.sfa_probe_tmem_rate.restype = i
     lib.sfa_probe_mma_rate.argtypes = [p, i, i, i, i, p]
     lib.sfa_probe_mma_rate.restype = i
+    lib.sfa_probe_mma_desc.argtypes = [p, c.POINTER(c.c_int), p]
+    lib.sfa_probe_mma_desc.restype = i
     lib.sfa_probe_tma_bw.argtypes = [p, i, i, i, i, i, i, i, p]
     lib.sfa_probe_tma_bw.restype = i
     lib.sfa_probe_umma.argtypes = [p, p, f32p, i, i, i, i, p]

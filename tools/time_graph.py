@@ -59,6 +59,7 @@ print("fwd            us (median, min):", graph_time(lambda: sa.sink_flash_atten
 print("bwd preprocess us:", graph_time(stage(1)))
 print("bwd dq         us:", graph_time(stage(2)))
 print("bwd dkdv       us:", graph_time(stage(4)))
+print("bwd dq+dkdv    us:", graph_time(stage(6)), "(fused kernel + fix-up when the shape allows)")
 print("bwd all        us:", graph_time(stage(7)))
 
 
