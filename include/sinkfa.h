@@ -53,7 +53,9 @@ int sfa_version(void);
 const char* sfa_last_error(void);
 int sfa_set_impl(int impl);
 /* timing aid for bench.py: run only the selected backward stages (bit0 = delta/ds_aux preprocess,
- * bit1 = dQ kernel, bit2 = dK/dV kernel); default 7 = all.  Results are complete only with 7. */
+ * bit1 = dQ kernel, bit2 = dK/dV kernel); default 7 = all.  Results are complete only with 7 or 15.
+ * bit3 (7 + 8 = 15): keep the dQ + dK/dV kernel pair where the one-kernel fused backward would apply
+ * (narrow window, no sink tokens, head_dim 64), so that both paths can be tested on the same shape. */
 int sfa_set_bwd_stages(int mask);
 /* performance-debug aid: a device buffer of 3*256*2 int64 into which CTA 0 of the dQ kernel appends
  * (role, event, index, clock64) records; NULL (the default) switches it off. */

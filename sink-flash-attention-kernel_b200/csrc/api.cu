@@ -81,7 +81,7 @@ int sfa_set_trace_buffer(void* device_buffer) {
 }
 
 int sfa_set_bwd_stages(int mask) {
-  g_bwd_stages = mask & 7;
+  g_bwd_stages = mask & 15;   // bit 3: keep the dQ + dK/dV kernel pair even where the fused kernel applies
   return 0;
 }
 
@@ -170,20 +170,20 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   const bool fused = use_tc && tc_bwd_fuses_delta(p, dtype);
   if ((g_bwd_stages & 1) && !fused)
     if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
-  if (use_tc && (g_bwd_stages & 6) == 6 && tc_bwd_fused_supported(p, dtype)) {
+  if (use_tc && (g_bwd_stages & 14) == 6 && tc_bwd_fused_supported(p, dtype)) {
     // narrow window, no sinks, head_dim 64: one kernel for dQ, dK and dV
     set_impl_name("tcgen05-fused");
     return cuda_ret(tc_bwd_fused(p, dtype, fused_part, st), "sfa_bwd(tcgen05 fused)");
   }
   if (use_tc) {
     set_impl_name("tcgen05");
-    if (int r = cuda_ret(tc_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(tcgen05)")) return r;
+    if (int r = cuda_ret(tc_bwd(p, dtype, g_bwd_stages & 7, st), "sfa_bwd(tcgen05)")) return r;
     if (fused && (g_bwd_stages & 2) && p.s_aux && p.ds_aux)
       return cuda_ret(ds_aux_reduce(p.dsrow, p.ds_aux, B, Hq, N, st), "sfa_bwd(ds_aux reduce)");
     return 0;
   }
   set_impl_name("simt");
-  return cuda_ret(simt_bwd(p, dtype, g_bwd_stages, st), "sfa_bwd(simt)");
+  return cuda_ret(simt_bwd(p, dtype, g_bwd_stages & 7, st), "sfa_bwd(simt)");
 }
 
 static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {

@@ -258,36 +258,58 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
   return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
+// Every thread owns one 16-byte slice of kRowsPerThread rows and issues all of its loads before the first use:
+// 2 x kRowsPerThread x 16 B in flight per thread (the one-row version reached 52 % of the DRAM bandwidth with 32 B
+// in flight per thread and 16 384 short-lived blocks).
+constexpr int kPreRowsPerThread = 4;
+__device__ __forceinline__ uint4 ld_nc_v4(const void* ptr) {   // streamed once: keep it out of L1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
 template <typename T, int LPR>
 __global__ void __launch_bounds__(256) preprocess_vec_kernel(AttnParams p, float* ds_partial) {
-  constexpr int RPB = 256 / LPR;   // rows per block
+  constexpr int RPB = 256 / LPR;   // rows per block and per round
+  constexpr int R = kPreRowsPerThread;
   __shared__ float part[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = tid % LPR;
-  const int i = blockIdx.x * RPB + tid / LPR, h = blockIdx.y, b = blockIdx.z;
-  float s = 0.f;
-  if (i < p.N) {
-    const T* o = static_cast<const T*>(p.o) + b * p.so.b + h * p.so.h + (int64_t)i * p.so.n + sub * 8;
-    const T* dO = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h + (int64_t)i * p.sdo.n + sub * 8;
-    const uint4 a = *reinterpret_cast<const uint4*>(o);
-    const uint4 c = *reinterpret_cast<const uint4*>(dO);
-    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, cu[4] = {c.x, c.y, c.z, c.w};
+  const int i0 = blockIdx.x * (RPB * R) + tid / LPR, h = blockIdx.y, b = blockIdx.z;
+  const T* o = static_cast<const T*>(p.o) + b * p.so.b + h * p.so.h + sub * 8;
+  const T* dO = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h + sub * 8;
+  uint4 a[R], c[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r * RPB;
+    a[r] = c[r] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < p.N) {
+      a[r] = ld_nc_v4(o + (int64_t)i * p.so.n);
+      c[r] = ld_nc_v4(dO + (int64_t)i * p.sdo.n);
+    }
+  }
+  const float sx = p.s_aux ? p.s_aux[h] : 0.f;
+  float contrib = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r * RPB;
+    const uint32_t au[4] = {a[r].x, a[r].y, a[r].z, a[r].w}, cu[4] = {c[r].x, c[r].y, c[r].z, c[r].w};
+    float s = 0.f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const float2 x = unpack2<T>(au[t]), y = unpack2<T>(cu[t]);
       s = fmaf(x.x, y.x, s);
       s = fmaf(x.y, y.y, s);
     }
-  }
 #pragma unroll
-  for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  float contrib = 0.f;
-  if (i < p.N && sub == 0) {
-    const int64_t row = ((int64_t)b * p.Hq + h) * p.N + i;
-    p.delta[row] = s;
-    if (p.s_aux) {
-      const float lse = p.lse[row];
-      contrib = (lse == -INFINITY) ? 0.f : -expf(p.s_aux[h] - lse) * s;
+    for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (i < p.N && sub == 0) {
+      const int64_t row = ((int64_t)b * p.Hq + h) * p.N + i;
+      p.delta[row] = s;
+      if (p.s_aux) {
+        const float lse = p.lse[row];
+        contrib += (lse == -INFINITY) ? 0.f : -expf(sx - lse) * s;
+      }
     }
   }
   if (ds_partial) {
@@ -416,7 +438,8 @@ cudaError_t simt_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
 template <typename T>
 cudaError_t launch_preprocess_vec(const AttnParams& p, float* ds_partial, int& nblk, cudaStream_t st) {
   const int lpr = p.D / 8;
-  nblk = (p.N + 256 / lpr - 1) / (256 / lpr);
+  const int rows = 256 / lpr * kPreRowsPerThread;
+  nblk = (p.N + rows - 1) / rows;
   dim3 grid(nblk, p.Hq, p.B);
   switch (lpr) {
     case 4: preprocess_vec_kernel<T, 4><<<grid, 256, 0, st>>>(p, ds_partial); break;

@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsinkfa.so")
+# SFA_LIB: developer override used by tools/trace_*.py to load the timeline build (`make trace`)
+LIB_PATH = os.environ.get("SFA_LIB") or os.path.join(_HERE, "libsinkfa.so")
 
 DTYPE_CODE = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
 OP_FWD, OP_BWD, OP_DECODE = 0, 1, 2

@@ -134,6 +134,18 @@ def test_fwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     assert maxdiff(lse_t, lse_ref) < 2e-3
 
 
+def _expected_bwd_impl(Hq, Hkv, N, D, S, W):
+    """Narrow windows without sink tokens at head_dim 64 with a GQA group of 4 or 8 take the one-kernel
+    backward (bwdf_sm100.cu: fused_geometry); everything else the dQ + dK/dV kernel pair."""
+    G = Hq // Hkv
+    if D == 64 and S == 0 and W >= 1 and G in (4, 8):
+        P = 128 // G
+        nb = (min(W, N) - 1 + P - 1) // P + 1
+        if nb * P <= 144 and (nb + 1) * P <= 160:
+            return "tcgen05-fused"
+    return "tcgen05"
+
+
 def _bwd(q, k, v, o, do, lse, S, W, s_aux, impl=None):
     if impl is not None:
         _lib.set_impl(impl)
@@ -173,7 +185,7 @@ def test_bwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     o, lse, _ = _fwd(q, k, v, S, W, s_aux)
     (dq_t, dk_t, dv_t, ds_t), name_t = _bwd(q, k, v, o, do, lse, S, W, s_aux)
     (dq_s, dk_s, dv_s, ds_s), name_s = _bwd(q, k, v, o, do, lse, S, W, s_aux, impl=_lib.IMPL_SIMT)
-    assert (name_t, name_s) == ("tcgen05", "simt")
+    assert (name_t, name_s) == (_expected_bwd_impl(Hq, Hkv, N, D, S, W), "simt")
     dq_r, dk_r, dv_r, ds_r = orc.sink_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), S, W, s_aux.cpu() if use_aux else None)
     # on-device cross-check (same inputs, fp32 CUDA-core math): only the 16-bit rounding of P/dS and of the
     # outputs separates the two -> 2e-2 absolute + 1e-2 relative (one bf16 ulp of a value near 4 is 3.1e-2)
@@ -185,6 +197,88 @@ def test_bwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     for got, ref in ((dq_t, dq_r), (dk_t, dk_r), (dv_t, dv_r)):
         assert excess(got, ref, 5e-2, 5e-2) <= 1.0
     assert maxdiff(dq_t, dq_r) < 5e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# fused one-kernel backward (narrow window, no sink tokens, head_dim 64) vs the kernel pair, the CUDA-core
+# path and the oracle
+# ------------------------------------------------------------------------------------------------
+def _bwd_pair(q, k, v, o, do, lse, S, W, s_aux):
+    lib = _lib.load()
+    lib.sfa_set_bwd_stages(15)
+    try:
+        return _bwd(q, k, v, o, do, lse, S, W, s_aux)
+    finally:
+        lib.sfa_set_bwd_stages(7)
+
+
+@pytest.mark.parametrize("dtype", LOW)
+@pytest.mark.parametrize("shape", [
+    # B, Hq, Hkv, N, W, hf_layout
+    (1, 8, 1, 256, 128, False),
+    (1, 8, 1, 200, 100, False),      # ragged N, window not a multiple of the 16-key block
+    (2, 16, 2, 777, 128, False),     # two batches x two KV heads: CTA runs cross sequence boundaries
+    (1, 8, 1, 4096, 128, False),     # long runs per CTA: ring slots recycled many times
+    (1, 8, 1, 512, 17, False),
+    (1, 8, 1, 300, 1, False),        # self only
+    (1, 4, 1, 640, 96, False),       # group 4 -> 32 positions per tile
+    (1, 8, 2, 1000, 64, False),
+    (1, 16, 2, 1024, 128, True),     # HF [B,N,H,D] views consumed in place
+    (1, 8, 1, 64, 128, False),       # window > N
+])
+def test_bwd_fused_vs_pair_simt_and_oracle(shape, dtype):
+    B, Hq, Hkv, N, W, hf = shape
+    D, S = 64, 0
+    g = torch.Generator().manual_seed(N + W)
+
+    def mk(H):
+        if hf:
+            return torch.randn(B, N, H, D, generator=g).to("cuda", dtype).transpose(1, 2)
+        return torch.randn(B, H, N, D, generator=g).to("cuda", dtype)
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    s_aux = (torch.randn(Hq, generator=g) * 0.5 + 1.0).cuda()
+    o, lse, _ = _fwd(q, k, v, S, W, s_aux)
+    (dq_f, dk_f, dv_f, ds_f), name_f = _bwd(q, k, v, o, do, lse, S, W, s_aux)
+    (dq_p, dk_p, dv_p, ds_p), name_p = _bwd_pair(q, k, v, o, do, lse, S, W, s_aux)
+    (dq_s, dk_s, dv_s, ds_s), name_s = _bwd(q, k, v, o, do, lse, S, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert (name_f, name_p, name_s) == ("tcgen05-fused", "tcgen05", "simt")
+    for got, ref in ((dq_f, dq_s), (dk_f, dk_s), (dv_f, dv_s), (dq_p, dq_s), (dk_p, dk_s), (dv_p, dv_s)):
+        assert excess(got, ref, 2e-2, 1e-2) <= 1.0
+    assert maxdiff(ds_f, ds_s) < 1e-4 and maxdiff(ds_p, ds_s) < 2e-3
+    dq_r, dk_r, dv_r, ds_r = orc.sink_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), S, W, s_aux.cpu())
+    for got, ref in ((dq_f, dq_r), (dk_f, dk_r), (dv_f, dv_r)):
+        assert excess(got, ref, 5e-2, 5e-2) <= 1.0
+    assert maxdiff(ds_f, ds_r) < 1e-2 * max(1.0, float(ds_r.abs().max()))   # delta = rowsum(dO o O) from the 16-bit O, as the reference (:582)
+    # determinism: the shared key blocks of neighbouring CTAs are summed by a fix-up kernel, no atomics
+    (dq2, dk2, dv2, _), _ = _bwd(q, k, v, o, do, lse, S, W, s_aux)
+    assert torch.equal(dq2, dq_f) and torch.equal(dk2, dk_f) and torch.equal(dv2, dv_f)
+
+
+def test_c1_full_size_backward():
+    """gpt-oss shape (BASELINE configs[1]) backward: the fused kernel against the CUDA-core path on the whole
+    tensors, plus size-independent properties: linearity in dO, and dV = P^T dO with V-independence."""
+    B, N, Hq, Hkv, D, W = 1, 8192, 64, 8, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(43)
+    mk = lambda H: torch.randn(B, H, N, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    s_aux = torch.randn(Hq, device="cuda", generator=g) * 0.5
+    o, lse, _ = _fwd(q, k, v, 0, W, s_aux)
+    (dq_f, dk_f, dv_f, ds_f), name_f = _bwd(q, k, v, o, do, lse, 0, W, s_aux)
+    (dq_s, dk_s, dv_s, ds_s), _ = _bwd(q, k, v, o, do, lse, 0, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert name_f == "tcgen05-fused"
+    for got, ref in ((dq_f, dq_s), (dk_f, dk_s), (dv_f, dv_s)):
+        assert excess(got, ref, 2e-2, 1e-2) <= 1.0
+    assert maxdiff(ds_f, ds_s) < 1e-3 * max(1.0, float(ds_s.abs().max()))
+    # linearity in dO: backward(2 dO) == 2 backward(dO) exactly (powers of two commute with every rounding)
+    (dq2, dk2, dv2, ds2), _ = _bwd(q, k, v, o, do * 2, lse, 0, W, s_aux)
+    assert torch.equal(dq2, dq_f * 2) and torch.equal(dk2, dk_f * 2) and torch.equal(dv2, dv_f * 2)
+    # causality of the gradients: dO rows >= t only reach keys > t - W
+    t = 5000
+    do_z = do.clone()
+    do_z[:, :, :t] = 0
+    (dq_z, dk_z, dv_z, _), _ = _bwd(q, k, v, o, do_z, lse, 0, W, s_aux)
+    assert float(dk_z[:, :, : t - W + 1].abs().max()) == 0.0 and float(dv_z[:, :, : t - W + 1].abs().max()) == 0.0
+    assert float(dq_z[:, :, :t].abs().max()) == 0.0
 
 
 # ------------------------------------------------------------------------------------------------

@@ -28,16 +28,12 @@ lib = _lib.load()
 o, lse = sa.sink_flash_attention_with_lse(q, k, v, S, W, s_aux)
 
 
-def graph_time(fn, reps=15):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    gr = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(gr):
-        fn()
+INNER = 10
+
+
+def _replay_us(gr, reps):
     ts = []
-    for it in range(reps):
-        flush.fill_(it)
+    for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         gr.replay()
@@ -45,6 +41,35 @@ def graph_time(fn, reps=15):
         b.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
     return statistics.median(ts), min(ts)
+
+
+def _capture(body):
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for it in range(INNER):
+            flush.fill_(it)
+            body()
+    return gr
+
+
+_flush_only = None
+
+
+def graph_time(fn, reps=7):
+    """(median, min) us of one `fn`: a graph of INNER x (L2 flush, fn) minus a graph of INNER x (L2 flush), / INNER.
+    (CUDA event timestamps on this box tick every 2.048 us: a single ~50 us replay cannot resolve a 1 us change.)"""
+    global _flush_only
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    if _flush_only is None:
+        g0 = _capture(lambda: None)
+        _replay_us(g0, 2)
+        _flush_only = _replay_us(g0, reps)
+    gr = _capture(fn)
+    _replay_us(gr, 2)
+    med, mn = _replay_us(gr, reps)
+    return round((med - _flush_only[0]) / INNER, 2), round((mn - _flush_only[1]) / INNER, 2)
 
 
 def stage(mask):
