@@ -217,8 +217,8 @@ def run_ours(args):
             o.backward(do)
 
         # The timed step is a CUDA-graph replay of exactly the launches the autograd Function makes (sfa_fwd,
-        # then sfa_bwd: delta/ds_aux preprocess, ds_aux reduce, fused dQ/dK/dV kernel, fix-up): the five kernels take
-        # ~0.25 ms, less than the Python/ctypes launch path around them, so the eager number measures the host.
+        # then sfa_bwd: fused delta/dQ/dK/dV kernel, fix-up, ds_aux reduce): the four kernels take
+        # ~0.2 ms, less than the Python/ctypes launch path around them, so the eager number measures the host.
         qd_, kd_, vd_, sd_ = q.detach(), k.detach(), v.detach(), s_aux.detach()
 
         def c_abi_step():
@@ -235,8 +235,8 @@ def run_ours(args):
         def step():
             step_graph.replay()
         n_total = N
-        launches_per_step = 5               # fwd; bwd = delta/ds_aux preprocess + ds_aux reduce + fused dQ/dK/dV + its fix-up
-                                            # (or, for wide windows / sinks: + dQ kernel + dK/dV kernel)
+        launches_per_step = 4               # fwd; bwd = fused delta/dQ/dK/dV kernel + its fix-up + ds_aux reduce
+                                            # (wide windows / sinks: preprocess + ds_aux reduce + dQ kernel + dK/dV kernel)
         workload = ("gpt-oss-20b attention layer fwd+bwd (BASELINE configs[1]): B=1 N=8192 Hq=64 Hkv=8 D=64 window=128 "
                     "s_aux bf16")
         parallelism = "single GPU"
@@ -354,7 +354,7 @@ def run_ours(args):
             _lib.bwd(qd, kd, vd, o_s, do, lse_s, S, W, sd)
             bwd_impl = _lib.last_impl()
             if bwd_impl == "tcgen05-fused":
-                stages = (("bwd_preprocess(delta,ds_aux)", 1), ("bwd_fused(dq,dk,dv)", 6))
+                stages = (("bwd_fused(delta,ds_aux,dq,dk,dv)", 6),)
             else:
                 stages = (("bwd_preprocess(delta,ds_aux)", 1), ("bwd_dq", 2), ("bwd_dkdv", 4))
             for name, mask in stages:
@@ -375,12 +375,13 @@ def run_ours(args):
                 "bwd_preprocess(delta,ds_aux)": 2 * B * Hq * N * D * e + 2 * 4 * B * Hq * N,
                 "bwd_dq": 3 * B * Hq * N * D * e + 2 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
                 "bwd_dkdv": 2 * B * Hq * N * D * e + 4 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
-                # Q, dO in, dQ out; K, V in, dK, dV out; lse, delta in
-                "bwd_fused(dq,dk,dv)": 3 * B * Hq * N * D * e + 4 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
+                # Q, O, dO in, dQ out; K, V in, dK, dV out; lse in (delta stays on chip / in L2)
+                "bwd_fused(delta,ds_aux,dq,dk,dv)": 4 * B * Hq * N * D * e + 4 * B * Hkv * N * D * e + 4 * B * Hq * N,
             }
             pairs = attended_pairs(N, S, W) * B * Hq
             flops_alg = {"fwd": 4 * D * pairs, "bwd_preprocess(delta,ds_aux)": 2 * B * Hq * N * D,
-                         "bwd_dq": 6 * D * pairs, "bwd_dkdv": 8 * D * pairs, "bwd_fused(dq,dk,dv)": 10 * D * pairs}
+                         "bwd_dq": 6 * D * pairs, "bwd_dkdv": 8 * D * pairs,
+                         "bwd_fused(delta,ds_aux,dq,dk,dv)": 10 * D * pairs}
             dom = max(stage_ms, key=stage_ms.get)
             dur = stage_ms[dom] * 1e-3
             ach = bytes_alg[dom] / dur / 1e9

@@ -165,16 +165,24 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   float* fused_part = reinterpret_cast<float*>(reinterpret_cast<char*>(p.dsrow) + rows_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool use_tc = g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype);
-  // narrow windows (one KV item per tile): the dQ kernel computes delta = rowsum(P o dP) and the ds_aux rows
+  // narrow window, no sink tokens, head_dim 64: ONE kernel computes delta, the ds_aux rows, dQ, dK and dV
+  if (use_tc && (g_bwd_stages & 14) == 6 && tc_bwd_fused_supported(p, dtype)) {
+    set_impl_name("tcgen05-fused");
+    if (!tc_bwd_fused_computes_delta()) {
+      if (g_bwd_stages & 1)
+        if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
+      return cuda_ret(tc_bwd_fused(p, dtype, fused_part, st), "sfa_bwd(tcgen05 fused)");
+    }
+    if (int r = cuda_ret(tc_bwd_fused(p, dtype, fused_part, st), "sfa_bwd(tcgen05 fused)")) return r;
+    if (p.s_aux && p.ds_aux)
+      return cuda_ret(ds_aux_from_delta(p.delta, p.lse, p.s_aux, p.ds_aux, B, Hq, N, st), "sfa_bwd(ds_aux)");
+    return 0;
+  }
+  // narrow windows (one KV item per tile): the dQ kernel can compute delta = rowsum(P o dP) and the ds_aux rows
   // itself -- no preprocess pass over O and dO
   const bool fused = use_tc && tc_bwd_fuses_delta(p, dtype);
   if ((g_bwd_stages & 1) && !fused)
     if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
-  if (use_tc && (g_bwd_stages & 14) == 6 && tc_bwd_fused_supported(p, dtype)) {
-    // narrow window, no sinks, head_dim 64: one kernel for dQ, dK and dV
-    set_impl_name("tcgen05-fused");
-    return cuda_ret(tc_bwd_fused(p, dtype, fused_part, st), "sfa_bwd(tcgen05 fused)");
-  }
   if (use_tc) {
     set_impl_name("tcgen05");
     if (int r = cuda_ret(tc_bwd(p, dtype, g_bwd_stages & 7, st), "sfa_bwd(tcgen05)")) return r;

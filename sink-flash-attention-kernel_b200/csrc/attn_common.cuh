@@ -145,6 +145,10 @@ __device__ __forceinline__ void tma_tile(void* dst, const CUtensorMap* m, uint64
   if (swap) tma_load_4d(dst, m, bar, d, h, n, b);
   else tma_load_4d(dst, m, bar, d, n, h, b);
 }
+__device__ __forceinline__ void tma_tile_prefetch(const CUtensorMap* m, int swap, int d, int n, int h, int b) {
+  if (swap) tma_prefetch_4d(m, d, h, n, b);
+  else tma_prefetch_4d(m, d, n, h, b);
+}
 __device__ __forceinline__ void tma_tile_store(const CUtensorMap* m, const void* src, int swap, int d, int n, int h, int b) {
   if (swap) tma_store_4d(m, src, d, h, n, b);
   else tma_store_4d(m, src, d, n, h, b);

@@ -69,11 +69,19 @@ struct FusedCfg {
 struct FusedArgs {
   int B, N, W, Hq, Hkv, G, P, lgP, nb, R, cols, nch, nblk, total_tiles, tiles_per_cta;
   int q_swap, k_swap, v_swap;
+  int prefetch;    // producer warp prefetches tiles into L2 ahead of the TMA loads
+  int fuse_delta;  // 1: the epilogue groups compute delta in the kernel; 0: a preprocess kernel wrote it before
   int fmt;       // 0 f16, 1 bf16
   float sl2;     // scale * log2(e)
   float scale;
   const float* lse;
-  const float* delta;
+  float* delta;          // [B,Hq,N] workspace: written by the epilogue groups, read back by the math warps
+  const void* o;         // forward output and its gradient, read directly (16-byte loads) for delta
+  const void* dout;
+  Strides4 so, sdo;
+  const void* k;         // L2 prefetch of the newest key block
+  const void* v;
+  Strides4 sk, sv;
   void* dq;
   void* dk;
   void* dv;
@@ -110,20 +118,25 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 
 // This CTA's contiguous run of tiles; tile id = (b * Hkv + y) * nblk + pb.
-struct FusedWalk {
-  const FusedArgs& a;
-  int tile, end, pb, y, b, it;
-  bool seg_first;     // first tile of a sequence segment inside this CTA
-  __device__ __forceinline__ explicit FusedWalk(const FusedArgs& a_) : a(a_), it(-1), seg_first(false) {
+// (the start coordinates need two integer divisions: computed ONCE per thread before the role dispatch -- every
+// role builds its own walker, and the kernel is instruction-cache bound)
+struct WalkInit {
+  int tile, end, pb, y, b;
+  __device__ __forceinline__ explicit WalkInit(const FusedArgs& a) {
     tile = static_cast<int>(blockIdx.x) * a.tiles_per_cta;
     end = min(tile + a.tiles_per_cta, a.total_tiles);
     pb = tile % a.nblk;
     const int r = tile / a.nblk;
     y = r % a.Hkv;
     b = r / a.Hkv;
-    --tile;
-    --pb;
   }
+};
+struct FusedWalk {
+  const FusedArgs& a;
+  int tile, end, pb, y, b, it;
+  bool seg_first;     // first tile of a sequence segment inside this CTA
+  __device__ __forceinline__ FusedWalk(const FusedArgs& a_, const WalkInit& wi)
+      : a(a_), tile(wi.tile - 1), end(wi.end), pb(wi.pb - 1), y(wi.y), b(wi.b), it(-1), seg_first(false) {}
   __device__ __forceinline__ bool next() {
     ++tile;
     ++it;
@@ -152,6 +165,65 @@ struct SlotTrack {
     else if (++slot0 == R) slot0 = 0;
   }
 };
+
+// delta = rowsum(dO o O) (sink_flash_attention.py:582) for rows 32 * quarter .. + 31 of one packed tile, written
+// to the workspace.  8 lanes x 16 B per row, 4 rows per warp load, 8 rows (2 per lane group) in flight per batch.
+// Inlined at ONE call site and small on purpose: the kernel is bound by instruction fetch (three inlined copies made
+// it 101 KB of SASS and 1.7x slower), and it must not spill -- with 227 KB of shared memory the L1 that backs local
+// memory is tiny, every spill reload is an L2 round trip (a spilling out-of-line version took 14 000 cycles per tile).
+struct DeltaGeom {
+  int64_t so_h, so_n, sdo_h, sdo_n;
+  int N, P, lgP, lgG, q_swap;
+};
+template <typename T>
+__device__ __forceinline__ void fused_delta_rows(const T* ob, const T* dob, float* drows, const DeltaGeom& g, int i0,
+                                                 int quarter, int lane) {
+  const int dsub = lane & 7, drow = lane >> 3;
+  ob += dsub * 8;
+  dob += dsub * 8;
+#pragma unroll 1
+  for (int bt = 0; bt < 4; ++bt) {
+    uint4 ov[2], gv[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r2 = quarter * 32 + bt * 8 + j * 4 + drow;
+      const int pr2 = g.q_swap ? (r2 >> g.lgG) : (r2 & (g.P - 1));
+      const int gr2 = g.q_swap ? (r2 & ((1 << g.lgG) - 1)) : (r2 >> g.lgP);
+      const int i = i0 + pr2;
+      ov[j] = gv[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < g.N) {
+        const T* po = ob + gr2 * g.so_h + i * g.so_n;
+        const T* pg = dob + gr2 * g.sdo_h + i * g.sdo_n;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(ov[j].x), "=r"(ov[j].y), "=r"(ov[j].z), "=r"(ov[j].w) : "l"(po));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(gv[j].x), "=r"(gv[j].y), "=r"(gv[j].z), "=r"(gv[j].w) : "l"(pg));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t ou[4] = {ov[j].x, ov[j].y, ov[j].z, ov[j].w}, gu[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float o0, o1, g0, g1;
+        unpack16f<T>(ou[e], o0, o1);
+        unpack16f<T>(gu[e], g0, g1);
+        s0 = fmaf(o0, g0, s0);
+        s1 = fmaf(o1, g1, s1);
+      }
+      float sum = s0 + s1;
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const int r2 = quarter * 32 + bt * 8 + j * 4 + drow;
+      const int pr2 = g.q_swap ? (r2 >> g.lgG) : (r2 & (g.P - 1));
+      const int gr2 = g.q_swap ? (r2 & ((1 << g.lgG) - 1)) : (r2 >> g.lgP);
+      const int i = i0 + pr2;
+      if (dsub == 0 && i < g.N) drows[static_cast<int64_t>(gr2) * g.N + i] = sum;
+    }
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -190,9 +262,13 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   uint64_t* dq_done = ds_free + 1;    // [2] all UMMAs of tile n complete       (issuers V + K -> epilogue group n & 1)
   uint64_t* dq_free = dq_done + 2;    // [2] dQ(n) read                         (epilogue group n & 1 -> issuer K)
   uint64_t* drain_done = dq_free + 2; // [2] ring drain of tile n finished      (epilogue group n & 1 -> issuers V, K)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drain_done + 2);
+  uint64_t* delta_ready = drain_done + 2;   // [4] delta rows of tile n in global memory: barrier n & 3, phase n >> 2
+                                            //     (epilogue group n & 1 -> math); four barriers because a group
+                                            //     produces up to two tiles ahead of the consumer (parity aliasing)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(delta_ready + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WalkInit wi(a);
 
   if (warp == 20 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -212,6 +288,8 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       mbar_init(dq_done + g, 3);
       mbar_init(dq_free + g, 4);
       mbar_init(drain_done + g, 4);
+      mbar_init(delta_ready + g, 4);
+      mbar_init(delta_ready + 2 + g, 4);
     }
     fence_barrier_init();
   }
@@ -238,29 +316,58 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
 
   if (warp >= 20) {
   if (warp == 20) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      FusedWalk w(a);
+    // ------------------------------------------------------------------ TMA producer (lane 0) + L2 prefetch (warp)
+    {
+      FusedWalk w(a, wi), wp(a, wi);
       const uint32_t kv_bytes = a.cols * C::D * 2;
       int tc = 0;
+      // The shared-memory rings are only two deep, so the HBM latency of a tile's loads sits on the critical cycle
+      // of the pipeline; an L2 prefetch kPrefetchAhead tiles ahead of the loads halves it.  Q / dO tiles by TMA
+      // prefetch; of K / V only the P newest rows are not in L2 yet (the tile before loaded the other nb - 1 blocks).
+      const int kPrefetchAhead = a.prefetch;
+      auto prefetch_tile = [&](const FusedWalk& t) {
+        const int q0 = t.pb * P, hq0 = t.y * a.G;
+        if (lane == 0) {
+          tma_tile_prefetch(&tmQ, a.q_swap, 0, q0, hq0, t.b);
+          tma_tile_prefetch(&tmdO, a.q_swap, 0, q0, hq0, t.b);
+        }
+        for (int r = lane; r < 2 * P; r += 32) {
+          const bool isv = r >= P;
+          const int key = q0 + (isv ? r - P : r);
+          if (key < a.N) {
+            const Strides4& sk = isv ? a.sv : a.sk;
+            const char* ptr = static_cast<const char*>(isv ? a.v : a.k) +
+                              (static_cast<int64_t>(t.b) * sk.b + static_cast<int64_t>(t.y) * sk.h +
+                               static_cast<int64_t>(key) * sk.n) * 2;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
+        }
+      };
+      if (a.prefetch)
+        for (int i = 0; i < kPrefetchAhead; ++i)
+          if (wp.next()) prefetch_tile(wp);
       while (w.next()) {
-        ftrace(a.trace, 0, tc, 1, w.it);
-        const int s = w.it & 1;
-        const uint32_t eph = ((w.it >> 1) & 1) ^ 1;
-        const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb - nb + 1) * P;
-        mbar_wait(q_empty + s, eph);
-        mbar_expect_tx(q_full + s, C::kQBytes);
-        tma_tile(q_s + s * C::kQBytes, &tmQ, q_full + s, a.q_swap, 0, q0, hq0, w.b);
-        mbar_wait(k_empty + s, eph);
-        mbar_expect_tx(k_full + s, kv_bytes);
-        tma_tile(k_s + s * C::kKVBytes, &tmK, k_full + s, a.k_swap, 0, kstart, w.y, w.b);
-        mbar_wait(do_empty + s, eph);
-        mbar_expect_tx(do_full + s, C::kQBytes);
-        tma_tile(do_s + s * C::kQBytes, &tmdO, do_full + s, a.q_swap, 0, q0, hq0, w.b);
-        mbar_wait(v_empty + s, eph);
-        mbar_expect_tx(v_full + s, kv_bytes);
-        tma_tile(v_s + s * C::kKVBytes, &tmV, v_full + s, a.v_swap, 0, kstart, w.y, w.b);
-        ftrace(a.trace, 0, tc, 3, w.it);
+        if (lane == 0) {
+          ftrace(a.trace, 0, tc, 1, w.it);
+          const int s = w.it & 1;
+          const uint32_t eph = ((w.it >> 1) & 1) ^ 1;
+          const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb - nb + 1) * P;
+          mbar_wait(q_empty + s, eph);
+          mbar_expect_tx(q_full + s, C::kQBytes);
+          tma_tile(q_s + s * C::kQBytes, &tmQ, q_full + s, a.q_swap, 0, q0, hq0, w.b);
+          mbar_wait(k_empty + s, eph);
+          mbar_expect_tx(k_full + s, kv_bytes);
+          tma_tile(k_s + s * C::kKVBytes, &tmK, k_full + s, a.k_swap, 0, kstart, w.y, w.b);
+          mbar_wait(do_empty + s, eph);
+          mbar_expect_tx(do_full + s, C::kQBytes);
+          tma_tile(do_s + s * C::kQBytes, &tmdO, do_full + s, a.q_swap, 0, q0, hq0, w.b);
+          mbar_wait(v_empty + s, eph);
+          mbar_expect_tx(v_full + s, kv_bytes);
+          tma_tile(v_s + s * C::kKVBytes, &tmV, v_full + s, a.v_swap, 0, kstart, w.y, w.b);
+          ftrace(a.trace, 0, tc, 3, w.it);
+        }
+        __syncwarp();
+        if (a.prefetch && wp.next()) prefetch_tile(wp);    // behind this tile's loads in the TMA queue, not in front
       }
     }
     __syncwarp();
@@ -270,7 +377,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       const uint32_t idesc = make_idesc(a.fmt, 128, a.cols, 0, 0);
       const uint64_t qd0 = make_sdesc(smem_u32(q_s), 16, 1024), kd0 = make_sdesc(smem_u32(k_s), 16, 1024);
       const uint64_t dod0 = make_sdesc(smem_u32(do_s), 16, 1024), vd0 = make_sdesc(smem_u32(v_s), 16, 1024);
-      FusedWalk w(a);
+      FusedWalk w(a, wi);
       int tc = 0;
       while (w.next()) {
         ftrace(a.trace, 1, tc, 1, w.it);
@@ -312,7 +419,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       const uint64_t dsa0 = make_sdesc_ns(smem_u32(ds_s), 2048, 128);
       const uint64_t kb0 = make_sdesc(smem_u32(k_s), C::kKVBytes, 1024);
       const uint32_t wrap16 = static_cast<uint32_t>(R * P) * 16u;
-      FusedWalk w(a);
+      FusedWalk w(a, wi);
       SlotTrack st;
       st.slot0 = 0;
       int tc = 0;
@@ -353,7 +460,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       uint64_t* const a_full = isK ? q_full : do_full;
       uint64_t* const a_empty = isK ? q_empty : do_empty;
       const int role = isK ? 5 : 2;
-      FusedWalk w(a);
+      FusedWalk w(a, wi);
       SlotTrack st;
       st.slot0 = 0;
       int tc = 0;
@@ -408,11 +515,25 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         }
         return v;
       };
-      FusedWalk w(a), wn(a);
+      // delta of tile t was written to global memory by epilogue group (t.it & 1) of THIS CTA: wait for its
+      // mbarrier (release / acquire at CTA scope), then read through L2 (no stale L1 line, no .nc)
+      auto load_delta = [&](const FusedWalk& t, bool valid) {
+        float v = 0.f;
+        if (valid) {
+          if (a.fuse_delta) mbar_wait_warp(delta_ready + (t.it & 3), (t.it >> 2) & 1);
+          const int i = t.pb * P + pr;
+          if (i < a.N) {
+            const int64_t row = (static_cast<int64_t>(t.b) * a.Hq + t.y * a.G + gr) * a.N + i;
+            asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(a.delta + row) : "memory");
+          }
+        }
+        return v;
+      };
+      FusedWalk w(a, wi), wn(a, wi);
       SlotTrack st;
       st.slot0 = 0;
       bool has_next = wn.next();
-      float l_next = load_row(a.lse, wn, has_next, INFINITY), d_next = load_row(a.delta, wn, has_next, 0.f);
+      float l_next = load_row(a.lse, wn, has_next, INFINITY), d_next = load_delta(wn, has_next);
       int tc = 0;
       const bool tr = SFA_TRACE && (threadIdx.x == 0);
       while (w.next()) {
@@ -421,7 +542,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         const float lse_i = l_next, dsc = d_next * a.scale;
         has_next = wn.next();
         l_next = load_row(a.lse, wn, has_next, INFINITY);
-        d_next = load_row(a.delta, wn, has_next, 0.f);
+        d_next = load_delta(wn, has_next);
         const float neg_l2 = (lse_i == -INFINITY) ? -INFINITY : -lse_i * kLog2e;   // lse = +-inf: P = 0
         const int i = w.pb * P + pr;
         const int kstart = (w.pb - nb + 1) * P;
@@ -536,17 +657,60 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         row_pr[t] = pr2;
         row_off[t] = static_cast<int64_t>(gr2) * a.sdq.h + static_cast<int64_t>(pr2) * a.sdq.n + (lane & 1) * 8;
       }
-      FusedWalk w(a);
-      SlotTrack st;
-      st.slot0 = 0;
-      int pa = 0;
+      // ---- delta = rowsum(dO o O) (sink_flash_attention.py:582) of this group's tiles, computed in the idle time
+      // between two epilogues, four tiles ahead of the epilogue and at least two ahead of the math warps' prefetch:
+      // replaces a separate pass over O and dO (the preprocess kernel, 33 us at the gpt-oss shape).  ds_aux
+      // (:653-665) is reduced from delta and lse by a small kernel afterwards.  8 lanes x 16 B per row, 4 rows per warp load; this
+      // warp owns rows 32 * quarter .. + 31 of the tile.
       int tc = 0;
       const bool tr = SFA_TRACE && (lane == 0) && (quarter == 0);
       const int trole = grp ? 6 : 4;
-      while (w.next()) {
-        st.step(w, R);
-        if (w.seg_first) pa = w.pb;
-        if ((w.it & 1) != grp) continue;
+      DeltaGeom dgeom;
+      dgeom.so_h = a.so.h; dgeom.so_n = a.so.n; dgeom.sdo_h = a.sdo.h; dgeom.sdo_n = a.sdo.n;
+      dgeom.N = a.N; dgeom.P = P; dgeom.lgP = a.lgP; dgeom.lgG = 7 - a.lgP; dgeom.q_swap = a.q_swap;
+      // L2 prefetch of the O and dO rows of the delta tile after next: this lane's row of the 128
+      auto delta_prefetch = [&](const FusedWalk& t) {
+        const int i = t.pb * P + pr;
+        if (i < a.N) {
+          const int h = t.y * a.G + gr;
+          const T* po = static_cast<const T*>(a.o) + t.b * a.so.b + h * a.so.h + static_cast<int64_t>(i) * a.so.n;
+          const T* pg = static_cast<const T*>(a.dout) + t.b * a.sdo.b + h * a.sdo.h + static_cast<int64_t>(i) * a.sdo.n;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(po));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pg));
+        }
+      };
+      auto delta_tile = [&](const FusedWalk& t) {
+        if (tr) ftrace(a.trace, trole, tc, 7, t.it);
+        const int h0 = t.y * a.G;
+        fused_delta_rows<T>(static_cast<const T*>(a.o) + t.b * a.so.b + h0 * a.so.h,
+                            static_cast<const T*>(a.dout) + t.b * a.sdo.b + h0 * a.sdo.h,
+                            a.delta + (static_cast<int64_t>(t.b) * a.Hq + h0) * a.N, dgeom, t.pb * P, quarter, lane);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(delta_ready + (t.it & 3));
+      };
+      FusedWalk wd(a, wi);
+      for (int t = 0; t <= grp; ++t) wd.next();          // wd.it == grp: this group's first tile
+      FusedWalk w(a, wi);
+      SlotTrack st;
+      st.slot0 = 0;
+      int pa = 0;
+      // One loop, ONE delta site: two lead-in rounds produce the deltas of the group's first two tiles, every later
+      // round is epilogue(tile n) followed by delta(tile n + 4).
+      int lead = a.fuse_delta ? 2 : 0;
+      while (true) {
+        if (lead > 0) {
+          --lead;
+        } else {
+        bool ok;
+        do {
+          ok = w.next();
+          if (ok) {
+            st.step(w, R);
+            if (w.seg_first) pa = w.pb;
+          }
+        } while (ok && (w.it & 1) != grp);
+        if (!ok) break;
         if (tr) ftrace(a.trace, trole, tc, 1, w.it);
         mbar_wait_warp(dq_done + grp, (w.it >> 1) & 1);
         tc_fence_after();
@@ -635,6 +799,19 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         __syncwarp();
         if (lane == 0) mbar_arrive(drain_done + grp);
         if (tr) ftrace(a.trace, trole, tc, 5, w.it);
+        }
+        // ---- delta of the group's tile four ahead (prefetch for the one after it first)
+        if (!a.fuse_delta) continue;
+        {
+          FusedWalk wf = wd;
+          wf.next();
+          wf.next();
+          if (wf.tile < wf.end) delta_prefetch(wf);
+        }
+        if (wd.tile < wd.end) delta_tile(wd);
+        wd.next();
+        wd.next();
+        if (tr) ftrace(a.trace, trole, tc, 6, w.it);
       }
     }
   }
@@ -725,10 +902,18 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, cudaStream
   if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;
   a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh;
   a.fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
+  a.fuse_delta = tc_bwd_fused_computes_delta() ? 1 : 0;
+  static const int prefetch = getenv("SFA_PREFETCH") ? atoi(getenv("SFA_PREFETCH")) : 0;
+  a.prefetch = prefetch;
   a.sl2 = p.scale * kLog2e;
   a.scale = p.scale;
   a.lse = p.lse;
   a.delta = p.delta;
+  a.o = p.o;
+  a.dout = p.dout;
+  a.k = p.k; a.v = p.v; a.sk = p.sk; a.sv = p.sv;
+  a.so = p.so;
+  a.sdo = p.sdo;
   a.dq = p.dq; a.dk = p.dk; a.dv = p.dv;
   a.sdq = p.sdq; a.sdk = p.sdk; a.sdv = p.sdv;
   a.part = part;
@@ -756,6 +941,14 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, cudaStream
 
 }  // namespace
 
+// Off by default: measured at the gpt-oss shape, delta inside the kernel (epilogue groups, 8 lanes x 16 B per row from
+// L2-prefetched O / dO rows) costs each epilogue group ~9 000 cycles per tile -- more than its idle time -- and the
+// backward takes 152 us against 108 + 37 us with the separate streaming preprocess kernel.  SFA_FUSED_DELTA=1 enables it.
+bool tc_bwd_fused_computes_delta() {
+  static const bool on = getenv("SFA_FUSED_DELTA") != nullptr;
+  return on;
+}
+
 size_t tc_bwd_fused_workspace_bytes() {
   return static_cast<size_t>(FusedCfg::kMaxCtas) * 2 * FusedCfg::kPartKeys * 128 * sizeof(float);
 }
@@ -769,8 +962,10 @@ bool tc_bwd_fused_supported(const AttnParams& p, int dtype) {
   if (!(tma_compatible(p.q, p.sq) && tma_compatible(p.k, p.sk) && tma_compatible(p.v, p.sv) &&
         tma_compatible(p.dout, p.sdo)))
     return false;
-  // dQ rows are written with 16-byte stores
+  // dQ rows are written with 16-byte stores; O and dO rows are read with 16-byte loads (delta)
   if (reinterpret_cast<uintptr_t>(p.dq) % 16 || p.sdq.n % 8 || p.sdq.h % 8 || p.sdq.b % 8) return false;
+  if (reinterpret_cast<uintptr_t>(p.o) % 16 || p.so.n % 8 || p.so.h % 8 || p.so.b % 8) return false;
+  if (reinterpret_cast<uintptr_t>(p.dout) % 16 || p.sdo.n % 8 || p.sdo.h % 8 || p.sdo.b % 8) return false;
   const bool q_swap = (p.Hq > 1 && p.N > 1) ? (p.sq.h < p.sq.n) : false;
   const bool do_swap = (p.Hq > 1 && p.N > 1) ? (p.sdo.h < p.sdo.n) : false;
   return q_swap == do_swap;

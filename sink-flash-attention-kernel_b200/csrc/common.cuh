@@ -81,6 +81,9 @@ cudaError_t tc_fwd64(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_bwd_supported(const AttnParams& p, int dtype);
 bool tc_bwd_fuses_delta(const AttnParams& p, int dtype);   // the dQ kernel derives delta (and ds_aux rows) itself: no preprocess pass
 cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st);
+bool tc_bwd_fused_computes_delta();
+cudaError_t ds_aux_from_delta(const float* delta, const float* lse, const float* s_aux, float* ds_aux, int B, int Hq,
+                              int N, cudaStream_t st);
 cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
 // fused dQ + dK + dV kernel for narrow windows without sink tokens (bwdf_sm100.cu); `part` = fp32 partials workspace
 bool tc_bwd_fused_supported(const AttnParams& p, int dtype);

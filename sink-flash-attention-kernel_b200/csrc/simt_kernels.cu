@@ -480,6 +480,39 @@ cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cu
   return e;
 }
 
+// ds_aux[h] = -sum_{b,i} exp(s_aux[h] - lse[b,h,i]) * delta[b,h,i] (sink_flash_attention.py:653-665) from the delta
+// rows the fused backward kernel left in its workspace; fixed summation order -> deterministic.
+__global__ void __launch_bounds__(512) ds_aux_from_delta_kernel(const float* __restrict__ delta,
+                                                                const float* __restrict__ lse,
+                                                                const float* __restrict__ s_aux, float* ds_aux, int B,
+                                                                int Hq, int N) {
+  __shared__ float red[512];
+  const int h = blockIdx.x;
+  const float sx = s_aux[h];
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* d = delta + ((int64_t)b * Hq + h) * N;
+    const float* l = lse + ((int64_t)b * Hq + h) * N;
+    for (int t = threadIdx.x; t < N; t += 512) {
+      const float lv = l[t];
+      s += (lv == -INFINITY) ? 0.f : -expf(sx - lv) * d[t];
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 256; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ds_aux[h] = red[0];
+}
+
+cudaError_t ds_aux_from_delta(const float* delta, const float* lse, const float* s_aux, float* ds_aux, int B, int Hq,
+                              int N, cudaStream_t st) {
+  ds_aux_from_delta_kernel<<<Hq, 512, 0, st>>>(delta, lse, s_aux, ds_aux, B, Hq, N);
+  return cudaGetLastError();
+}
+
 cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st) {
   ds_aux_reduce_kernel<<<Hq, 256, 0, st>>>(partial, ds_aux, B, Hq, nblk);
   return cudaGetLastError();

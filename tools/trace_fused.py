@@ -39,9 +39,9 @@ CODES = [
     {1: "begin", 2: "S inputs ready", 3: "S issued", 4: "dP inputs ready", 5: "dP issued"},
     {1: "begin", 2: "P ready + drain ok", 3: "dV issued"},
     {1: "begin", 2: "S full + P free", 3: "pass 1 done", 4: "dP full + dS free", 5: "pass 2 done"},
-    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done"},
+    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done", 6: "delta(+4) done", 7: "delta begin", 8: "delta loads issued", 9: "delta half done"},
     {1: "begin", 2: "dS ready + drain ok", 3: "dK issued"},
-    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done"},
+    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done", 6: "delta(+4) done", 7: "delta begin", 8: "delta loads issued", 9: "delta half done"},
     {1: "begin", 2: "dS ready + dq_free ok", 3: "dQ issued"},
 ]
 ev = []
