@@ -217,7 +217,7 @@ def run_ours(args):
             o.backward(do)
 
         # The timed step is a CUDA-graph replay of exactly the launches the autograd Function makes (sfa_fwd,
-        # then sfa_bwd: fused delta/dQ/dK/dV kernel, fix-up, ds_aux reduce): the four kernels take
+        # then sfa_bwd: delta/ds_aux preprocess, ds_aux reduce, fused dQ/dK/dV kernel, fix-up): the five kernels take
         # ~0.2 ms, less than the Python/ctypes launch path around them, so the eager number measures the host.
         qd_, kd_, vd_, sd_ = q.detach(), k.detach(), v.detach(), s_aux.detach()
 
@@ -235,7 +235,7 @@ def run_ours(args):
         def step():
             step_graph.replay()
         n_total = N
-        launches_per_step = 4               # fwd; bwd = fused delta/dQ/dK/dV kernel + its fix-up + ds_aux reduce
+        launches_per_step = 4               # fwd; bwd = delta/ds_aux preprocess + fused dQ/dK/dV + its fix-up (which also reduces ds_aux)
                                             # (wide windows / sinks: preprocess + ds_aux reduce + dQ kernel + dK/dV kernel)
         workload = ("gpt-oss-20b attention layer fwd+bwd (BASELINE configs[1]): B=1 N=8192 Hq=64 Hkv=8 D=64 window=128 "
                     "s_aux bf16")
@@ -333,16 +333,44 @@ def run_ours(args):
             qd, kd, vd = q.detach(), k.detach(), v.detach()
             sd = s_aux.detach()
 
-            def graph_timed(fn, steps=10):
+            INNER = 10
+            flush_only = {}
+
+            def _replay_ms(gr, reps):
+                ts = []
+                for _ in range(reps):
+                    a, b = ev(), ev()
+                    a.record()
+                    gr.replay()
+                    b.record()
+                    b.synchronize()
+                    ts.append(a.elapsed_time(b))
+                return statistics.median(ts)
+
+            def _capture(body):
+                gr = torch.cuda.CUDAGraph()
+                keep = []
+                with torch.cuda.graph(gr):
+                    for it in range(INNER):
+                        flush_buf.fill_(it)
+                        keep.append(body())
+                return gr, keep
+
+            def graph_timed(fn, reps=7):
+                """ms of one `fn`: a graph of INNER x (L2 flush, fn) minus a graph of INNER x (L2 flush), / INNER --
+                the CUDA event clock of this box ticks every ~2 us, too coarse for one 40-100 us kernel."""
                 for _ in range(3):
                     fn()
                 torch.cuda.synchronize()
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr):
-                    keep = fn()
-                ts = timed(gr.replay, steps, 2)
+                if not flush_only:
+                    g0, _ = _capture(lambda: None)
+                    _replay_ms(g0, 2)
+                    flush_only["ms"] = _replay_ms(g0, reps)
+                gr, keep = _capture(fn)
+                _replay_ms(gr, 2)
+                ms_ = (_replay_ms(gr, reps) - flush_only["ms"]) / INNER
                 del keep
-                return statistics.median(ts)
+                return ms_
 
             t_eager = timed(eager_step, 5, 3)
             stage_ms = {}
@@ -353,8 +381,10 @@ def run_ours(args):
             # dQ, dK and dV (bwdf_sm100.cu) + a small fix-up; otherwise the dQ / dK/dV kernel pair
             _lib.bwd(qd, kd, vd, o_s, do, lse_s, S, W, sd)
             bwd_impl = _lib.last_impl()
-            if bwd_impl == "tcgen05-fused":
+            if bwd_impl == "tcgen05-fused" and os.environ.get("SFA_FUSED_DELTA"):
                 stages = (("bwd_fused(delta,ds_aux,dq,dk,dv)", 6),)
+            elif bwd_impl == "tcgen05-fused":
+                stages = (("bwd_preprocess(delta,ds_aux)", 1), ("bwd_fused(dq,dk,dv)", 6))
             else:
                 stages = (("bwd_preprocess(delta,ds_aux)", 1), ("bwd_dq", 2), ("bwd_dkdv", 4))
             for name, mask in stages:
@@ -375,13 +405,15 @@ def run_ours(args):
                 "bwd_preprocess(delta,ds_aux)": 2 * B * Hq * N * D * e + 2 * 4 * B * Hq * N,
                 "bwd_dq": 3 * B * Hq * N * D * e + 2 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
                 "bwd_dkdv": 2 * B * Hq * N * D * e + 4 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
+                # Q, dO in, dQ out; K, V in, dK, dV out; lse, delta in
+                "bwd_fused(dq,dk,dv)": 3 * B * Hq * N * D * e + 4 * B * Hkv * N * D * e + 2 * 4 * B * Hq * N,
                 # Q, O, dO in, dQ out; K, V in, dK, dV out; lse in (delta stays on chip / in L2)
                 "bwd_fused(delta,ds_aux,dq,dk,dv)": 4 * B * Hq * N * D * e + 4 * B * Hkv * N * D * e + 4 * B * Hq * N,
             }
             pairs = attended_pairs(N, S, W) * B * Hq
             flops_alg = {"fwd": 4 * D * pairs, "bwd_preprocess(delta,ds_aux)": 2 * B * Hq * N * D,
                          "bwd_dq": 6 * D * pairs, "bwd_dkdv": 8 * D * pairs,
-                         "bwd_fused(delta,ds_aux,dq,dk,dv)": 10 * D * pairs}
+                         "bwd_fused(dq,dk,dv)": 10 * D * pairs, "bwd_fused(delta,ds_aux,dq,dk,dv)": 10 * D * pairs}
             dom = max(stage_ms, key=stage_ms.get)
             dur = stage_ms[dom] * 1e-3
             ach = bytes_alg[dom] / dur / 1e9

@@ -169,11 +169,16 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   if (use_tc && (g_bwd_stages & 14) == 6 && tc_bwd_fused_supported(p, dtype)) {
     set_impl_name("tcgen05-fused");
     if (!tc_bwd_fused_computes_delta()) {
+      // delta + ds_aux block partials (streaming pass over O and dO), then the fused kernel; the ds_aux partials
+      // are reduced by extra blocks of the fused kernel's fix-up launch
+      int ds_nblk = 0;
       if (g_bwd_stages & 1)
-        if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st), "sfa_bwd(preprocess)")) return r;
-      return cuda_ret(tc_bwd_fused(p, dtype, fused_part, st), "sfa_bwd(tcgen05 fused)");
+        if (int r = cuda_ret(bwd_preprocess(p, dtype, ds_partial, st, &ds_nblk), "sfa_bwd(preprocess)")) return r;
+      const bool red = (g_bwd_stages & 1) && p.s_aux && p.ds_aux;
+      return cuda_ret(tc_bwd_fused(p, dtype, fused_part, red ? ds_partial : nullptr, red ? ds_nblk : 0, st),
+                      "sfa_bwd(tcgen05 fused)");
     }
-    if (int r = cuda_ret(tc_bwd_fused(p, dtype, fused_part, st), "sfa_bwd(tcgen05 fused)")) return r;
+    if (int r = cuda_ret(tc_bwd_fused(p, dtype, fused_part, nullptr, 0, st), "sfa_bwd(tcgen05 fused)")) return r;
     if (p.s_aux && p.ds_aux)
       return cuda_ret(ds_aux_from_delta(p.delta, p.lse, p.s_aux, p.ds_aux, B, Hq, N, st), "sfa_bwd(ds_aux)");
     return 0;

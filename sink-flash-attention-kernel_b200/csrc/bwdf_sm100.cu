@@ -823,9 +823,29 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
 // Sums the fp32 partials of the key blocks shared by two neighbouring CTAs (tail of c - 1, head of c).
 // grid (boundaries, float4 groups / 256): one float4 per thread -- every load is independent and in flight at once
 // (the first version looped 64 dependent-latency iterations per thread and took 40 us for 2.4 MB).
+// Blocks x >= nbound (y == 0) reduce the ds_aux block partials of head x - nbound instead (fixed order: deterministic;
+// sink_flash_attention.py:653-665) -- one launch less on the backward's critical path.
 template <typename T>
-__global__ void __launch_bounds__(256) bwd_fused_fixup_kernel(const FusedArgs a, const int vec_ok) {
+__global__ void __launch_bounds__(256) bwd_fused_fixup_kernel(const FusedArgs a, const int vec_ok, const int nbound,
+                                                              const float* __restrict__ ds_partial, float* ds_aux,
+                                                              const int ds_nblk) {
   using C = FusedCfg;
+  if (static_cast<int>(blockIdx.x) >= nbound) {
+    if (blockIdx.y != 0) return;
+    __shared__ float red[256];
+    const int h = blockIdx.x - nbound;
+    float s = 0.f;
+    for (int b = 0; b < a.B; ++b)
+      for (int t = threadIdx.x; t < ds_nblk; t += 256) s += ds_partial[(static_cast<int64_t>(b) * a.Hq + h) * ds_nblk + t];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (static_cast<int>(threadIdx.x) < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) ds_aux[h] = red[0];
+    return;
+  }
   const int c = blockIdx.x + 1;
   const int t0 = c * a.tiles_per_cta;
   const int pa = t0 % a.nblk;
@@ -878,7 +898,8 @@ bool fused_geometry(const AttnParams& p, int& G, int& P, int& nb) {
 }
 
 template <typename T>
-cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, cudaStream_t st) {
+cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const float* ds_partial, int ds_nblk,
+                         cudaStream_t st) {
   using C = FusedCfg;
   int G, P, nb;
   if (!fused_geometry(p, G, P, nb)) return cudaErrorInvalidValue;
@@ -927,13 +948,16 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, cudaStream
   bwd_fused64_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (grid > 1 && nb > 1) {      // nb == 1 (window <= one block): no key block is shared between tiles
+  const int nbound = (grid > 1 && nb > 1) ? grid - 1 : 0;   // nb == 1 (window <= one block): no shared key block
+  const int nred = (ds_partial != nullptr && ds_nblk > 0) ? p.Hq : 0;
+  if (nbound + nred > 0) {
     auto al8 = [](const void* ptr, const Strides4& sd) {
       return reinterpret_cast<uintptr_t>(ptr) % 8 == 0 && sd.n % 4 == 0 && sd.h % 4 == 0 && sd.b % 4 == 0;
     };
     const int vec_ok = al8(p.dk, p.sdk) && al8(p.dv, p.sdv);
-    const int groups = (nb - 1) * P * 128 / 4;
-    bwd_fused_fixup_kernel<T><<<dim3(grid - 1, (groups + 255) / 256), 256, 0, st>>>(a, vec_ok);
+    const int groups = nbound ? (nb - 1) * P * 128 / 4 : 1;
+    bwd_fused_fixup_kernel<T><<<dim3(nbound + nred, (groups + 255) / 256), 256, 0, st>>>(a, vec_ok, nbound, ds_partial,
+                                                                                         p.ds_aux, ds_nblk);
     e = cudaGetLastError();
   }
   return e;
@@ -971,9 +995,10 @@ bool tc_bwd_fused_supported(const AttnParams& p, int dtype) {
   return q_swap == do_swap;
 }
 
-cudaError_t tc_bwd_fused(const AttnParams& p, int dtype, float* part, cudaStream_t st) {
-  if (dtype == SFA_DTYPE_BF16) return launch_fused<__nv_bfloat16>(p, dtype, part, st);
-  return launch_fused<__half>(p, dtype, part, st);
+cudaError_t tc_bwd_fused(const AttnParams& p, int dtype, float* part, const float* ds_partial, int ds_nblk,
+                         cudaStream_t st) {
+  if (dtype == SFA_DTYPE_BF16) return launch_fused<__nv_bfloat16>(p, dtype, part, ds_partial, ds_nblk, st);
+  return launch_fused<__half>(p, dtype, part, ds_partial, ds_nblk, st);
 }
 
 }  // namespace sfa

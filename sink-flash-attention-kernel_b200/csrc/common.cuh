@@ -72,7 +72,9 @@ __host__ __device__ __forceinline__ bool attended(int i, int j, int S, int W) {
 cudaError_t simt_fwd(const AttnParams& p, int dtype, cudaStream_t st);
 cudaError_t simt_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
 cudaError_t simt_decode(const DecodeParams& p, int dtype, cudaStream_t st);
-cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st);
+// defer_reduce_nblk != nullptr: do not launch the ds_aux reduce; *defer_reduce_nblk = partials per (b, head)
+cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st,
+                           int* defer_reduce_nblk = nullptr);
 
 bool tc_fwd_supported(const AttnParams& p, int dtype);
 cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st);
@@ -88,7 +90,10 @@ cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);
 // fused dQ + dK + dV kernel for narrow windows without sink tokens (bwdf_sm100.cu); `part` = fp32 partials workspace
 bool tc_bwd_fused_supported(const AttnParams& p, int dtype);
 size_t tc_bwd_fused_workspace_bytes();
-cudaError_t tc_bwd_fused(const AttnParams& p, int dtype, float* part, cudaStream_t st);
+// ds_partial / ds_nblk: block partials of ds_aux left by bwd_preprocess, reduced by extra blocks of the fix-up launch
+// (nullptr / 0: nothing to reduce)
+cudaError_t tc_bwd_fused(const AttnParams& p, int dtype, float* part, const float* ds_partial, int ds_nblk,
+                         cudaStream_t st);
 
 bool mma_decode_supported(const DecodeParams& p, int dtype);
 int mma_decode_splits(int B, int Hkv, int total_len);

@@ -279,13 +279,17 @@ __global__ void __launch_bounds__(256) preprocess_vec_kernel(AttnParams p, float
   const T* o = static_cast<const T*>(p.o) + b * p.so.b + h * p.so.h + sub * 8;
   const T* dO = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h + sub * 8;
   uint4 a[R], c[R];
+  float lse_r[R];           // loaded with the rows, not after the reduction: one memory round trip per block
+  const float* lse_h = p.lse + ((int64_t)b * p.Hq + h) * p.N;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int i = i0 + r * RPB;
     a[r] = c[r] = make_uint4(0u, 0u, 0u, 0u);
+    lse_r[r] = -INFINITY;
     if (i < p.N) {
       a[r] = ld_nc_v4(o + (int64_t)i * p.so.n);
       c[r] = ld_nc_v4(dO + (int64_t)i * p.sdo.n);
+      if (p.s_aux && sub == 0) lse_r[r] = __ldg(lse_h + i);
     }
   }
   const float sx = p.s_aux ? p.s_aux[h] : 0.f;
@@ -306,10 +310,7 @@ __global__ void __launch_bounds__(256) preprocess_vec_kernel(AttnParams p, float
     if (i < p.N && sub == 0) {
       const int64_t row = ((int64_t)b * p.Hq + h) * p.N + i;
       p.delta[row] = s;
-      if (p.s_aux) {
-        const float lse = p.lse[row];
-        contrib += (lse == -INFINITY) ? 0.f : -expf(sx - lse) * s;
-      }
+      if (p.s_aux) contrib += (lse_r[r] == -INFINITY) ? 0.f : -expf(sx - lse_r[r]) * s;
     }
   }
   if (ds_partial) {
@@ -455,7 +456,7 @@ static bool vec16_ok(const void* ptr, const Strides4& s) {
   return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && s.n % 8 == 0 && s.h % 8 == 0 && s.b % 8 == 0;
 }
 
-cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st) {
+cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cudaStream_t st, int* defer_reduce_nblk) {
   float* dsp = p.s_aux ? ds_partial : nullptr;
   int nblk = (p.N + 7) / 8;
   cudaError_t e;
@@ -473,6 +474,10 @@ cudaError_t bwd_preprocess(const AttnParams& p, int dtype, float* ds_partial, cu
     });
   }
   if (e != cudaSuccess) return e;
+  if (defer_reduce_nblk != nullptr) {      // the caller folds the reduce into a later launch
+    *defer_reduce_nblk = nblk;
+    return e;
+  }
   if (p.s_aux && p.ds_aux) {
     ds_aux_reduce_kernel<<<p.Hq, 256, 0, st>>>(ds_partial, p.ds_aux, p.B, p.Hq, nblk);
     e = cudaGetLastError();
