@@ -247,7 +247,10 @@ def run_ours(args):
         k = torch.randn(B, N, Hkv, D, device=dev, generator=g).to(dt).requires_grad_(True)
         v = torch.randn(B, N, Hkv, D, device=dev, generator=g).to(dt).requires_grad_(True)
         do = torch.randn(B, N, Hq, D, device=dev, generator=g).to(dt)
-        uly = sa.UlyssesSinkAttention(num_sink=S, window_size=W, sp_group=None, head_chunks=1)
+        # The exchange runs as peer-memory scatter kernels of libsinkfa over NVLink (sp_utils._UlyssesP2PAttention:
+        # no NCCL call, no pack / unpack copies); SFA_BENCH_ULY=nccl selects the NCCL all-to-all path instead.
+        want_p2p = os.environ.get("SFA_BENCH_ULY", "p2p") != "nccl"
+        uly = sa.UlyssesSinkAttention(num_sink=S, window_size=W, sp_group=None, head_chunks=1, p2p=want_p2p)
 
         def eager_uly_step():
             for t in (q, k, v, s_aux):
@@ -255,12 +258,26 @@ def run_ours(args):
             o = uly(q, k, v, s_aux)
             o.backward(do)
 
+        if want_p2p:
+            ok = torch.ones(1, device=dev)
+            try:
+                eager_uly_step()
+                torch.cuda.synchronize()
+            except Exception as e:      # noqa: BLE001  -- symmetric memory unavailable on this box
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL",
+                      file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                want_p2p = False
+                uly = sa.UlyssesSinkAttention(num_sink=S, window_size=W, sp_group=None, head_chunks=1)
         step = eager_uly_step
-        step_mode = "eager autograd step with NCCL all-to-all each side"
-        # The eager step is ~40 small torch launches + 4 NCCL calls around 0.35 ms of attention kernels, i.e. bound
-        # by the host.  Capture the whole step (attention kernels, pack/unpack copies and the all-to-alls) in one
-        # CUDA graph; every rank replays it in lock-step.  Falls back to the eager step if capture is refused.
-        if os.environ.get("SFA_BENCH_ULY_GRAPH") == "1":     # opt-in: the capture hung once on a 2-GPU box (round 1)
+        exch = "peer-memory scatter kernels over NVLink" if want_p2p else "NCCL all-to-all"
+        step_mode = f"eager autograd step, {exch} each side"
+        # The eager step is bound by the host (~25 launches around 0.2 ms of attention kernels).  The peer-memory
+        # step is plain kernels on one stream, so the whole fwd+bwd is captured in ONE CUDA graph that every rank
+        # replays (the NCCL path is captured only on request: its capture hung once on a 2-GPU box).
+        if want_p2p or os.environ.get("SFA_BENCH_ULY_GRAPH") == "1":
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -276,14 +293,16 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 step = uly_graph.replay
                 step_graph = uly_graph
-                step_mode = "CUDA-graph replay of the autograd Ulysses step (attention kernels + NCCL all-to-all each side)"
+                step_mode = f"CUDA-graph replay of the autograd Ulysses step (attention kernels + {exch} each side)"
             except Exception as e:      # noqa: BLE001
                 print(f"[bench] rank {rank}: graph capture of the Ulysses step failed ({type(e).__name__}: {e}); timing the eager step",
                       file=sys.stderr)
                 step = eager_uly_step
-        launches_per_step = 1 + 4
+        # fwd: 3 scatter + barrier + attention + scatter + barrier (+ clone); bwd: scatter + barrier + preprocess +
+        # fused + fix-up + 3 scatter + barrier (+ 3 copies)  ->  13 kernels of libsinkfa per step (p2p path)
+        launches_per_step = 13 if want_p2p else 1 + 3
         workload = (f"gpt-oss-20b attention layer fwd+bwd under Ulysses SP: {N}-token chunk per rank of a {n_total}-token "
-                    f"sequence, Hq=64 Hkv=8 D=64 window=128 s_aux bf16, all-to-all over NVLink each side")
+                    f"sequence, Hq=64 Hkv=8 D=64 window=128 s_aux bf16, {exch} each side")
         parallelism = f"ulysses_sp{world}"
 
     # ---- the timed region: warm-up, barrier + sync, K steps (per-step CUDA events, L2 flushed between), sync

@@ -93,6 +93,17 @@ int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const
                     const int64_t win_strides[3], const int64_t o_strides[2],
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Ulysses sequence-parallel exchange (BASELINE configs[4]; the reference leaves this all-to-all to verl,
+ * verl_patch.py:15-20): one kernel reads the local tensor and stores every row into its final place in the
+ * destination rank's receive buffer through CUDA peer mappings (peer_dst: HOST array of P device pointers, entry
+ * `rank` being the local buffer).  A cross-rank barrier on the same stream must follow.
+ *   mode 0 (sequence -> heads): src [B, L=n, H, D] with element strides src_strides (batch, position, head);
+ *           head h -> rank h / (H/P), row (b, rank*n + i, head_off + h % (H/P)) of dst [B, P*n, dst_heads, D].
+ *   mode 1 (heads -> sequence): src [B, L=P*n, H=hl, D]; position i -> rank i / n,
+ *           row (b, i % n, head_off + rank*hl + h) of dst [B, n, dst_heads, D]. */
+int sfa_ulysses_scatter(const void* src, void* const* peer_dst, int P, int rank, int mode, int B, int L, int H, int D,
+                        int dtype, const int64_t src_strides[3], int dst_heads, int head_off, void* stream);
+
 /* tcgen05/TMA self-test: C[M=128,N] = A[128,K] * B^T (+ variants).  Returns 0 and fills c (fp32, device).
  * mode 0: A,B K-major in smem; mode 1: B given as [K,N] (MN-major); mode 2: A through TMEM (TS form). */
 int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream);

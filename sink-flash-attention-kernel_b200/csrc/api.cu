@@ -276,6 +276,40 @@ int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const
   return decode_impl(p, dtype, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int sfa_ulysses_scatter(const void* src, void* const* peer_dst, int P, int rank, int mode, int B, int L, int H, int D,
+                        int dtype, const int64_t src_strides[3], int dst_heads, int head_off, void* stream) {
+  if (!src || !peer_dst) {
+    set_error("null tensor pointer");
+    return -6;
+  }
+  if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16 && dtype != SFA_DTYPE_FP32) {
+    set_error("unknown dtype %d", dtype);
+    return -4;
+  }
+  const int es = dtype == SFA_DTYPE_FP32 ? 4 : 2;
+  if (P < 1 || P > 16 || rank < 0 || rank >= P || (mode != 0 && mode != 1) || B < 1 || L < 1 || H < 1 || D < 1) {
+    set_error("invalid exchange geometry P=%d rank=%d mode=%d B=%d L=%d H=%d D=%d", P, rank, mode, B, L, H, D);
+    return -1;
+  }
+  if ((mode == 0 ? H : L) % P != 0) {
+    set_error("%s (%d) must be divisible by the sequence-parallel size (%d)", mode == 0 ? "heads" : "sequence length",
+              mode == 0 ? H : L, P);
+    return -2;
+  }
+  if ((D * es) % 16 != 0 || reinterpret_cast<uintptr_t>(src) % 16 != 0 || (src_strides[0] * es) % 16 != 0 ||
+      (src_strides[1] * es) % 16 != 0 || (src_strides[2] * es) % 16 != 0) {
+    set_error("rows must be 16-byte aligned multiples of 16 bytes");
+    return -5;
+  }
+  for (int r = 0; r < P; ++r)
+    if (peer_dst[r] == nullptr || reinterpret_cast<uintptr_t>(peer_dst[r]) % 16 != 0) {
+      set_error("peer buffer %d is null or not 16-byte aligned", r);
+      return -6;
+    }
+  return cuda_ret(ulysses_scatter(src, peer_dst, P, rank, mode, B, L, H, D, es, src_strides, dst_heads, head_off,
+                                  static_cast<cudaStream_t>(stream)), "sfa_ulysses_scatter");
+}
+
 int sfa_probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode, void* stream) {
   return cuda_ret(probe_tma_bw(src, H, N, box_n, box_h, stages, grid, mode, static_cast<cudaStream_t>(stream)),
                   "sfa_probe_tma_bw");

@@ -108,6 +108,10 @@ cudaError_t probe_tmem_rate(long long* out, float* sink, int mode, int iters, in
 void set_trace_buffer(long long* p);   // performance-debug timeline (device buffer, 3*256*2 int64) or nullptr
 long long* trace_buffer();
 
+// Ulysses exchange by peer-memory stores (ulysses_p2p.cu)
+cudaError_t ulysses_scatter(const void* src, void* const* peer_dst, int P, int rank, int mode, int B, int L, int H,
+                            int D, int elem_size, const int64_t src_strides[3], int dst_heads, int head_off,
+                            cudaStream_t st);
 cudaError_t probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, cudaStream_t st);
 
 }  // namespace sfa

@@ -21,7 +21,7 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_mma_desc", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_mma_desc", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
 )
 
 _lib = None
@@ -66,6 +66,8 @@ def load() -> ctypes.CDLL:
     lib.sfa_decode.restype = i
     lib.sfa_decode_ring.argtypes = [p] * 6 + [f32p] + [i] * 7 + [i64p] * 4 + [p, c.c_size_t, p]
     lib.sfa_decode_ring.restype = i
+    lib.sfa_ulysses_scatter.argtypes = [p, c.POINTER(c.c_void_p)] + [i] * 8 + [i64p, i, i, p]
+    lib.sfa_ulysses_scatter.restype = i
     lib.sfa_probe_math_rate.argtypes = [p, p, i, i, i, p]
     lib.sfa_probe_math_rate.restype = i
     lib.sfa_probe_tmem_rate.argtypes = [p, p, i, i, i, p]
@@ -235,6 +237,20 @@ def decode_ring(q, sink_k, sink_v, win_k, win_v, sink_len: int, window_len: int,
             ws.data_ptr(), ws_bytes, _stream(q))
     _check(rc, "sfa_decode_ring")
     return o
+
+
+def ulysses_scatter(src: torch.Tensor, peer_ptrs: Sequence[int], rank: int, mode: int, dst_heads: int, head_off: int):
+    """src [B, L, H, D] (unit channel stride) -> rows stored into the peers' receive buffers (see include/sinkfa.h)."""
+    lib = load()
+    _require_cuda(src)
+    src = _unit_last(src)
+    B, L, H, D = src.shape
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+    with torch.cuda.device(src.device):
+        rc = lib.sfa_ulysses_scatter(src.data_ptr(), arr, len(peer_ptrs), int(rank), int(mode), B, L, H, D,
+                                     DTYPE_CODE[src.dtype], _i64(src.stride()[:3]), int(dst_heads), int(head_off),
+                                     _stream(src))
+    _check(rc, "sfa_ulysses_scatter")
 
 
 def probe_umma(a: torch.Tensor, b: torch.Tensor, n: int, k: int, mode: int) -> torch.Tensor:

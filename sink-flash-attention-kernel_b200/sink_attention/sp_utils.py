@@ -145,6 +145,99 @@ def ulysses_head_to_seq(x: torch.Tensor, group=None) -> torch.Tensor:
     return _HeadToSeq.apply(x, group)
 
 
+# =============================================================================================
+# Ulysses over peer memory: the exchange fused into single scatter kernels (no NCCL, no pack / unpack copies)
+# =============================================================================================
+class _P2PBuffers:
+    """Symmetric-memory receive buffers of ONE attention layer (torch symmetric memory gives every rank peer
+    mappings of the same allocation on all ranks of the group; the scatter kernel of libsinkfa stores into them
+    over NVLink).  Four regions, all in the layout their consumer reads in place:
+
+      qkv_full [B, P*n, hq_l + 2*hkv_l, D]   q | k | v of this rank's heads for all positions   (forward input)
+      o_seq    [B, n, Hq, D]                 O of all heads for this rank's positions           (forward output)
+      do_full  [B, P*n, hq_l, D]             dO of this rank's heads for all positions          (backward input)
+      g_seq    [B, n, Hq + 2*Hkv, D]         dq | dk | dv of all heads for this rank's positions (backward output)
+
+    One cross-rank barrier follows every exchange.  A region is overwritten by the peers only in the next
+    forward / backward of the same layer, and at least one such barrier (which every rank reaches only after its
+    own reads of the region were issued on the stream) lies in between -- so no barrier is needed in front."""
+
+    def __init__(self, group, B, n, Hq, Hkv, D, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        P, rank = _group_size_rank(group)
+        self.P, self.rank, self.key = P, rank, (B, n, Hq, Hkv, D, dtype)
+        hq_l, hkv_l = Hq // P, Hkv // P
+        self.tot = hq_l + 2 * hkv_l
+        sizes = [B * P * n * self.tot * D, B * n * Hq * D, B * P * n * hq_l * D, B * n * (Hq + 2 * Hkv) * D]
+        offs, total = [], 0
+        for sz in sizes:
+            offs.append(total)
+            total += (sz + 127) // 128 * 128                  # regions stay 256-byte aligned
+        self.buf = symm_mem.empty(total, dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        es = self.buf.element_size()
+        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        self.peer = [[ptr + off * es for ptr in ptrs] for off in offs]     # [region][rank] -> device pointer
+        self.qkv_full = self.buf[offs[0]:offs[0] + sizes[0]].view(B, P * n, self.tot, D)
+        self.o_seq = self.buf[offs[1]:offs[1] + sizes[1]].view(B, n, Hq, D)
+        self.do_full = self.buf[offs[2]:offs[2] + sizes[2]].view(B, P * n, hq_l, D)
+        self.g_seq = self.buf[offs[3]:offs[3] + sizes[3]].view(B, n, Hq + 2 * Hkv, D)
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
+class _UlyssesP2PAttention(torch.autograd.Function):
+    """seq->head exchange, attention, head->seq exchange as one autograd node; forward and backward are each
+    [scatter kernels, barrier, attention kernels, scatter kernels, barrier] on the current stream."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, s_loc, bufs, num_sink, window_size):
+        from . import _lib
+        P, rank = bufs.P, bufs.rank
+        B, n, Hq, D = q.shape
+        Hkv = k.shape[2]
+        hq_l, hkv_l = Hq // P, Hkv // P
+        _lib.ulysses_scatter(q, bufs.peer[0], rank, 0, bufs.tot, 0)
+        _lib.ulysses_scatter(k, bufs.peer[0], rank, 0, bufs.tot, hq_l)
+        _lib.ulysses_scatter(v, bufs.peer[0], rank, 0, bufs.tot, hq_l + hkv_l)
+        bufs.barrier()
+        full = bufs.qkv_full
+        qh = full[:, :, :hq_l].transpose(1, 2)               # [B, hq_l, P*n, D] views, consumed in place
+        kh = full[:, :, hq_l:hq_l + hkv_l].transpose(1, 2)
+        vh = full[:, :, hq_l + hkv_l:].transpose(1, 2)
+        s32 = _lib._s_aux_f32(s_loc, hq_l)
+        o, lse = _lib.fwd(qh, kh, vh, num_sink, window_size, s32)
+        _lib.ulysses_scatter(o.transpose(1, 2), bufs.peer[1], rank, 1, Hq, 0)
+        bufs.barrier()
+        out = bufs.o_seq.clone()                              # the region is reused by the next step
+        ctx.save_for_backward(qh, kh, vh, o, lse, s32 if s32 is not None else torch.empty(0, device=q.device))
+        ctx.bufs, ctx.cfg, ctx.has_aux = bufs, (num_sink, window_size, Hq, Hkv), s_loc is not None
+        ctx.s_dtype = s_loc.dtype if s_loc is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import _lib
+        qh, kh, vh, o, lse, s32 = ctx.saved_tensors
+        bufs = ctx.bufs
+        num_sink, window_size, Hq, Hkv = ctx.cfg
+        P, rank = bufs.P, bufs.rank
+        hq_l = Hq // P
+        _lib.ulysses_scatter(dout, bufs.peer[2], rank, 0, hq_l, 0)
+        bufs.barrier()
+        do_h = bufs.do_full.transpose(1, 2)
+        dq, dk, dv, ds = _lib.bwd(qh, kh, vh, o, do_h, lse, num_sink, window_size, s32 if ctx.has_aux else None)
+        _lib.ulysses_scatter(dq.transpose(1, 2), bufs.peer[3], rank, 1, Hq + 2 * Hkv, 0)
+        _lib.ulysses_scatter(dk.transpose(1, 2), bufs.peer[3], rank, 1, Hq + 2 * Hkv, Hq)
+        _lib.ulysses_scatter(dv.transpose(1, 2), bufs.peer[3], rank, 1, Hq + 2 * Hkv, Hq + Hkv)
+        bufs.barrier()
+        g = bufs.g_seq
+        gq, gk, gv = g[:, :, :Hq].contiguous(), g[:, :, Hq:Hq + Hkv].contiguous(), g[:, :, Hq + Hkv:].contiguous()
+        gs = ds.to(ctx.s_dtype) if ctx.has_aux else None
+        return gq, gk, gv, gs, None, None, None
+
+
 def slice_s_aux_for_rank(s_aux: Optional[torch.Tensor], local_heads: int, rank: int) -> Optional[torch.Tensor]:
     """Reference rule (verl_patch.py:140-151): rank r owns s_aux[r*H_local : (r+1)*H_local]."""
     if s_aux is None or s_aux.shape[0] == local_heads:
@@ -160,12 +253,19 @@ class UlyssesSinkAttention(torch.nn.Module):
     (``P`` must divide ``H_kv``); ``s_aux`` holds ALL ``H_q`` logits.  Returns ``O [B, N/P, H_q, D]``.
     """
 
-    def __init__(self, num_sink: int = 0, window_size: int = 4096, sp_group=None, head_chunks: int = 1):
+    def __init__(self, num_sink: int = 0, window_size: int = 4096, sp_group=None, head_chunks: int = 1,
+                 p2p: bool = False):
         super().__init__()
         self.num_sink = num_sink
         self.window_size = window_size
         self.sp_group = sp_group
         self.head_chunks = max(1, int(head_chunks))
+        # p2p=True: the exchange runs as peer-memory scatter kernels of libsinkfa over NVLink instead of NCCL
+        # all-to-alls (one node, 16-bit / fp32 CUDA tensors).  The layer then owns symmetric receive buffers sized
+        # for its input shape; its saved q/k/v live in them until the layer's backward, so one instance must not
+        # run a second forward before the backward of the first (one instance per transformer layer).
+        self.p2p = bool(p2p)
+        self._bufs = None
 
     def forward(self, q, k, v, s_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
         from .sink_flash_attention import sink_flash_attention
@@ -174,6 +274,12 @@ class UlyssesSinkAttention(torch.nn.Module):
         assert H_kv % P == 0 and H_q % P == 0, "the sequence-parallel size must divide H_kv and H_q"
         hq_l, hkv_l = H_q // P, H_kv // P
         s_loc = slice_s_aux_for_rank(s_aux, hq_l, rank)
+        if self.p2p and P > 1:
+            B, n, _, D = q.shape
+            key = (B, n, H_q, H_kv, D, q.dtype)
+            if self._bufs is None or self._bufs.key != key:
+                self._bufs = _P2PBuffers(self.sp_group, B, n, H_q, H_kv, D, q.dtype, q.device)
+            return _UlyssesP2PAttention.apply(q, k, v, s_loc, self._bufs, self.num_sink, self.window_size)
         # head chunks are whole GQA groups so every chunk is an independent attention problem
         nchunk = min(self.head_chunks, hkv_l) if P > 1 else 1
         while hkv_l % nchunk:

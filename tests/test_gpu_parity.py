@@ -466,6 +466,43 @@ def test_c3_decode_full_size():
     assert maxdiff(o, o_r) < 1e-2
 
 
+# ------------------------------------------------------------------------------------------------
+# Ulysses exchange by peer-memory scatter (sfa_ulysses_scatter): P ranks emulated on one device -- every "rank"
+# owns its own receive buffer, the kernel is launched once per rank -- against the all-to-all written in torch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("P,B,n,H,D,extra", [(2, 1, 24, 8, 64, 3), (4, 2, 10, 8, 64, 0), (8, 1, 6, 16, 128, 5)])
+def test_ulysses_scatter_bit_exact(P, B, n, H, D, extra, dtype):
+    g = torch.Generator().manual_seed(P + n)
+    hl = H // P
+    # ---- mode 0: sequence chunks [B, n, H, D] -> rank r holds [B, P*n, dst_heads, D] with its heads at head_off
+    dst_heads, head_off = hl + extra, extra
+    src = [torch.randn(B, n, H, D, generator=g).to("cuda", dtype) for _ in range(P)]
+    dst = [torch.zeros(B, P * n, dst_heads, D, device="cuda", dtype=dtype) for _ in range(P)]
+    for r in range(P):
+        hf_view = src[r].transpose(1, 2).contiguous().transpose(1, 2)        # arbitrary strides are accepted
+        _lib.ulysses_scatter(hf_view, [d.data_ptr() for d in dst], r, 0, dst_heads, head_off)
+    torch.cuda.synchronize()
+    for r in range(P):
+        expect = torch.cat([src[s][:, :, r * hl:(r + 1) * hl] for s in range(P)], dim=1)   # [B, P*n, hl, D]
+        assert torch.equal(dst[r][:, :, head_off:head_off + hl], expect)
+        assert float(dst[r][:, :, :head_off].abs().sum()) == 0.0
+    # ---- mode 1: rank r holds [B, P*n, hl, D] (its heads, all positions) -> rank s gets [B, n, dst_heads, D]
+    dst_heads, head_off = H + extra, extra
+    src = [torch.randn(B, P * n, hl, D, generator=g).to("cuda", dtype) for _ in range(P)]
+    dst = [torch.zeros(B, n, dst_heads, D, device="cuda", dtype=dtype) for _ in range(P)]
+    for r in range(P):
+        _lib.ulysses_scatter(src[r], [d.data_ptr() for d in dst], r, 1, dst_heads, head_off)
+    torch.cuda.synchronize()
+    for s_ in range(P):
+        expect = torch.cat([src[r][:, s_ * n:(s_ + 1) * n] for r in range(P)], dim=2)      # [B, n, H, D]
+        assert torch.equal(dst[s_][:, :, head_off:head_off + H], expect)
+    with pytest.raises(ValueError):
+        _lib.ulysses_scatter(src[0], [0] * P, 0, 1, dst_heads, head_off)                   # null peer pointer
+    with pytest.raises(ValueError):
+        _lib.ulysses_scatter(src[0][:, :P * n - 1], [d.data_ptr() for d in dst], 0, 1, dst_heads, head_off)
+
+
 def test_errors_are_loud():
     q = torch.randn(1, 4, 16, 64)
     with pytest.raises(RuntimeError):
