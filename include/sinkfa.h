@@ -104,6 +104,30 @@ int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const
 int sfa_ulysses_scatter(const void* src, void* const* peer_dst, int P, int rank, int mode, int B, int L, int H, int D,
                         int dtype, const int64_t src_strides[3], int dst_heads, int head_off, void* stream);
 
+/* Fused exchange on the output side of the Ulysses layout: the forward stores every O tile ALSO into the receive
+ * buffer of the rank that owns its positions (TMA store to a peer mapping, same staged tile as the local store),
+ * the backward stores dQ ONLY there -- no separate scatter pass over O / dQ.  peer[s] is rank s's buffer
+ * [B, n_local, heads_total, D] contiguous; this rank's head h lands at head_off + h; position i goes to rank
+ * i / n_local.  Supported by the head_dim-64 tcgen05 forward (local O in [B, N, H, D] stride order, n_local a
+ * multiple of the tile's positions) and the fused backward; otherwise the call returns -10 and nothing is launched
+ * (fall back to sfa_fwd / sfa_bwd + sfa_ulysses_scatter). */
+typedef struct sfa_sp_route {
+  int P, n_local, heads_total, head_off;
+  void* peer[8];
+} sfa_sp_route;
+int sfa_fwd_sp(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux,
+               int B, int Hq, int Hkv, int N, int D, int num_sink, int window, int dtype,
+               const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+               const int64_t o_strides[4], void* workspace, size_t workspace_bytes, void* stream,
+               const sfa_sp_route* o_route);
+int sfa_bwd_sp(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+               const float* s_aux, void* dk, void* dv, float* ds_aux,
+               int B, int Hq, int Hkv, int N, int D, int num_sink, int window, int dtype,
+               const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+               const int64_t o_strides[4], const int64_t do_strides[4],
+               const int64_t dk_strides[4], const int64_t dv_strides[4],
+               void* workspace, size_t workspace_bytes, void* stream, const sfa_sp_route* dq_route);
+
 /* tcgen05/TMA self-test: C[M=128,N] = A[128,K] * B^T (+ variants).  Returns 0 and fills c (fp32, device).
  * mode 0: A,B K-major in smem; mode 1: B given as [K,N] (MN-major); mode 2: A through TMEM (TS form). */
 int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream);

@@ -101,10 +101,19 @@ size_t sfa_workspace_bytes(int op, int B, int Hq, int Hkv, int N, int D, int dty
   return 0;
 }
 
-int sfa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux, int B, int Hq, int Hkv,
-            int N, int D, int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
-            const int64_t v_strides[4], const int64_t o_strides[4], void* workspace, size_t workspace_bytes,
-            void* stream) {
+static bool route_from_c(const sfa_sp_route* in, SpRoute& out) {
+  if (in->P < 1 || in->P > 8 || in->n_local < 1 || in->heads_total < 1 || in->head_off < 0) return false;
+  out.P = in->P; out.n_local = in->n_local; out.heads_total = in->heads_total; out.head_off = in->head_off;
+  for (int r = 0; r < 8; ++r) out.peer[r] = r < in->P ? in->peer[r] : nullptr;
+  for (int r = 0; r < in->P; ++r)
+    if (out.peer[r] == nullptr) return false;
+  return true;
+}
+
+static int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux, int B, int Hq,
+                    int Hkv, int N, int D, int num_sink, int window, int dtype, const int64_t q_strides[4],
+                    const int64_t k_strides[4], const int64_t v_strides[4], const int64_t o_strides[4], void* workspace,
+                    size_t workspace_bytes, void* stream, const sfa_sp_route* o_route) {
   (void)workspace;
   (void)workspace_bytes;
   const int64_t* ss[4] = {q_strides, k_strides, v_strides, o_strides};
@@ -122,6 +131,18 @@ int sfa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, co
   p.W = window < 0 ? 0 : window;
   p.scale = 1.0f / sqrtf((float)D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SpRoute rt;
+  if (o_route != nullptr) {
+    if (!route_from_c(o_route, rt)) {
+      set_error("invalid sequence-parallel route");
+      return -9;
+    }
+    p.o_route = &rt;
+    if (g_force_impl == SFA_IMPL_SIMT || !tc_fwd_supported(p, dtype) || !tc_fwd64_route_supported(p, dtype)) {
+      set_error("routed O store needs the head_dim-64 tcgen05 forward, an HF-order local O and n_local a multiple of the tile");
+      return -10;
+    }
+  }
   if (g_force_impl != SFA_IMPL_SIMT && tc_fwd_supported(p, dtype)) {
     set_impl_name("tcgen05");
     if (tc_fwd64_supported(p, dtype) && !getenv("SFA_FWD_V1")) return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
@@ -131,15 +152,35 @@ int sfa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, co
   return cuda_ret(simt_fwd(p, dtype, st), "sfa_fwd(simt)");
 }
 
-int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+int sfa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux, int B, int Hq, int Hkv,
+            int N, int D, int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
+            const int64_t v_strides[4], const int64_t o_strides[4], void* workspace, size_t workspace_bytes,
+            void* stream) {
+  return fwd_impl(q, k, v, o, lse, s_aux, B, Hq, Hkv, N, D, num_sink, window, dtype, q_strides, k_strides, v_strides,
+                  o_strides, workspace, workspace_bytes, stream, nullptr);
+}
+
+int sfa_fwd_sp(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux, int B, int Hq,
+               int Hkv, int N, int D, int num_sink, int window, int dtype, const int64_t q_strides[4],
+               const int64_t k_strides[4], const int64_t v_strides[4], const int64_t o_strides[4], void* workspace,
+               size_t workspace_bytes, void* stream, const sfa_sp_route* o_route) {
+  if (o_route == nullptr) {
+    set_error("sfa_fwd_sp needs a route");
+    return -9;
+  }
+  return fwd_impl(q, k, v, o, lse, s_aux, B, Hq, Hkv, N, D, num_sink, window, dtype, q_strides, k_strides, v_strides,
+                  o_strides, workspace, workspace_bytes, stream, o_route);
+}
+
+static int bwd_impl(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
             const float* s_aux, void* dq, void* dk, void* dv, float* ds_aux, int B, int Hq, int Hkv, int N, int D,
             int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
             const int64_t v_strides[4], const int64_t o_strides[4], const int64_t do_strides[4],
             const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], void* workspace,
-            size_t workspace_bytes, void* stream) {
+            size_t workspace_bytes, void* stream, const sfa_sp_route* dq_route) {
   const int64_t* ss[8] = {q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides};
   if (int r = check_common(B, Hq, Hkv, N, D, dtype, ss, 8)) return r;
-  if (!q || !k || !v || !o || !dout || !lse || !dq || !dk || !dv) {
+  if (!q || !k || !v || !o || !dout || !lse || (!dq && !dq_route) || !dk || !dv) {
     set_error("null tensor pointer");
     return -6;
   }
@@ -165,6 +206,18 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   float* fused_part = reinterpret_cast<float*>(reinterpret_cast<char*>(p.dsrow) + rows_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool use_tc = g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype);
+  SpRoute rt;
+  if (dq_route != nullptr) {
+    if (!route_from_c(dq_route, rt)) {
+      set_error("invalid sequence-parallel route");
+      return -9;
+    }
+    p.dq_route = &rt;
+    if (!use_tc || (g_bwd_stages & 14) != 6 || !tc_bwd_fused_supported(p, dtype)) {
+      set_error("routed dQ store needs the fused head_dim-64 backward (narrow window, no sink tokens)");
+      return -10;
+    }
+  }
   // narrow window, no sink tokens, head_dim 64: ONE kernel computes delta, the ds_aux rows, dQ, dK and dV
   if (use_tc && (g_bwd_stages & 14) == 6 && tc_bwd_fused_supported(p, dtype)) {
     set_impl_name("tcgen05-fused");
@@ -197,6 +250,34 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
   }
   set_impl_name("simt");
   return cuda_ret(simt_bwd(p, dtype, g_bwd_stages & 7, st), "sfa_bwd(simt)");
+}
+
+int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+            const float* s_aux, void* dq, void* dk, void* dv, float* ds_aux, int B, int Hq, int Hkv, int N, int D,
+            int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
+            const int64_t v_strides[4], const int64_t o_strides[4], const int64_t do_strides[4],
+            const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], void* workspace,
+            size_t workspace_bytes, void* stream) {
+  return bwd_impl(q, k, v, o, dout, lse, s_aux, dq, dk, dv, ds_aux, B, Hq, Hkv, N, D, num_sink, window, dtype, q_strides,
+                  k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides, workspace,
+                  workspace_bytes, stream, nullptr);
+}
+
+int sfa_bwd_sp(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+               const float* s_aux, void* dk, void* dv, float* ds_aux, int B, int Hq, int Hkv, int N, int D, int num_sink,
+               int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+               const int64_t o_strides[4], const int64_t do_strides[4], const int64_t dk_strides[4],
+               const int64_t dv_strides[4], void* workspace, size_t workspace_bytes, void* stream,
+               const sfa_sp_route* dq_route) {
+  if (dq_route == nullptr) {
+    set_error("sfa_bwd_sp needs a route");
+    return -9;
+  }
+  const int64_t dq_strides[4] = {(int64_t)dq_route->n_local * dq_route->heads_total * D, D,
+                                 (int64_t)dq_route->heads_total * D, 1};
+  return bwd_impl(q, k, v, o, dout, lse, s_aux, nullptr, dk, dv, ds_aux, B, Hq, Hkv, N, D, num_sink, window, dtype,
+                  q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides, workspace,
+                  workspace_bytes, stream, dq_route);
 }
 
 static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {

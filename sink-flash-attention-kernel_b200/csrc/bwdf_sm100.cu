@@ -86,6 +86,8 @@ struct FusedArgs {
   void* dk;
   void* dv;
   Strides4 sdq, sdk, sdv;
+  void* dq_peer[8];   // Ulysses routing of dQ: rows of positions [k*dq_seg_n, (k+1)*dq_seg_n) go to dq_peer[k] (sdq = peer strides)
+  int dq_seg_n;       // 0: off, dq / sdq describe the local tensor
   float* part;   // [grid][2 sides][kPartKeys][2 (dV, dK)][64] fp32
   long long* trace;   // optional timeline buffer (sfa_set_trace_buffer, -DSFA_TRACE=1 builds); nullptr in production
 };
@@ -716,8 +718,15 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         tc_fence_after();
         if (tr) ftrace(a.trace, trole, tc, 2, w.it);
         {
-          T* const tile_dq = static_cast<T*>(a.dq) + static_cast<int64_t>(w.b) * a.sdq.b +
-                             static_cast<int64_t>(w.y * a.G) * a.sdq.h + static_cast<int64_t>(w.pb * P) * a.sdq.n;
+          T* dq_base = static_cast<T*>(a.dq);
+          int il0 = w.pb * P;
+          if (a.dq_seg_n > 0) {       // straight into the sequence owner's buffer over NVLink
+            const int seg = il0 / a.dq_seg_n;
+            dq_base = static_cast<T*>(a.dq_peer[seg]);
+            il0 -= seg * a.dq_seg_n;
+          }
+          T* const tile_dq = dq_base + static_cast<int64_t>(w.b) * a.sdq.b +
+                             static_cast<int64_t>(w.y * a.G) * a.sdq.h + static_cast<int64_t>(il0) * a.sdq.n;
           const bool ok0 = w.pb * P + row_pr[0] < a.N, ok1 = w.pb * P + row_pr[1] < a.N;
 #pragma unroll 1
           for (int hq = 0; hq < 4; ++hq) {                  // channels 16 hq .. 16 hq + 15
@@ -937,6 +946,19 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   a.sdo = p.sdo;
   a.dq = p.dq; a.dk = p.dk; a.dv = p.dv;
   a.sdq = p.sdq; a.sdk = p.sdk; a.sdv = p.sdv;
+  a.dq_seg_n = 0;
+  for (int r = 0; r < 8; ++r) a.dq_peer[r] = nullptr;
+  if (p.dq_route != nullptr) {
+    const SpRoute& rt = *p.dq_route;
+    if (rt.P < 1 || rt.P > 8 || rt.n_local % P != 0 || static_cast<int64_t>(rt.n_local) * rt.P != p.N)
+      return cudaErrorInvalidValue;
+    a.sdq = Strides4{static_cast<int64_t>(rt.n_local) * rt.heads_total * C::D, C::D, static_cast<int64_t>(rt.heads_total) * C::D};
+    for (int r = 0; r < rt.P; ++r) {
+      if (rt.peer[r] == nullptr || reinterpret_cast<uintptr_t>(rt.peer[r]) % 16 != 0) return cudaErrorInvalidValue;
+      a.dq_peer[r] = static_cast<char*>(rt.peer[r]) + static_cast<int64_t>(rt.head_off) * C::D * 2;
+    }
+    a.dq_seg_n = rt.n_local;
+  }
   a.part = part;
   a.trace = trace_buffer();
   static bool attr_done = false;
@@ -987,7 +1009,9 @@ bool tc_bwd_fused_supported(const AttnParams& p, int dtype) {
         tma_compatible(p.dout, p.sdo)))
     return false;
   // dQ rows are written with 16-byte stores; O and dO rows are read with 16-byte loads (delta)
-  if (reinterpret_cast<uintptr_t>(p.dq) % 16 || p.sdq.n % 8 || p.sdq.h % 8 || p.sdq.b % 8) return false;
+  if (p.dq_route == nullptr &&
+      (reinterpret_cast<uintptr_t>(p.dq) % 16 || p.sdq.n % 8 || p.sdq.h % 8 || p.sdq.b % 8)) return false;
+  if (p.dq_route != nullptr && (P > 0) && (p.dq_route->n_local % P != 0)) return false;
   if (reinterpret_cast<uintptr_t>(p.o) % 16 || p.so.n % 8 || p.so.h % 8 || p.so.b % 8) return false;
   if (reinterpret_cast<uintptr_t>(p.dout) % 16 || p.sdo.n % 8 || p.sdo.h % 8 || p.sdo.b % 8) return false;
   const bool q_swap = (p.Hq > 1 && p.N > 1) ? (p.sq.h < p.sq.n) : false;

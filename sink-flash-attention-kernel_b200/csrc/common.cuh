@@ -14,6 +14,13 @@ struct Strides4 {  // element strides for (batch, head, position); channel strid
   int64_t b, h, n;
 };
 
+// Sequence-parallel output routing (Ulysses): instead of (fwd: in addition to) the local tensor, rows of position i
+// go to peer[i / n_local], a [B, n_local, heads_total, D] contiguous buffer of that rank, as head head_off + h.
+struct SpRoute {
+  int P, n_local, heads_total, head_off;
+  void* peer[8];
+};
+
 // Prefill / training problem.  Mask: sink_flash_attention.py:30-39 of the reference.
 struct AttnParams {
   const void* q;
@@ -32,6 +39,8 @@ struct AttnParams {
   Strides4 sq, sk, sv, so, sdo, sdq, sdk, sdv;
   int B, Hq, Hkv, N, D, S, W;
   float scale;
+  const SpRoute* o_route;    // host pointers, nullptr = off; only the head_dim-64 tcgen05 kernels route
+  const SpRoute* dq_route;
 };
 
 struct DecodeParams {
@@ -80,6 +89,7 @@ bool tc_fwd_supported(const AttnParams& p, int dtype);
 cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_fwd64_supported(const AttnParams& p, int dtype);   // persistent warp-specialised forward, head_dim 64
 cudaError_t tc_fwd64(const AttnParams& p, int dtype, cudaStream_t st);
+bool tc_fwd64_route_supported(const AttnParams& p, int dtype);
 bool tc_bwd_supported(const AttnParams& p, int dtype);
 bool tc_bwd_fuses_delta(const AttnParams& p, int dtype);   // the dQ kernel derives delta (and ds_aux rows) itself: no preprocess pass
 cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st);

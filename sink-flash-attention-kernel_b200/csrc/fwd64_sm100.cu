@@ -31,6 +31,10 @@ struct Fwd64Args {
   const float* s_aux;
   float* lse;
   long long* trace;
+  int sp_n;      // > 0: O tiles are ALSO stored into the peer buffer of the rank owning positions [k*sp_n, (k+1)*sp_n)
+};
+struct PeerMaps {
+  CUtensorMap m[8];
 };
 #ifndef SFA_TRACE
 #define SFA_TRACE 0
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV,
                                                                       const __grid_constant__ CUtensorMap tmO,
+                                                                      const __grid_constant__ PeerMaps pm,
                                                                       const Fwd64Args a) {
   using C = Fwd64Cfg;
   constexpr int D = C::D;
@@ -412,6 +417,10 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       named_bar_sync(5, 128);
       if (et == 0) {
         tma_tile_store(&tmO, stage_s, a.o_swap, 0, w.q0, w.y * a.G, w.b);
+        if (a.sp_n > 0) {       // Ulysses: the same staged tile goes to the sequence owner over NVLink (TMA store to a peer mapping)
+          const int seg = w.q0 / a.sp_n;
+          tma_tile_store(&pm.m[seg], stage_s, a.o_swap, 0, w.q0 - seg * a.sp_n, w.y * a.G, w.b);
+        }
         tma_store_commit();
         tev(a.trace, 6, mtc, 3, w.n);
       }
@@ -467,8 +476,26 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
   a.s_aux = p.s_aux;
   a.lse = p.lse;
   a.trace = trace_buffer();
+  a.sp_n = 0;
+  PeerMaps pm;
+  for (int r = 0; r < 8; ++r) pm.m[r] = mo.map;
+  if (p.o_route != nullptr) {
+    const SpRoute& rt = *p.o_route;
+    if (rt.P < 1 || rt.P > 8 || rt.n_local % P != 0 || static_cast<int64_t>(rt.n_local) * rt.P != p.N)
+      return cudaErrorInvalidValue;
+    const Strides4 sp{static_cast<int64_t>(rt.n_local) * rt.heads_total * D, D, static_cast<int64_t>(rt.heads_total) * D};
+    const int es = 2;
+    for (int r = 0; r < rt.P; ++r) {
+      TileMap mp;
+      void* base = static_cast<char*>(rt.peer[r]) + static_cast<int64_t>(rt.head_off) * D * es;
+      if (!make_tile_map(&mp, base, dtype, D, rt.n_local, p.Hq, p.B, sp, P, G)) return cudaErrorInvalidValue;
+      if (mp.swap_nh != mo.swap_nh) return cudaErrorInvalidValue;      // one staged tile serves both stores
+      pm.m[r] = mp.map;
+    }
+    a.sp_n = rt.n_local;
+  }
   const int grid = a.total_tiles < sm_count_fwd() ? a.total_tiles : sm_count_fwd();
-  fwd64_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, a);
+  fwd64_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, pm, a);
   return cudaGetLastError();
 }
 
@@ -476,6 +503,17 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
 
 bool tc_fwd64_supported(const AttnParams& p, int dtype) {
   return p.D == 64 && (p.S > 0 || p.W > 0);     // nothing attended at all: the one-tile-per-CTA kernel writes the O = 0 rows
+}
+
+// the routed store reuses the staged tile of the local store: the local O must be in HF order too ([B, N, H, D]
+// strides, as the peer buffers are) and a tile must not straddle two owners
+bool tc_fwd64_route_supported(const AttnParams& p, int dtype) {
+  if (!tc_fwd64_supported(p, dtype) || p.o_route == nullptr) return false;
+  int G, P;
+  pick_packing(p.Hq, p.Hkv, G, P);
+  const SpRoute& rt = *p.o_route;
+  const bool hf = (p.Hq > 1 && p.N > 1) ? (p.so.h < p.so.n) : true;
+  return hf && rt.P >= 1 && rt.P <= 8 && rt.n_local % P == 0 && static_cast<int64_t>(rt.n_local) * rt.P == p.N;
 }
 
 cudaError_t tc_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {

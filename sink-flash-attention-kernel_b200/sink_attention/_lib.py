@@ -21,10 +21,26 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_mma_desc", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_mma_desc", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
 )
 
 _lib = None
+
+
+class SpRoute(ctypes.Structure):
+    """sfa_sp_route of include/sinkfa.h: output routing of the Ulysses layout (peer receive buffers)."""
+    _fields_ = [("P", ctypes.c_int), ("n_local", ctypes.c_int), ("heads_total", ctypes.c_int),
+                ("head_off", ctypes.c_int), ("peer", ctypes.c_void_p * 8)]
+
+
+def make_route(peer_ptrs: Sequence[int], n_local: int, heads_total: int, head_off: int) -> SpRoute:
+    if len(peer_ptrs) > 8:
+        raise ValueError("at most 8 ranks per route")
+    r = SpRoute()
+    r.P, r.n_local, r.heads_total, r.head_off = len(peer_ptrs), int(n_local), int(heads_total), int(head_off)
+    for i, ptr in enumerate(peer_ptrs):
+        r.peer[i] = int(ptr)
+    return r
 
 
 class SinkFAError(RuntimeError):
@@ -62,6 +78,10 @@ def load() -> ctypes.CDLL:
     lib.sfa_fwd.restype = i
     lib.sfa_bwd.argtypes = [p] * 5 + [f32p, f32p] + [p] * 3 + [f32p] + [i] * 8 + [i64p] * 8 + [p, c.c_size_t, p]
     lib.sfa_bwd.restype = i
+    lib.sfa_fwd_sp.argtypes = lib.sfa_fwd.argtypes + [c.POINTER(SpRoute)]
+    lib.sfa_fwd_sp.restype = i
+    lib.sfa_bwd_sp.argtypes = [p] * 5 + [f32p, f32p] + [p] * 2 + [f32p] + [i] * 8 + [i64p] * 7 + [p, c.c_size_t, p, c.POINTER(SpRoute)]
+    lib.sfa_bwd_sp.restype = i
     lib.sfa_decode.argtypes = [p, p, p, p, f32p] + [i] * 6 + [i64p] * 4 + [p, c.c_size_t, p]
     lib.sfa_decode.restype = i
     lib.sfa_decode_ring.argtypes = [p] * 6 + [f32p] + [i] * 7 + [i64p] * 4 + [p, c.c_size_t, p]
@@ -137,8 +157,9 @@ def _s_aux_f32(s_aux: Optional[torch.Tensor], hq: int) -> Optional[torch.Tensor]
     return s_aux.detach().contiguous().float()
 
 
-def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32):
-    """-> (o, lse).  q [B,Hq,N,D] (any strides with unit channel stride), k/v [B,Hkv,N,D]."""
+def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32, o_route: Optional[SpRoute] = None):
+    """-> (o, lse).  q [B,Hq,N,D] (any strides with unit channel stride), k/v [B,Hkv,N,D].
+    o_route: also store O into the peers' receive buffers (sfa_fwd_sp); ValueError if the shape cannot route."""
     lib = load()
     _require_cuda(q, k, v, s_aux_f32)
     B, Hq, N, D = q.shape
@@ -148,19 +169,23 @@ def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32):
     if o.stride(-1) != 1:
         o = torch.empty((B, Hq, N, D), device=q.device, dtype=q.dtype)
     lse = torch.empty((B, Hq, N), device=q.device, dtype=torch.float32)
-    with torch.cuda.device(q.device):
-        rc = lib.sfa_fwd(
-            q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+    args = (q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
             s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
             B, Hq, Hkv, N, D, int(num_sink), int(window_size), DTYPE_CODE[q.dtype],
             _i64(q.stride()), _i64(k.stride()), _i64(v.stride()), _i64(o.stride()),
             None, 0, _stream(q))
+    with torch.cuda.device(q.device):
+        if o_route is None:
+            rc = lib.sfa_fwd(*args)
+        else:
+            rc = lib.sfa_fwd_sp(*args, ctypes.byref(o_route))
     _check(rc, "sfa_fwd")
     return o, lse
 
 
-def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32):
-    """-> (dq, dk, dv, ds_aux|None); dk/dv are already reduced over the GQA group (fp32 accumulate)."""
+def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32, dq_route: Optional[SpRoute] = None):
+    """-> (dq, dk, dv, ds_aux|None); dk/dv are already reduced over the GQA group (fp32 accumulate).
+    dq_route: dQ is stored ONLY into the peers' receive buffers (sfa_bwd_sp) and returned as None."""
     lib = load()
     _require_cuda(q, k, v, o, do, lse, s_aux_f32)
     B, Hq, N, D = q.shape
@@ -172,11 +197,24 @@ def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32):
         return t.shape[1] > 1 and t.shape[2] > 1 and t.stride(1) < t.stride(2)
     if _hf_order(do) != _hf_order(q):
         do = do.transpose(1, 2).contiguous().transpose(1, 2) if _hf_order(q) else do.contiguous()
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dk, dv = torch.empty_like(k), torch.empty_like(v)
+    dq = torch.empty_like(q) if dq_route is None else None
     ds_aux = torch.empty((Hq,), device=q.device, dtype=torch.float32) if s_aux_f32 is not None else None
     code = DTYPE_CODE[q.dtype]
     ws_bytes = lib.sfa_workspace_bytes(OP_BWD, B, Hq, Hkv, N, D, code)
     ws = torch.empty((ws_bytes,), device=q.device, dtype=torch.uint8)
+    if dq_route is not None:
+        with torch.cuda.device(q.device):
+            rc = lib.sfa_bwd_sp(
+                q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
+                dk.data_ptr(), dv.data_ptr(), ds_aux.data_ptr() if ds_aux is not None else None,
+                B, Hq, Hkv, N, D, int(num_sink), int(window_size), code,
+                _i64(q.stride()), _i64(k.stride()), _i64(v.stride()), _i64(o.stride()), _i64(do.stride()),
+                _i64(dk.stride()), _i64(dv.stride()),
+                ws.data_ptr(), ws_bytes, _stream(q), ctypes.byref(dq_route))
+        _check(rc, "sfa_bwd_sp")
+        return None, dk, dv, ds_aux
     with torch.cuda.device(q.device):
         rc = lib.sfa_bwd(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),

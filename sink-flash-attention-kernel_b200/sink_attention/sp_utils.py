@@ -19,6 +19,7 @@ Two schemes live here.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -183,6 +184,9 @@ class _P2PBuffers:
         self.do_full = self.buf[offs[2]:offs[2] + sizes[2]].view(B, P * n, hq_l, D)
         self.g_seq = self.buf[offs[3]:offs[3] + sizes[3]].view(B, n, Hq + 2 * Hkv, D)
 
+        # fused output side: O and dQ are stored into the peers' buffers by the attention kernels themselves
+        self.route_o = self.route_dq = P <= 8 and os.environ.get("SFA_ULY_NO_ROUTE") is None
+
     def barrier(self):
         self.hdl.barrier(channel=0)
 
@@ -207,8 +211,18 @@ class _UlyssesP2PAttention(torch.autograd.Function):
         kh = full[:, :, hq_l:hq_l + hkv_l].transpose(1, 2)
         vh = full[:, :, hq_l + hkv_l:].transpose(1, 2)
         s32 = _lib._s_aux_f32(s_loc, hq_l)
-        o, lse = _lib.fwd(qh, kh, vh, num_sink, window_size, s32)
-        _lib.ulysses_scatter(o.transpose(1, 2), bufs.peer[1], rank, 1, Hq, 0)
+        o = None
+        if bufs.route_o:
+            # the forward kernel stores every O tile into the sequence owner's buffer as well (TMA store to a peer
+            # mapping): no scatter pass over O.  Shapes the routed kernels do not cover fall back for good.
+            try:
+                o, lse = _lib.fwd(qh, kh, vh, num_sink, window_size, s32,
+                                  o_route=_lib.make_route(bufs.peer[1], n, Hq, rank * hq_l))
+            except ValueError:
+                bufs.route_o = False
+        if o is None:
+            o, lse = _lib.fwd(qh, kh, vh, num_sink, window_size, s32)
+            _lib.ulysses_scatter(o.transpose(1, 2), bufs.peer[1], rank, 1, Hq, 0)
         bufs.barrier()
         out = bufs.o_seq.clone()                              # the region is reused by the next step
         ctx.save_for_backward(qh, kh, vh, o, lse, s32 if s32 is not None else torch.empty(0, device=q.device))
@@ -227,8 +241,17 @@ class _UlyssesP2PAttention(torch.autograd.Function):
         _lib.ulysses_scatter(dout, bufs.peer[2], rank, 0, hq_l, 0)
         bufs.barrier()
         do_h = bufs.do_full.transpose(1, 2)
-        dq, dk, dv, ds = _lib.bwd(qh, kh, vh, o, do_h, lse, num_sink, window_size, s32 if ctx.has_aux else None)
-        _lib.ulysses_scatter(dq.transpose(1, 2), bufs.peer[3], rank, 1, Hq + 2 * Hkv, 0)
+        n = dout.shape[1]
+        dq = None
+        if bufs.route_dq:
+            try:                                             # dQ goes straight to the sequence owners
+                dq, dk, dv, ds = _lib.bwd(qh, kh, vh, o, do_h, lse, num_sink, window_size, s32 if ctx.has_aux else None,
+                                          dq_route=_lib.make_route(bufs.peer[3], n, Hq + 2 * Hkv, rank * hq_l))
+            except ValueError:
+                bufs.route_dq = False
+        if not bufs.route_dq:
+            dq, dk, dv, ds = _lib.bwd(qh, kh, vh, o, do_h, lse, num_sink, window_size, s32 if ctx.has_aux else None)
+            _lib.ulysses_scatter(dq.transpose(1, 2), bufs.peer[3], rank, 1, Hq + 2 * Hkv, 0)
         _lib.ulysses_scatter(dk.transpose(1, 2), bufs.peer[3], rank, 1, Hq + 2 * Hkv, Hq)
         _lib.ulysses_scatter(dv.transpose(1, 2), bufs.peer[3], rank, 1, Hq + 2 * Hkv, Hq + Hkv)
         bufs.barrier()

@@ -503,6 +503,40 @@ def test_ulysses_scatter_bit_exact(P, B, n, H, D, extra, dtype):
         _lib.ulysses_scatter(src[0][:, :P * n - 1], [d.data_ptr() for d in dst], 0, 1, dst_heads, head_off)
 
 
+def test_routed_output_stores_match_unrouted():
+    """sfa_fwd_sp / sfa_bwd_sp (Ulysses output side fused into the kernels): with the "peers" emulated by two
+    buffers on one device, the routed O / dQ rows must be bit-identical to the unrouted tensors."""
+    B, Hq, Hkv, N, D, W, P = 1, 16, 2, 512, 64, 128, 2
+    n, extra, off = N // P, 5, 3                                    # receive buffers hold extra heads around ours
+    g = torch.Generator().manual_seed(5)
+    mk = lambda H: torch.randn(B, N, H, D, generator=g).to("cuda", torch.bfloat16).transpose(1, 2)   # HF-order views
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    s_aux = (torch.randn(Hq, generator=g) * 0.5).cuda()
+    o_ref, lse_ref, _ = _fwd(q, k, v, 0, W, s_aux)
+    peers = [torch.zeros(B, n, Hq + extra, D, device="cuda", dtype=torch.bfloat16) for _ in range(P)]
+    route = _lib.make_route([t.data_ptr() for t in peers], n, Hq + extra, off)
+    o, lse = _lib.fwd(q, k, v, 0, W, s_aux, o_route=route)
+    torch.cuda.synchronize()
+    assert torch.equal(o, o_ref) and torch.equal(lse, lse_ref)
+    for s_ in range(P):
+        assert torch.equal(peers[s_][:, :, off:off + Hq], o_ref[:, :, s_ * n:(s_ + 1) * n].transpose(1, 2))
+        assert float(peers[s_][:, :, :off].abs().sum()) == 0.0 and float(peers[s_][:, :, off + Hq:].abs().sum()) == 0.0
+    (dq_ref, dk_ref, dv_ref, ds_ref), name = _bwd(q, k, v, o, do, lse, 0, W, s_aux)
+    assert name == "tcgen05-fused"
+    gpeers = [torch.zeros(B, n, Hq + extra, D, device="cuda", dtype=torch.bfloat16) for _ in range(P)]
+    groute = _lib.make_route([t.data_ptr() for t in gpeers], n, Hq + extra, off)
+    dq, dk, dv, ds = _lib.bwd(q, k, v, o, do, lse, 0, W, s_aux, dq_route=groute)
+    torch.cuda.synchronize()
+    assert dq is None and torch.equal(dk, dk_ref) and torch.equal(dv, dv_ref) and torch.equal(ds, ds_ref)
+    for s_ in range(P):
+        assert torch.equal(gpeers[s_][:, :, off:off + Hq], dq_ref[:, :, s_ * n:(s_ + 1) * n].transpose(1, 2))
+    # shapes the routed kernels do not cover are refused (nothing launched), not silently unrouted
+    with pytest.raises(ValueError):
+        _lib.fwd(q.contiguous(), k, v, 0, W, s_aux, o_route=route)               # local O not in HF order
+    with pytest.raises(ValueError):
+        _lib.bwd(q, k, v, o, do, lse, 4, W, s_aux, dq_route=groute)               # sink tokens: kernel pair, no routing
+
+
 def test_errors_are_loud():
     q = torch.randn(1, 4, 16, 64)
     with pytest.raises(RuntimeError):

@@ -89,5 +89,33 @@ try:
     print(f"[rank {rank}] graph replay of the p2p step: {t_graph:.3f} ms", flush=True)
 except Exception as e:  # noqa: BLE001
     print(f"[rank {rank}] graph capture failed: {type(e).__name__}: {e}", flush=True)
+# ---- pieces: one scatter of q (67 MB, half of it to the peer), one barrier, one clone
+from sink_attention import _lib  # noqa: E402
+bufs = p2p._bufs
+
+
+def ev_time(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / reps * 1e3
+
+
+hq_l = Hq // world
+t_sc = ev_time(lambda: _lib.ulysses_scatter(q, bufs.peer[0], rank, 0, bufs.tot, 0))
+t_sc1 = ev_time(lambda: _lib.ulysses_scatter(bufs.do_full, bufs.peer[1], rank, 1, Hq, 0))
+t_bar = ev_time(lambda: bufs.barrier())
+t_cl = ev_time(lambda: bufs.o_seq.clone())
+nbytes = q.numel() * 2
+print(f"[rank {rank}] scatter q (mode 0, {nbytes / 1e6:.0f} MB, {(world - 1) / world:.2f} remote): {t_sc:.1f} us = "
+      f"{nbytes * (world - 1) / world / t_sc / 1e3:.0f} GB/s over NVLink; mode 1: {t_sc1:.1f} us; barrier {t_bar:.1f} us; "
+      f"clone {t_cl:.1f} us", flush=True)
 dist.barrier()
 dist.destroy_process_group()
