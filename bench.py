@@ -202,6 +202,47 @@ def run_ours(args):
             ts.append(a.elapsed_time(b))
         return ts
 
+    def e2e_pipelined(host_in, host_out, run_step, steps, warm=2):
+        """End-to-end steps through the public API from pinned HOST buffers, software-pipelined like a training loop
+        with input prefetch: step i's H2D copy (copy stream), step i-1's kernels (main stream) and step i-2's D2H
+        copy of O, dQ, dK, dV, ds_aux (second copy stream) overlap; EVERY step still moves all of its inputs in and
+        all of its results out.  Wall clock over `steps` steps between full device synchronisations -> ms per step."""
+        s_in, s_out, main = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+        slots = [[torch.empty_like(h, device=dev).requires_grad_(h.is_floating_point()) for h in host_in] for _ in range(2)]
+        done = [None, None]
+
+        def one(i):
+            sl = i % 2
+            with torch.cuda.stream(s_in), torch.no_grad():
+                if done[sl] is not None:
+                    s_in.wait_event(done[sl])                # the kernels of step i-2 have read this slot
+                for d_, h_ in zip(slots[sl], host_in):
+                    d_.copy_(h_, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            main.wait_event(ready)
+            for d_ in slots[sl]:
+                d_.grad = None
+            results = run_step(slots[sl])
+            done[sl] = torch.cuda.Event()
+            done[sl].record(main)
+            with torch.cuda.stream(s_out), torch.no_grad():
+                s_out.wait_event(done[sl])
+                for r_, h_ in zip(results, host_out):
+                    h_.copy_(r_, non_blocking=True)
+                    r_.record_stream(s_out)
+
+        for i in range(warm):
+            one(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(warm, warm + steps):
+            one(i)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps * 1e3
+
     s_aux = (torch.randn(Hq, device=dev, generator=g) * 0.5).requires_grad_(True)
     step_graph = None
     if world == 1:
@@ -474,21 +515,19 @@ def run_ours(args):
             hdq, hdk, hdv = torch.empty_like(hq_).pin_memory(), torch.empty_like(hk_).pin_memory(), torch.empty_like(hv_).pin_memory()
             hds = torch.empty_like(hs_).pin_memory()
 
-            def e2e_step():
-                dq_, dk_, dv_, ddo_ = (t.to(dev, non_blocking=True) for t in (hq_, hk_, hv_, hdo_))
-                ds_ = hs_.to(dev, non_blocking=True).requires_grad_(True)
-                dq_.requires_grad_(True); dk_.requires_grad_(True); dv_.requires_grad_(True)
+            def run_api(dev_in):
+                dq_, dk_, dv_, ddo_, ds_ = dev_in
                 o = sa.sink_flash_attention(dq_, dk_, dv_, S, W, ds_)
-                o.backward(ddo_)
-                ho.copy_(o.detach(), non_blocking=True)
-                hdq.copy_(dq_.grad, non_blocking=True); hdk.copy_(dk_.grad, non_blocking=True)
-                hdv.copy_(dv_.grad, non_blocking=True); hds.copy_(ds_.grad, non_blocking=True)
-            te = timed(e2e_step, max(3, min(args.steps, 10)), 2)
-            ems = sum(te) / len(te)
+                o.backward(ddo_.detach())
+                return [o.detach(), dq_.grad, dk_.grad, dv_.grad, ds_.grad]
+            ems = e2e_pipelined([hq_, hk_, hv_, hdo_, hs_], [ho, hdq, hdk, hdv, hds], run_api, max(5, min(args.steps, 20)))
             h2d = sum(t.numel() * t.element_size() for t in (hq_, hk_, hv_, hdo_, hs_))
             d2h = sum(t.numel() * t.element_size() for t in (ho, hdq, hdk, hdv, hds))
             e2e = {"value": job_flops / (ems * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": d2h, "ms_per_step": ems}
+                   "d2h_bytes_per_step": d2h, "ms_per_step": ems,
+                   "how": "public API (sink_flash_attention + backward) from pinned host buffers; every step copies q, k, v, "
+                          "dO, s_aux in and O, dQ, dK, dV, ds_aux out; copies of neighbouring steps overlap the kernels "
+                          "(double-buffered inputs, three streams); wall clock between device synchronisations"}
             # ---- CPU baseline beside it (bounded sample, ~10-30 s)
             threads = os.cpu_count() or 1
             n_s, h_s = 2048, 16
@@ -528,16 +567,13 @@ def run_ours(args):
         ho = torch.empty_like(hq_).pin_memory()
         hdq, hdk, hdv = torch.empty_like(hq_).pin_memory(), torch.empty_like(hk_).pin_memory(), torch.empty_like(hv_).pin_memory()
 
-        def e2e_step():
-            dq_, dk_, dv_, ddo_ = (t.to(dev, non_blocking=True) for t in (hq_, hk_, hv_, hdo_))
-            ds_ = hs_.to(dev, non_blocking=True).requires_grad_(True)
-            dq_.requires_grad_(True); dk_.requires_grad_(True); dv_.requires_grad_(True)
+        def run_uly(dev_in):
+            dq_, dk_, dv_, ddo_, ds_ = dev_in
             o = uly(dq_, dk_, dv_, ds_)
-            o.backward(ddo_)
-            ho.copy_(o.detach(), non_blocking=True)
-            hdq.copy_(dq_.grad, non_blocking=True); hdk.copy_(dk_.grad, non_blocking=True); hdv.copy_(dv_.grad, non_blocking=True)
-        te = timed(e2e_step, max(3, min(args.steps, 10)), 2)
-        t = torch.tensor([sum(te) / len(te)], device=dev)
+            o.backward(ddo_.detach())
+            return [o.detach(), dq_.grad, dk_.grad, dv_.grad]
+        ems_n = e2e_pipelined([hq_, hk_, hv_, hdo_, hs_], [ho, hdq, hdk, hdv], run_uly, max(5, min(args.steps, 20)))
+        t = torch.tensor([ems_n], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             h2d = sum(x.numel() * x.element_size() for x in (hq_, hk_, hv_, hdo_, hs_)) * world
