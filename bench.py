@@ -561,6 +561,26 @@ def run_ours(args):
         if e2e is not None:
             line["e2e"] = e2e
     if world > 1:
+        # decode at N GPUs (BASELINE configs[3] per rank: the batch shards with no collective -> aggregate GB/s)
+        Bd, Nkv = C3["B"], C3["Nkv"]
+        qq = torch.randn(Bd, Hq, 1, D, device=dev, generator=g).to(dt)
+        kk = torch.randn(Bd, Hkv, Nkv, D, device=dev, generator=g).to(dt)
+        vv = torch.randn(Bd, Hkv, Nkv, D, device=dev, generator=g).to(dt)
+        sdd = s_aux.detach()
+        dist.barrier()
+        td = timed(lambda: sa.sink_decode_attention(qq, kk, vv, sdd), 20, 5)
+        tdm = torch.tensor([statistics.median(td)], device=dev)
+        dist.all_reduce(tdm, op=dist.ReduceOp.MAX)
+        dbytes = (2 * Bd * Hkv * Nkv * D * 2 + 2 * Bd * Hq * D * 2) * world
+        if rank == 0:
+            hbm_peak_ = load_peaks()[0]
+            line["decode"] = {"workload": f"KV-cache decode (BASELINE configs[3]) on every rank: batch 64 per GPU ({Bd * world} total), "
+                                          "sink 4 + window 4096, Hq=64 Hkv=8 D=64 s_aux bf16; batch-sharded, no collective",
+                              "ms_per_step": tdm.item(), "hbm_GBps": dbytes / (tdm.item() * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": dbytes / (tdm.item() * 1e-3) / 1e9 / (hbm_peak_ * world),
+                              "tokens_per_s": Bd * world / (tdm.item() * 1e-3), "algorithmic_bytes": dbytes,
+                              "impl": _lib.last_impl(), "scaling": "weak"}
+        del qq, kk, vv
         # e2e at N GPUs: every rank feeds its chunk from pinned host memory and reads its O chunk back
         hq_, hk_, hv_, hdo_ = (t.detach().cpu().pin_memory() for t in (q, k, v, do))
         hs_ = s_aux.detach().cpu().pin_memory()

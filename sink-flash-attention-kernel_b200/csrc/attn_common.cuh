@@ -138,6 +138,35 @@ template <> __device__ __forceinline__ uint32_t pack16<__half>(float a, float b)
 }
 // Measured (tools/time_graph.py): replacing the cvt by integer rounding (IADD + PRMT) made every kernel SLOWER
 // (dQ 94 -> 112 us): the math warps are bound by TMEM round-trip latency and issue slots, not by the XU pipe.
+// ---- packed math (fewer issued instructions per element: the tcgen05 kernels are bound by instruction issue)
+// two fp32 lanes in one 64-bit register; fma.rn.f32x2 is one FFMA2 on sm_100
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint32_t a_lo, uint32_t a_hi, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("{\n\t.reg .b64 ra;\n\tmov.b64 ra, {%1, %2};\n\tfma.rn.f32x2 %0, ra, %3, %4;\n\t}"
+      : "=l"(d) : "r"(a_lo), "r"(a_hi), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// 16-bit pair product: a (packed pair) * b (packed pair), rounded once to the 16-bit type (HMUL2)
+template <typename T> __device__ __forceinline__ uint32_t mul16x2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t mul16x2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t mul16x2<__half>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
 template <typename T> __device__ __forceinline__ uint32_t pack16_fast(float a, float b) { return pack16<T>(a, b); }
 
 __device__ __forceinline__ void tma_tile(void* dst, const CUtensorMap* m, uint64_t* bar, int swap, int d, int n, int h,

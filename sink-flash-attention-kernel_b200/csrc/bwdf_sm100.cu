@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         }
         return v;
       };
+      const uint64_t scale2 = pack_f32x2(a.scale, a.scale), sl2_2 = pack_f32x2(a.sl2, a.sl2);
       FusedWalk w(a, wi), wn(a, wi);
       SlotTrack st;
       st.slot0 = 0;
@@ -542,10 +543,12 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         if (tr) ftrace(a.trace, 3, tc, 1, w.it);
         st.step(w, R);
         const float lse_i = l_next, dsc = d_next * a.scale;
+        const uint64_t ndsc2 = pack_f32x2(-dsc, -dsc);
         has_next = wn.next();
         l_next = load_row(a.lse, wn, has_next, INFINITY);
         d_next = load_delta(wn, has_next);
         const float neg_l2 = (lse_i == -INFINITY) ? -INFINITY : -lse_i * kLog2e;   // lse = +-inf: P = 0
+        const uint64_t negl2_2 = pack_f32x2(neg_l2, neg_l2);
         const int i = w.pb * P + pr;
         const int kstart = (w.pb - nb + 1) * P;
         const int c_lo = max(i - a.W + 1, 0) - kstart;
@@ -574,9 +577,11 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           const int lo = c_lo - cb * 16, hi = c_hi - cb * 16;      // attended elements of this chunk: [lo, hi]
           if (__all_sync(0xffffffffu, lo <= 0 && hi >= 15)) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 2)
-              pk[e >> 1] = pack16<T>(fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, neg_l2)),
-                                     fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, neg_l2)));
+            for (int e = 0; e < 16; e += 2) {
+              float x0, x1;
+              unpack_f32x2(fma_f32x2(sv[e], sv[e + 1], sl2_2, negl2_2), x0, x1);
+              pk[e >> 1] = pack16<T>(fast_exp2(x0), fast_exp2(x1));
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
@@ -618,12 +623,14 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                        : "=r"(pk[4]), "=r"(pk[5]), "=r"(pk[6]), "=r"(pk[7]) : "r"(p_a + off + 2048u) : "memory");
           tmem_ld_wait();
+          // t = scale * (dP - delta) as one FFMA2 per pair, rounded to 16 bit, then dS = P * t as one HMUL2 per
+          // pair on the packed P straight from the image: 3 issued instructions per pair instead of 7 (masked P is
+          // exactly 0 and dP is finite: dS = 0 there)
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            float p0, p1;
-            unpack16f<T>(pk[e >> 1], p0, p1);              // masked P is exactly 0 and dP is finite: dS = 0 there
-            dk[e >> 1] = pack16<T>(p0 * fmaf(__uint_as_float(dv[e]), a.scale, -dsc),
-                                   p1 * fmaf(__uint_as_float(dv[e + 1]), a.scale, -dsc));
+            float t0, t1;
+            unpack_f32x2(fma_f32x2(dv[e], dv[e + 1], scale2, ndsc2), t0, t1);
+            dk[e >> 1] = mul16x2<T>(pk[e >> 1], pack16<T>(t0, t1));
           }
           st_shared_v4(ds_a + off, dk[0], dk[1], dk[2], dk[3]);
           st_shared_v4(ds_a + off + 2048u, dk[4], dk[5], dk[6], dk[7]);
