@@ -279,12 +279,13 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
     tma_prefetch_desc(&tmV);
     for (int s = 0; s < 16; ++s) mbar_init(bars + s, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_free, C::kMathWarps);
+    mbar_init(s_free, C::kMathWarps * 32);       // per-thread arrivals and waits in the math warps: measured faster than
+                                                 // one polling / arriving lane per warp + __syncwarp (fwd64: 62 vs 67 us)
     mbar_init(dp_full, 1);
-    mbar_init(dp_free, C::kMathWarps);
-    mbar_init(p_ready, C::kMathWarps);
+    mbar_init(dp_free, C::kMathWarps * 32);
+    mbar_init(p_ready, C::kMathWarps * 32);
     mbar_init(p_free, 1);
-    mbar_init(ds_ready, C::kMathWarps);
+    mbar_init(ds_ready, C::kMathWarps * 32);
     mbar_init(ds_free, 2);
     for (int g = 0; g < 2; ++g) {
       mbar_init(dq_done + g, 3);
@@ -559,9 +560,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         // ---- pass 1: P = exp2(S * c - lse), masked, 16-bit -> P image (ring-column order).  The loops over this
         // warp's chunks are ROLLED: the kernel's roles run concurrently and share a ~32 KB instruction cache (the
         // fully unrolled version, 73 KB of code, ran 2x slower in every role).
-        mbar_wait_warp(s_full, w.it & 1);
+        mbar_wait(s_full, w.it & 1);
         tc_fence_after();
-        if (w.it >= 1) mbar_wait_warp(p_free, (w.it - 1) & 1);
+        if (w.it >= 1) mbar_wait(p_free, (w.it - 1) & 1);
         if (tr) ftrace(a.trace, 3, tc, 2, w.it);
         if (part == 1)
           for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(p_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
@@ -597,17 +598,14 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(s_free);
-          mbar_arrive(p_ready);
-        }
+        mbar_arrive(s_free);
+        mbar_arrive(p_ready);
         if (tr) ftrace(a.trace, 3, tc, 3, w.it);
         // ---- pass 2: dS = scale * P o (dP - delta), 16-bit -> dS image (dQ and dK both carry the scale); P comes
         // back from the image (this thread's own row)
-        mbar_wait_warp(dp_full, w.it & 1);
+        mbar_wait(dp_full, w.it & 1);
         tc_fence_after();
-        if (w.it >= 1) mbar_wait_warp(ds_free, (w.it - 1) & 1);
+        if (w.it >= 1) mbar_wait(ds_free, (w.it - 1) & 1);
         if (tr) ftrace(a.trace, 3, tc, 4, w.it);
         if (part == 1)
           for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(ds_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
@@ -637,11 +635,8 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(dp_free);
-          mbar_arrive(ds_ready);
-        }
+        mbar_arrive(dp_free);
+        mbar_arrive(ds_ready);
         if (tr) ftrace(a.trace, 3, tc, 5, w.it);
       }
     } else {
