@@ -441,6 +441,58 @@ def test_c1_full_size_properties():
     assert torch.equal(o_l[:, :, 1000 + W - 1:], o_t[:, :, 1000 + W - 1:])
 
 
+def test_c2_full_size():
+    """Llama-3-8B-style StreamingLLM shape (BASELINE configs[2]): B=4 N=16384 Hq=32 Hkv=8 D=128 S=4 W=4096 bf16,
+    forward + backward at full size on the tensor-core kernels; properties on all batches, CUDA-core cross-check on
+    batch 0 (batches are independent)."""
+    B, N, Hq, Hkv, D, S, W = 4, 16384, 32, 8, 128, 4, 4096
+    g = torch.Generator(device="cuda").manual_seed(44)
+    mk = lambda H: torch.randn(B, H, N, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    q, k = mk(Hq), mk(Hkv)
+    ones = torch.ones(B, Hkv, N, D, device="cuda", dtype=torch.bfloat16)
+    o1, _, name = _fwd(q, k, ones, S, W, None)
+    assert name == "tcgen05"
+    assert (o1.float() - 1.0).abs().max().item() < 1e-2            # rows of P sum to 1 (no s_aux)
+    del o1, ones
+    v, do = mk(Hkv), mk(Hq)
+    o, lse, _ = _fwd(q, k, v, S, W, None)
+    o_s, lse_s, _ = _fwd(q[:1], k[:1], v[:1], S, W, None, impl=_lib.IMPL_SIMT)
+    assert maxdiff(o[:1], o_s) < 2e-2 and maxdiff(lse[:1], lse_s) < 2e-3
+    # locality + sinks: negating keys 100 .. 999 changes no row i >= 999 + W (they only see sinks 0..3 and their window)
+    k3 = k.clone()
+    k3[:, :, 100:1000] *= -1.0
+    o_l, _, _ = _fwd(q, k3, v, S, W, None)
+    assert torch.equal(o_l[:, :, 999 + W:], o[:, :, 999 + W:])
+    del k3, o_l
+    (dq, dk, dv, _), name_b = _bwd(q, k, v, o, do, lse, S, W, None)
+    assert name_b == "tcgen05"
+    (dq_s, dk_s, dv_s, _), _ = _bwd(q[:1], k[:1], v[:1], o[:1], do[:1], lse[:1], S, W, None, impl=_lib.IMPL_SIMT)
+    for got, ref in ((dq[:1], dq_s), (dk[:1], dk_s), (dv[:1], dv_s)):
+        assert excess(got, ref, 5e-2, 2e-2) <= 1.0                  # the reference's gradient bar is atol = rtol = 5e-2
+    # the sink keys collect gradient from every later row: far larger than a window key's
+    assert float(dv[:, :, :S].float().abs().mean()) > 4 * float(dv[:, :, S:].float().abs().mean())
+
+
+def test_c4_rank_shard_full_size():
+    """Ulysses layout of BASELINE configs[4] at P = 8: one rank's problem after the exchange -- the whole 131072-token
+    sequence for 8 q heads / 1 KV head (D=64, W=128, s_aux, bf16) -- forward and fused backward against the CUDA-core
+    path."""
+    B, N, Hq, Hkv, D, W = 1, 131072, 8, 1, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(45)
+    mk = lambda H: torch.randn(B, N, H, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16).transpose(1, 2)
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)                   # HF-order views, as the exchange delivers them
+    s_aux = torch.randn(Hq, device="cuda", generator=g) * 0.5
+    o, lse, name = _fwd(q, k, v, 0, W, s_aux)
+    o_s, lse_s, _ = _fwd(q, k, v, 0, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert name == "tcgen05" and maxdiff(o, o_s) < 2e-2 and maxdiff(lse, lse_s) < 2e-3
+    (dq, dk, dv, ds), name_b = _bwd(q, k, v, o, do, lse, 0, W, s_aux)
+    (dq_s, dk_s, dv_s, ds_s), _ = _bwd(q, k, v, o, do, lse, 0, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert name_b == "tcgen05-fused"
+    for got, ref in ((dq, dq_s), (dk, dk_s), (dv, dv_s)):
+        assert excess(got, ref, 2e-2, 1e-2) <= 1.0
+    assert maxdiff(ds, ds_s) < 1e-3 * max(1.0, float(ds_s.abs().max()))
+
+
 def test_c3_decode_full_size():
     """BASELINE configs[3]: batch 64, sink 4 + window 4096 cache, Hq=64/Hkv=8, D=64, s_aux, bf16."""
     B, Hq, Hkv, Nkv, D = 64, 64, 8, 4100, 64
