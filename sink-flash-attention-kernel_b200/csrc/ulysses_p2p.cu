@@ -12,6 +12,7 @@
 //   mode 1, heads -> sequence:  src [B, P*n, hl, D] (all positions, this rank's heads).  Position i goes to
 //           rank s = i / n:  dst_s [B, n, dst_heads, D] contiguous, row (b, i % n, head_off + rank*hl + h).
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -53,8 +54,11 @@ __device__ __forceinline__ char* scatter_dst(const ScatterArgs& a, const PeerPtr
   return static_cast<char*>(peers.p[dst_rank]) + (drow * a.row16 + c) * 16;
 }
 
-// kUnroll independent 16-byte loads in flight per thread before the first (possibly remote) store
-constexpr int kScatterUnroll = 4;
+// kScatterUnroll independent 16-byte loads in flight per thread before the first (possibly remote) store.
+// Measured at N = 2 with both directions busy (tools/tune_scatter.py): 507-580 GB/s per direction for every grid
+// size (4-32 blocks per SM) and unroll (1-8), and 560 GB/s for a cp.async.bulk variant moving 4 KB rows through
+// shared memory -- the link, not the kernel, sets the rate, so the simple kernel stays.
+template <int kScatterUnroll>
 __global__ void __launch_bounds__(256) ulysses_scatter_kernel(const ScatterArgs a, const PeerPtrs peers) {
   const int64_t total = static_cast<int64_t>(a.B) * a.L * a.H * a.row16;
   const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -113,9 +117,16 @@ cudaError_t ulysses_scatter(const void* src, void* const* peer_dst, int P, int r
   const int64_t total = static_cast<int64_t>(B) * L * H * a.row16;
   if (total == 0) return cudaSuccess;
   int64_t blocks = (total + 255) / 256;
-  const int64_t cap = 148 * 16;          // grid-stride: every thread keeps several 16-byte stores in flight
+  // tuning knobs (tools/dev_p2p.py): blocks per SM of the grid-stride loop, loads in flight per thread
+  const char* eb = getenv("SFA_SCATTER_BLOCKS");
+  const char* eu = getenv("SFA_SCATTER_UNROLL");
+  const int64_t cap = 148 * (eb ? atoi(eb) : 16);
   if (blocks > cap) blocks = cap;
-  ulysses_scatter_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);
+  const int unroll = eu ? atoi(eu) : 4;
+  if (unroll >= 8) ulysses_scatter_kernel<8><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);
+  else if (unroll >= 4) ulysses_scatter_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);
+  else if (unroll >= 2) ulysses_scatter_kernel<2><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);
+  else ulysses_scatter_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);
   return cudaGetLastError();
 }
 

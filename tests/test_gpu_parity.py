@@ -523,7 +523,8 @@ def test_c3_decode_full_size():
 # owns its own receive buffer, the kernel is launched once per rank -- against the all-to-all written in torch
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("P,B,n,H,D,extra", [(2, 1, 24, 8, 64, 3), (4, 2, 10, 8, 64, 0), (8, 1, 6, 16, 128, 5)])
+@pytest.mark.parametrize("P,B,n,H,D,extra", [(2, 1, 24, 8, 64, 3), (4, 2, 10, 8, 64, 0), (8, 1, 6, 16, 128, 5),
+                                             (2, 1, 40, 64, 64, 2), (8, 2, 9, 64, 64, 0)])
 def test_ulysses_scatter_bit_exact(P, B, n, H, D, extra, dtype):
     g = torch.Generator().manual_seed(P + n)
     hl = H // P
@@ -531,14 +532,18 @@ def test_ulysses_scatter_bit_exact(P, B, n, H, D, extra, dtype):
     dst_heads, head_off = hl + extra, extra
     src = [torch.randn(B, n, H, D, generator=g).to("cuda", dtype) for _ in range(P)]
     dst = [torch.zeros(B, P * n, dst_heads, D, device="cuda", dtype=dtype) for _ in range(P)]
+    dst_c = [torch.zeros(B, P * n, dst_heads, D, device="cuda", dtype=dtype) for _ in range(P)]
     for r in range(P):
         hf_view = src[r].transpose(1, 2).contiguous().transpose(1, 2)        # arbitrary strides are accepted
         _lib.ulysses_scatter(hf_view, [d.data_ptr() for d in dst], r, 0, dst_heads, head_off)
+        # contiguous [B, n, H, D] source: rows of >= 1 KB per destination may take the bulk-copy variant
+        _lib.ulysses_scatter(src[r], [d.data_ptr() for d in dst_c], r, 0, dst_heads, head_off)
     torch.cuda.synchronize()
     for r in range(P):
         expect = torch.cat([src[s][:, :, r * hl:(r + 1) * hl] for s in range(P)], dim=1)   # [B, P*n, hl, D]
         assert torch.equal(dst[r][:, :, head_off:head_off + hl], expect)
-        assert float(dst[r][:, :, :head_off].abs().sum()) == 0.0
+        assert torch.equal(dst_c[r][:, :, head_off:head_off + hl], expect)
+        assert float(dst[r][:, :, :head_off].abs().sum()) == 0.0 and float(dst_c[r][:, :, :head_off].abs().sum()) == 0.0
     # ---- mode 1: rank r holds [B, P*n, hl, D] (its heads, all positions) -> rank s gets [B, n, dst_heads, D]
     dst_heads, head_off = H + extra, extra
     src = [torch.randn(B, P * n, hl, D, generator=g).to("cuda", dtype) for _ in range(P)]
