@@ -58,8 +58,15 @@ struct Fwd64Cfg {
   static constexpr uint32_t kColS = 0;               // S buffers at 0 and kBNMax
   static constexpr uint32_t kColO = 2 * kBNMax;      // O accumulators at +0 and +D
   static constexpr int kMaxCh = (kBNMax / 16 + 1) / 2;
-  static constexpr int kSoftWarps = 12;              // three warps per TMEM lane quarter, each a third of the key columns (144 = 3 x 48)
-  static constexpr int kParts = kSoftWarps / 4;
+  // Two softmax GROUPS take alternate tiles (ping-pong): the warps of one group move in lock-step through a tile
+  // (S wait, max exchange, P hand-over), so with a single group every scheduler's warps stall on the same latency
+  // at the same time -- the timeline showed 4 200 cycles per tile against 1 470 of MUFU work.  With two groups half
+  // a tile apart each scheduler always has a group in a math pass.  Per group: kParts warps per TMEM lane quarter,
+  // each owning 1 / kParts of the key columns of its rows.
+  static constexpr int kGroups = 2;
+  static constexpr int kParts = 2;
+  static constexpr int kGroupWarps = 4 * kParts;
+  static constexpr int kSoftWarps = kGroups * kGroupWarps;
   static constexpr int kThreads = (kSoftWarps + 4 + 3) * 32;
   static constexpr int kStatFloats = 2 * 128 + 2 * kParts * 128 + 2 * kParts * 128 + 64;   // row_m, row_l, xch, s_aux (<= 64 heads cached)
   static constexpr int kSmem = 1024 + (kQStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + kStatFloats * 4 + 512;
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     for (int s = 0; s < C::kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full + s, 1);
-      mbar_init(p_full + s, C::kSoftWarps * 32);
+      mbar_init(p_full + s, C::kGroupWarps * 32);     // an item is handled by ONE group
       mbar_init(sbuf_free + s, 1);
       mbar_init(o_done + s, 1);
       mbar_init(o_free + s, 128);
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     __syncwarp();
   } else if (warp < C::kSoftWarps) {
     // ------------------------------------------------------------------ softmax: row == TMEM lane, one part of the columns
-    const int quarter = warp & 3, part = warp >> 2;
+    const int quarter = warp & 3, part = (warp >> 2) % C::kParts, grp = warp / C::kGroupWarps;
     float* saux_s = xch + 2 * C::kParts * 128;          // s_aux * log2e of the first 64 heads (a global load per tile cost ~400 cycles)
     if (a.s_aux != nullptr && threadIdx.x < 64 && threadIdx.x < a.Hq) saux_s[threadIdx.x] = a.s_aux[threadIdx.x] * kLog2e;
     named_bar_sync(7, C::kSoftWarps * 32);
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     int i = 0, mtc = 0;
     Walk w(a);
     while (w.next()) {
+      if ((w.it & (C::kGroups - 1)) != grp) continue;      // the other group's tile
       const int sb = w.n & 1, tb = w.it & 1;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
       if (w.t == 0) {
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       float* xb = xch + (w.n & 1) * (C::kParts * 128);
       xb[part * 128 + r] = mx;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 6, w.n);
-      named_bar_sync(1 + quarter, C::kParts * 32);
+      named_bar_sync(1 + quarter + 8 * grp, C::kParts * 32);      // ids 1-4 (group 0), 9-12 (group 1); 5-7 are taken
 #pragma unroll
       for (int pp = 0; pp < C::kParts; ++pp) mx = fmaxf(mx, xb[pp * 128 + r]);
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 4, w.n);
