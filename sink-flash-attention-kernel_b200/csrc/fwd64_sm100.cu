@@ -5,14 +5,15 @@
 // single-thread role 200-300 cycles, MUFU.EX2 runs at 16/clk/SM, and the old kernel paid ~18 TMEM round trips
 // plus a full prologue per tile.  Here:
 //
+//   warps 0-15   softmax           two groups of eight warps on alternate tiles (ping-pong); in a group two warps
+//                                  per TMEM lane quarter, each owning half of the key columns of its rows; two
+//                                  rolled passes (max, exp) over 16-column chunks -- small loop bodies, the
+//                                  kernels are instruction-cache bound otherwise; P written as 16-bit over the
+//                                  consumed S columns
+//   warps 16-19  epilogue          O / l -> 16-bit -> swizzled smem -> TMA store, LSE = m ln2 + log l
 //   warp 20      TMA producer      Q ring (3 tiles), K and V rings (3 items of up to 144 keys each)
 //   warp 21      UMMA issuer S     S(n) = Q K^T -> S buffer n & 1, two items ahead of the softmax
 //   warp 22      UMMA issuer PV    O(tile & 1) += P(n) V(n)   (TS form, P read from the S buffer)
-//   warps 0-15   softmax           four warps per TMEM lane quarter, each owning a quarter of the key columns of
-//                                  its rows; two rolled passes (max, exp) with one masked code path -- small loop
-//                                  bodies, the kernels are instruction-cache bound otherwise; P written as 16-bit
-//                                  over the consumed S columns
-//   warps 16-19  epilogue          O / l -> 16-bit -> swizzled smem -> TMA store, LSE = m ln2 + log l
 //
 // Online softmax in exp2 units seeded with (m, l) = (s_aux, 1) (:139-146); O is rescaled lazily (only when a
 // row max moves by more than 2^8), which never happens for single-item tiles such as window 128.
@@ -62,7 +63,9 @@ struct Fwd64Cfg {
   // (S wait, max exchange, P hand-over), so with a single group every scheduler's warps stall on the same latency
   // at the same time -- the timeline showed 4 200 cycles per tile against 1 470 of MUFU work.  With two groups half
   // a tile apart each scheduler always has a group in a math pass.  Per group: kParts warps per TMEM lane quarter,
-  // each owning 1 / kParts of the key columns of its rows.
+  // each owning 1 / kParts of the key columns of its rows.  Measured at the gpt-oss shape: one group x 3 parts
+  // 62.2 us, two groups x 2 parts 54.7 us, two groups x 3 parts (992 threads) 60.3 us.  A separate (single) TMEM
+  // region for P, so that S(n + 2) need not wait for PV(n), serialises the two groups on that region: 63.3 us.
   static constexpr int kGroups = 2;
   static constexpr int kParts = 2;
   static constexpr int kGroupWarps = 4 * kParts;
