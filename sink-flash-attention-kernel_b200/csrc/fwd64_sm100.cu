@@ -50,6 +50,7 @@ __device__ __forceinline__ void tev(long long* trace, int role, int& cnt, int co
 using Walk = ItemWalkT<Fwd64Args>;
 
 struct Fwd64Cfg {
+  // (the full-width fast path of the PV issuer assumes kParts == 2: parts split 9 chunks as 5 + 4)
   static constexpr int D = 64;
   static constexpr int kBNMax = 144;
   static constexpr int kQStages = 3, kKStages = 3, kVStages = 3;
@@ -217,15 +218,27 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         if (w.t == 0 && w.it >= 2) mbar_wait(o_free + tb, ((w.it - 2) >> 1) & 1);
         tc_fence_after();
         tev(a.trace, 3, tc, 2, w.n);
+        if (nk == C::kBNMax / 16) {
+          // full-width item (every tile of a 128-wide window): no per-UMMA predicates or selects -- this thread's
+          // issue time gates S(n + 2), which reuses the S buffer P(n) sits in
+          const uint32_t dO_ = tmem + C::kColO + tb * D;
 #pragma unroll
-        for (int kk = 0; kk < C::kBNMax / 16; ++kk)
-          if (kk < nk) {
-            int pstart = 0;
-#pragma unroll
-            for (int pp = 1; pp < C::kParts; ++pp) pstart = (kk >= cs[pp]) ? cs[pp] : pstart;
-            umma_ts(tmem + C::kColO + tb * D, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv,
-                    (w.t > 0 || kk > 0));
+          for (int kk = 0; kk < C::kBNMax / 16; ++kk) {
+            constexpr int kSplit = (C::kBNMax / 16 + C::kParts - 1) / C::kParts;      // cs[1] for kParts == 2
+            const int pstart = (C::kParts == 2) ? (kk >= kSplit ? kSplit : 0) : 0;
+            umma_ts(dO_, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv, (w.t > 0 || kk > 0));
           }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < C::kBNMax / 16; ++kk)
+            if (kk < nk) {
+              int pstart = 0;
+#pragma unroll
+              for (int pp = 1; pp < C::kParts; ++pp) pstart = (kk >= cs[pp]) ? cs[pp] : pstart;
+              umma_ts(tmem + C::kColO + tb * D, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv,
+                      (w.t > 0 || kk > 0));
+            }
+        }
         umma_commit(sbuf_free + sb);
         umma_commit(v_empty + vst);
         if (w.last_of_tile()) umma_commit(o_done + tb);
