@@ -197,9 +197,9 @@ __device__ __forceinline__ void fused_delta_rows(const T* ob, const T* dob, floa
       if (i < g.N) {
         const T* po = ob + gr2 * g.so_h + i * g.so_n;
         const T* pg = dob + gr2 * g.sdo_h + i * g.sdo_n;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(ov[j].x), "=r"(ov[j].y), "=r"(ov[j].z), "=r"(ov[j].w) : "l"(po));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(gv[j].x), "=r"(gv[j].y), "=r"(gv[j].z), "=r"(gv[j].w) : "l"(pg));
       }
     }

@@ -449,7 +449,12 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         tev(a.trace, 6, mtc, 3, w.n);
       }
     }
-    if (et == 0) tma_store_wait_all0();
+    if (et == 0) {
+      tma_store_wait_all0();
+      // routed tiles went to another GPU: order them before everything that follows this kernel at system scope
+      // (the host side's cross-rank barrier signals the peer right after the kernel)
+      if (a.sp_n > 0) __threadfence_system();
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -27,7 +27,7 @@ __device__ __forceinline__ float warp_sum(float x) {
 }
 
 template <typename T>
-__device__ __forceinline__ float dot_row(const T* __restrict__ row, const float* __restrict__ qs, int D) {
+__device__ __forceinline__ float dot_row(const T* row, const float* __restrict__ qs, int D) {   // row: no __restrict__ (no LDG.NC: K / V may sit in a peer-written buffer)
   float s = 0.f;
   for (int d = 0; d < D; ++d) s = fmaf(to_f<T>(row[d]), qs[d], s);
   return s;
@@ -262,9 +262,12 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
 // 2 x kRowsPerThread x 16 B in flight per thread (the one-row version reached 52 % of the DRAM bandwidth with 32 B
 // in flight per thread and 16 384 short-lived blocks).
 constexpr int kPreRowsPerThread = 4;
-__device__ __forceinline__ uint4 ld_nc_v4(const void* ptr) {   // streamed once: keep it out of L1
+// Streamed once: keep it out of L1.  NOT the non-coherent (.nc) path: under Ulysses dO sits in a buffer the peer GPUs
+// write between launches, and .nc loads returned rows of the PREVIOUS step there (tools/dev_p2p.py, fresh data per
+// round: delta, hence dQ and dK, came out stale on one rank while dV -- dO through TMA -- was right).
+__device__ __forceinline__ uint4 ld_nc_v4(const void* ptr) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
   return v;
 }

@@ -35,15 +35,25 @@ def run(mod):
 
 nccl = sa.UlyssesSinkAttention(S, W, None)
 p2p = sa.UlyssesSinkAttention(S, W, None, p2p=True)
-ref = run(nccl)
-got = run(p2p)
-torch.cuda.synchronize()
+# fresh data every round: a peer store that is not yet visible when the barrier releases the reader shows up as
+# stale rows of the previous round
+worst = {}
 ok = True
-for name, a, b in zip(("o", "dq", "dk", "dv", "ds_aux"), got, ref):
-    d = (a.float() - b.float()).abs().max().item()
-    ok &= d == 0.0 if name != "ds_aux" else d < 1e-5
-    print(f"[rank {rank}] {name}: max |p2p - nccl| = {d:.3e}", flush=True)
-print(f"[rank {rank}] {'MATCH' if ok else 'MISMATCH'}", flush=True)
+for rnd in range(int(os.environ.get("ROUNDS", 6))):
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    ref = run(nccl)
+    got = run(p2p)
+    ref2 = run(nccl)
+    got2 = run(p2p)
+    torch.cuda.synchronize()
+    for name, a, b, a2, b2 in zip(("o", "dq", "dk", "dv", "ds_aux"), got, ref, got2, ref2):
+        d = (a.float() - b.float()).abs().max().item()
+        worst[name] = max(worst.get(name, 0.0), d)
+        worst[name + "(p2p rerun)"] = max(worst.get(name + "(p2p rerun)", 0.0), (a.float() - a2.float()).abs().max().item())
+        worst[name + "(nccl rerun)"] = max(worst.get(name + "(nccl rerun)", 0.0), (b.float() - b2.float()).abs().max().item())
+        ok &= (d == 0.0) if name != "ds_aux" else (d < 1e-5)
+print(f"[rank {rank}] " + ("MATCH" if ok else "MISMATCH") + " over the rounds; max |p2p - nccl| = " +
+      ", ".join(f"{n} {d:.3e}" for n, d in worst.items()) + "\n", end="", flush=True)
 
 
 def timeit(fn, steps=20):
