@@ -187,8 +187,9 @@ class _P2PBuffers:
         # fused output side: O (and optionally dQ) are stored into the peers' buffers by the attention kernels
         # themselves.  Routed dQ is OFF by default: with it tools/dev_p2p.py (fresh data every round, every call run
         # twice) found dq and dk differing between two runs on the same inputs on 2 GPUs, while the single-GPU emulation
-        # (tests: test_routed_output_stores_match_unrouted) is bit-exact -- an open timing-dependent issue of the fused
-        # backward under slow remote stores.  SFA_ULY_ROUTE_DQ=1 enables it; SFA_ULY_NO_ROUTE=1 disables both.
+        # (tests: test_routed_output_stores_match_unrouted) and the fully synchronised 2-GPU run (tools/diag_route_dq.py)
+        # are bit-exact -- an open ordering issue of the un-synchronised flow.  SFA_ULY_ROUTE_DQ=1 enables it;
+        # SFA_ULY_NO_ROUTE=1 disables both.
         self.route_o = P <= 8 and os.environ.get("SFA_ULY_NO_ROUTE") is None
         self.route_dq = self.route_o and os.environ.get("SFA_ULY_ROUTE_DQ") == "1"
 
