@@ -192,6 +192,8 @@ class _P2PBuffers:
         # SFA_ULY_NO_ROUTE=1 disables both.
         self.route_o = P <= 8 and os.environ.get("SFA_ULY_NO_ROUTE") is None
         self.route_dq = self.route_o and os.environ.get("SFA_ULY_ROUTE_DQ") == "1"
+        if os.environ.get("SFA_ULY_NO_ROUTE_O"):          # diagnostics: routed dQ without routed O
+            self.route_o = False
 
     def barrier(self):
         self.hdl.barrier(channel=0)
