@@ -31,7 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "sink-flash-attention-kernel_b200"))
 
 C1 = dict(B=1, N=8192, Hq=64, Hkv=8, D=64, S=0, W=128)            # BASELINE.json configs[1]
+C2 = dict(B=4, N=16384, Hq=32, Hkv=8, D=128, S=4, W=4096)          # BASELINE.json configs[2]
 C3 = dict(B=64, Nkv=4100, Hq=64, Hkv=8, D=64)                      # BASELINE.json configs[3]
+C4_N_TOTAL = 131072                                                # BASELINE.json configs[4]: Ulysses SP, N=131072 in total
 METRIC = "fwd+bwd masked-FLOP TFLOPS (gpt-oss-20b attention layer, bf16)"
 UNIT = "TFLOP/s"
 
@@ -202,6 +204,45 @@ def run_ours(args):
             ts.append(a.elapsed_time(b))
         return ts
 
+    flush_only = {}
+
+    def _replay_ms(gr, reps):
+        ts = []
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record()
+            gr.replay()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    def _capture(body, inner):
+        gr = torch.cuda.CUDAGraph()
+        keep = []
+        with torch.cuda.graph(gr):
+            for it in range(inner):
+                flush_buf.fill_(it)
+                keep.append(body())
+        return gr, keep
+
+    def graph_timed(fn, reps=7, inner=10):
+        """ms of one `fn`: a graph of `inner` x (L2 flush, fn) minus a graph of `inner` x (L2 flush), / inner --
+        the CUDA event clock of this box ticks every ~2 us, too coarse for one 40-100 us kernel, and an eager
+        Python call between two events measures the host launch path, not the kernel."""
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if inner not in flush_only:
+            g0, _ = _capture(lambda: None, inner)
+            _replay_ms(g0, 2)
+            flush_only[inner] = _replay_ms(g0, reps)
+        gr, keep = _capture(fn, inner)
+        _replay_ms(gr, 2)
+        ms_ = (_replay_ms(gr, reps) - flush_only[inner]) / inner
+        del keep
+        return ms_
+
     def e2e_pipelined(host_in, host_out, run_step, steps, warm=2):
         """End-to-end steps through the public API from pinned HOST buffers, software-pipelined like a training loop
         with input prefetch: step i's H2D copy (copy stream), step i-1's kernels (main stream) and step i-2's D2H
@@ -283,7 +324,21 @@ def run_ours(args):
         parallelism = "single GPU"
     else:
         assert Hkv % world == 0, "Ulysses needs the GPU count to divide H_kv=8"
-        n_total = N * world
+        # BASELINE configs[4]: ONE 131072-token sequence sharded over the ranks (SFA_BENCH_NTOTAL overrides for development)
+        n_total = int(os.environ.get("SFA_BENCH_NTOTAL", C4_N_TOTAL))
+        N = n_total // world
+        # ---- parity of the sharded path BEFORE timing it (tools/check_ulysses_p2p.py): peer-memory path vs NCCL path
+        # (bit-exact, multi-round, skewed ranks), vs the un-sharded operator on one GQA group, fwd-fwd-bwd-bwd
+        parity_check = None
+        if os.environ.get("SFA_BENCH_SKIP_PARITY") is None and os.environ.get("SFA_BENCH_ULY", "p2p") != "nccl":
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            try:
+                import check_ulysses_p2p
+                parity_check = check_ulysses_p2p.verify(dev, n_local=2048, rounds=4)
+            except Exception as e:      # noqa: BLE001
+                parity_check = {"ok": False, "ok_all_ranks": False, "error": f"{type(e).__name__}: {e}"}
+            torch.cuda.synchronize()
+            dist.barrier()
         q = torch.randn(B, N, Hq, D, device=dev, generator=g).to(dt).requires_grad_(True)       # HF layout chunk
         k = torch.randn(B, N, Hkv, D, device=dev, generator=g).to(dt).requires_grad_(True)
         v = torch.randn(B, N, Hkv, D, device=dev, generator=g).to(dt).requires_grad_(True)
@@ -342,8 +397,8 @@ def run_ours(args):
         # fwd: 3 scatter + barrier + attention + scatter + barrier (+ clone); bwd: scatter + barrier + preprocess +
         # fused + fix-up + 3 scatter + barrier (+ 3 copies)  ->  13 kernels of libsinkfa per step (p2p path)
         launches_per_step = 13 if want_p2p else 1 + 3
-        workload = (f"gpt-oss-20b attention layer fwd+bwd under Ulysses SP: {N}-token chunk per rank of a {n_total}-token "
-                    f"sequence, Hq=64 Hkv=8 D=64 window=128 s_aux bf16, {exch} each side")
+        workload = (f"gpt-oss-20b attention layer fwd+bwd under Ulysses SP (BASELINE configs[4]): ONE {n_total}-token sequence, "
+                    f"{N}-token chunk per rank, Hq=64 Hkv=8 D=64 window=128 s_aux bf16, {exch} each side")
         parallelism = f"ulysses_sp{world}"
 
     # ---- the timed region: warm-up, barrier + sync, K steps (per-step CUDA events, L2 flushed between), sync
@@ -392,45 +447,6 @@ def run_ours(args):
             # CUDA events around the replay (on the launching stream) -> dominant kernel roofline
             qd, kd, vd = q.detach(), k.detach(), v.detach()
             sd = s_aux.detach()
-
-            INNER = 10
-            flush_only = {}
-
-            def _replay_ms(gr, reps):
-                ts = []
-                for _ in range(reps):
-                    a, b = ev(), ev()
-                    a.record()
-                    gr.replay()
-                    b.record()
-                    b.synchronize()
-                    ts.append(a.elapsed_time(b))
-                return statistics.median(ts)
-
-            def _capture(body):
-                gr = torch.cuda.CUDAGraph()
-                keep = []
-                with torch.cuda.graph(gr):
-                    for it in range(INNER):
-                        flush_buf.fill_(it)
-                        keep.append(body())
-                return gr, keep
-
-            def graph_timed(fn, reps=7):
-                """ms of one `fn`: a graph of INNER x (L2 flush, fn) minus a graph of INNER x (L2 flush), / INNER --
-                the CUDA event clock of this box ticks every ~2 us, too coarse for one 40-100 us kernel."""
-                for _ in range(3):
-                    fn()
-                torch.cuda.synchronize()
-                if not flush_only:
-                    g0, _ = _capture(lambda: None)
-                    _replay_ms(g0, 2)
-                    flush_only["ms"] = _replay_ms(g0, reps)
-                gr, keep = _capture(fn)
-                _replay_ms(gr, 2)
-                ms_ = (_replay_ms(gr, reps) - flush_only["ms"]) / INNER
-                del keep
-                return ms_
 
             t_eager = timed(eager_step, 5, 3)
             stage_ms = {}
@@ -500,14 +516,44 @@ def run_ours(args):
             qq = torch.randn(Bd, Hq, 1, D, device=dev, generator=g).to(dt)
             kk = torch.randn(Bd, Hkv, Nkv, D, device=dev, generator=g).to(dt)
             vv = torch.randn(Bd, Hkv, Nkv, D, device=dev, generator=g).to(dt)
-            td = timed(lambda: sa.sink_decode_attention(qq, kk, vv, sd), 20, 5)
-            dms = statistics.median(td)
+            dms = graph_timed(lambda: sa.sink_decode_attention(qq, kk, vv, sd))
             dbytes = 2 * Bd * Hkv * Nkv * D * 2 + 2 * Bd * Hq * D * 2
             decode = {"workload": "KV-cache decode (BASELINE configs[3]): batch 64, sink 4 + window 4096, Hq=64 Hkv=8 D=64 "
                                   "s_aux bf16", "ms_per_step": dms, "hbm_GBps": dbytes / (dms * 1e-3) / 1e9,
                       "frac_of_hbm_peak": dbytes / (dms * 1e-3) / 1e9 / hbm_peak, "tokens_per_s": Bd / (dms * 1e-3),
-                      "algorithmic_bytes": dbytes, "impl": _lib.last_impl(), "gpu_launches_per_step": 2}
+                      "algorithmic_bytes": dbytes, "impl": _lib.last_impl(),
+                      "timing": "CUDA graph of 10 x (L2 flush, decode) minus flush-only graph, CUDA events, median of 7 replays"}
             del qq, kk, vv
+            # ---- BASELINE configs[2] (Llama-style StreamingLLM layer, the tensor-bound config): fwd+bwd device time
+            c2 = None
+            if os.environ.get("SFA_BENCH_SKIP_C2") is None:
+                B2, N2, Hq2, Hkv2, D2, S2, W2 = (C2[k_] for k_ in ("B", "N", "Hq", "Hkv", "D", "S", "W"))
+                q2 = torch.randn(B2, Hq2, N2, D2, device=dev, generator=g).to(dt)
+                k2 = torch.randn(B2, Hkv2, N2, D2, device=dev, generator=g).to(dt)
+                v2 = torch.randn(B2, Hkv2, N2, D2, device=dev, generator=g).to(dt)
+                do2 = torch.randn(B2, Hq2, N2, D2, device=dev, generator=g).to(dt)
+
+                def c2_fwd():
+                    return _lib.fwd(q2, k2, v2, S2, W2, None)
+                o2, lse2 = c2_fwd()
+
+                def c2_bwd():
+                    return _lib.bwd(q2, k2, v2, o2, do2, lse2, S2, W2, None)
+                t_f2 = graph_timed(c2_fwd, reps=5, inner=2)
+                fwd2_impl = _lib.last_impl()
+                t_b2 = graph_timed(c2_bwd, reps=5, inner=2)
+                pairs2 = attended_pairs(N2, S2, W2) * B2 * Hq2
+                fl2 = 14 * D2 * pairs2
+                c2 = {"workload": "Llama-3-8B-style StreamingLLM layer fwd+bwd (BASELINE configs[2]): B=4 N=16384 Hq=32 Hkv=8 "
+                                  "D=128 num_sink=4 window=4096 bf16",
+                      "fwd_ms": t_f2, "bwd_ms": t_b2, "ms_per_step": t_f2 + t_b2, "masked_flops_per_step": fl2,
+                      "tflops": fl2 / ((t_f2 + t_b2) * 1e-3) / 1e12,
+                      "fwd_tflops": 4 * D2 * pairs2 / (t_f2 * 1e-3) / 1e12, "bwd_tflops": 10 * D2 * pairs2 / (t_b2 * 1e-3) / 1e12,
+                      "frac_of_bf16_burst_peak": fl2 / ((t_f2 + t_b2) * 1e-3) / 1e12 / tf_burst,
+                      "bound": "tensor", "impl": {"fwd": fwd2_impl, "bwd": _lib.last_impl()},
+                      "timing": "CUDA graph of 2 x (L2 flush, call) minus flush-only graph, CUDA events, median of 5 replays"}
+                del q2, k2, v2, do2, o2, lse2
+                torch.cuda.empty_cache()
             # ---- e2e: the public API from pinned HOST buffers, H2D + D2H inside the timed region
             hq_, hk_, hv_, hdo_ = (t.detach().cpu().pin_memory() for t in (q, k, v, do))
             hs_ = s_aux.detach().cpu().pin_memory()
@@ -542,7 +588,9 @@ def run_ours(args):
             e2e = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            # N = 1 is configs[1] (one 8192-token layer); N > 1 is configs[4], whose 131072 tokens are fixed as N grows
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "parallelism": parallelism, "global_tokens": n_total * B,
                        "masked_flops_per_step": job_flops,
@@ -558,6 +606,10 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_base
         if decode is not None:
             line["decode"] = decode
+        if world == 1 and c2 is not None:
+            line["c2"] = c2
+        if world > 1:
+            line["parity_check"] = parity_check
         if e2e is not None:
             line["e2e"] = e2e
     if world > 1:
@@ -568,8 +620,7 @@ def run_ours(args):
         vv = torch.randn(Bd, Hkv, Nkv, D, device=dev, generator=g).to(dt)
         sdd = s_aux.detach()
         dist.barrier()
-        td = timed(lambda: sa.sink_decode_attention(qq, kk, vv, sdd), 20, 5)
-        tdm = torch.tensor([statistics.median(td)], device=dev)
+        tdm = torch.tensor([graph_timed(lambda: sa.sink_decode_attention(qq, kk, vv, sdd))], device=dev)
         dist.all_reduce(tdm, op=dist.ReduceOp.MAX)
         dbytes = (2 * Bd * Hkv * Nkv * D * 2 + 2 * Bd * Hq * D * 2) * world
         if rank == 0:

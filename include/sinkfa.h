@@ -57,6 +57,12 @@ int sfa_set_impl(int impl);
  * bit3 (7 + 8 = 15): keep the dQ + dK/dV kernel pair where the one-kernel fused backward would apply
  * (narrow window, no sink tokens, head_dim 64), so that both paths can be tested on the same shape. */
 int sfa_set_bwd_stages(int mask);
+/* test / diagnostics knobs, all 0 by default (process-wide, atomic):
+ *   knob 0: the fused backward sleeps `value` ns in its part-1 math warps before pass 2 and 4x that in epilogue
+ *           group 0 before its dQ stores -- widens every cross-warp window of the kernel's pipeline (stress test);
+ *   knob 1: value 1 drops the barrier that orders the P-image reads of one tile before the writes of the next
+ *           (reproduces the round-1 run-to-run difference in dQ / dK on one GPU; tests only). */
+int sfa_set_debug(int knob, int value);
 /* performance-debug aid: a device buffer of 3*256*2 int64 into which CTA 0 of the dQ kernel appends
  * (role, event, index, clock64) records; NULL (the default) switches it off. */
 int sfa_set_trace_buffer(void* device_buffer);
@@ -127,23 +133,6 @@ int sfa_bwd_sp(const void* q, const void* k, const void* v, const void* o, const
                const int64_t o_strides[4], const int64_t do_strides[4],
                const int64_t dk_strides[4], const int64_t dv_strides[4],
                void* workspace, size_t workspace_bytes, void* stream, const sfa_sp_route* dq_route);
-
-/* tcgen05/TMA self-test: C[M=128,N] = A[128,K] * B^T (+ variants).  Returns 0 and fills c (fp32, device).
- * mode 0: A,B K-major in smem; mode 1: B given as [K,N] (MN-major); mode 2: A through TMEM (TS form). */
-int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream);
-
-/* UMMA issue-rate probe: out2 = device int64[2] <- {cycles to issue, cycles until complete} for reps*ksteps UMMAs */
-int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, void* stream);
-/* UMMA operand-layout timing probe: prm16 = {M, N, a_mn_major, b_mn_major, a_swizzle128, a_lbo, a_sbo, a_kstep_bytes,
-   b_swizzle128, b_lbo, b_sbo, b_kstep_bytes, n_mmas, ksteps, d_lane_offset, 0}; out2 as sfa_probe_mma_rate */
-int sfa_probe_mma_desc(void* out2, const int* prm16, void* stream);
-/* math-pipe probe: out1 = device int64[1] <- cycles for `iters` 16-element softmax steps of one warp (see probe_sm100.cu) */
-int sfa_probe_math_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream);
-/* TMEM read-throughput probe: out1 <- cycles for `iters` tcgen05.ld round trips per warp (mode 0: x16, 1: x32, 2: 2 x x32) */
-int sfa_probe_tmem_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream);
-/* load-throughput probe (performance work): streams a bf16 [H,N,64] tensor through shared memory with TMA
- * boxes of box_n positions x box_h heads (mode 0) or per-thread cp.async (mode 1), `stages` boxes in flight. */
-int sfa_probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,9 +10,13 @@
 namespace sfa {
 
 static thread_local char g_err[512] = "";
-static const char* volatile g_impl = "";   // process-wide: autograd runs backward on its own thread
-static int g_force_impl = SFA_IMPL_AUTO;
-static int g_bwd_stages = 7;
+// Selectors are process-wide ON PURPOSE (autograd runs backward on its own thread: a thread-local selector set by
+// the test thread would not reach it) and atomic, so concurrent callers never see a torn or stale-forever value.
+static std::atomic<const char*> g_impl{""};
+static std::atomic<int> g_force_impl{SFA_IMPL_AUTO};
+static std::atomic<int> g_bwd_stages{7};
+static std::atomic<int> g_debug[4] = {{0}, {0}, {0}, {0}};
+static const bool g_env_fwd_v1 = getenv("SFA_FWD_V1") != nullptr;   // diagnostics: read once, not per call
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,7 +24,22 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void set_impl_name(const char* name) { g_impl = name; }
+void set_impl_name(const char* name) { g_impl.store(name, std::memory_order_relaxed); }
+int debug_knob(int which) { return (which >= 0 && which < 4) ? g_debug[which].load(std::memory_order_relaxed) : 0; }
+
+int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
 
 static Strides4 mk(const int64_t* s) { return Strides4{s[0], s[1], s[2]}; }
 
@@ -65,13 +84,22 @@ extern "C" {
 
 int sfa_version(void) { return 100; }
 const char* sfa_last_error(void) { return g_err; }
-const char* sfa_last_impl(void) { return g_impl; }
+const char* sfa_last_impl(void) { return g_impl.load(std::memory_order_relaxed); }
 int sfa_set_impl(int impl) {
   if (impl != SFA_IMPL_AUTO && impl != SFA_IMPL_SIMT) {
     set_error("unknown impl %d", impl);
     return -1;
   }
-  g_force_impl = impl;
+  g_force_impl.store(impl);
+  return 0;
+}
+
+int sfa_set_debug(int knob, int value) {
+  if (knob < 0 || knob >= 4) {
+    set_error("unknown debug knob %d", knob);
+    return -1;
+  }
+  g_debug[knob].store(value);
   return 0;
 }
 
@@ -81,7 +109,7 @@ int sfa_set_trace_buffer(void* device_buffer) {
 }
 
 int sfa_set_bwd_stages(int mask) {
-  g_bwd_stages = mask & 15;   // bit 3: keep the dQ + dK/dV kernel pair even where the fused kernel applies
+  g_bwd_stages.store(mask & 15);   // bit 3: keep the dQ + dK/dV kernel pair even where the fused kernel applies
   return 0;
 }
 
@@ -116,6 +144,7 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
                     size_t workspace_bytes, void* stream, const sfa_sp_route* o_route) {
   (void)workspace;
   (void)workspace_bytes;
+  const int g_force_impl = sfa::g_force_impl.load();
   const int64_t* ss[4] = {q_strides, k_strides, v_strides, o_strides};
   if (int r = check_common(B, Hq, Hkv, N, D, dtype, ss, 4)) return r;
   if (!q || !k || !v || !o || !lse) {
@@ -145,7 +174,7 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
   }
   if (g_force_impl != SFA_IMPL_SIMT && tc_fwd_supported(p, dtype)) {
     set_impl_name("tcgen05");
-    if (tc_fwd64_supported(p, dtype) && !getenv("SFA_FWD_V1")) return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
+    if (tc_fwd64_supported(p, dtype) && !(g_env_fwd_v1 && p.o_route == nullptr)) return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
     return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");
   }
   set_impl_name("simt");
@@ -178,6 +207,7 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
             const int64_t v_strides[4], const int64_t o_strides[4], const int64_t do_strides[4],
             const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], void* workspace,
             size_t workspace_bytes, void* stream, const sfa_sp_route* dq_route) {
+  const int g_force_impl = sfa::g_force_impl.load(), g_bwd_stages = sfa::g_bwd_stages.load();
   const int64_t* ss[8] = {q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides};
   if (int r = check_common(B, Hq, Hkv, N, D, dtype, ss, 8)) return r;
   if (!q || !k || !v || !o || !dout || !lse || (!dq && !dq_route) || !dk || !dv) {
@@ -281,6 +311,7 @@ int sfa_bwd_sp(const void* q, const void* k, const void* v, const void* o, const
 }
 
 static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int g_force_impl = sfa::g_force_impl.load();
   const int L = p.len[0] + p.len[1];
   if (L < 1) {
     set_error("decode needs at least one cached key");
@@ -389,34 +420,6 @@ int sfa_ulysses_scatter(const void* src, void* const* peer_dst, int P, int rank,
     }
   return cuda_ret(ulysses_scatter(src, peer_dst, P, rank, mode, B, L, H, D, es, src_strides, dst_heads, head_off,
                                   static_cast<cudaStream_t>(stream)), "sfa_ulysses_scatter");
-}
-
-int sfa_probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode, void* stream) {
-  return cuda_ret(probe_tma_bw(src, H, N, box_n, box_h, stages, grid, mode, static_cast<cudaStream_t>(stream)),
-                  "sfa_probe_tma_bw");
-}
-
-int sfa_probe_mma_rate(void* out2, int N, int ksteps, int reps, int uniform, void* stream) {
-  return cuda_ret(probe_mma_rate(static_cast<long long*>(out2), N, ksteps, reps, uniform, static_cast<cudaStream_t>(stream)),
-                  "sfa_probe_mma_rate");
-}
-
-int sfa_probe_mma_desc(void* out2, const int* prm16, void* stream) {
-  return cuda_ret(probe_mma_desc(static_cast<long long*>(out2), prm16, static_cast<cudaStream_t>(stream)), "sfa_probe_mma_desc");
-}
-
-int sfa_probe_math_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream) {
-  return cuda_ret(probe_math_rate(static_cast<long long*>(out1), static_cast<float*>(sink), mode, iters, threads,
-                                  static_cast<cudaStream_t>(stream)), "sfa_probe_math_rate");
-}
-
-int sfa_probe_tmem_rate(void* out1, void* sink, int mode, int iters, int threads, void* stream) {
-  return cuda_ret(probe_tmem_rate(static_cast<long long*>(out1), static_cast<float*>(sink), mode, iters, threads,
-                                  static_cast<cudaStream_t>(stream)), "sfa_probe_tmem_rate");
-}
-
-int sfa_probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, void* stream) {
-  return cuda_ret(probe_umma(a, b, c, N, K, mode, dtype, static_cast<cudaStream_t>(stream)), "sfa_probe_umma");
 }
 
 }  // extern "C"

@@ -1558,16 +1558,7 @@ void set_trace_buffer(long long* p) { g_trace = p; }
 long long* trace_buffer() { return g_trace; }
 namespace {
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count() { return device_sm_count(); }
 
 // Fused delta: possible when every packed tile has exactly one KV item (no sinks, the band of a tile fits one
 // item).  OFF by default -- measured at the C1 shape it saves the 43 us preprocess pass but costs the dS warps
@@ -1593,13 +1584,12 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
   if (stages & 2) {
     constexpr int kBNMax = (D == 64) ? Dq64Cfg::kBNMax : DqCfg<D>::kBNMax;
     constexpr int kSmemDq = (D == 64) ? Dq64Cfg::kSmem : DqCfg<D>::kSmem;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    {
       cudaError_t e;
-      if constexpr (D == 64) e = cudaFuncSetAttribute(dq64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDq);
-      else e = cudaFuncSetAttribute(dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDq);
+      if constexpr (D == 64) e = ensure_dyn_smem(dq64_kernel<T>, kSmemDq, attr_done);
+      else e = ensure_dyn_smem(dq_kernel<T, D>, kSmemDq, attr_done);
       if (e != cudaSuccess) return e;
-      attr_done = true;
     }
     const int BN = pick_bn(p.W, p.N, P, kBNMax);
     TileMap mk, mv, mdq;
@@ -1634,13 +1624,12 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
   if (stages & 4) {
     constexpr int kBK = 128;
     constexpr int kSmemKv = (D == 64) ? Dkv64Cfg::kSmem : DkvCfg<D>::kSmem;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    {
       cudaError_t e;
-      if constexpr (D == 64) e = cudaFuncSetAttribute(dkdv64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemKv);
-      else e = cudaFuncSetAttribute(dkdv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemKv);
+      if constexpr (D == 64) e = ensure_dyn_smem(dkdv64_kernel<T>, kSmemKv, attr_done);
+      else e = ensure_dyn_smem(dkdv_kernel<T, D>, kSmemKv, attr_done);
       if (e != cudaSuccess) return e;
-      attr_done = true;
     }
     TileMap mk, mv;
     if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, kBK, 1)) return cudaErrorInvalidValue;
@@ -1680,8 +1669,8 @@ bool tc_bwd_supported(const AttnParams& p, int dtype) {
   if (p.D != 64 && p.D != 128) return false;
   if (p.N < 1) return false;
   if (p.S <= 0 && p.W <= 0) return false;     // nothing attended: the CUDA-core path writes the zeros
-  if (!(tma_compatible(p.q, p.sq) && tma_compatible(p.k, p.sk) && tma_compatible(p.v, p.sv) &&
-        tma_compatible(p.dout, p.sdo) && tma_compatible(p.dq, p.sdq)))
+  if (!(tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.N) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.N) &&
+        tma_compatible(p.dout, p.sdo, p.B, p.Hq, p.N) && tma_compatible(p.dq, p.sdq, p.B, p.Hq, p.N)))
     return false;
   // dK/dV rows are written with 16-byte stores
   if (reinterpret_cast<uintptr_t>(p.dk) % 16 || reinterpret_cast<uintptr_t>(p.dv) % 16) return false;

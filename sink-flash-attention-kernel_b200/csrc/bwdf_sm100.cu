@@ -72,6 +72,10 @@ struct FusedArgs {
   int order_dp;    // issuer A queues dP(n + 1) behind dK^T(n) / dQ(n)
   int prefetch;    // producer warp prefetches tiles into L2 ahead of the TMA loads
   int fuse_delta;  // 1: the epilogue groups compute delta in the kernel; 0: a preprocess kernel wrote it before
+  int dbg_delay;   // test knob (sfa_set_debug): the part-1 math warps sleep this many ns before pass 2, the epilogue
+                   // groups before their dQ stores -- widens every cross-warp window of the pipeline
+  int dbg_norace;  // test knob: 1 drops the per-quarter barrier that orders the P-image reads of pass 2(n) before the
+                   // writes of pass 1(n + 1) (reproduces the round-1 run-to-run difference in dQ / dK on one GPU)
   int fmt;       // 0 f16, 1 bf16
   float sl2;     // scale * log2(e)
   float scale;
@@ -576,6 +580,13 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         tc_fence_after();
         if (w.it >= 1) mbar_wait(p_free, (w.it - 1) & 1);
         if (tr) ftrace(a.trace, 3, tc, 2, w.it);
+        // Pass 2(n) reads P back from the image, and the ring-column order shifts by one key block per tile: the cell
+        // [row r, ring chunk c] this thread writes now for tile n + 1 was natural chunk cb + 1 of tile n, owned -- and
+        // read in pass 2(n) -- by the warp of the NEXT part of the same lane quarter (and the zeroed slot by part 0).
+        // p_free only orders the tensor pipe's reads; the three warps of a quarter (same rows, all chunks) must agree
+        // that pass 2(n) is over before any of them overwrites the image.  Without this barrier a warp that ran a full
+        // pass ahead of its neighbour fed P(n + 1) into dS(n): dQ and dK changed from run to run, dV never (round 1).
+        if (w.it >= 1 && !a.dbg_norace) named_bar_sync(1 + quarter, 96);
         if (part == 1)
           for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(p_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
         const int rc0 = st.slot0 * P;
@@ -618,6 +629,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         mbar_wait(dp_full, w.it & 1);
         tc_fence_after();
         if (w.it >= 1) mbar_wait(ds_free, (w.it - 1) & 1);
+        if (a.dbg_delay && part == 1) __nanosleep(a.dbg_delay);
         if (tr) ftrace(a.trace, 3, tc, 4, w.it);
         if (part == 1)
           for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(ds_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
@@ -742,6 +754,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           T* const tile_dq = dq_base + static_cast<int64_t>(w.b) * a.sdq.b +
                              static_cast<int64_t>(w.y * a.G) * a.sdq.h + static_cast<int64_t>(il0) * a.sdq.n;
           const bool ok0 = w.pb * P + row_pr[0] < a.N, ok1 = w.pb * P + row_pr[1] < a.N;
+          if (a.dbg_delay && grp == 0) __nanosleep(a.dbg_delay * 4);
 #pragma unroll 1
           for (int hq = 0; hq < 4; ++hq) {                  // channels 16 hq .. 16 hq + 15
             uint32_t x[16];
@@ -812,6 +825,10 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           }
         }
         if (last) {
+          // The clear below covers EVERY slot, also the one the other epilogue group may still be reading for tile
+          // n - 1 (the block that left the window with it): wait for that drain first.  (The groups only meet here:
+          // everywhere else a slot is recycled by the issuers, which wait for its drain themselves.)
+          if (w.it >= 1) mbar_wait_warp(drain_done + (grp ^ 1), ((w.it - 1) >> 1) & 1);
           uint32_t z[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) z[e] = 0u;
@@ -895,16 +912,7 @@ __global__ void __launch_bounds__(256) bwd_fused_fixup_kernel(const FusedArgs a,
   }
 }
 
-int fused_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int fused_sm_count() { return device_sm_count(); }
 
 // geometry of the fused path; false when the problem does not fit it
 bool fused_geometry(const AttnParams& p, int& G, int& P, int& nb) {
@@ -947,6 +955,8 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh;
   a.fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
   a.fuse_delta = tc_bwd_fused_computes_delta() ? 1 : 0;
+  a.dbg_delay = debug_knob(0);
+  a.dbg_norace = debug_knob(1);
   // measured: 104.1 us with dP(n + 1) queued behind dK^T(n) / dQ(n), 99.3 us without -> off (SFA_ORDER_DP=1 enables)
   static const int order_dp = getenv("SFA_ORDER_DP") ? atoi(getenv("SFA_ORDER_DP")) : 0;
   a.order_dp = order_dp;
@@ -978,12 +988,8 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   }
   a.part = part;
   a.trace = trace_buffer();
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bwd_fused64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (cudaError_t e = ensure_dyn_smem(bwd_fused64_kernel<T>, C::kSmem, attr_done)) return e;
   bwd_fused64_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -1022,8 +1028,8 @@ bool tc_bwd_fused_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
   int G, P, nb;
   if (!fused_geometry(p, G, P, nb)) return false;
-  if (!(tma_compatible(p.q, p.sq) && tma_compatible(p.k, p.sk) && tma_compatible(p.v, p.sv) &&
-        tma_compatible(p.dout, p.sdo)))
+  if (!(tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.N) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.N) &&
+        tma_compatible(p.dout, p.sdo, p.B, p.Hq, p.N)))
     return false;
   // dQ rows are written with 16-byte stores; O and dO rows are read with 16-byte loads (delta)
   if (p.dq_route == nullptr &&

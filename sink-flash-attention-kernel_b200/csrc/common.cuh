@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <atomic>
 
 #include "../../include/sinkfa.h"
 
@@ -62,6 +63,22 @@ struct DecodeParams {
 
 void set_error(const char* fmt, ...);
 void set_impl_name(const char* name);
+int debug_knob(int which);     // test / diagnostics knobs set through sfa_set_debug (0 when unset)
+
+// Per-DEVICE one-time state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a device,
+// not to the process: a second GPU in the same process (device_map="auto", autograd's per-device threads) must get
+// its own attribute call.  One bit per device ordinal; devices >= 64 simply repeat the (idempotent) call.
+template <class K>
+inline cudaError_t ensure_dyn_smem(K* kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  return e;
+}
+int device_sm_count();         // SM count of the CURRENT device (cached per device ordinal)
 
 template <typename T> __device__ __forceinline__ float to_f(T x);
 template <> __device__ __forceinline__ float to_f<float>(float x) { return x; }
@@ -109,12 +126,6 @@ bool mma_decode_supported(const DecodeParams& p, int dtype);
 int mma_decode_splits(int B, int Hkv, int total_len);
 cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st);
 
-cudaError_t probe_tma_bw(const void* src, int H, int N, int box_n, int box_h, int stages, int grid, int mode,
-                         cudaStream_t st);
-cudaError_t probe_mma_rate(long long* out, int N, int ksteps, int reps, int uniform, cudaStream_t st);
-cudaError_t probe_mma_desc(long long* out, const int* prm16, cudaStream_t st);
-cudaError_t probe_math_rate(long long* out, float* sink, int mode, int iters, int threads, cudaStream_t st);
-cudaError_t probe_tmem_rate(long long* out, float* sink, int mode, int iters, int threads, cudaStream_t st);
 void set_trace_buffer(long long* p);   // performance-debug timeline (device buffer, 3*256*2 int64) or nullptr
 long long* trace_buffer();
 
@@ -122,6 +133,4 @@ long long* trace_buffer();
 cudaError_t ulysses_scatter(const void* src, void* const* peer_dst, int P, int rank, int mode, int B, int L, int H,
                             int D, int elem_size, const int64_t src_strides[3], int dst_heads, int head_off,
                             cudaStream_t st);
-cudaError_t probe_umma(const void* a, const void* b, float* c, int N, int K, int mode, int dtype, cudaStream_t st);
-
 }  // namespace sfa

@@ -335,12 +335,8 @@ __global__ void decode_combine_kernel(DecodeParams p) {
 template <typename T, int D>
 cudaError_t launch(const DecodeParams& p, cudaStream_t st) {
   using C = DecodeCfg<D>;
-  static bool attr_done = false;  // benign race: the attribute call is idempotent
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(decode_mma_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (cudaError_t e = ensure_dyn_smem(decode_mma_kernel<T, D>, C::kSmem, attr_done)) return e;
   const int G = p.Hq / p.Hkv;
   const int g_tiles = (G + 15) / 16;
   const int L = p.len[0] + p.len[1];

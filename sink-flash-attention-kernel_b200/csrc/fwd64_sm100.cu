@@ -461,27 +461,14 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   if (warp == kWIssS) tmem_dealloc(tmem, C::kTmemCols);
 }
 
-int sm_count_fwd() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count_fwd() { return device_sm_count(); }
 
 template <typename T>
 cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
   using C = Fwd64Cfg;
   constexpr int D = 64;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fwd64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T>, C::kSmem, attr_done)) return e;
   const int group = p.Hq / p.Hkv;
   int G, P;
   pick_packing(p.Hq, p.Hkv, G, P);

@@ -288,12 +288,8 @@ __global__ void __launch_bounds__(192) fwd_kernel(const __grid_constant__ CUtens
 template <typename T, int D>
 cudaError_t launch_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
   using C = FwdCfg<D>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (cudaError_t e = ensure_dyn_smem(fwd_kernel<T, D>, C::kSmem, attr_done)) return e;
   const int group = p.Hq / p.Hkv;
   int G, P;
   pick_packing(p.Hq, p.Hkv, G, P);
@@ -324,8 +320,8 @@ bool tc_fwd_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
   if (p.D != 64 && p.D != 128) return false;
   if (p.N < 1) return false;
-  return tma_compatible(p.q, p.sq) && tma_compatible(p.k, p.sk) && tma_compatible(p.v, p.sv) &&
-         tma_compatible(p.o, p.so);
+  return tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.N) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.N) &&
+         tma_compatible(p.o, p.so, p.B, p.Hq, p.N);
 }
 
 cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st) {

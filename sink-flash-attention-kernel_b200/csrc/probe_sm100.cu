@@ -9,6 +9,7 @@
 //   mode 5: mode 3 with B written by the threads in the un-swizzled core-matrix layout
 //   mode 6: M = 128, A [128,K] K-major written by the threads un-swizzled, B [K,N] MN-major SWIZZLE_128B
 #include "common.cuh"
+#include "probe.cuh"
 #include "tmap.cuh"
 #include "umma.cuh"
 

@@ -63,9 +63,17 @@ inline bool make_tile_map(TileMap* out, const void* ptr, int dtype, int D, int N
   dims[3] = B;
   strides[2] = (cuuint64_t)s.b * 2;
   box[3] = 1;
-  // size-1 dims may carry arbitrary strides in torch; any 16-B multiple is acceptable for the encoder
+  // size-1 dims may carry arbitrary strides in torch (0 included); any 16-B multiple is acceptable for the encoder.
+  // A zero stride on a dim of extent > 1 (expand()ed / broadcast tensor) is NOT patched: TMA cannot express it and
+  // tma_compatible() keeps such tensors off this path.
   for (int i = 0; i < 3; ++i)
-    if (dims[i + 1] == 1 || strides[i] == 0) strides[i] = (cuuint64_t)16 * ((dims[0] * 2 + 15) / 16);
+    if (dims[i + 1] == 1) strides[i] = (cuuint64_t)16 * ((dims[0] * 2 + 15) / 16);
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0) {
+      set_error("TMA tensor map: zero stride on a dimension of extent %llu (broadcast views need a copy)",
+                (unsigned long long)dims[i + 1]);
+      return false;
+    }
   if (D < 64) box[0] = D;
   CUresult r = enc(&out->map, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -80,9 +88,12 @@ inline bool make_tile_map(TileMap* out, const void* ptr, int dtype, int D, int N
   return true;
 }
 
-// TMA needs 16-B aligned base and 16-B multiple strides
-inline bool tma_compatible(const void* ptr, const Strides4& s) {
-  return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (s.n % 8 == 0) && (s.h % 8 == 0) && (s.b % 8 == 0);
+// TMA needs a 16-B aligned base and, on every dim of extent > 1, a non-zero 16-B multiple stride (a zero stride is
+// what expand() produces: k.expand(B, ...), or dO = out.mean(dim=2) expanded back -- the tensor map cannot walk it;
+// those tensors take the CUDA-core path, which honours the true strides).  Extent-1 dims carry no constraint.
+inline bool tma_compatible(const void* ptr, const Strides4& s, int B, int H, int N) {
+  auto ok = [](int64_t st, int extent) { return extent <= 1 || (st != 0 && st % 8 == 0); };
+  return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && ok(s.n, N) && ok(s.h, H) && ok(s.b, B);
 }
 
 }  // namespace sfa

@@ -118,11 +118,11 @@ cudaError_t ulysses_scatter(const void* src, void* const* peer_dst, int P, int r
   if (total == 0) return cudaSuccess;
   int64_t blocks = (total + 255) / 256;
   // tuning knobs (tools/dev_p2p.py): blocks per SM of the grid-stride loop, loads in flight per thread
-  const char* eb = getenv("SFA_SCATTER_BLOCKS");
-  const char* eu = getenv("SFA_SCATTER_UNROLL");
-  const int64_t cap = 148 * (eb ? atoi(eb) : 16);
+  static const int env_blocks = getenv("SFA_SCATTER_BLOCKS") ? atoi(getenv("SFA_SCATTER_BLOCKS")) : 16;
+  static const int env_unroll = getenv("SFA_SCATTER_UNROLL") ? atoi(getenv("SFA_SCATTER_UNROLL")) : 4;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * env_blocks;
   if (blocks > cap) blocks = cap;
-  const int unroll = eu ? atoi(eu) : 4;
+  const int unroll = env_unroll;
   if (unroll >= 8) ulysses_scatter_kernel<8><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);
   else if (unroll >= 4) ulysses_scatter_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);
   else if (unroll >= 2) ulysses_scatter_kernel<2><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pp);

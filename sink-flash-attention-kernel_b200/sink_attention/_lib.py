@@ -21,7 +21,7 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_probe_umma", "sfa_probe_tma_bw", "sfa_probe_mma_rate", "sfa_probe_mma_desc", "sfa_probe_math_rate", "sfa_probe_tmem_rate",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_set_debug",
 )
 
 _lib = None
@@ -88,18 +88,8 @@ def load() -> ctypes.CDLL:
     lib.sfa_decode_ring.restype = i
     lib.sfa_ulysses_scatter.argtypes = [p, c.POINTER(c.c_void_p)] + [i] * 8 + [i64p, i, i, p]
     lib.sfa_ulysses_scatter.restype = i
-    lib.sfa_probe_math_rate.argtypes = [p, p, i, i, i, p]
-    lib.sfa_probe_math_rate.restype = i
-    lib.sfa_probe_tmem_rate.argtypes = [p, p, i, i, i, p]
-    lib.sfa_probe_tmem_rate.restype = i
-    lib.sfa_probe_mma_rate.argtypes = [p, i, i, i, i, p]
-    lib.sfa_probe_mma_rate.restype = i
-    lib.sfa_probe_mma_desc.argtypes = [p, c.POINTER(c.c_int), p]
-    lib.sfa_probe_mma_desc.restype = i
-    lib.sfa_probe_tma_bw.argtypes = [p, i, i, i, i, i, i, i, p]
-    lib.sfa_probe_tma_bw.restype = i
-    lib.sfa_probe_umma.argtypes = [p, p, f32p, i, i, i, i, p]
-    lib.sfa_probe_umma.restype = i
+    lib.sfa_set_debug.argtypes = [i, i]
+    lib.sfa_set_debug.restype = i
     _lib = lib
     return lib
 
@@ -125,8 +115,12 @@ def _stream(t: torch.Tensor) -> int:
 
 
 def _unit_last(t: torch.Tensor) -> torch.Tensor:
-    """Kernels accept any (batch, head, position) strides but need channel stride 1."""
-    return t if t.stride(-1) == 1 else t.contiguous()
+    """Kernels accept any (batch, head, position) strides but need channel stride 1.  Broadcast views (stride 0 on
+    a dim of size > 1: ``k.expand(B, ...)``, a ``dO`` that autograd expanded from a reduction) are materialised, as
+    the reference's ``.contiguous()`` does (sink_flash_attention.py:507-509,581): a TMA tensor map cannot walk them."""
+    if t.stride(-1) != 1 or any(st == 0 and sz > 1 for st, sz in zip(t.stride(), t.shape)):
+        return t.contiguous()
+    return t
 
 
 def _dense_non_overlapping(t: torch.Tensor) -> bool:
@@ -291,11 +285,6 @@ def ulysses_scatter(src: torch.Tensor, peer_ptrs: Sequence[int], rank: int, mode
     _check(rc, "sfa_ulysses_scatter")
 
 
-def probe_umma(a: torch.Tensor, b: torch.Tensor, n: int, k: int, mode: int) -> torch.Tensor:
-    lib = load()
-    _require_cuda(a, b)
-    c = torch.empty((128, n), device=a.device, dtype=torch.float32)
-    with torch.cuda.device(a.device):
-        rc = lib.sfa_probe_umma(a.data_ptr(), b.data_ptr(), c.data_ptr(), n, k, mode, DTYPE_CODE[a.dtype], _stream(a))
-    _check(rc, "sfa_probe_umma")
-    return c
+def set_debug(knob: int, value: int):
+    """Test / diagnostics knobs of the library (include/sinkfa.h: sfa_set_debug)."""
+    _check(load().sfa_set_debug(int(knob), int(value)), "sfa_set_debug")

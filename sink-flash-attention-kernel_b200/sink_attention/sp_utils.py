@@ -184,16 +184,21 @@ class _P2PBuffers:
         self.do_full = self.buf[offs[2]:offs[2] + sizes[2]].view(B, P * n, hq_l, D)
         self.g_seq = self.buf[offs[3]:offs[3] + sizes[3]].view(B, n, Hq + 2 * Hkv, D)
 
-        # fused output side: O (and optionally dQ) are stored into the peers' buffers by the attention kernels
-        # themselves.  Routed dQ is OFF by default: with it tools/dev_p2p.py (fresh data every round, every call run
-        # twice) found dq and dk differing between two runs on the same inputs on 2 GPUs, while the single-GPU emulation
-        # (tests: test_routed_output_stores_match_unrouted) and the fully synchronised 2-GPU run (tools/diag_route_dq.py)
-        # are bit-exact -- an open ordering issue of the un-synchronised flow.  SFA_ULY_ROUTE_DQ=1 enables it;
-        # SFA_ULY_NO_ROUTE=1 disables both.
+        # fused output side: O and dQ are stored into the peers' buffers by the attention kernels themselves (TMA /
+        # vector stores to peer mappings): no scatter pass over O / dQ.  (Round 1 shipped routed dQ switched off: on 2
+        # GPUs dq and dk differed from run to run.  The cause was a shared-memory race INSIDE the fused backward that
+        # the slower remote stores merely exposed -- csrc/bwdf_sm100.cu, "Pass 2(n) reads P back from the image" --
+        # fixed in round 2; tools/check_ulysses_p2p.py runs the multi-round bit-exactness check with skewed ranks.)
+        # SFA_ULY_NO_ROUTE=1 disables both, SFA_ULY_ROUTE_DQ=0 only the dQ side.
         self.route_o = P <= 8 and os.environ.get("SFA_ULY_NO_ROUTE") is None
-        self.route_dq = self.route_o and os.environ.get("SFA_ULY_ROUTE_DQ") == "1"
+        self.route_dq = self.route_o and os.environ.get("SFA_ULY_ROUTE_DQ", "1") != "0"
         if os.environ.get("SFA_ULY_NO_ROUTE_O"):          # diagnostics: routed dQ without routed O
             self.route_o = False
+        # The autograd node saves VIEWS of qkv_full for its backward, and the peers overwrite that region in this
+        # buffer set's next forward -- remote writes, which autograd's version counters cannot see.  `pending` marks a
+        # set whose backward has not run yet; the layer then takes another set (fwd, fwd, bwd, bwd: pipeline
+        # micro-batches, weight-shared layers, two loss terms through one module).
+        self.pending = False
 
     def barrier(self):
         self.hdl.barrier(channel=0)
@@ -233,6 +238,7 @@ class _UlyssesP2PAttention(torch.autograd.Function):
             _lib.ulysses_scatter(o.transpose(1, 2), bufs.peer[1], rank, 1, Hq, 0)
         bufs.barrier()
         out = bufs.o_seq.clone()                              # the region is reused by the next step
+        bufs.pending = any(ctx.needs_input_grad[:4])         # a backward will read the saved views of qkv_full
         ctx.save_for_backward(qh, kh, vh, o, lse, s32 if s32 is not None else torch.empty(0, device=q.device))
         ctx.bufs, ctx.cfg, ctx.has_aux = bufs, (num_sink, window_size, Hq, Hkv), s_loc is not None
         ctx.s_dtype = s_loc.dtype if s_loc is not None else None
@@ -266,6 +272,7 @@ class _UlyssesP2PAttention(torch.autograd.Function):
         g = bufs.g_seq
         gq, gk, gv = g[:, :, :Hq].contiguous(), g[:, :, Hq:Hq + Hkv].contiguous(), g[:, :, Hq + Hkv:].contiguous()
         gs = ds.to(ctx.s_dtype) if ctx.has_aux else None
+        bufs.pending = False                                  # qkv_full may be overwritten again
         return gq, gk, gv, gs, None, None, None
 
 
@@ -284,6 +291,8 @@ class UlyssesSinkAttention(torch.nn.Module):
     (``P`` must divide ``H_kv``); ``s_aux`` holds ALL ``H_q`` logits.  Returns ``O [B, N/P, H_q, D]``.
     """
 
+    MAX_PENDING_FORWARDS = 8
+
     def __init__(self, num_sink: int = 0, window_size: int = 4096, sp_group=None, head_chunks: int = 1,
                  p2p: bool = False):
         super().__init__()
@@ -293,10 +302,10 @@ class UlyssesSinkAttention(torch.nn.Module):
         self.head_chunks = max(1, int(head_chunks))
         # p2p=True: the exchange runs as peer-memory scatter kernels of libsinkfa over NVLink instead of NCCL
         # all-to-alls (one node, 16-bit / fp32 CUDA tensors).  The layer then owns symmetric receive buffers sized
-        # for its input shape; its saved q/k/v live in them until the layer's backward, so one instance must not
-        # run a second forward before the backward of the first (one instance per transformer layer).
+        # for its input shape; its saved q/k/v live in them until the layer's backward -- a second forward before that
+        # backward takes a second buffer set (see _P2PBuffers.pending).
         self.p2p = bool(p2p)
-        self._bufs = None
+        self._bufs = []       # symmetric buffer sets; more than one only while several forwards await their backward
 
     def forward(self, q, k, v, s_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
         from .sink_flash_attention import sink_flash_attention
@@ -308,9 +317,18 @@ class UlyssesSinkAttention(torch.nn.Module):
         if self.p2p and P > 1:
             B, n, _, D = q.shape
             key = (B, n, H_q, H_kv, D, q.dtype)
-            if self._bufs is None or self._bufs.key != key:
-                self._bufs = _P2PBuffers(self.sp_group, B, n, H_q, H_kv, D, q.dtype, q.device)
-            return _UlyssesP2PAttention.apply(q, k, v, s_loc, self._bufs, self.num_sink, self.window_size)
+            self._bufs = [b for b in self._bufs if b.key == key]
+            # every rank runs the same program, so every rank picks (or collectively allocates) the same set
+            bufs = next((b for b in self._bufs if not b.pending), None)
+            if bufs is None:
+                if len(self._bufs) >= self.MAX_PENDING_FORWARDS:
+                    raise RuntimeError(
+                        f"UlyssesSinkAttention(p2p=True): {len(self._bufs)} forwards of this layer are waiting for their "
+                        "backward; each holds a symmetric receive buffer set (raise MAX_PENDING_FORWARDS, or run the "
+                        "forwards that need no gradient under torch.no_grad())")
+                bufs = _P2PBuffers(self.sp_group, B, n, H_q, H_kv, D, q.dtype, q.device)
+                self._bufs.append(bufs)
+            return _UlyssesP2PAttention.apply(q, k, v, s_loc, bufs, self.num_sink, self.window_size)
         # head chunks are whole GQA groups so every chunk is an independent attention problem
         nchunk = min(self.head_chunks, hkv_l) if P > 1 else 1
         while hkv_l % nchunk:

@@ -27,6 +27,16 @@ def test_library_exports_every_declared_symbol():
     assert lib.sfa_version() >= 100
     assert lib.sfa_workspace_bytes(_lib.OP_FWD, 1, 8, 8, 256, 64, 0) == 0
     assert lib.sfa_workspace_bytes(_lib.OP_BWD, 1, 8, 8, 256, 64, 0) >= 8 * 256 * 4
+    # the product library exports the operator surface only; the micro-probes live in their own library
+    assert not any(hasattr(lib, n) for n in ("sfa_probe_umma", "sfa_probe_tma_bw"))
+    from sink_attention import _probe
+    plib = _probe.load()
+    with open(os.path.join(ROOT, "include", "sinkfa_probe.h")) as f:
+        phdr = f.read()
+    pdecl = sorted(set(re.findall(r"\b(sfa_probe_[a-z_]+)\s*\(", phdr)))
+    assert set(pdecl) == set(_probe.EXPORTS)
+    for name in pdecl:
+        assert hasattr(plib, name), f"libsinkfa_probe.so does not export {name}"
 
 
 def test_public_api_surface_matches_reference():

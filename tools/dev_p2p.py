@@ -101,7 +101,7 @@ except Exception as e:  # noqa: BLE001
     print(f"[rank {rank}] graph capture failed: {type(e).__name__}: {e}", flush=True)
 # ---- pieces: one scatter of q (67 MB, half of it to the peer), one barrier, one clone
 from sink_attention import _lib  # noqa: E402
-bufs = p2p._bufs
+bufs = p2p._bufs[0]
 
 
 def ev_time(fn, reps=20):

@@ -7,7 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "sink-flash-attention-kernel_b200"))
-from sink_attention import _lib  # noqa: E402
+from sink_attention import _probe as _lib  # noqa: E402
 
 lib = _lib.load()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")

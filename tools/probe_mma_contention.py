@@ -3,7 +3,7 @@ background-load bits: 1 = 12 warps streaming st.shared.v4, 2 = streaming tcgen05
 operand data instead of zeros; 16, 32, 48 = alternate shapes / accumulators from one thread; 256, 512 = one or two MORE threads issue the same UMMA stream into their own accumulators)"""
 import ctypes, sys, torch
 sys.path.insert(0, "/root/repo/sink-flash-attention-kernel_b200")
-from sink_attention import _lib
+from sink_attention import _probe as _lib
 lib = _lib.load()
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
 

@@ -2,7 +2,7 @@
 core at full rate.  prm = M, N, a_mn, b_mn, a_swz, a_lbo, a_sbo, a_kstep, b_swz, b_lbo, b_sbo, b_kstep, n, ksteps, lane."""
 import ctypes, sys, torch
 sys.path.insert(0, "/root/repo/sink-flash-attention-kernel_b200")
-from sink_attention import _lib
+from sink_attention import _probe as _lib
 lib = _lib.load()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 

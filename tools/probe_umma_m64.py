@@ -3,7 +3,7 @@ mode 3: one accumulator.  mode 4: two independent M = 64 accumulators in the SAM
 lane offset 16 (it only sums the first half of K) -- the question is whether the hardware accepts the lane offset."""
 import sys, os, torch
 sys.path.insert(0, "/root/repo/sink-flash-attention-kernel_b200")
-from sink_attention import _lib
+from sink_attention import _probe as _lib
 for mode in (4,):
     for dtype in (torch.bfloat16,):
         for n, k in ((64, 128), (144, 128), (160, 128), (128, 64)):

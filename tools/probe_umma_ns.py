@@ -2,7 +2,7 @@
 (sfa_probe_umma modes 5 and 6): checks the LBO / SBO convention of make_sdesc_ns."""
 import sys, torch
 sys.path.insert(0, "/root/repo/sink-flash-attention-kernel_b200")
-from sink_attention import _lib
+from sink_attention import _probe as _lib
 dtype = torch.bfloat16
 for n, k in ((64, 128), (144, 128), (160, 128), (16, 128), (48, 64)):
     g = torch.Generator().manual_seed(n + k)
