@@ -99,6 +99,15 @@ int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const
                     const int64_t win_strides[3], const int64_t o_strides[2],
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Device-side append of one decoded token to the ring window buffers (replaces the two strided copies of
+ * SinkCacheLayer._decode, cache.py:129-147): k_new / v_new [B,Hkv,1,D] with (batch, head) element strides are written
+ * to position write_pos (0 <= write_pos < window_size) of win_k / win_v [B,Hkv,window_size,D] with (batch, head,
+ * position) strides.  Channel stride 1.  The ring state (write_pos, window_len) stays with the caller, as in the
+ * reference.  Pair it with sfa_decode_ring: no per-step linearisation of the cache (cache.py:185-216). */
+int sfa_cache_append(const void* k_new, const void* v_new, void* win_k, void* win_v, int B, int Hkv, int D, int dtype,
+                     const int64_t new_strides[2], const int64_t win_strides[3], int window_size, int write_pos,
+                     void* stream);
+
 /* Ulysses sequence-parallel exchange (BASELINE configs[4]; the reference leaves this all-to-all to verl,
  * verl_patch.py:15-20): one kernel reads the local tensor and stores every row into its final place in the
  * destination rank's receive buffer through CUDA peer mappings (peer_dst: HOST array of P device pointers, entry

@@ -388,6 +388,25 @@ int sfa_decode_ring(const void* q, const void* sink_k, const void* sink_v, const
   return decode_impl(p, dtype, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int sfa_cache_append(const void* k_new, const void* v_new, void* win_k, void* win_v, int B, int Hkv, int D, int dtype,
+                     const int64_t new_strides[2], const int64_t win_strides[3], int window_size, int write_pos,
+                     void* stream) {
+  if (!k_new || !v_new || !win_k || !win_v) {
+    set_error("null tensor pointer");
+    return -6;
+  }
+  if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16 && dtype != SFA_DTYPE_FP32) {
+    set_error("unknown dtype %d", dtype);
+    return -4;
+  }
+  if (B < 1 || Hkv < 1 || D < 1 || window_size < 1 || write_pos < 0 || write_pos >= window_size) {
+    set_error("invalid append geometry B=%d Hkv=%d D=%d window_size=%d write_pos=%d", B, Hkv, D, window_size, write_pos);
+    return -1;
+  }
+  return cuda_ret(cache_append(k_new, v_new, win_k, win_v, B, Hkv, D, dtype == SFA_DTYPE_FP32 ? 4 : 2, new_strides,
+                               win_strides, write_pos, static_cast<cudaStream_t>(stream)), "sfa_cache_append");
+}
+
 int sfa_ulysses_scatter(const void* src, void* const* peer_dst, int P, int rank, int mode, int B, int L, int H, int D,
                         int dtype, const int64_t src_strides[3], int dst_heads, int head_off, void* stream) {
   if (!src || !peer_dst) {

@@ -122,6 +122,11 @@ size_t tc_bwd_fused_workspace_bytes();
 cudaError_t tc_bwd_fused(const AttnParams& p, int dtype, float* part, const float* ds_partial, int ds_nblk,
                          cudaStream_t st);
 
+// one decoded token's K and V rows -> ring slot write_pos of the window buffers (cache_ops.cu)
+cudaError_t cache_append(const void* k_new, const void* v_new, void* win_k, void* win_v, int B, int H, int D,
+                         int elem_size, const int64_t new_strides[2], const int64_t win_strides[3], int write_pos,
+                         cudaStream_t st);
+
 bool mma_decode_supported(const DecodeParams& p, int dtype);
 int mma_decode_splits(int B, int Hkv, int total_len);
 cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st);

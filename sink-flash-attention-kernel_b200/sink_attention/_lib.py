@@ -21,7 +21,7 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_set_debug",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_set_debug", "sfa_cache_append",
 )
 
 _lib = None
@@ -88,6 +88,8 @@ def load() -> ctypes.CDLL:
     lib.sfa_decode_ring.restype = i
     lib.sfa_ulysses_scatter.argtypes = [p, c.POINTER(c.c_void_p)] + [i] * 8 + [i64p, i, i, p]
     lib.sfa_ulysses_scatter.restype = i
+    lib.sfa_cache_append.argtypes = [p] * 4 + [i] * 4 + [i64p] * 2 + [i, i, p]
+    lib.sfa_cache_append.restype = i
     lib.sfa_set_debug.argtypes = [i, i]
     lib.sfa_set_debug.restype = i
     _lib = lib
@@ -269,6 +271,24 @@ def decode_ring(q, sink_k, sink_v, win_k, win_v, sink_len: int, window_len: int,
             ws.data_ptr(), ws_bytes, _stream(q))
     _check(rc, "sfa_decode_ring")
     return o
+
+
+def cache_append(k_new, v_new, win_k, win_v, write_pos: int):
+    """One decoded token ([B,Hkv,1,D]) -> ring slot `write_pos` of the window buffers, K and V in one launch."""
+    lib = load()
+    _require_cuda(k_new, v_new, win_k, win_v)
+    B, H, W, D = win_k.shape
+    k_new, v_new = _unit_last(k_new), _unit_last(v_new)
+    if k_new.stride()[:2] != v_new.stride()[:2]:
+        v_new = v_new.contiguous()
+        k_new = k_new.contiguous()
+    if win_k.stride() != win_v.stride() or win_k.stride(-1) != 1:
+        raise ValueError("K and V ring buffers must share strides (unit channel stride)")
+    with torch.cuda.device(win_k.device):
+        rc = lib.sfa_cache_append(k_new.data_ptr(), v_new.data_ptr(), win_k.data_ptr(), win_v.data_ptr(), B, H, D,
+                                  DTYPE_CODE[win_k.dtype], _i64(k_new.stride()[:2]), _i64(win_k.stride()[:3]), W,
+                                  int(write_pos), _stream(win_k))
+    _check(rc, "sfa_cache_append")
 
 
 def ulysses_scatter(src: torch.Tensor, peer_ptrs: Sequence[int], rank: int, mode: int, dst_heads: int, head_off: int):

@@ -11,19 +11,44 @@ HF ``Cache`` glue.  Additions for the B200 path:
     that costs more bytes than the attention itself (reference cache.py:185-216).
   * ``is_initialized`` exists without transformers too (the reference only gets it from the HF mixin).
 
+  * ``append()`` is ONE kernel launch for K and V (``sfa_cache_append``) on CUDA tensors.
+  * ring fast path: under ``patch_for_generation`` a decode-step ``update()`` returns zero-copy VIEWS of the ring
+    instead of the linearised copy, and registers the layer under the view's data pointer; the generation hook
+    finds the layer from the key tensor it receives and calls ``decode_attention`` on the buffers in place.
+    Direct users of ``update()`` / ``get_kv()`` (no patch active) keep the chronological contract.
+
 All batch rows share one sequence length; ring state is host-side integers (as in the reference).
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Tuple
 
 import torch
+
+# ring buffers that a decode-step update() handed out as views while the generation patch was active:
+# data_ptr of window_k -> SinkCacheLayer (weak).  The generation hook looks its key tensor up here.
+_RING_VIEWS: "weakref.WeakValueDictionary[int, SinkCacheLayer]" = weakref.WeakValueDictionary()
+_FAST_DECODE = {"enabled": False}      # switched by patch_for_generation / unpatch_generation
+
+
+def ring_layer_of(key_states: torch.Tensor) -> Optional["SinkCacheLayer"]:
+    """The cache layer whose ring buffer `key_states` is a view of (None if it is an ordinary tensor)."""
+    if not _FAST_DECODE["enabled"] or not _RING_VIEWS:
+        return None
+    layer = _RING_VIEWS.get(key_states.data_ptr())
+    if layer is None or layer.window_k is None or layer.window_k.data_ptr() != key_states.data_ptr():
+        return None
+    return layer
 
 try:  # HF is optional: without it the classes are plain Python objects
     from transformers.cache_utils import Cache as _HFCache, CacheLayerMixin as _HFLayer
     _HAS_HF = True
 except Exception:  # pragma: no cover - transformers missing or too old
     _HFCache, _HFLayer, _HAS_HF = object, object, False
+
+
+_APPEND_DTYPES = (torch.bfloat16, torch.float16, torch.float32)
 
 
 class SinkCacheLayer(_HFLayer):
@@ -82,13 +107,23 @@ class SinkCacheLayer(_HFLayer):
     def append(self, k: torch.Tensor, v: torch.Tensor) -> None:
         """Write one token ([B,H_kv,1,D]) into the ring, evicting the oldest when full."""
         self.seen_tokens += 1
-        self.window_k[:, :, self.write_pos].copy_(k[:, :, 0])
-        self.window_v[:, :, self.write_pos].copy_(v[:, :, 0])
+        if self.window_k.is_cuda and self.window_k.dtype in _APPEND_DTYPES:
+            from . import _lib
+            _lib.cache_append(k, v, self.window_k, self.window_v, self.write_pos)      # K and V, one launch
+        else:
+            self.window_k[:, :, self.write_pos].copy_(k[:, :, 0])
+            self.window_v[:, :, self.write_pos].copy_(v[:, :, 0])
         self.write_pos = (self.write_pos + 1) % self.window_size
         self.window_len = min(self.window_len + 1, self.window_size)
 
     def _decode(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         self.append(k, v)
+        if _FAST_DECODE["enabled"] and self.window_k.is_cuda and k.shape[2] == 1:
+            # generation fast path: no linearisation copy (reference cache.py:185-216 copies the whole cache every
+            # step).  The views carry the right LENGTH (sink_len + window_len keys) for HF's bookkeeping only when
+            # sink_len == 0, so the hook never reads them: it resolves the layer and attends the buffers in place.
+            _RING_VIEWS[self.window_k.data_ptr()] = self
+            return self.window_k[:, :, :self.window_len], self.window_v[:, :, :self.window_len]
         return self.get_kv()
 
     def update(self, key_states: torch.Tensor, value_states: torch.Tensor,

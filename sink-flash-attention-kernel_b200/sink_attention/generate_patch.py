@@ -14,6 +14,7 @@ from typing import Optional
 
 import torch
 
+from . import cache as _cache
 from .cache import SinkAttentionCache
 from .decode_kernel import sink_decode_attention
 from .sink_flash_attention import sink_flash_attention
@@ -64,7 +65,13 @@ def _generation_flash_attention_forward(
         out = sink_flash_attention(q, k, v, num_sink=_GENERATION_CONFIG["num_sink"],
                                    window_size=_GENERATION_CONFIG["window_size"])
     else:
-        out = sink_decode_attention(q, k, v)  # every cached key is attended
+        layer = _cache.ring_layer_of(key_states)
+        if layer is not None:
+            # the cache handed out views of its ring: attend sink + ring buffers in place (sfa_decode_ring) --
+            # softmax is order-invariant and RoPE is already applied, so no linearisation copy is needed
+            out = layer.decode_attention(q)
+        else:
+            out = sink_decode_attention(q, k, v)  # every cached key is attended
     out = out.transpose(1, 2)
     return out if out.is_contiguous() else out.contiguous()
 
@@ -76,6 +83,7 @@ def patch_for_generation(model=None, num_sink: int = 4, window_size: int = 4096)
     """
     global _original_flash_attention_forward
     _GENERATION_CONFIG.update(num_sink=num_sink, window_size=window_size, enabled=True)
+    _cache._FAST_DECODE["enabled"] = True
     import transformers.modeling_flash_attention_utils as fa_utils
     if fa_utils._flash_attention_forward is not _generation_flash_attention_forward:
         _original_flash_attention_forward = fa_utils._flash_attention_forward   # never save our own hook
@@ -101,4 +109,5 @@ def unpatch_generation():
     except (ImportError, AttributeError):
         pass
     _GENERATION_CONFIG["enabled"] = False
+    _cache._FAST_DECODE["enabled"] = False
     _original_flash_attention_forward = None

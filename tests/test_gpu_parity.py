@@ -658,6 +658,29 @@ def test_broadcast_views_match_materialised_tensors():
     assert maxdiff(o, o_ref) < 2e-2
 
 
+@pytest.mark.parametrize("dtype,D", [(torch.bfloat16, 64), (torch.float32, 16), (torch.float16, 80), (torch.bfloat16, 3)])
+def test_cache_append_kernel_matches_reference_copies(dtype, D):
+    """sfa_cache_append (one launch for K and V) == the two strided copies of SinkCacheLayer._decode
+    (reference cache.py:141-145), incl. ring wrap-around, HF-layout (transposed) new rows and odd head dims."""
+    B, H, W = 3, 2, 5
+    g = torch.Generator().manual_seed(D)
+    layer = sa.SinkCacheLayer(num_sink=1, window_size=W)
+    ref_k = torch.zeros(B, H, W, D, dtype=dtype, device="cuda")
+    ref_v = torch.zeros_like(ref_k)
+    pre = torch.randn(B, H, 3, D, generator=g).to("cuda", dtype)
+    layer.update(pre, pre * 2)
+    ref_k[:, :, :2], ref_v[:, :, :2] = pre[:, :, 1:], (pre * 2)[:, :, 1:]
+    wp = 2
+    for step in range(9):
+        kn = torch.randn(B, 1, H, D, generator=g).to("cuda", dtype).transpose(1, 2)     # HF layout view
+        vn = torch.randn(B, H, 1, D, generator=g).to("cuda", dtype)
+        layer.append(kn, vn)
+        ref_k[:, :, wp], ref_v[:, :, wp] = kn[:, :, 0], vn[:, :, 0]
+        wp = (wp + 1) % W
+        assert torch.equal(layer.window_k, ref_k) and torch.equal(layer.window_v, ref_v)
+        assert layer.write_pos == wp and layer.window_len == min(3 + step, W)
+
+
 def test_errors_are_loud():
     q = torch.randn(1, 4, 16, 64)
     with pytest.raises(RuntimeError):
