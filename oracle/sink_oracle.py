@@ -161,6 +161,120 @@ def eager_sink_attention(q, k, v, num_sink: int = 0, window_size: Optional[int] 
 
 
 # ---------------------------------------------------------------------------
+# row-sampled oracle: the same arithmetic for SELECTED query rows / key rows, O((S + W) * D) per row and no N x N
+# matrix -- lets the parity tests compare the CUDA path with the oracle directly at the full BASELINE sizes
+# (C1 / C2 / C4), where sink_attention_fwd / _bwd above would need terabytes.  Pinned against the full functions on
+# small shapes by tests/test_oracle.py (test_sampled_oracle_matches_full_oracle).
+# ---------------------------------------------------------------------------
+def _row_keys(i: torch.Tensor, num_sink: int, window_size: int, n_kv: int):
+    """For query positions i [R]: candidate key indices [R, C] (sinks then the window band) and their validity
+    under sink_flash_attention.py:36-39 (sinks that fall inside the band are counted once, as band keys)."""
+    S, W = max(num_sink, 0), max(window_size, 0)
+    dev = i.device
+    cand = []
+    if S > 0:
+        cand.append(torch.arange(S, device=dev).unsqueeze(0).expand(i.numel(), S))
+    if W > 0:
+        cand.append(i.unsqueeze(1) - (W - 1) + torch.arange(W, device=dev).unsqueeze(0))
+    if not cand:
+        z = torch.zeros(i.numel(), 1, dtype=torch.long, device=dev)
+        return z, torch.zeros_like(z, dtype=torch.bool)
+    j = torch.cat(cand, dim=1)
+    valid = (j >= 0) & (j < n_kv) & (j <= i.unsqueeze(1))
+    if S > 0:
+        is_sink_col = torch.zeros_like(valid)
+        is_sink_col[:, :S] = True
+        lo = i.unsqueeze(1) - W + 1
+        valid &= torch.where(is_sink_col, j < lo if W > 0 else torch.ones_like(valid), j >= 0)
+        if W > 0:
+            valid &= torch.where(is_sink_col, torch.ones_like(valid), (j >= S) | (j >= lo))   # band keys keep j >= lo
+    return j.clamp(0, n_kv - 1), valid
+
+
+def sampled_fwd(q, k, v, num_sink: int, window_size: int, s_aux, rows: torch.Tensor, dtype=torch.float64,
+                chunk: int = 128) -> Tuple[torch.Tensor, torch.Tensor]:
+    """O [R, D] and natural-log LSE [R] for the sampled rows ``rows`` = int64 [R, 3] of (batch, q head, position).
+    Same definition as sink_attention_fwd (sink_flash_attention.py:93-194), evaluated row by row."""
+    B, Hq, N, D = q.shape
+    g = Hq // k.shape[1]
+    scale = 1.0 / math.sqrt(D)
+    outs, lses = [], []
+    for c0 in range(0, rows.shape[0], chunk):
+        r = rows[c0:c0 + chunk]
+        b, h, i = r[:, 0], r[:, 1], r[:, 2]
+        j, valid = _row_keys(i, num_sink, window_size, N)
+        kk = k[b.unsqueeze(1), (h // g).unsqueeze(1), j].to(dtype)                 # [R, C, D]
+        vv = v[b.unsqueeze(1), (h // g).unsqueeze(1), j].to(dtype)
+        qq = q[b, h, i].to(dtype)                                                  # [R, D]
+        sc = torch.einsum("rd,rcd->rc", qq, kk) * scale
+        sc = sc.masked_fill(~valid, float("-inf"))
+        if s_aux is not None:
+            sc_all = torch.cat([sc, s_aux.to(dtype)[h].unsqueeze(1)], dim=1)
+        else:
+            sc_all = sc
+        lse = torch.logsumexp(sc_all, dim=1)
+        p = torch.nan_to_num(torch.exp(sc - lse.unsqueeze(1)), nan=0.0)
+        outs.append(torch.einsum("rc,rcd->rd", p, vv))
+        lses.append(lse)
+    return torch.cat(outs), torch.cat(lses)
+
+
+def sampled_dq(q, k, v, do, o, lse, num_sink: int, window_size: int, rows: torch.Tensor, dtype=torch.float64,
+               chunk: int = 128) -> torch.Tensor:
+    """dQ [R, D] of the sampled rows.  ``o`` and ``lse`` are the forward's outputs as the backward receives them
+    (delta = rowsum(dO * O) uses the stored O, sink_flash_attention.py:582; P = exp(S - LSE), :242)."""
+    B, Hq, N, D = q.shape
+    g = Hq // k.shape[1]
+    scale = 1.0 / math.sqrt(D)
+    outs = []
+    for c0 in range(0, rows.shape[0], chunk):
+        r = rows[c0:c0 + chunk]
+        b, h, i = r[:, 0], r[:, 1], r[:, 2]
+        j, valid = _row_keys(i, num_sink, window_size, N)
+        kk = k[b.unsqueeze(1), (h // g).unsqueeze(1), j].to(dtype)
+        vv = v[b.unsqueeze(1), (h // g).unsqueeze(1), j].to(dtype)
+        qq, dd, oo = q[b, h, i].to(dtype), do[b, h, i].to(dtype), o[b, h, i].to(dtype)
+        sc = torch.einsum("rd,rcd->rc", qq, kk) * scale
+        p = torch.exp(sc - lse[b, h, i].to(dtype).unsqueeze(1))
+        p = torch.nan_to_num(torch.where(valid, p, torch.zeros_like(p)), nan=0.0)
+        delta = (dd * oo).sum(1, keepdim=True)
+        dp = torch.einsum("rd,rcd->rc", dd, vv)
+        ds = p * (dp - delta)
+        outs.append(torch.einsum("rc,rcd->rd", ds, kk) * scale)
+    return torch.cat(outs)
+
+
+def sampled_dkdv(q, k, v, do, o, lse, num_sink: int, window_size: int, keys: torch.Tensor, dtype=torch.float64,
+                 max_rows: int = 8192) -> Tuple[torch.Tensor, torch.Tensor]:
+    """dK, dV [R, D] for the sampled key rows ``keys`` = int64 [R, 3] of (batch, kv head, position): sums over every
+    query row of the GQA group that attends the key (sink keys: all later rows; others: the W rows from the key on).
+    dV = P^T dO, dK = scale * dS^T Q, GQA group sum (sink_flash_attention.py:242-251, 648-651)."""
+    B, Hq, N, D = q.shape
+    g = Hq // k.shape[1]
+    scale = 1.0 / math.sqrt(D)
+    S, W = max(num_sink, 0), max(window_size, 0)
+    dks, dvs = [], []
+    for b, y, j in keys.tolist():
+        hi = N - 1 if j < S else min(j + W - 1, N - 1)
+        dk = torch.zeros(D, dtype=dtype, device=q.device)
+        dv = torch.zeros(D, dtype=dtype, device=q.device)
+        kj, vj = k[b, y, j].to(dtype), v[b, y, j].to(dtype)
+        if hi >= j and (j < S or W > 0):
+            for i0 in range(j, hi + 1, max_rows):
+                i1 = min(i0 + max_rows, hi + 1)
+                hs = slice(y * g, (y + 1) * g)
+                qq = q[b, hs, i0:i1].to(dtype)                                     # [g, r, D]
+                dd, oo = do[b, hs, i0:i1].to(dtype), o[b, hs, i0:i1].to(dtype)
+                p = torch.nan_to_num(torch.exp(torch.einsum("grd,d->gr", qq, kj) * scale - lse[b, hs, i0:i1].to(dtype)), nan=0.0)
+                ds = p * (torch.einsum("grd,d->gr", dd, vj) - (dd * oo).sum(-1))
+                dv += torch.einsum("gr,grd->d", p, dd)
+                dk += torch.einsum("gr,grd->d", ds, qq) * scale
+        dks.append(dk)
+        dvs.append(dv)
+    return torch.stack(dks), torch.stack(dvs)
+
+
+# ---------------------------------------------------------------------------
 # decode
 # ---------------------------------------------------------------------------
 def decode_attention(q, k, v, s_aux=None, dtype=torch.float64):

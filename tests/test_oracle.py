@@ -90,3 +90,25 @@ def test_ring_cache_model_matches_reference_traces():
         for expect in case["trace"]:
             m.decode()
             assert m.linear() == expect
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 2, 70, 16, 3, 9), (1, 4, 4, 50, 8, 0, 7), (1, 2, 1, 40, 8, 50, 5),
+                                   (1, 2, 1, 40, 8, 4, 0), (1, 2, 2, 33, 8, 2, 1), (1, 2, 1, 30, 8, 0, 64)])
+def test_sampled_oracle_matches_full_oracle(shape):
+    """The row-sampled oracle (no N x N matrix; used by the GPU suite at the full BASELINE sizes) is the same
+    arithmetic as the full oracle, which the golden vectors pin to the reference."""
+    B, Hq, Hkv, N, D, S, W = shape
+    g = torch.Generator().manual_seed(N + W)
+    mk = lambda H: torch.randn(B, H, N, D, generator=g, dtype=torch.float64)
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    s_aux = torch.randn(Hq, generator=g, dtype=torch.float64)
+    o, lse = orc.sink_attention_fwd(q, k, v, S, W, s_aux)
+    dq, dk, dv, _ = orc.sink_attention_bwd(q, k, v, do, S, W, s_aux)
+    rows = torch.stack(torch.meshgrid(torch.arange(B), torch.arange(Hq), torch.arange(N), indexing="ij"), -1).reshape(-1, 3)
+    keys = torch.stack(torch.meshgrid(torch.arange(B), torch.arange(Hkv), torch.arange(N), indexing="ij"), -1).reshape(-1, 3)
+    o_s, l_s = orc.sampled_fwd(q, k, v, S, W, s_aux, rows)
+    dq_s = orc.sampled_dq(q, k, v, do, o, lse, S, W, rows)
+    dk_s, dv_s = orc.sampled_dkdv(q, k, v, do, o, lse, S, W, keys)
+    for got, ref in ((o_s, o), (dq_s, dq), (dk_s, dk), (dv_s, dv)):
+        assert (got - ref.reshape(-1, D)).abs().max().item() < 1e-12
+    assert (l_s - lse.reshape(-1)).abs().max().item() < 1e-12
