@@ -84,6 +84,41 @@ int sfa_bwd(const void* q, const void* k, const void* v, const void* o, const vo
             const int64_t dk_strides[4], const int64_t dv_strides[4],
             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Extended geometry: packed (varlen) sequences and chunked prefill / halo keys, inside the kernels -- the cases the
+ * reference hands to stock FlashAttention (verl_patch.py:73-93, dropping s_aux and the sinks) or cannot run
+ * (1 < N_q < N_kv asserts, decode_kernel.py:146).
+ *   q, o, dout, dq, lse: N query rows;  k, v, dk, dv: n_kv key rows (n_kv = 0 means N).
+ *   Query row iq sits at absolute key position i = iq + q_off (q_off >= 0, q_off + N <= n_kv) and attends key j iff
+ *       lo(iq) <= j <= i   and   (j - lo(iq) < num_sink  or  j >= i - window + 1),
+ *   lo(iq) = seq_lo ? seq_lo[b * seq_batch_stride + iq] : 0.  With ext == NULL this is sink_flash_attention.py:30-39.
+ *   seq_lo [B or 1][N] int32 (device): first key position of the sequence that query row iq belongs to (from
+ *   cu_seq_lens: constant over a sequence, non-decreasing);  seq_hi [B or 1][n_kv] int32 (device): for key j, one
+ *   past the last absolute query position of its sequence (the key-stationary backward stops there).  Both or none.
+ *   seq_batch_stride: elements between batch rows of the two arrays; 0 = one row shared by the whole batch.
+ * Tensor-core paths: head_dim 64, 16-bit -- the persistent forward (packed sequences need num_sink == 0) and the fused
+ * backward (narrow window, num_sink == 0, q_off a multiple of the tile's positions); everything else runs on the
+ * CUDA-core kernels, which implement the full predicate.  Keys no query attends get dk = dv = 0 only if the caller
+ * zero-fills dk / dv when q_off > 0 (the fused kernel writes the key blocks its tiles touch). */
+typedef struct sfa_attn_ext {
+  const int32_t* seq_lo;
+  const int32_t* seq_hi;
+  int64_t seq_batch_stride;
+  int n_kv;
+  int q_off;
+} sfa_attn_ext;
+int sfa_fwd_ex(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux,
+               int B, int Hq, int Hkv, int N, int D, int num_sink, int window, int dtype,
+               const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+               const int64_t o_strides[4], void* workspace, size_t workspace_bytes, void* stream,
+               const sfa_attn_ext* ext);
+int sfa_bwd_ex(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+               const float* s_aux, void* dq, void* dk, void* dv, float* ds_aux,
+               int B, int Hq, int Hkv, int N, int D, int num_sink, int window, int dtype,
+               const int64_t q_strides[4], const int64_t k_strides[4], const int64_t v_strides[4],
+               const int64_t o_strides[4], const int64_t do_strides[4], const int64_t dq_strides[4],
+               const int64_t dk_strides[4], const int64_t dv_strides[4],
+               void* workspace, size_t workspace_bytes, void* stream, const sfa_attn_ext* ext);
+
 /* q,o: [B,Hq,1,D] (strides for batch, head); k,v: [B,Hkv,Nkv,D] (strides for batch, head, position) */
 int sfa_decode(const void* q, const void* k, const void* v, void* o, const float* s_aux,
                int B, int Hq, int Hkv, int Nkv, int D, int dtype,

@@ -129,6 +129,35 @@ size_t sfa_workspace_bytes(int op, int B, int Hq, int Hkv, int N, int D, int dty
   return 0;
 }
 
+// extended geometry (sfa_attn_ext): validated and copied into the problem descriptor
+static int apply_ext(AttnParams& p, const sfa_attn_ext* ext) {
+  p.Nkv = p.N;
+  p.q_off = 0;
+  p.seq_lo = p.seq_hi = nullptr;
+  p.seq_bs = 0;
+  if (ext == nullptr) return 0;
+  const int nkv = ext->n_kv > 0 ? ext->n_kv : p.N;
+  if (ext->q_off < 0 || (int64_t)ext->q_off + p.N > nkv) {
+    set_error("invalid chunk geometry: q_off=%d, %d query rows, %d key rows (need q_off >= 0 and q_off + N <= n_kv)",
+              ext->q_off, p.N, nkv);
+    return -11;
+  }
+  if ((ext->seq_lo == nullptr) != (ext->seq_hi == nullptr)) {
+    set_error("seq_lo and seq_hi must be given together");
+    return -11;
+  }
+  if (ext->seq_lo != nullptr && ext->seq_batch_stride != 0 && ext->seq_batch_stride < nkv) {
+    set_error("seq_batch_stride (%lld) must be 0 (shared) or >= n_kv", (long long)ext->seq_batch_stride);
+    return -11;
+  }
+  p.Nkv = nkv;
+  p.q_off = ext->q_off;
+  p.seq_lo = ext->seq_lo;
+  p.seq_hi = ext->seq_hi;
+  p.seq_bs = ext->seq_batch_stride;
+  return 0;
+}
+
 static bool route_from_c(const sfa_sp_route* in, SpRoute& out) {
   if (in->P < 1 || in->P > 8 || in->n_local < 1 || in->heads_total < 1 || in->head_off < 0) return false;
   out.P = in->P; out.n_local = in->n_local; out.heads_total = in->heads_total; out.head_off = in->head_off;
@@ -141,7 +170,7 @@ static bool route_from_c(const sfa_sp_route* in, SpRoute& out) {
 static int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux, int B, int Hq,
                     int Hkv, int N, int D, int num_sink, int window, int dtype, const int64_t q_strides[4],
                     const int64_t k_strides[4], const int64_t v_strides[4], const int64_t o_strides[4], void* workspace,
-                    size_t workspace_bytes, void* stream, const sfa_sp_route* o_route) {
+                    size_t workspace_bytes, void* stream, const sfa_sp_route* o_route, const sfa_attn_ext* ext = nullptr) {
   (void)workspace;
   (void)workspace_bytes;
   const int g_force_impl = sfa::g_force_impl.load();
@@ -159,6 +188,7 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
   p.S = num_sink < 0 ? 0 : num_sink;
   p.W = window < 0 ? 0 : window;
   p.scale = 1.0f / sqrtf((float)D);
+  if (int r = apply_ext(p, ext)) return r;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SpRoute rt;
   if (o_route != nullptr) {
@@ -174,8 +204,9 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
   }
   if (g_force_impl != SFA_IMPL_SIMT && tc_fwd_supported(p, dtype)) {
     set_impl_name("tcgen05");
-    if (tc_fwd64_supported(p, dtype) && !(g_env_fwd_v1 && p.o_route == nullptr)) return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
-    return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");
+    if (tc_fwd64_supported(p, dtype) && !(g_env_fwd_v1 && p.o_route == nullptr && !p.has_ext()))
+      return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
+    if (!p.has_ext()) return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");
   }
   set_impl_name("simt");
   return cuda_ret(simt_fwd(p, dtype, st), "sfa_fwd(simt)");
@@ -206,7 +237,7 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
             int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
             const int64_t v_strides[4], const int64_t o_strides[4], const int64_t do_strides[4],
             const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], void* workspace,
-            size_t workspace_bytes, void* stream, const sfa_sp_route* dq_route) {
+            size_t workspace_bytes, void* stream, const sfa_sp_route* dq_route, const sfa_attn_ext* ext = nullptr) {
   const int g_force_impl = sfa::g_force_impl.load(), g_bwd_stages = sfa::g_bwd_stages.load();
   const int64_t* ss[8] = {q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides};
   if (int r = check_common(B, Hq, Hkv, N, D, dtype, ss, 8)) return r;
@@ -229,13 +260,17 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
   p.S = num_sink < 0 ? 0 : num_sink;
   p.W = window < 0 ? 0 : window;
   p.scale = 1.0f / sqrtf((float)D);
+  if (int r = apply_ext(p, ext)) return r;
   p.delta = static_cast<float*>(workspace);
   const size_t rows_bytes = align_up((size_t)B * Hq * N * 4, 256);
   float* ds_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes);
   p.dsrow = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256));
   float* fused_part = reinterpret_cast<float*>(reinterpret_cast<char*>(p.dsrow) + rows_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool use_tc = g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype);
+  const bool use_tc = g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype);      // the dQ + dK/dV kernel pair
+  // with the extended geometry (packed sequences, chunked prefill) the fused kernel is the only tensor-core path
+  const bool use_fused = g_force_impl != SFA_IMPL_SIMT && (g_bwd_stages & 14) == 6 && (use_tc || p.has_ext()) &&
+                         tc_bwd_fused_supported(p, dtype);
   SpRoute rt;
   if (dq_route != nullptr) {
     if (!route_from_c(dq_route, rt)) {
@@ -243,13 +278,13 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
       return -9;
     }
     p.dq_route = &rt;
-    if (!use_tc || (g_bwd_stages & 14) != 6 || !tc_bwd_fused_supported(p, dtype)) {
+    if (!use_fused) {
       set_error("routed dQ store needs the fused head_dim-64 backward (narrow window, no sink tokens)");
       return -10;
     }
   }
   // narrow window, no sink tokens, head_dim 64: ONE kernel computes delta, the ds_aux rows, dQ, dK and dV
-  if (use_tc && (g_bwd_stages & 14) == 6 && tc_bwd_fused_supported(p, dtype)) {
+  if (use_fused) {
     set_impl_name("tcgen05-fused");
     if (!tc_bwd_fused_computes_delta()) {
       // delta + ds_aux block partials (streaming pass over O and dO), then the fused kernel; the ds_aux partials
@@ -308,6 +343,25 @@ int sfa_bwd_sp(const void* q, const void* k, const void* v, const void* o, const
   return bwd_impl(q, k, v, o, dout, lse, s_aux, nullptr, dk, dv, ds_aux, B, Hq, Hkv, N, D, num_sink, window, dtype,
                   q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides, workspace,
                   workspace_bytes, stream, dq_route);
+}
+
+int sfa_fwd_ex(const void* q, const void* k, const void* v, void* o, float* lse, const float* s_aux, int B, int Hq, int Hkv,
+               int N, int D, int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
+               const int64_t v_strides[4], const int64_t o_strides[4], void* workspace, size_t workspace_bytes,
+               void* stream, const sfa_attn_ext* ext) {
+  return fwd_impl(q, k, v, o, lse, s_aux, B, Hq, Hkv, N, D, num_sink, window, dtype, q_strides, k_strides, v_strides,
+                  o_strides, workspace, workspace_bytes, stream, nullptr, ext);
+}
+
+int sfa_bwd_ex(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+               const float* s_aux, void* dq, void* dk, void* dv, float* ds_aux, int B, int Hq, int Hkv, int N, int D,
+               int num_sink, int window, int dtype, const int64_t q_strides[4], const int64_t k_strides[4],
+               const int64_t v_strides[4], const int64_t o_strides[4], const int64_t do_strides[4],
+               const int64_t dq_strides[4], const int64_t dk_strides[4], const int64_t dv_strides[4], void* workspace,
+               size_t workspace_bytes, void* stream, const sfa_attn_ext* ext) {
+  return bwd_impl(q, k, v, o, dout, lse, s_aux, dq, dk, dv, ds_aux, B, Hq, Hkv, N, D, num_sink, window, dtype, q_strides,
+                  k_strides, v_strides, o_strides, do_strides, dq_strides, dk_strides, dv_strides, workspace,
+                  workspace_bytes, stream, nullptr, ext);
 }
 
 static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t st) {

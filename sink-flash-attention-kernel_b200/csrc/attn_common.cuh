@@ -49,9 +49,17 @@ __device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W
 __device__ __forceinline__ TilePlan make_plan(int q0, int P, int N, int S, int W, int BN) {
   return make_plan(q0, P, N, S, W, BN, bn_magic(BN));
 }
+// Packed (varlen) sequences without sink tokens: the band of a tile never starts before the first key of the
+// sequence its FIRST row belongs to (sequence starts are non-decreasing along the rows), so whole KV tiles of earlier
+// sequences are skipped, not just masked -- a full-attention layer over a packed batch stays O(sum len^2).
+__device__ __forceinline__ void clamp_plan(TilePlan& pl, int seq_lo_q0, int W, int BN, unsigned long long magic) {
+  pl.w_lo = max(pl.w_lo, seq_lo_q0);
+  const int n_win = (W > 0 && pl.w_lo <= pl.q_hi) ? div_bn(pl.q_hi - pl.w_lo + BN, magic) : 0;
+  pl.n_tiles = pl.n_sink + n_win;
+}
 
 // Persistent-kernel work walker.  Args type A provides N, S, W, P, BN, ny, nblk, total_tiles, tiles_per_cta,
-// bn_mul.  Tile id = (b * ny + y) * nblk + pb (pb: position block of P positions, y: packed head group).
+// bn_mul, and the extended geometry q_off (absolute position of query row 0), seq_lo / seq_bs (packed sequences).  Tile id = (b * ny + y) * nblk + pb (pb: position block of P positions, y: packed head group).
 template <class A>
 __device__ __forceinline__ void decode_tile(const A& a, int tile, int& pb, int& y, int& b) {
   pb = tile % a.nblk;
@@ -105,7 +113,9 @@ struct ItemWalkT {
       if (tile >= end) return false;
       advance(a, step, pb, y, b);
       q0 = pb * a.P;
-      pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN, a.bn_mul);
+      // the plan lives in ABSOLUTE key positions: row iq of the tile sits at iq + q_off
+      pl = make_plan(q0 + a.q_off, a.P, a.N + a.q_off, a.S, a.W, a.BN, a.bn_mul);
+      if (a.seq_lo != nullptr) clamp_plan(pl, a.seq_lo[b * a.seq_bs + q0], a.W, a.BN, a.bn_mul);
       t = 0;
     }
     ++n;

@@ -49,6 +49,10 @@ struct BwdArgs {
   float* delta_out;
   float* dsrow;        // -exp(s_aux - lse) * delta per row, or nullptr
   const float* s_aux;
+  // extended geometry of the shared tile walker (attn_common.cuh); these kernels run with q_off = 0 and no packing
+  int q_off;
+  const int* seq_lo;
+  int64_t seq_bs;
 };
 
 // Timeline probe for performance work: CTA 0 appends (role, code, index, clock64) records.
@@ -1610,6 +1614,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.delta = p.delta;
     a.trace = trace_buffer();
     a.bn_mul = bn_magic(BN);
+    a.q_off = 0; a.seq_lo = nullptr; a.seq_bs = 0;
     a.fuse_delta = (D == 64 && fuses_delta(p, P, BN)) ? 1 : 0;
     a.delta_out = p.delta;
     a.dsrow = (p.s_aux != nullptr && p.ds_aux != nullptr) ? p.dsrow : nullptr;
@@ -1666,6 +1671,7 @@ bool tc_bwd_fuses_delta(const AttnParams& p, int dtype) {
 
 bool tc_bwd_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
+  if (p.has_ext()) return false;               // packed sequences / chunked prefill: fused kernel or CUDA-core path
   if (p.D != 64 && p.D != 128) return false;
   if (p.N < 1) return false;
   if (p.S <= 0 && p.W <= 0) return false;     // nothing attended: the CUDA-core path writes the zeros

@@ -93,6 +93,11 @@ struct FusedArgs {
   Strides4 sdq, sdk, sdv;
   void* dq_peer[8];   // Ulysses routing of dQ: rows of positions [k*dq_seg_n, (k+1)*dq_seg_n) go to dq_peer[k] (sdq = peer strides)
   int dq_seg_n;       // 0: off, dq / sdq describe the local tensor
+  // extended geometry (sfa_bwd_ex): query tile pb covers key blocks pb + qb - nb + 1 .. pb + qb (qb = q_off / P: the
+  // queries are the LAST rows of a longer key axis of Nkv rows -- chunked prefill, halo keys); seq_lo: packed sequences
+  int qb, Nkv;
+  const int* seq_lo;
+  int64_t seq_bs;
   float* part;   // [grid][2 sides][kPartKeys][2 (dV, dK)][64] fp32
   long long* trace;   // optional timeline buffer (sfa_set_trace_buffer, -DSFA_TRACE=1 builds); nullptr in production
 };
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           ftrace(a.trace, 0, tc, 1, w.it);
           const int s = w.it & 1;
           const uint32_t eph = ((w.it >> 1) & 1) ^ 1;
-          const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb - nb + 1) * P;
+          const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb + a.qb - nb + 1) * P;
           mbar_wait(q_empty + s, eph);
           mbar_expect_tx(q_full + s, C::kQBytes);
           tma_tile(q_s + s * C::kQBytes, &tmQ, q_full + s, a.q_swap, 0, q0, hq0, w.b);
@@ -553,22 +558,35 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       SlotTrack st;
       st.slot0 = 0;
       bool has_next = wn.next();
+      // first key of the row's packed sequence, in query-row units (absolute - q_off); INT_MIN/2 when not packed
+      auto load_lo = [&](const FusedWalk& t, bool valid) {
+        int v = -(1 << 30);
+        if (a.seq_lo != nullptr && valid) {
+          const int i = t.pb * P + pr;
+          if (i < a.N) v = __ldg(a.seq_lo + t.b * a.seq_bs + i) - a.qb * P;
+        }
+        return v;
+      };
       float l_next = load_row(a.lse, wn, has_next, INFINITY), d_next = load_delta(wn, has_next);
+      int lo_next = load_lo(wn, has_next);
       int tc = 0;
       const bool tr = SFA_TRACE && (threadIdx.x == 0);
       while (w.next()) {
         if (tr) ftrace(a.trace, 3, tc, 1, w.it);
         st.step(w, R);
         const float lse_i = l_next, dsc = d_next * a.scale;
+        const int lo_row = lo_next;
         const uint64_t ndsc2 = pack_f32x2(-dsc, -dsc);
         has_next = wn.next();
         l_next = load_row(a.lse, wn, has_next, INFINITY);
         d_next = load_delta(wn, has_next);
+        lo_next = load_lo(wn, has_next);
         const float neg_l2 = (lse_i == -INFINITY) ? -INFINITY : -lse_i * kLog2e;   // lse = +-inf: P = 0
         const uint64_t negl2_2 = pack_f32x2(neg_l2, neg_l2);
         const int i = w.pb * P + pr;
-        const int kstart = (w.pb - nb + 1) * P;
-        const int c_lo = max(i - a.W + 1, 0) - kstart;
+        const int kstart = (w.pb - nb + 1) * P;            // in QUERY-row units: absolute key = this + q_off
+        // attended keys of the row: [max(i - W + 1, first key of its sequence), i]; keys start at absolute 0
+        const int c_lo = max(max(i - a.W + 1, -a.qb * P), lo_row) - kstart;
         const int c_hi = (i < a.N) ? (i - kstart) : -1;
         int xs = st.slot0 + nb;                            // slot whose block left the window: zero image columns
         if (xs >= R) xs -= R;
@@ -796,8 +814,8 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         const int nh = P >> 4;
 #pragma unroll 1
         for (int jb = 0; jb < nd; ++jb) {
-          const int j = w.pb - nb + 1 + jb;
-          if (j < 0) continue;
+          const int j = w.pb - nb + 1 + jb;                 // key block in query-tile units; absolute block j + qb
+          if (j + a.qb < 0) continue;
           int slot = st.slot0 + jb;
           if (slot >= R) slot -= R;
 #pragma unroll 1
@@ -805,17 +823,19 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
             uint32_t x[16];
             tmem_ld16(tl + C::kColR + slot * P + h * 16, x);
             tmem_ld_wait();
-            const bool head = j < pa, tail = tails && jb >= 1;
+            // blocks before the first tile of the run are shared with the previous CTA -- unless the run starts a
+            // sequence (pa == 0): then they are halo keys (qb > 0) that only this CTA touches
+            const bool head = pa > 0 && j < pa, tail = tails && jb >= 1;
             if (head || tail) {
               const int idx = head ? (j - (pa - nb + 1)) : (jb - 1);
               float* dst = part_cta + (static_cast<size_t>(tail ? 1 : 0) * C::kPartKeys + idx * P + h * 16) * 128;
 #pragma unroll
               for (int e = 0; e < 16; ++e) dst[e * 128] = __uint_as_float(x[e]);
             } else {
-              const int key0 = j * P + h * 16;
+              const int key0 = (j + a.qb) * P + h * 16;
               T* dst = okv + static_cast<int64_t>(w.b) * skv.b + static_cast<int64_t>(w.y) * skv.h +
                        static_cast<int64_t>(key0) * skv.n + dch;
-              const int nv = a.N - key0;
+              const int nv = a.Nkv - key0;
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 if (e < nv) *dst = from_f<T>(__uint_as_float(x[e]));
@@ -892,8 +912,8 @@ __global__ void __launch_bounds__(256) bwd_fused_fixup_kernel(const FusedArgs a,
   if (pa == 0) return;                       // the boundary coincides with a sequence start: nothing shared
   const int e = (blockIdx.y * 256 + threadIdx.x) * 4;
   if (e >= (a.nb - 1) * a.P * 128) return;
-  const int key = (pa - a.nb + 1) * a.P + (e >> 7);
-  if (key < 0 || key >= a.N) return;
+  const int key = (pa + a.qb - a.nb + 1) * a.P + (e >> 7);
+  if (key < 0 || key >= a.Nkv) return;
   const int seq = t0 / a.nblk, y = seq % a.Hkv, b = seq / a.Hkv;
   const float4 tl = *reinterpret_cast<const float4*>(a.part + (static_cast<size_t>(c - 1) * 2 + 1) * C::kPartKeys * 128 + e);
   const float4 hd = *reinterpret_cast<const float4*>(a.part + (static_cast<size_t>(c) * 2 + 0) * C::kPartKeys * 128 + e);
@@ -920,7 +940,8 @@ bool fused_geometry(const AttnParams& p, int& G, int& P, int& nb) {
   pick_packing(p.Hq, p.Hkv, G, P);
   if ((p.Hq / p.Hkv) != G) return false;              // one packed tile must hold the whole GQA group
   if (P != 16 && P != 32) return false;
-  const int64_t weff = p.W < p.N ? p.W : p.N;
+  if (p.q_off % P != 0) return false;                 // the key-block ring advances in whole query tiles
+  const int64_t weff = p.W < p.Nkv ? p.W : p.Nkv;
   const int64_t nb64 = (weff - 1 + P - 1) / P + 1;
   if (nb64 * P > FusedCfg::kColsMax || (nb64 + 1) * P > FusedCfg::kRingCols) return false;
   nb = static_cast<int>(nb64);
@@ -949,12 +970,13 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   TileMap mq, mdo, mk, mv;
   if (!make_tile_map(&mq, p.q, dtype, C::D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
   if (!make_tile_map(&mdo, p.dout, dtype, C::D, p.N, p.Hq, p.B, p.sdo, P, G)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mk, p.k, dtype, C::D, p.N, p.Hkv, p.B, p.sk, a.cols, 1)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mv, p.v, dtype, C::D, p.N, p.Hkv, p.B, p.sv, a.cols, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mk, p.k, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sk, a.cols, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mv, p.v, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sv, a.cols, 1)) return cudaErrorInvalidValue;
   if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;
   a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh;
   a.fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
   a.fuse_delta = tc_bwd_fused_computes_delta() ? 1 : 0;
+  a.qb = p.q_off / P; a.Nkv = p.Nkv; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
   a.dbg_delay = debug_knob(0);
   a.dbg_norace = debug_knob(1);
   // measured: 104.1 us with dP(n + 1) queued behind dK^T(n) / dQ(n), 99.3 us without -> off (SFA_ORDER_DP=1 enables)
@@ -1028,7 +1050,8 @@ bool tc_bwd_fused_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
   int G, P, nb;
   if (!fused_geometry(p, G, P, nb)) return false;
-  if (!(tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.N) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.N) &&
+  if (p.has_ext() && p.dq_route != nullptr) return false;
+  if (!(tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.Nkv) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.Nkv) &&
         tma_compatible(p.dout, p.sdo, p.B, p.Hq, p.N)))
     return false;
   // dQ rows are written with 16-byte stores; O and dO rows are read with 16-byte loads (delta)

@@ -38,10 +38,19 @@ struct AttnParams {
   float* delta;     // workspace [B,Hq,N]
   float* dsrow;     // workspace [B,Hq,N]: per-row ds_aux contributions when the dQ kernel computes delta itself
   Strides4 sq, sk, sv, so, sdo, sdq, sdk, sdv;
-  int B, Hq, Hkv, N, D, S, W;
+  int B, Hq, Hkv, N, D, S, W;      // N: number of QUERY rows (== keys unless Nkv says otherwise)
   float scale;
   const SpRoute* o_route;    // host pointers, nullptr = off; only the head_dim-64 tcgen05 kernels route
   const SpRoute* dq_route;
+  // ---- extended geometry (sfa_fwd_ex / sfa_bwd_ex): packed (varlen) sequences and chunked prefill / halo keys.
+  // Query row iq sits at absolute position i = iq + q_off of a key axis of length Nkv (k, v, dk, dv have Nkv rows);
+  // it attends key j iff  lo(iq) <= j <= i  and  (j - lo(iq) < S  or  j >= i - W + 1),  lo = seq_lo ? seq_lo[b][iq] : 0
+  // -- with q_off = 0, Nkv = N and no seq_lo this is the reference predicate (sink_flash_attention.py:30-39).
+  const int* seq_lo;         // device [B or 1][N]: first key position of the sequence query row iq belongs to
+  const int* seq_hi;         // device [B or 1][Nkv]: one past the last absolute QUERY position that may attend key j
+  int64_t seq_bs;            // elements between the batch rows of seq_lo / seq_hi (0: one row shared by the batch)
+  int Nkv, q_off;
+  __host__ __device__ bool has_ext() const { return seq_lo != nullptr || q_off != 0 || Nkv != N; }
 };
 
 struct DecodeParams {

@@ -33,6 +33,11 @@ struct Fwd64Args {
   float* lse;
   long long* trace;
   int sp_n;      // > 0: O tiles are ALSO stored into the peer buffer of the rank owning positions [k*sp_n, (k+1)*sp_n)
+  // extended geometry (sfa_fwd_ex): query row iq sits at absolute key position iq + q_off (chunked prefill, halo keys
+  // of the sequence-chunk parallel mode); seq_lo[b][iq] = first key of the packed sequence row iq belongs to
+  int q_off;
+  const int* seq_lo;
+  int64_t seq_bs;
 };
 struct PeerMaps {
   CUtensorMap m[8];
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     const int gr = a.q_swap ? (r % a.G) : (r / a.P);
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     float m_used = -INFINITY, l = 0.f;
-    int i = 0, mtc = 0;
+    int i = 0, mtc = 0, row_lo = 0;
     Walk w(a);
     while (w.next()) {
       if ((w.it & (C::kGroups - 1)) != grp) continue;      // the other group's tile
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
       if (w.t == 0) {
         i = w.q0 + pr;
+        if (a.seq_lo != nullptr) row_lo = (i < a.N) ? __ldg(a.seq_lo + w.b * a.seq_bs + i) : 0;
         const int h = w.y * a.G + gr;
         m_used = a.s_aux ? (h < 64 ? saux_s[h] : __ldg(a.s_aux + h) * kLog2e) : -INFINITY;
         l = (a.s_aux && part == 0) ? 1.f : 0.f;
@@ -273,7 +279,8 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       int kstart, cols; bool is_sink;
       w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
       int c_lo, c_hi;
-      row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+      row_range(is_sink, i + a.q_off, kstart, cols, a.S, a.W, c_lo, c_hi);
+      if (a.seq_lo != nullptr) c_lo = max(c_lo, row_lo - kstart);      // never across a packed-sequence boundary
       if (i >= a.N) c_hi = -1;
       const int nch = cols >> 4;
       const int pbase = nch / C::kParts, prem = nch % C::kParts;       // same split as part_starts()
@@ -472,11 +479,11 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
   const int group = p.Hq / p.Hkv;
   int G, P;
   pick_packing(p.Hq, p.Hkv, G, P);
-  const int BN = pick_bn(p.W, p.N, P, C::kBNMax);
+  const int BN = pick_bn(p.W, p.Nkv, P, C::kBNMax);
   TileMap mq, mk, mv, mo;
   if (!make_tile_map(&mq, p.q, dtype, D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mk, p.k, dtype, D, p.Nkv, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mv, p.v, dtype, D, p.Nkv, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
   if (!make_tile_map(&mo, p.o, dtype, D, p.N, p.Hq, p.B, p.so, P, G)) return cudaErrorInvalidValue;
   Fwd64Args a;
   a.B = p.B; a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.G = G; a.P = P; a.BN = BN;
@@ -492,6 +499,7 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
   a.s_aux = p.s_aux;
   a.lse = p.lse;
   a.trace = trace_buffer();
+  a.q_off = p.q_off; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
   a.sp_n = 0;
   PeerMaps pm;
   for (int r = 0; r < 8; ++r) pm.m[r] = mo.map;
@@ -518,6 +526,8 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
 }  // namespace
 
 bool tc_fwd64_supported(const AttnParams& p, int dtype) {
+  if (p.seq_lo != nullptr && p.S > 0) return false;      // per-sequence sink tokens: CUDA-core path
+  if (p.has_ext() && p.o_route != nullptr) return false;
   return p.D == 64 && (p.S > 0 || p.W > 0);     // nothing attended at all: the one-tile-per-CTA kernel writes the O = 0 rows
 }
 

@@ -320,7 +320,7 @@ bool tc_fwd_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
   if (p.D != 64 && p.D != 128) return false;
   if (p.N < 1) return false;
-  return tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.N) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.N) &&
+  return tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.Nkv) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.Nkv) &&
          tma_compatible(p.o, p.so, p.B, p.Hq, p.N);
 }
 

@@ -54,9 +54,12 @@ __global__ void __launch_bounds__(128) simt_fwd_kernel(AttnParams p) {
 #pragma unroll
   for (int t = 0; t < kDPL; ++t) acc[t] = 0.f;
 
-  // two disjoint key ranges: sinks [0, min(S, i+1)) and the window [max(S, i-W+1, 0), i]
-  int lo[2] = {0, max(max(S, i - W + 1), 0)};
-  int hi[2] = {min(S, i + 1), (W > 0) ? i + 1 : 0};
+  // two disjoint key ranges: sinks [s0, min(s0 + S, ia + 1)) and the window [max(s0 + S, ia - W + 1), ia], with
+  // ia = i + q_off the row's absolute position and s0 the start of its (packed) sequence
+  const int ia = i + p.q_off;
+  const int s0 = p.seq_lo ? p.seq_lo[b * p.seq_bs + i] : 0;
+  int lo[2] = {s0, max(s0 + S, ia - W + 1)};
+  int hi[2] = {min(s0 + S, ia + 1), (W > 0) ? ia + 1 : 0};
   for (int r = 0; r < 2; ++r) {
     for (int j0 = lo[r]; j0 < hi[r]; j0 += 32) {
       const int j = j0 + lane;
@@ -115,8 +118,10 @@ __global__ void __launch_bounds__(128) simt_dq_kernel(AttnParams p) {
   float acc[kDPL];
 #pragma unroll
   for (int t = 0; t < kDPL; ++t) acc[t] = 0.f;
-  int lo[2] = {0, max(max(S, i - W + 1), 0)};
-  int hi[2] = {min(S, i + 1), (W > 0) ? i + 1 : 0};
+  const int ia = i + p.q_off;
+  const int s0 = p.seq_lo ? p.seq_lo[b * p.seq_bs + i] : 0;
+  int lo[2] = {s0, max(s0 + S, ia - W + 1)};
+  int hi[2] = {min(s0 + S, ia + 1), (W > 0) ? ia + 1 : 0};
   for (int r = 0; r < 2; ++r) {
     for (int j0 = lo[r]; j0 < hi[r]; j0 += 32) {
       const int j = j0 + lane;
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(128) simt_dkdv_kernel(AttnParams p) {
   __shared__ float vs[4][kMaxD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 4 + warp, kvh = blockIdx.y, b = blockIdx.z;
-  if (j >= p.N) return;
+  if (j >= p.Nkv) return;
   const int D = p.D, S = p.S, W = p.W, N = p.N;
   const int g = p.Hq / p.Hkv;
   const T* kr = static_cast<const T*>(p.k) + b * p.sk.b + kvh * p.sk.h + (int64_t)j * p.sk.n;
@@ -168,19 +173,31 @@ __global__ void __launch_bounds__(128) simt_dkdv_kernel(AttnParams p) {
   float dk[kDPL], dv[kDPL];
 #pragma unroll
   for (int t = 0; t < kDPL; ++t) dk[t] = dv[t] = 0.f;
-  // queries that attend key j: i >= j and (j < S or i <= j + W - 1)
-  const int i_end = (j < S) ? N : ((W > 0) ? min(N, j + W) : j);
+  // query rows (index iq, absolute position iq + q_off) that attend key j: position >= j, inside j's sequence, and
+  // (j is one of the S sinks of that sequence or position <= j + W - 1).  Without sinks the band ends at j + W - 1;
+  // with sinks every later row of the sequence is a candidate and the per-row predicate decides.
+  const int qo = p.q_off;
+  int e_abs = p.seq_hi ? p.seq_hi[b * p.seq_bs + j] : N + qo;            // one past the last candidate position
+  bool maybe_sink = S > 0;
+  if (maybe_sink) {
+    if (p.seq_lo == nullptr) maybe_sink = j < S;
+    else if (j >= qo && j - qo < N) maybe_sink = j - p.seq_lo[b * p.seq_bs + (j - qo)] < S;   // key j shares the sequence of the query at its position
+  }
+  if (!maybe_sink) e_abs = (W > 0) ? min(e_abs, j + W) : j;
+  const int i_beg = max(j - qo, 0), i_end = min(e_abs - qo, N);
   for (int hh = 0; hh < g; ++hh) {
     const int h = kvh * g + hh;
     const T* qb = static_cast<const T*>(p.q) + b * p.sq.b + h * p.sq.h;
     const T* dob = static_cast<const T*>(p.dout) + b * p.sdo.b + h * p.sdo.h;
     const int64_t rowb = ((int64_t)b * p.Hq + h) * N;
-    for (int i0 = j; i0 < i_end; i0 += 32) {
+    for (int i0 = i_beg; i0 < i_end; i0 += 32) {
       const int i = i0 + lane;
       float pr = 0.f, ds = 0.f;
       if (i < i_end) {
         const float lse = p.lse[rowb + i];
-        if (lse != -INFINITY) {
+        const int s0 = p.seq_lo ? p.seq_lo[b * p.seq_bs + i] : 0;
+        const bool att = j >= s0 && (j - s0 < S || j >= i + qo - W + 1);
+        if (att && lse != -INFINITY) {
           const float s = dot_row<T>(qb + (int64_t)i * p.sq.n, ks[warp], D) * p.scale;
           pr = expf(s - lse);
           const float dp = dot_row<T>(dob + (int64_t)i * p.sdo.n, vs[warp], D);
@@ -537,7 +554,7 @@ cudaError_t simt_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st
       if (e != cudaSuccess) return e;
     }
     if (stages & 4) {
-      dim3 gk((p.N + 3) / 4, p.Hkv, p.B);
+      dim3 gk((p.Nkv + 3) / 4, p.Hkv, p.B);
       simt_dkdv_kernel<T><<<gk, 128, 0, st>>>(p);
       e = cudaGetLastError();
     }

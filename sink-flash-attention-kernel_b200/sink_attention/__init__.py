@@ -3,7 +3,13 @@
 Same 12 public names as the reference package (sink_attention/__init__.py:1-28); the Triton kernels
 are replaced by hand-written CUDA behind the C ABI in ``include/sinkfa.h`` (``libsinkfa.so``).
 """
-from .sink_flash_attention import sink_flash_attention, sink_flash_attention_with_lse, SinkFlashAttentionFunc
+from .sink_flash_attention import (
+    sink_flash_attention,
+    sink_flash_attention_with_lse,
+    sink_flash_attention_varlen,
+    sink_flash_attention_chunk,
+    SinkFlashAttentionFunc,
+)
 from .verl_patch import patch_verl_with_sink_attention, unpatch_verl
 from .sp_utils import (
     prepare_sink_kv_for_sp,
@@ -35,6 +41,8 @@ __all__ = [
     "subprocess_generate",
     # B200 additions
     "sink_flash_attention_with_lse",
+    "sink_flash_attention_varlen",
+    "sink_flash_attention_chunk",
     "UlyssesSinkAttention",
     "ulysses_seq_to_head",
     "ulysses_head_to_seq",

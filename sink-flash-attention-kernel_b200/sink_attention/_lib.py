@@ -21,7 +21,7 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_set_debug", "sfa_cache_append",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_set_debug", "sfa_cache_append", "sfa_fwd_ex", "sfa_bwd_ex",
 )
 
 _lib = None
@@ -41,6 +41,35 @@ def make_route(peer_ptrs: Sequence[int], n_local: int, heads_total: int, head_of
     for i, ptr in enumerate(peer_ptrs):
         r.peer[i] = int(ptr)
     return r
+
+
+class AttnExt(ctypes.Structure):
+    """sfa_attn_ext of include/sinkfa.h: packed (varlen) sequences and chunked prefill / halo keys."""
+    _fields_ = [("seq_lo", ctypes.c_void_p), ("seq_hi", ctypes.c_void_p), ("seq_batch_stride", ctypes.c_int64),
+                ("n_kv", ctypes.c_int), ("q_off", ctypes.c_int)]
+
+
+def make_ext(n_q: int, n_kv: int, q_off: int = 0, seq_lo: Optional[torch.Tensor] = None,
+             seq_hi: Optional[torch.Tensor] = None) -> Optional["AttnExt"]:
+    """seq_lo [N_q] or [B, N_q], seq_hi [N_kv] or [B, N_kv]: int32 CUDA tensors (both or none)."""
+    if seq_lo is None and q_off == 0 and n_kv == n_q:
+        return None
+    e = AttnExt()
+    e.n_kv, e.q_off = int(n_kv), int(q_off)
+    e.seq_lo = e.seq_hi = None
+    e.seq_batch_stride = 0
+    if seq_lo is not None:
+        if seq_hi is None or seq_lo.dtype != torch.int32 or seq_hi.dtype != torch.int32:
+            raise ValueError("seq_lo and seq_hi must both be int32 tensors")
+        if not (seq_lo.is_contiguous() and seq_hi.is_contiguous()):
+            raise ValueError("seq_lo / seq_hi must be contiguous")
+        if seq_lo.dim() == 2:
+            # one allocation per array, rows n_kv apart: the C ABI takes ONE batch stride for both
+            if seq_lo.shape[1] != seq_hi.shape[1]:
+                raise ValueError("batched seq_lo / seq_hi need equal row lengths (q_off == 0)")
+            e.seq_batch_stride = seq_lo.shape[1] if seq_lo.shape[0] > 1 else 0
+        e.seq_lo, e.seq_hi = seq_lo.data_ptr(), seq_hi.data_ptr()
+    return e
 
 
 class SinkFAError(RuntimeError):
@@ -82,6 +111,10 @@ def load() -> ctypes.CDLL:
     lib.sfa_fwd_sp.restype = i
     lib.sfa_bwd_sp.argtypes = [p] * 5 + [f32p, f32p] + [p] * 2 + [f32p] + [i] * 8 + [i64p] * 7 + [p, c.c_size_t, p, c.POINTER(SpRoute)]
     lib.sfa_bwd_sp.restype = i
+    lib.sfa_fwd_ex.argtypes = lib.sfa_fwd.argtypes + [c.POINTER(AttnExt)]
+    lib.sfa_fwd_ex.restype = i
+    lib.sfa_bwd_ex.argtypes = lib.sfa_bwd.argtypes + [c.POINTER(AttnExt)]
+    lib.sfa_bwd_ex.restype = i
     lib.sfa_decode.argtypes = [p, p, p, p, f32p] + [i] * 6 + [i64p] * 4 + [p, c.c_size_t, p]
     lib.sfa_decode.restype = i
     lib.sfa_decode_ring.argtypes = [p] * 6 + [f32p] + [i] * 7 + [i64p] * 4 + [p, c.c_size_t, p]
@@ -153,9 +186,11 @@ def _s_aux_f32(s_aux: Optional[torch.Tensor], hq: int) -> Optional[torch.Tensor]
     return s_aux.detach().contiguous().float()
 
 
-def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32, o_route: Optional[SpRoute] = None):
-    """-> (o, lse).  q [B,Hq,N,D] (any strides with unit channel stride), k/v [B,Hkv,N,D].
-    o_route: also store O into the peers' receive buffers (sfa_fwd_sp); ValueError if the shape cannot route."""
+def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32, o_route: Optional[SpRoute] = None,
+        ext: Optional[AttnExt] = None):
+    """-> (o, lse).  q [B,Hq,N,D] (any strides with unit channel stride), k/v [B,Hkv,N,D] ([B,Hkv,n_kv,D] with ext).
+    o_route: also store O into the peers' receive buffers (sfa_fwd_sp); ValueError if the shape cannot route.
+    ext: packed sequences / chunked prefill (sfa_fwd_ex)."""
     lib = load()
     _require_cuda(q, k, v, s_aux_f32)
     B, Hq, N, D = q.shape
@@ -171,7 +206,9 @@ def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32, o_route: Optional[S
             _i64(q.stride()), _i64(k.stride()), _i64(v.stride()), _i64(o.stride()),
             None, 0, _stream(q))
     with torch.cuda.device(q.device):
-        if o_route is None:
+        if ext is not None:
+            rc = lib.sfa_fwd_ex(*args, ctypes.byref(ext))
+        elif o_route is None:
             rc = lib.sfa_fwd(*args)
         else:
             rc = lib.sfa_fwd_sp(*args, ctypes.byref(o_route))
@@ -179,7 +216,8 @@ def fwd(q, k, v, num_sink: int, window_size: int, s_aux_f32, o_route: Optional[S
     return o, lse
 
 
-def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32, dq_route: Optional[SpRoute] = None):
+def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32, dq_route: Optional[SpRoute] = None,
+        ext: Optional[AttnExt] = None):
     """-> (dq, dk, dv, ds_aux|None); dk/dv are already reduced over the GQA group (fp32 accumulate).
     dq_route: dQ is stored ONLY into the peers' receive buffers (sfa_bwd_sp) and returned as None."""
     lib = load()
@@ -193,7 +231,10 @@ def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32, dq_rout
         return t.shape[1] > 1 and t.shape[2] > 1 and t.stride(1) < t.stride(2)
     if _hf_order(do) != _hf_order(q):
         do = do.transpose(1, 2).contiguous().transpose(1, 2) if _hf_order(q) else do.contiguous()
-    dk, dv = torch.empty_like(k), torch.empty_like(v)
+    if ext is not None and (ext.q_off != 0 or ext.n_kv != N):
+        dk, dv = torch.zeros_like(k), torch.zeros_like(v)      # keys no query row attends keep a zero gradient
+    else:
+        dk, dv = torch.empty_like(k), torch.empty_like(v)
     dq = torch.empty_like(q) if dq_route is None else None
     ds_aux = torch.empty((Hq,), device=q.device, dtype=torch.float32) if s_aux_f32 is not None else None
     code = DTYPE_CODE[q.dtype]
@@ -211,15 +252,15 @@ def bwd(q, k, v, o, do, lse, num_sink: int, window_size: int, s_aux_f32, dq_rout
                 ws.data_ptr(), ws_bytes, _stream(q), ctypes.byref(dq_route))
         _check(rc, "sfa_bwd_sp")
         return None, dk, dv, ds_aux
+    bargs = (q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+             s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
+             dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ds_aux.data_ptr() if ds_aux is not None else None,
+             B, Hq, Hkv, N, D, int(num_sink), int(window_size), code,
+             _i64(q.stride()), _i64(k.stride()), _i64(v.stride()), _i64(o.stride()), _i64(do.stride()),
+             _i64(dq.stride()), _i64(dk.stride()), _i64(dv.stride()),
+             ws.data_ptr(), ws_bytes, _stream(q))
     with torch.cuda.device(q.device):
-        rc = lib.sfa_bwd(
-            q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
-            s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
-            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ds_aux.data_ptr() if ds_aux is not None else None,
-            B, Hq, Hkv, N, D, int(num_sink), int(window_size), code,
-            _i64(q.stride()), _i64(k.stride()), _i64(v.stride()), _i64(o.stride()), _i64(do.stride()),
-            _i64(dq.stride()), _i64(dk.stride()), _i64(dv.stride()),
-            ws.data_ptr(), ws_bytes, _stream(q))
+        rc = lib.sfa_bwd(*bargs) if ext is None else lib.sfa_bwd_ex(*bargs, ctypes.byref(ext))
     _check(rc, "sfa_bwd")
     return dq, dk, dv, ds_aux
 

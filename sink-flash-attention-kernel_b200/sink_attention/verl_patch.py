@@ -2,10 +2,17 @@
 
 Behaviour follows the reference's ``sink_attention/verl_patch.py`` (:33-263): the replacement takes
 HF's ``[B, N, H, D]`` tensors, pops gpt-oss's ``s_aux`` from ``**kwargs``, falls back to the saved
-original for varlen / packed / non-causal / padded / soft-capped calls, routes ``N_q != N_kv`` to
-the decode kernel, uses ``num_sink=0`` with ``window = sliding_window or N`` for prefill, slices
-``s_aux`` to the local heads under Ulysses sequence parallelism, and ignores ``softmax_scale``
-(the kernels use 1/sqrt(D), as the reference does).
+original for non-causal / padded / soft-capped calls, routes ``N_q != N_kv`` to the decode kernel,
+uses ``num_sink=0`` with ``window = sliding_window or N`` for prefill, slices ``s_aux`` to the local
+heads under Ulysses sequence parallelism, and ignores ``softmax_scale`` (the kernels use 1/sqrt(D),
+as the reference does).
+
+Difference (packed sequences stay on the sink kernels): the reference sends varlen (``cu_seq_lens``)
+and packed (``position_ids`` restarting mid-row) calls to stock FlashAttention (:73-93), which
+silently drops ``s_aux`` -- for exactly the padding-free batches verl trains on.  Here the sequence
+boundaries go INTO the kernels (``sink_flash_attention_varlen``: a row never attends across a
+boundary), and a chunked-prefill call (``1 < N_q < N_kv``), which the reference's decode kernel
+rejects (decode_kernel.py:146), runs on ``sink_flash_attention_chunk``.
 
 Difference (layout-fused boundary): the kernels take strides, so the ``transpose(1, 2)`` views are
 consumed in place and the output is produced directly in ``[B, N, H, D]`` memory -- the
@@ -18,7 +25,8 @@ from typing import Optional
 import torch
 
 from .decode_kernel import sink_decode_attention
-from .sink_flash_attention import sink_flash_attention
+from .sink_flash_attention import (sequence_bounds_from_cu_seqlens, sequence_bounds_from_position_ids,
+                                   sink_flash_attention, sink_flash_attention_chunk, sink_flash_attention_varlen)
 
 _original_flash_attention_forward = None
 
@@ -78,8 +86,14 @@ def _sink_flash_attention_forward(
 ):
     s_aux = kwargs.pop("s_aux", None)
     varlen = all(x is not None for x in (cu_seq_lens_q, cu_seq_lens_k, max_length_q, max_length_k))
-    packed = position_ids is not None and query_states.size(0) > 0 and _is_packed(position_ids)
-    if varlen or packed or not is_causal or attention_mask is not None or softcap is not None:
+    packed = (not varlen) and position_ids is not None and query_states.size(0) > 0 and _is_packed(position_ids)
+    n_q, n_kv, h_q = query_states.shape[1], key_states.shape[1], query_states.shape[2]
+    # varlen self-attention only: the same boundaries on both sides (what padding-free training passes)
+    varlen_ok = varlen and n_q == n_kv and cu_seq_lens_q.shape == cu_seq_lens_k.shape and \
+        (cu_seq_lens_q is cu_seq_lens_k or cu_seq_lens_q.data_ptr() == cu_seq_lens_k.data_ptr() or
+         bool(torch.equal(cu_seq_lens_q, cu_seq_lens_k)))
+    if (varlen and not varlen_ok) or (packed and n_q != n_kv) or not is_causal or attention_mask is not None \
+            or softcap is not None:
         if s_aux is not None:
             kwargs["s_aux"] = s_aux          # the stock FA path ignores it
         return _original_flash_attention_forward(
@@ -90,14 +104,34 @@ def _sink_flash_attention_forward(
             max_length_q=max_length_q, max_length_k=max_length_k, target_dtype=target_dtype,
             implementation=implementation, **kwargs)
 
-    n_q, n_kv, h_q = query_states.shape[1], key_states.shape[1], query_states.shape[2]
     q = query_states.transpose(1, 2)         # [B,H,N,D] views; no copies
     k = key_states.transpose(1, 2)
     v = value_states.transpose(1, 2)
     s_local = _local_s_aux(s_aux, h_q, True)
-    if n_q != n_kv:                          # cached decode step (reference :98-126)
-        out = sink_decode_attention(q, k, v, s_aux=s_local)
-        return out.transpose(1, 2).contiguous()
+    if varlen or packed:
+        # packed sequences: boundaries go into the kernels, s_aux and the per-layer window are kept
+        window = sliding_window if sliding_window is not None else n_q
+        if varlen:
+            B = query_states.shape[0]
+            if B > 1:                        # cu_seq_lens index the flattened batch
+                q, k, v = (t.transpose(1, 2).reshape(1, B * n_q, t.shape[1], t.shape[3]).transpose(1, 2) for t in (q, k, v))
+            bounds = sequence_bounds_from_cu_seqlens(cu_seq_lens_q, q.shape[2])
+            window = sliding_window if sliding_window is not None else (max_length_q if isinstance(max_length_q, int) else q.shape[2])
+        else:
+            bounds = sequence_bounds_from_position_ids(position_ids)
+        out = sink_flash_attention_varlen(q, k, v, num_sink=0, window_size=window, s_aux=s_local, seq_bounds=bounds)
+        out = out.transpose(1, 2)
+        out = out if out.is_contiguous() else out.contiguous()
+        return out.reshape(query_states.shape)
+    if n_q != n_kv:
+        if n_q == 1:                         # cached decode step (reference :98-126)
+            out = sink_decode_attention(q, k, v, s_aux=s_local)
+            return out.transpose(1, 2).contiguous()
+        # chunked prefill: the queries are the last n_q positions of the cached context
+        window = sliding_window if sliding_window is not None else n_kv
+        out = sink_flash_attention_chunk(q, k, v, num_sink=0, window_size=window, s_aux=s_local)
+        out = out.transpose(1, 2)
+        return out if out.is_contiguous() else out.contiguous()
     window = sliding_window if sliding_window is not None else n_q
     out = sink_flash_attention(q, k, v, num_sink=0, window_size=window, s_aux=s_local)
     out = out.transpose(1, 2)

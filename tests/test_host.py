@@ -167,6 +167,12 @@ def test_verl_forward_routing(monkeypatch):
                             ("prefill", tuple(q.shape), num_sink, window_size, s_aux)) or q)
     monkeypatch.setattr(verl_patch, "sink_decode_attention",
                         lambda q, k, v, s_aux=None: calls.append(("decode", tuple(q.shape), tuple(k.shape), s_aux)) or q)
+    monkeypatch.setattr(verl_patch, "sink_flash_attention_chunk",
+                        lambda q, k, v, num_sink, window_size, s_aux: calls.append(
+                            ("chunk", tuple(q.shape), tuple(k.shape), num_sink, window_size, s_aux)) or q)
+    monkeypatch.setattr(verl_patch, "sink_flash_attention_varlen",
+                        lambda q, k, v, num_sink, window_size, s_aux, seq_bounds: calls.append(
+                            ("varlen", tuple(q.shape), num_sink, window_size, s_aux, seq_bounds)) or q)
     f = verl_patch._sink_flash_attention_forward
     q = torch.zeros(2, 10, 8, 16)          # HF layout [B, N, H, D]
     kv = torch.zeros(2, 10, 2, 16)
@@ -183,19 +189,44 @@ def test_verl_forward_routing(monkeypatch):
     assert calls[-1][4].tolist() == list(range(8))
     f(q, kv, kv, None, 10, s_aux=torch.arange(5.0))              # mismatch -> dropped
     assert calls[-1][4] is None
-    # decode: N_q != N_kv
+    # decode: N_q == 1 over a longer cache
     f(q[:, :1], kv, kv, None, 1, s_aux=s_aux)
     assert calls[-1][:3] == ("decode", (2, 8, 1, 16), (2, 2, 10, 16))
-    # fallbacks
+    # chunked prefill (1 < N_q < N_kv): the reference's decode kernel asserts N_q == 1 (decode_kernel.py:146); here the
+    # chunk kernel takes it, still with num_sink = 0, window = sliding_window or N_kv, s_aux
+    f(q[:, :4], kv, kv, None, 4, s_aux=s_aux, sliding_window=6)
+    assert calls[-1][:5] == ("chunk", (2, 8, 4, 16), (2, 2, 10, 16), 0, 6) and calls[-1][5] is s_aux
+    # packed sequences stay on the sink kernels WITH s_aux (the reference falls back to stock FA and drops it, :73-93)
+    cu = torch.tensor([0, 4, 10], dtype=torch.int32)
+    f(q[:1], kv[:1], kv[:1], None, 10, s_aux=s_aux, sliding_window=5, cu_seq_lens_q=cu, cu_seq_lens_k=cu,
+      max_length_q=6, max_length_k=6)
+    assert calls[-1][:4] == ("varlen", (1, 8, 10, 16), 0, 5) and calls[-1][4] is s_aux
+    lo, hi = calls[-1][5]
+    assert lo.tolist() == [0, 0, 0, 0, 4, 4, 4, 4, 4, 4] and hi.tolist() == [4, 4, 4, 4, 10, 10, 10, 10, 10, 10]
+    f(q, kv, kv, None, 10, s_aux=s_aux, position_ids=torch.tensor([[0, 1, 2, 0, 1, 2, 3, 4, 5, 6], [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]]))
+    assert calls[-1][:4] == ("varlen", (2, 8, 10, 16), 0, 10)
+    lo, hi = calls[-1][5]
+    assert lo.tolist() == [[0, 0, 0, 3, 3, 3, 3, 3, 3, 3], [0] * 8 + [8, 8]]
+    assert hi.tolist() == [[3, 3, 3, 10, 10, 10, 10, 10, 10, 10], [8] * 8 + [10, 10]]
+    # fallbacks to the saved original: non-causal, soft-capped, padded, cross-length varlen
+    cu_k = torch.tensor([0, 5, 10], dtype=torch.int32)
     for kw in (dict(is_causal=False), dict(softcap=30.0),
-               dict(cu_seq_lens_q=torch.tensor([0, 10]), cu_seq_lens_k=torch.tensor([0, 10]), max_length_q=10, max_length_k=10),
-               dict(position_ids=torch.tensor([[0, 1, 2, 0, 1, 2, 3, 4, 5, 6]] * 2))):
-        assert f(q, kv, kv, None, 10, s_aux=s_aux, **kw) == "orig"
+               dict(cu_seq_lens_q=cu, cu_seq_lens_k=cu_k, max_length_q=6, max_length_k=6)):
+        assert f(q[:1], kv[:1], kv[:1], None, 10, s_aux=s_aux, **kw) == "orig"
         assert calls[-1][0] == "orig" and calls[-1][1]["s_aux"] is s_aux
     assert f(q, kv, kv, torch.ones(2, 10), 10) == "orig"          # padding mask
     # monotone position ids are not "packed"
     f(q, kv, kv, None, 10, position_ids=torch.arange(10)[None].expand(2, -1))
     assert calls[-1][0] == "prefill"
+
+
+def test_sequence_bounds_helpers():
+    from sink_attention.sink_flash_attention import sequence_bounds_from_cu_seqlens, sequence_bounds_from_position_ids
+    lo, hi = sequence_bounds_from_cu_seqlens(torch.tensor([0, 3, 3, 7]), 9)       # an empty sequence, 2 padding slots
+    assert lo.tolist() == [0, 0, 0, 3, 3, 3, 3, 7, 8] and hi.tolist() == [3, 3, 3, 7, 7, 7, 7, 8, 9]
+    lo, hi = sequence_bounds_from_position_ids(torch.tensor([[0, 1, 0, 0, 1, 2]]))
+    assert lo.tolist() == [[0, 0, 2, 3, 3, 3]] and hi.tolist() == [[2, 2, 3, 6, 6, 6]]
+    assert lo.dtype == torch.int32 and hi.dtype == torch.int32
 
 
 def test_generation_forward_routing(monkeypatch):
