@@ -558,9 +558,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       SlotTrack st;
       st.slot0 = 0;
       bool has_next = wn.next();
-      // first key of the row's packed sequence, in query-row units (absolute - q_off); INT_MIN/2 when not packed
+      // first key of the row's packed sequence, in query-row units (absolute - q_off); unused when not packed
       auto load_lo = [&](const FusedWalk& t, bool valid) {
-        int v = -(1 << 30);
+        int v = 0;
         if (a.seq_lo != nullptr && valid) {
           const int i = t.pb * P + pr;
           if (i < a.N) v = __ldg(a.seq_lo + t.b * a.seq_bs + i) - a.qb * P;
@@ -586,7 +586,11 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         const int i = w.pb * P + pr;
         const int kstart = (w.pb - nb + 1) * P;            // in QUERY-row units: absolute key = this + q_off
         // attended keys of the row: [max(i - W + 1, first key of its sequence), i]; keys start at absolute 0
-        const int c_lo = max(max(i - a.W + 1, -a.qb * P), lo_row) - kstart;
+        // (kept as two plain steps: the one-expression form with a -2^30 "no sequence" sentinel folded into a
+        // three-way max came out of ptxas 12.9 with the sign of the q_off term lost -- caught by the chunked-prefill tests)
+        int key_lo = -a.qb * P;                            // absolute key 0
+        if (a.seq_lo != nullptr) key_lo = max(key_lo, lo_row);
+        const int c_lo = max(i - a.W + 1, key_lo) - kstart;
         const int c_hi = (i < a.N) ? (i - kstart) : -1;
         int xs = st.slot0 + nb;                            // slot whose block left the window: zero image columns
         if (xs >= R) xs -= R;
