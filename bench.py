@@ -394,6 +394,56 @@ def run_ours(args):
                 print(f"[bench] rank {rank}: graph capture of the Ulysses step failed ({type(e).__name__}: {e}); timing the eager step",
                       file=sys.stderr)
                 step = eager_uly_step
+        # ---- halo-exchange sequence parallelism beside it (narrow window, no sink tokens: only the W - 1 keys in front
+        # of each chunk cross NVLink, sp_utils.HaloSinkAttention) -- same 131072-token sequence, same chunks
+        halo_line = None
+        if os.environ.get("SFA_BENCH_SKIP_HALO") is None and S == 0 and W - 1 <= N:
+            try:
+                hmod = sa.HaloSinkAttention(W, None, p2p=True)
+
+                def halo_step():
+                    for t in (q, k, v, s_aux):
+                        t.grad = None
+                    hmod(q, k, v, s_aux).backward(do)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        halo_step()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                dist.barrier()
+                hgraph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(hgraph):
+                    halo_step()
+                torch.cuda.synchronize()
+                for _ in range(3):
+                    hgraph.replay()
+                torch.cuda.synchronize()
+                ht = []
+                for _ in range(args.steps):
+                    flush_l2()
+                    dist.barrier()
+                    a_, b_ = ev(), ev()
+                    a_.record()
+                    hgraph.replay()
+                    b_.record()
+                    b_.synchronize()
+                    ht.append(a_.elapsed_time(b_))
+                hms = torch.tensor([sum(ht) / len(ht)], device=dev)
+                dist.all_reduce(hms, op=dist.ReduceOp.MAX)
+                halo_rows = hmod._bufs[0].halo
+                halo_line = {"ms_per_step": hms.item(),
+                             "value": 14 * D * attended_pairs(n_total, S, W) * B * Hq / (hms.item() * 1e-3) / 1e12, "unit": UNIT,
+                             "halo_rows": halo_rows,
+                             "nvlink_bytes_per_rank_per_step": 2 * 2 * B * halo_rows * Hkv * D * 2,
+                             "how": "CUDA-graph replay of HaloSinkAttention(p2p=True) fwd+bwd: K/V halo rows stored into the next "
+                                    "rank's symmetric buffer, attention kernels with q_off = halo, halo dK/dV stored back; max over ranks"}
+                del hgraph
+            except Exception as e:      # noqa: BLE001
+                halo_line = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.synchronize()
+            dist.barrier()
         # fwd: 3 scatter + barrier + attention + scatter + barrier (+ clone); bwd: scatter + barrier + preprocess +
         # fused + fix-up + 3 scatter + barrier (+ 3 copies)  ->  13 kernels of libsinkfa per step (p2p path)
         launches_per_step = 13 if want_p2p else 1 + 3
@@ -610,6 +660,7 @@ def run_ours(args):
             line["c2"] = c2
         if world > 1:
             line["parity_check"] = parity_check
+            line["halo_sp"] = halo_line
         if e2e is not None:
             line["e2e"] = e2e
     if world > 1:

@@ -16,6 +16,7 @@ from .sp_utils import (
     reduce_sink_kv_grads,
     SinkAttentionSPWrapper,
     UlyssesSinkAttention,
+    HaloSinkAttention,
     ulysses_seq_to_head,
     ulysses_head_to_seq,
 )
@@ -44,6 +45,7 @@ __all__ = [
     "sink_flash_attention_varlen",
     "sink_flash_attention_chunk",
     "UlyssesSinkAttention",
+    "HaloSinkAttention",
     "ulysses_seq_to_head",
     "ulysses_head_to_seq",
 ]

@@ -1,6 +1,6 @@
 """Sequence parallelism for sink attention.
 
-Two schemes live here.
+Three schemes live here (the third, HaloSinkAttention, exchanges only the W - 1 keys a narrow window needs).
 
 1. Ulysses (what the north-star layout asks for; the reference leaves the all-to-all to verl,
    verl_patch.py:15-20, and only slices ``s_aux``, :132-154).  Activations arrive sequence-sharded
@@ -359,6 +359,213 @@ class UlyssesSinkAttention(torch.nn.Module):
                                       self.num_sink, self.window_size, sc).transpose(1, 2)
             outs.append(ulysses_head_to_seq(oh, self.sp_group).reshape(B, n, P, kv_per * g, -1))
         return torch.cat(outs, dim=3).reshape(B, n, H_q, -1)
+
+
+# =============================================================================================
+# Halo-exchange sequence parallelism for narrow windows (no sink tokens)
+# =============================================================================================
+# With a sliding window of W keys a sequence chunk only needs the last W - 1 keys / values of the chunk before it.
+# At the gpt-oss shape (W = 128, 8 KV heads, D = 64) that is 127 x 8 x 64 x 2 B x (K, V) = 260 KB per boundary, against
+# the 264 MB per rank (P = 8) that the Ulysses all-to-all moves for the same layer: the exchange drops out of the
+# step time and every rank runs the attention kernels on its own chunk with `halo` extra keys in front
+# (sink_flash_attention_chunk: the queries are the last rows of a longer key axis).  Backward sends the halo keys'
+# dK / dV back to the rank that owns them.  This is what the reference's sequence-chunk helpers (sp_utils.py:28-129)
+# are missing -- they broadcast the sink K/V but have no window halo -- and it replaces the
+# all-to-all only where the window is narrow and there are no sink tokens; otherwise use UlyssesSinkAttention.
+def _halo_rows(window_size: int, n_local: int) -> int:
+    halo = (max(window_size - 1, 0) + 15) // 16 * 16        # whole 16-key blocks: the fused backward's granularity
+    return min(halo, n_local)
+
+
+class _HaloFromPrev(torch.autograd.Function):
+    """Portable exchange (any torch.distributed backend): my last `halo` rows of [K | V] go to rank + 1, I receive
+    rank - 1's (rank 0 receives zeros it never attends).  Backward runs the mirror image with the gradients."""
+
+    @staticmethod
+    def forward(ctx, tail, group):
+        P, rank = _group_size_rank(group)
+        ctx.group = group
+        recv = torch.zeros_like(tail)
+        ops = []
+        gr = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        if rank + 1 < P:
+            ops.append(dist.P2POp(dist.isend, tail.contiguous(), gr(rank + 1), group))
+        if rank > 0:
+            ops.append(dist.P2POp(dist.irecv, recv, gr(rank - 1), group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return recv
+
+    @staticmethod
+    def backward(ctx, g):
+        group = ctx.group
+        P, rank = _group_size_rank(group)
+        recv = torch.zeros_like(g)
+        ops = []
+        gr = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        if rank > 0:
+            ops.append(dist.P2POp(dist.isend, g.contiguous(), gr(rank - 1), group))
+        if rank + 1 < P:
+            ops.append(dist.P2POp(dist.irecv, recv, gr(rank + 1), group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return recv, None
+
+
+class _HaloBuffers:
+    """Symmetric-memory buffers of one layer for the peer-memory halo exchange:
+         kv_ext [2][B, halo + n, Hkv, D]   rows [0, halo): written by rank - 1 (its last keys / values);
+                                           rows [halo, halo + n): this rank's K / V  -> consumed in place by the kernels
+         g_halo [2][B, halo, Hkv, D]       dK / dV of this rank's last `halo` keys, written by rank + 1 in backward"""
+
+    def __init__(self, group, B, n, Hkv, D, halo, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        P, rank = _group_size_rank(group)
+        self.P, self.rank, self.halo, self.key = P, rank, halo, (B, n, Hkv, D, halo, dtype)
+        ext, gh = B * (halo + n) * Hkv * D, B * halo * Hkv * D
+        sizes = [ext, ext, gh, gh]
+        offs, total = [], 0
+        for sz in sizes:
+            offs.append(total)
+            total += (sz + 127) // 128 * 128
+        self.buf = symm_mem.empty(total, dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        shapes = [(B, halo + n, Hkv, D)] * 2 + [(B, halo, Hkv, D)] * 2
+
+        def views(r):
+            if r == rank:
+                base = self.buf
+                return [base[o:o + sz].view(sh) for o, sz, sh in zip(offs, sizes, shapes)]
+            return [self.hdl.get_buffer(r, sh, dtype, storage_offset=o) for o, sh in zip(offs, shapes)]
+        self.k_ext, self.v_ext, self.gk_halo, self.gv_halo = views(rank)
+        self.next = views(rank + 1) if rank + 1 < P else None      # peer mappings: stores go over NVLink
+        self.prev = views(rank - 1) if rank > 0 else None
+        self.pending = False
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
+class _HaloP2PAttention(torch.autograd.Function):
+    """[copy K/V into the extended buffer + halo rows into the next rank's buffer, barrier, attention kernels] and the
+    mirror image in backward: plain kernels on one stream (CUDA-graph capturable), no NCCL call."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, s_aux, bufs, window_size):
+        from . import _lib
+        B, n, Hq, D = q.shape
+        halo, rank = bufs.halo, bufs.rank
+        bufs.k_ext[:, halo:].copy_(k)
+        bufs.v_ext[:, halo:].copy_(v)
+        if bufs.next is not None:
+            bufs.next[0][:, :halo].copy_(k[:, n - halo:])           # peer stores
+            bufs.next[1][:, :halo].copy_(v[:, n - halo:])
+        bufs.barrier()
+        s32 = _lib._s_aux_f32(s_aux, Hq)
+        qh = q.transpose(1, 2)
+        if rank == 0:
+            kh, vh = bufs.k_ext[:, halo:].transpose(1, 2), bufs.v_ext[:, halo:].transpose(1, 2)
+            ext = None
+        else:
+            kh, vh = bufs.k_ext.transpose(1, 2), bufs.v_ext.transpose(1, 2)
+            ext = _lib.make_ext(n, halo + n, halo)
+        o, lse = _lib.fwd(qh, kh, vh, 0, window_size, s32, ext=ext)
+        bufs.pending = any(ctx.needs_input_grad[:4])
+        ctx.save_for_backward(qh, kh, vh, o, lse, s32 if s32 is not None else torch.empty(0, device=q.device))
+        ctx.bufs, ctx.cfg = bufs, (window_size, n, s_aux is not None, s_aux.dtype if s_aux is not None else None)
+        return o.transpose(1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import _lib
+        qh, kh, vh, o, lse, s32 = ctx.saved_tensors
+        bufs = ctx.bufs
+        window_size, n, has_aux, s_dtype = ctx.cfg
+        halo, rank = bufs.halo, bufs.rank
+        ext = None if rank == 0 else _lib.make_ext(n, halo + n, halo)
+        dq, dk, dv, ds = _lib.bwd(qh, kh, vh, o, dout.transpose(1, 2), lse, 0, window_size, s32 if has_aux else None, ext=ext)
+        dk, dv = dk.transpose(1, 2), dv.transpose(1, 2)              # [B, (halo +) n, Hkv, D]
+        if bufs.prev is not None:                                   # the halo keys belong to rank - 1
+            bufs.prev[2].copy_(dk[:, :halo])
+            bufs.prev[3].copy_(dv[:, :halo])
+        bufs.barrier()
+        if rank > 0:
+            dk, dv = dk[:, halo:], dv[:, halo:]
+        if bufs.next is not None:
+            dk[:, n - halo:] += bufs.gk_halo
+            dv[:, n - halo:] += bufs.gv_halo
+        bufs.pending = False
+        return dq.transpose(1, 2), dk, dv, (ds.to(s_dtype) if has_aux else None), None, None
+
+
+class HaloSinkAttention(torch.nn.Module):
+    """Sequence-chunk parallel sink attention for narrow sliding windows without sink tokens.
+
+    Inputs are this rank's sequence chunk in HF layout: ``q [B, n, H_q, D]``, ``k, v [B, n, H_kv, D]`` (rank r holds
+    positions ``[r n, (r + 1) n)``; ``window_size - 1 <= n``); ``s_aux`` holds all ``H_q`` logits.  Returns
+    ``O [B, n, H_q, D]``.  ``s_aux.grad`` is this rank's partial sum over its positions: sum it over the group (as
+    the trainer does for every replicated parameter), or pass ``reduce_s_aux_grad=True``.
+
+    ``p2p=True`` runs the exchange as stores into the neighbours' symmetric-memory buffers (one node, CUDA); the
+    default uses ``torch.distributed`` point-to-point ops and works with any backend.
+    """
+
+    MAX_PENDING_FORWARDS = 8
+
+    def __init__(self, window_size: int = 128, sp_group=None, p2p: bool = False, reduce_s_aux_grad: bool = False):
+        super().__init__()
+        self.window_size = int(window_size)
+        self.sp_group = sp_group
+        self.p2p = bool(p2p)
+        self.reduce_s_aux_grad = bool(reduce_s_aux_grad)
+        self._bufs = []
+
+    def forward(self, q, k, v, s_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from .sink_flash_attention import sink_flash_attention, sink_flash_attention_chunk
+        P, rank = _group_size_rank(self.sp_group)
+        B, n, H_q, D = q.shape
+        H_kv = k.shape[2]
+        W = self.window_size
+        if s_aux is not None and self.reduce_s_aux_grad and P > 1:
+            s_aux = _AllReduceGrad.apply(s_aux, self.sp_group)
+        if P == 1:
+            return sink_flash_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), 0, W, s_aux).transpose(1, 2)
+        assert W - 1 <= n, f"halo exchange needs window_size - 1 ({W - 1}) <= chunk length ({n}); use UlyssesSinkAttention"
+        halo = _halo_rows(W, n)
+        if self.p2p:
+            key = (B, n, H_kv, D, halo, q.dtype)
+            self._bufs = [b for b in self._bufs if b.key == key]
+            bufs = next((b for b in self._bufs if not b.pending), None)
+            if bufs is None:
+                if len(self._bufs) >= self.MAX_PENDING_FORWARDS:
+                    raise RuntimeError("HaloSinkAttention(p2p=True): too many forwards waiting for their backward")
+                bufs = _HaloBuffers(self.sp_group, B, n, H_kv, D, halo, q.dtype, q.device)
+                self._bufs.append(bufs)
+            return _HaloP2PAttention.apply(q, k, v, s_aux, bufs, W)
+        tail = torch.cat([k[:, n - halo:], v[:, n - halo:]], dim=2)          # [B, halo, 2 H_kv, D]
+        recv = _HaloFromPrev.apply(tail, self.sp_group)
+        if rank == 0:
+            o = sink_flash_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), 0, W, s_aux).transpose(1, 2)
+            return o + (recv.sum() * 0).to(o.dtype)     # keeps the exchange in the graph: its backward must run on every rank
+        k_ext = torch.cat([recv[:, :, :H_kv], k], dim=1)
+        v_ext = torch.cat([recv[:, :, H_kv:], v], dim=1)
+        return sink_flash_attention_chunk(q.transpose(1, 2), k_ext.transpose(1, 2), v_ext.transpose(1, 2), 0, W,
+                                          s_aux).transpose(1, 2)
+
+
+class _AllReduceGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
 
 
 # =============================================================================================

@@ -100,7 +100,39 @@ def verify(dev, n_local=2048, rounds=4, Hq=64, Hkv=8, D=64, S=0, W=128, skew=Tru
         for a, b in zip((o.detach(), l[0].grad, l[1].grad, l[2].grad), ref[:4]):
             ffbb = max(ffbb, (a.float() - b.float()).abs().max().item())
     ok_ffbb = ffbb == 0.0
-    res = {"ok": bool(ok_nccl and ok_rerun and ok_un and ok_ffbb), "rounds": rounds, "n_local": n_local, "world": world,
+    # ---- 4. halo-exchange mode (narrow window, no sink tokens): peer-memory path vs the portable point-to-point path
+    # (same kernels on the same data: bit-identical) and vs the un-sharded operator on the gathered sequence
+    halo_res = None
+    if S == 0 and W - 1 <= n_local:
+        hp = sa.HaloSinkAttention(W, None, p2p=True)
+        hn = sa.HaloSinkAttention(W, None, p2p=False)
+        hw = {n: 0.0 for n in names}
+        for rnd in range(max(2, rounds // 2)):
+            q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+            if skew and (rnd % world) == rank:
+                torch.cuda._sleep(int(2e6))
+            a = run(hp, q, k, v, do)
+            b = run(hn, q, k, v, do)
+            torch.cuda.synchronize()
+            for n, x, y in zip(names, a, b):
+                hw[n] = max(hw[n], (x.float() - y.float()).abs().max().item())
+        qf, kf, vf, dof = gather(q), gather(k), gather(v), gather(do)
+        qq, kk, vv = (t.transpose(1, 2).detach().requires_grad_(True) for t in (qf, kf, vf))
+        ss = s_aux.clone().requires_grad_(True)
+        o_u = sa.sink_flash_attention(qq, kk, vv, 0, W, ss)
+        o_u.backward(dof.transpose(1, 2))
+        hu = {"o": (a[0].float() - o_u.transpose(1, 2)[:, sl].float()).abs().max().item()}
+        for n, x, y in (("dq", a[1], qq.grad.transpose(1, 2)[:, sl]), ("dk", a[2], kk.grad.transpose(1, 2)[:, sl]),
+                        ("dv", a[3], vv.grad.transpose(1, 2)[:, sl])):
+            hu[n] = ((x.float() - y.float()).abs() / (2e-2 + 1e-2 * y.float().abs())).max().item()
+        ds_sum = a[4].clone()
+        dist.all_reduce(ds_sum)
+        hu["ds_aux_rel"] = ((ds_sum - ss.grad).abs().max() / ss.grad.abs().max().clamp_min(1e-6)).item()
+        ok_halo = all(hw[n] == 0.0 for n in names) and hu["o"] < 2e-2 and max(hu["dq"], hu["dk"], hu["dv"]) <= 1.0 and \
+            hu["ds_aux_rel"] < 1e-3
+        halo_res = {"ok": bool(ok_halo), "max_abs_p2p_vs_portable": hw, "vs_unsharded": hu}
+    ok_halo_all = halo_res is None or halo_res["ok"]
+    res = {"ok": bool(ok_nccl and ok_rerun and ok_un and ok_ffbb and ok_halo_all), "halo": halo_res, "rounds": rounds, "n_local": n_local, "world": world,
            "routed": routed, "max_abs_p2p_vs_nccl": worst, "max_abs_rerun": rerun, "vs_unsharded_group0": un,
            "fwd_fwd_bwd_bwd_max_abs": ffbb, "buffer_sets": len(p2p._bufs)}
     flag = torch.tensor([1.0 if res["ok"] else 0.0], device=dev)
