@@ -123,7 +123,7 @@ size_t sfa_workspace_bytes(int op, int B, int Hq, int Hkv, int N, int D, int dty
            align_up(tc_bwd_fused_workspace_bytes(), 256);
   }
   if (op == SFA_OP_DECODE) {
-    const int splits = mma_decode_splits(B, Hkv, N);
+    const int splits = mma_decode_splits(B, Hq, Hkv, N);
     return align_up((size_t)B * Hq * splits * 2 * 4, 256) + align_up((size_t)B * Hq * splits * D * 4, 256);
   }
   return 0;
@@ -380,8 +380,8 @@ static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t works
       p.sv[s] = p.sv[1 - s];
     }
   if (g_force_impl != SFA_IMPL_SIMT && mma_decode_supported(p, dtype)) {
-    p.splits = mma_decode_splits(p.B, p.Hkv, L);
-    if (p.splits > 1) {
+    p.splits = mma_decode_splits(p.B, p.Hq, p.Hkv, L);
+    {
       const size_t ml = align_up((size_t)p.B * p.Hq * p.splits * 2 * 4, 256);
       const size_t po = align_up((size_t)p.B * p.Hq * p.splits * p.D * 4, 256);
       if (!workspace || workspace_bytes < ml + po) {

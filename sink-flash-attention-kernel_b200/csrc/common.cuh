@@ -137,7 +137,7 @@ cudaError_t cache_append(const void* k_new, const void* v_new, void* win_k, void
                          cudaStream_t st);
 
 bool mma_decode_supported(const DecodeParams& p, int dtype);
-int mma_decode_splits(int B, int Hkv, int total_len);
+int mma_decode_splits(int B, int Hq, int Hkv, int total_len);   // workspace slots per q head
 cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st);
 
 void set_trace_buffer(long long* p);   // performance-debug timeline (device buffer, 3*256*2 int64) or nullptr

@@ -1,7 +1,6 @@
 // Split-KV decode over the sink+window cache (reference: decode_kernel.py:28-226).
 //
-// Bandwidth-bound design for B200: one CTA per (split, kv-head, batch) serves ALL q heads of the
-// GQA group from a single pass over K/V (the reference grids over q heads and re-reads each kv
+// Bandwidth-bound design for B200: a CTA serves ALL q heads of the GQA group from a single pass over its K/V range (the reference grids over q heads and re-reads each kv
 // head H_q/H_kv times, decode_kernel.py:57-62,175).  Each of the 4 warps owns a private
 // cp.async ring of 16-key blocks (16-byte coalesced requests, kStages blocks in flight per warp,
 // no CTA-wide barrier in the loop); scores and PV run on mma.sync m16n8k16 with the q heads
@@ -60,11 +59,11 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int D> struct DecodeCfg {
-  // keys per pipeline block: at D = 64 a 16-key block is only 4 KB of K+V and the per-block fixed work (softmax
-  // update, shuffles, loop, cp.async wait) dominated (66 % of HBM peak vs 81 % at D = 128), so D = 64 uses 32 keys
-  static constexpr int kKB = (D <= 64) ? 32 : 16;
-  static constexpr int kStages = 3 - (D > 128 ? 1 : 0);     // x 4 warps x 2 x kBlkBytes: 96 KB -> 2 CTAs per SM
+// V: pipeline variant (0 = default).  keys per pipeline block / ring depth are a trade between per-block fixed work
+// (softmax update, shuffles, loop, cp.async wait), bytes in flight, and CTAs per SM (shared memory bound).
+template <int D, int V = 0> struct DecodeCfg {
+  static constexpr int kKB = (V == 2 || V == 3) ? 16 : (V == 4 ? 64 : ((D <= 64) ? 32 : 16));
+  static constexpr int kStages = (V == 1) ? 2 : (V == 3 ? 4 : (V == 4 ? 2 : 3 - (D > 128 ? 1 : 0)));
   static constexpr int kRowBytes = D * 2;
   static constexpr int kBlkBytes = kKB * kRowBytes;           // one block of K (or V)
   static constexpr int kWarpBytes = kStages * 2 * kBlkBytes;  // K+V ring of one warp
@@ -83,23 +82,41 @@ __device__ __forceinline__ float ex2_fast(float x) {
 // byte offset of 16-B chunk `c` of row `r` in a [16][D] 16-bit tile, XOR-swizzled for ldmatrix
 template <int D> __device__ __forceinline__ int tile_off(int r, int c) { return r * (D * 2) + ((c ^ (r & 7)) << 4); }
 
-template <typename T, int D>
+// Work decomposition: the B * Hkv * g_tiles units (one KV head of one batch row, 16 q heads) x L keys are laid end to
+// end and cut into gridDim.x EQUAL key ranges, one per CTA, all resident at once (2 CTAs per SM).  The round-1 grid of
+// one CTA per unit ran BASELINE configs[3] (512 units) as 1.73 waves of 296 CTAs -- 13.5 % of the machine idle in the
+// second wave.  A CTA's range covers the tail of one unit, possibly whole units, and the head of another: every
+// (unit, key range) segment is one pass of the pipeline below; a unit cut into pieces leaves (m, l, o) partials that
+// the combine kernel merges, a unit inside one range is finished here.
+template <typename T, int D, int V>
 __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chunk_keys, int g_tiles) {
-  using C = DecodeCfg<D>;
+  using C = DecodeCfg<D, V>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x;
-  const int kvh = blockIdx.y / g_tiles, gt = blockIdx.y % g_tiles;
-  const int b = blockIdx.z;
   const int G = p.Hq / p.Hkv;
-  const int h0 = kvh * G + gt * 16;                 // first q head served by this CTA
-  const int nh = min(16, G - gt * 16);              // real heads among the 16 MMA rows
   const int L = p.len[0] + p.len[1];
-  const int k_begin = split * chunk_keys;
-  const int k_end = min(L, k_begin + chunk_keys);
-
+  const int64_t f_total = static_cast<int64_t>(p.B) * p.Hkv * g_tiles * L;
+  int64_t f = static_cast<int64_t>(blockIdx.x) * chunk_keys;
+  const int64_t f_end = min(f + chunk_keys, f_total);
   unsigned char* q_s = smem + 4 * C::kWarpBytes;
   unsigned char* ring = smem + warp * C::kWarpBytes;
+  const float sl2 = p.scale * kLog2e;
+  constexpr int KB = C::kKB;
+
+  while (f < f_end) {
+  const int unit = static_cast<int>(f / L);
+  const int k_begin = static_cast<int>(f - static_cast<int64_t>(unit) * L);
+  const int64_t k_lim = static_cast<int64_t>(k_begin) + (f_end - f);
+  const int k_end = k_lim < L ? static_cast<int>(k_lim) : L;
+  f += k_end - k_begin;
+  const int gt = unit % g_tiles;
+  const int kvh = (unit / g_tiles) % p.Hkv, b = unit / (g_tiles * p.Hkv);
+  const int h0 = kvh * G + gt * 16;                 // first q head served by this segment
+  const int nh = min(16, G - gt * 16);              // real heads among the 16 MMA rows
+  // pieces of this unit: CTAs first_cta .. last_cta touch it
+  const int first_cta = static_cast<int>((static_cast<int64_t>(unit) * L) / chunk_keys);
+  const int last_cta = static_cast<int>((static_cast<int64_t>(unit + 1) * L - 1) / chunk_keys);
+  const int piece = static_cast<int>(blockIdx.x) - first_cta;
 
   // ---- Q tile [16][D] -> smem (rows >= nh are zero), then A fragments in registers
   for (int c = threadIdx.x; c < 16 * (D / 8); c += 128) {
@@ -125,15 +142,38 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
   }
   const int len0 = p.len[0];
 
-  // blocks of kKB keys; warp w owns blocks w, w+4, ... of this split
-  constexpr int KB = C::kKB;
+  // blocks of kKB keys; warp w owns blocks w, w+4, ... of this segment
   const int nblk_total = (k_end - k_begin + KB - 1) / KB;
   const int nblk = (nblk_total > warp) ? (nblk_total - warp + 3) / 4 : 0;
 
+  // per-lane constants of the block copy: lane owns 16-byte chunk `lch` of rows lr0, lr0 + 32 / (D / 8), ...
+  constexpr int kCPR = D / 8;                 // 16-byte chunks per row
+  constexpr int kRowsPerIt = 32 / kCPR;       // rows covered by one warp-wide cp.async (D <= 256)
+  const int lch = lane % kCPR, lr0 = lane / kCPR;
   auto load_block = [&](int it) {
     const int key0 = k_begin + (warp + 4 * it) * KB;
     unsigned char* ks_ = ring + (it % C::kStages) * 2 * C::kBlkBytes;
     unsigned char* vs_ = ks_ + C::kBlkBytes;
+    const bool in0 = key0 + KB <= len0, in1 = key0 >= len0;
+    if (key0 + KB <= k_end && (in0 || in1)) {
+      // fast path (all but the edge blocks): the block lies inside one segment and inside the range -- one pointer
+      // per lane, advanced by a constant stride; no per-chunk bounds / segment arithmetic (the instruction count of
+      // the copy loop, not HBM, limited the head_dim-64 kernel: 77 % of the copy bandwidth vs 82 % at head_dim 128)
+      const int seg = in0 ? 0 : 1;
+      const int64_t pos0 = (seg ? key0 - len0 : key0) + lr0;
+      const T* ksrc = kb[seg] + pos0 * p.sk[seg].n + lch * 8;
+      const T* vsrc = vb[seg] + pos0 * p.sv[seg].n + lch * 8;
+      const int64_t kstep = kRowsPerIt * p.sk[seg].n, vstep = kRowsPerIt * p.sv[seg].n;
+#pragma unroll
+      for (int j = 0; j < KB / kRowsPerIt; ++j) {
+        const int r = lr0 + j * kRowsPerIt;
+        cp_async16(ks_ + tile_off<D>(r, lch), ksrc, true);
+        cp_async16(vs_ + tile_off<D>(r, lch), vsrc, true);
+        ksrc += kstep;
+        vsrc += vstep;
+      }
+      return;
+    }
 #pragma unroll
     for (int c = lane; c < KB * (D / 8); c += 32) {
       const int r = c / (D / 8), ch = c % (D / 8);
@@ -153,7 +193,6 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
   float o[D / 8][4];
 #pragma unroll
   for (int n = 0; n < D / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-  const float sl2 = p.scale * kLog2e;
 
 #pragma unroll
   for (int s = 0; s < C::kStages - 1; ++s) {
@@ -277,7 +316,7 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
     }
   }
   __syncthreads();
-  const bool final_out = (p.splits == 1);
+  const bool final_out = (first_cta == last_cta);      // the whole unit sits inside this CTA's range
   for (int idx = threadIdx.x; idx < nh * D; idx += 128) {
     const int r = idx / D, d = idx % D;
     const int h = h0 + r;
@@ -298,7 +337,7 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
     if (final_out) {
       static_cast<T*>(p.o)[b * p.so_b + h * p.so_h + d] = from_f<T>(og / fmaxf(lg, 1e-8f));
     } else {
-      const int64_t pr = ((int64_t)b * p.Hq + h) * p.splits + split;
+      const int64_t pr = ((int64_t)b * p.Hq + h) * p.splits + piece;
       p.part_o[pr * D + d] = og;
       if (d == 0) {
         p.part_ml[pr * 2 + 0] = mg;
@@ -306,25 +345,35 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
       }
     }
   }
+  __syncthreads();      // the merge buffers alias the rings and the Q tile of the next segment
+  }
 }
 
 // Phase 2 (decode_kernel.py:201-226): merge the split partials with the s_aux virtual split.
 template <typename T>
-__global__ void decode_combine_kernel(DecodeParams p) {
+__global__ void decode_combine_kernel(DecodeParams p, int chunk_keys, int g_tiles) {
   const int h = blockIdx.x, b = blockIdx.y;
+  const int G = p.Hq / p.Hkv;
+  const int L = p.len[0] + p.len[1];
+  const int kvh = h / G, gt = (h % G) / 16;
+  const int64_t unit = (static_cast<int64_t>(b) * p.Hkv + kvh) * g_tiles + gt;
+  const int first_cta = static_cast<int>((unit * L) / chunk_keys);
+  const int last_cta = static_cast<int>(((unit + 1) * L - 1) / chunk_keys);
+  const int np = last_cta - first_cta + 1;
+  if (np == 1) return;                       // finished by the decode kernel itself
   const int64_t base = ((int64_t)b * p.Hq + h) * p.splits;
   const float sa = p.s_aux ? p.s_aux[h] * kLog2e : -INFINITY;
   float mg = sa;
-  for (int s = 0; s < p.splits; ++s) mg = fmaxf(mg, p.part_ml[(base + s) * 2]);
+  for (int s = 0; s < np; ++s) mg = fmaxf(mg, p.part_ml[(base + s) * 2]);
   float lg = (sa == -INFINITY) ? 0.f : exp2f(sa - mg);
-  for (int s = 0; s < p.splits; ++s) {
+  for (int s = 0; s < np; ++s) {
     const float ms = p.part_ml[(base + s) * 2];
     lg += (ms == -INFINITY) ? 0.f : p.part_ml[(base + s) * 2 + 1] * exp2f(ms - mg);
   }
   lg = fmaxf(lg, 1e-8f);
   for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
     float og = 0.f;
-    for (int s = 0; s < p.splits; ++s) {
+    for (int s = 0; s < np; ++s) {
       const float ms = p.part_ml[(base + s) * 2];
       if (ms != -INFINITY) og += p.part_o[(base + s) * p.D + d] * exp2f(ms - mg);
     }
@@ -332,21 +381,54 @@ __global__ void decode_combine_kernel(DecodeParams p) {
   }
 }
 
-template <typename T, int D>
+// Key range per CTA and the worst-case number of pieces a unit is cut into (= workspace slots per head).
+// One CTA per 2-CTA-per-SM slot when there is enough work, never less than kMinChunk keys per CTA.
+struct DecodePlan {
+  int chunk, ncta, max_pieces;
+};
+DecodePlan make_decode_plan(int B, int Hq, int Hkv, int L) {
+  constexpr int kMinChunk = 256;
+  const int g_tiles = (Hq / Hkv + 15) / 16;
+  const int64_t total = static_cast<int64_t>(B) * Hkv * g_tiles * L;
+  static const int forced = getenv("SFA_DECODE_CTAS") ? atoi(getenv("SFA_DECODE_CTAS")) : 0;   // experiments only
+  const int64_t units = static_cast<int64_t>(B) * Hkv * g_tiles;
+  const int64_t slots = static_cast<int64_t>(device_sm_count()) * 2;
+  int64_t chunk;
+  if (forced > 0) {
+    chunk = (total + forced - 1) / forced;
+  } else if (units >= slots && (units % slots == 0 || units % slots >= slots / 2 || units >= 4 * slots)) {
+    // enough whole units to keep every slot busy: one unit per CTA, no cut, no partials, no combine launch.  The
+    // kernel is bandwidth-bound, so the partly filled last wave costs little (its CTAs get the whole memory system):
+    // measured at BASELINE configs[3] (512 units on 296 slots) 106.5 us this way vs 112.6 us with 296 equal ranges.
+    chunk = L;
+  } else {
+    chunk = (total + slots - 1) / slots;          // few units (small batch) or a thin last wave: equal key ranges
+  }
+  DecodePlan pl;
+  pl.chunk = static_cast<int>(chunk);
+  pl.ncta = static_cast<int>((total + chunk - 1) / chunk);
+  pl.max_pieces = static_cast<int>((L + chunk - 1) / chunk) + 1;
+  return pl;
+}
+
+template <typename T, int D, int V = 0>
 cudaError_t launch(const DecodeParams& p, cudaStream_t st) {
-  using C = DecodeCfg<D>;
+  using C = DecodeCfg<D, V>;
   static std::atomic<unsigned long long> attr_done{0};
-  if (cudaError_t e = ensure_dyn_smem(decode_mma_kernel<T, D>, C::kSmem, attr_done)) return e;
+  if (cudaError_t e = ensure_dyn_smem(decode_mma_kernel<T, D, V>, C::kSmem, attr_done)) return e;
   const int G = p.Hq / p.Hkv;
   const int g_tiles = (G + 15) / 16;
   const int L = p.len[0] + p.len[1];
-  int chunk = (L + p.splits - 1) / p.splits;
-  chunk = ((chunk + 63) / 64) * 64;
-  dim3 grid(p.splits, p.Hkv * g_tiles, p.B);
-  decode_mma_kernel<T, D><<<grid, 128, C::kSmem, st>>>(p, chunk, g_tiles);
+  const DecodePlan pl = make_decode_plan(p.B, p.Hq, p.Hkv, L);
+  if (pl.max_pieces > p.splits) return cudaErrorInvalidValue;      // workspace carved for fewer pieces
+  decode_mma_kernel<T, D, V><<<pl.ncta, 128, C::kSmem, st>>>(p, pl.chunk, g_tiles);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess || p.splits == 1) return e;
-  decode_combine_kernel<T><<<dim3(p.Hq, p.B), (D < 128 ? 64 : 128), 0, st>>>(p);
+  if (e != cudaSuccess) return e;
+  // units cut by a range boundary are merged here (every unit when the ranges are shorter than a unit; none when
+  // the ranges happen to end on unit boundaries)
+  const bool any_cut = !(pl.chunk % L == 0);
+  if (!any_cut) return e;
+  decode_combine_kernel<T><<<dim3(p.Hq, p.B), (D < 128 ? 64 : 128), 0, st>>>(p, pl.chunk, g_tiles);
   return cudaGetLastError();
 }
 
@@ -368,38 +450,23 @@ bool mma_decode_supported(const DecodeParams& p, int dtype) {
   return true;
 }
 
-// Split count.  The kernel runs 2 CTAs per SM; B*Hkv*splits CTAs execute in ceil(ctas / 296) rounds and a partly
-// filled last round wastes bandwidth, but every extra split costs a pipeline fill plus partial (m, l, o) traffic
-// and any split > 1 costs the combine launch.  Measured at BASELINE configs[3] (B*Hkv = 512, 4100 keys, D = 64):
-// splits 1 / 2 / 3 / 4 / 6 / 8 -> 112.6 / 118.8 / 120.8 / 118.8 / 127.0 / 133.1 us.  The cost model below
-// (round efficiency x 4 % per extra split + 6 % for the second kernel) reproduces that ordering and still
-// splits small batches enough to fill the machine.
-int mma_decode_splits(int B, int Hkv, int total_len) {
-  static const int forced = getenv("SFA_DECODE_SPLITS") ? atoi(getenv("SFA_DECODE_SPLITS")) : 0;   // experiments only
-  if (forced > 0) return forced;
-  const long long base = (long long)B * Hkv;
-  int max_s = (total_len + 255) / 256;
-  if (max_s > 64) max_s = 64;
-  if (max_s < 1) max_s = 1;
-  const double slots = 148.0 * 2.0;
-  int best = 1;
-  double best_cost = 1e30;
-  for (int s = 1; s <= max_s; ++s) {
-    const double rounds = (double)(base * s) / slots;
-    const double eff = rounds / (double)(long long)(rounds + 0.999999);     // filled fraction of the rounds
-    const double cost = (1.0 / eff) * (1.0 + 0.04 * (s - 1)) + (s > 1 ? 0.06 : 0.0);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = s;
-    }
-  }
-  return best;
+// Workspace slots per head (= the most pieces any unit can be cut into) for the balanced decomposition above.
+// History: with one CTA per (unit, split) BASELINE configs[3] measured 112.6 / 118.8 / 120.8 / 118.8 / 127.0 / 133.1 us
+// for 1 / 2 / 3 / 4 / 6 / 8 uniform splits -- every uniform choice leaves a partly filled last wave.
+int mma_decode_splits(int B, int Hq, int Hkv, int total_len) {
+  return make_decode_plan(B, Hq, Hkv, total_len).max_pieces;
 }
 
 cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st) {
+  static const int variant = getenv("SFA_DECODE_VARIANT") ? atoi(getenv("SFA_DECODE_VARIANT")) : 0;   // experiments only
 #define SFA_DEC(T)                                     \
   switch (p.D) {                                       \
-    case 64: return launch<T, 64>(p, st);              \
+    case 64:                                           \
+      if (variant == 1) return launch<T, 64, 1>(p, st); \
+      if (variant == 2) return launch<T, 64, 2>(p, st); \
+      if (variant == 3) return launch<T, 64, 3>(p, st); \
+      if (variant == 4) return launch<T, 64, 4>(p, st); \
+      return launch<T, 64>(p, st);                     \
     case 128: return launch<T, 128>(p, st);            \
     case 256: return launch<T, 256>(p, st);            \
   }
