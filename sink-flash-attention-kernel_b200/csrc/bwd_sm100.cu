@@ -897,6 +897,7 @@ struct DkvArgs {
   void* dk;
   void* dv;
   Strides4 sdk, sdv;
+  int Dl;        // logical head_dim (<= the kernel's D): channels Dl .. D-1 are TMA zero fill and are not stored
 };
 
 // position blocks [pb_lo, pb_hi] (P positions each) whose queries can attend a key in [j0, j0+BK)
@@ -1135,10 +1136,14 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
         pv[e >> 1] = pack16<T>(__uint_as_float(vv_[e]), __uint_as_float(vv_[e + 1]));
       }
       if (j < a.N) {
-        *reinterpret_cast<uint4*>(dkr + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dkr + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        *reinterpret_cast<uint4*>(dvr + c0) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
-        *reinterpret_cast<uint4*>(dvr + c0 + 8) = make_uint4(pv[4], pv[5], pv[6], pv[7]);
+        if (c0 < a.Dl) {                 // head dims between 64 and 128 (80, 96, ...) run with zero-padded channels
+          *reinterpret_cast<uint4*>(dkr + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(dvr + c0) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+        }
+        if (c0 + 8 < a.Dl) {
+          *reinterpret_cast<uint4*>(dkr + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(dvr + c0 + 8) = make_uint4(pv[4], pv[5], pv[6], pv[7]);
+        }
       }
     }
   }
@@ -1581,8 +1586,8 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
   pick_packing(p.Hq, p.Hkv, G, P);
   const int fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
   TileMap mq, mdo;
-  if (!make_tile_map(&mq, p.q, dtype, D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mdo, p.dout, dtype, D, p.N, p.Hq, p.B, p.sdo, P, G)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mq, p.q, dtype, p.D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mdo, p.dout, dtype, p.D, p.N, p.Hq, p.B, p.sdo, P, G)) return cudaErrorInvalidValue;
   if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;   // guarded by tc_bwd_supported
 
   if (stages & 2) {
@@ -1597,9 +1602,9 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     }
     const int BN = pick_bn(p.W, p.N, P, kBNMax);
     TileMap mk, mv, mdq;
-    if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
-    if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
-    if (!make_tile_map(&mdq, p.dq, dtype, D, p.N, p.Hq, p.B, p.sdq, P, G)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mk, p.k, dtype, p.D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mv, p.v, dtype, p.D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mdq, p.dq, dtype, p.D, p.N, p.Hq, p.B, p.sdq, P, G)) return cudaErrorInvalidValue;
     BwdArgs a;
     a.B = p.B; a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.G = G; a.P = P; a.BN = BN;
     a.groups_per_kv = group / G;
@@ -1637,8 +1642,8 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
       if (e != cudaSuccess) return e;
     }
     TileMap mk, mv;
-    if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, kBK, 1)) return cudaErrorInvalidValue;
-    if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, kBK, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mk, p.k, dtype, p.D, p.N, p.Hkv, p.B, p.sk, kBK, 1)) return cudaErrorInvalidValue;
+    if (!make_tile_map(&mv, p.v, dtype, p.D, p.N, p.Hkv, p.B, p.sv, kBK, 1)) return cudaErrorInvalidValue;
     DkvArgs a;
     a.B = p.B; a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.Hkv = p.Hkv; a.G = G; a.P = P;
     a.groups_per_kv = group / G;
@@ -1649,6 +1654,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.lse = p.lse;
     a.delta = p.delta;
     a.dk = p.dk; a.dv = p.dv; a.sdk = p.sdk; a.sdv = p.sdv;
+    a.Dl = p.D;
     a.trace = trace_buffer();
     dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
     if constexpr (D == 64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
@@ -1672,7 +1678,9 @@ bool tc_bwd_fuses_delta(const AttnParams& p, int dtype) {
 bool tc_bwd_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
   if (p.has_ext()) return false;               // packed sequences / chunked prefill: fused kernel or CUDA-core path
-  if (p.D != 64 && p.D != 128) return false;
+  // head dims 72 .. 120 (multiples of 8: 80, 96, 112, ...) run on the head_dim-128 kernels: the TMA boxes cover 128
+  // channels, the tensor only has D, so the tail is hardware zero fill on loads and clipped on stores
+  if (p.D != 64 && !(p.D > 64 && p.D <= 128 && p.D % 8 == 0)) return false;
   if (p.N < 1) return false;
   if (p.S <= 0 && p.W <= 0) return false;     // nothing attended: the CUDA-core path writes the zeros
   if (!(tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.N) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.N) &&
@@ -1690,7 +1698,7 @@ bool tc_bwd_supported(const AttnParams& p, int dtype) {
 cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
   if (dtype == SFA_DTYPE_BF16)
     return p.D == 64 ? launch_bwd<__nv_bfloat16, 64>(p, dtype, stages, st) : launch_bwd<__nv_bfloat16, 128>(p, dtype, stages, st);
-  return p.D == 64 ? launch_bwd<__half, 64>(p, dtype, stages, st) : launch_bwd<__half, 128>(p, dtype, stages, st);
+  return p.D == 64 ? launch_bwd<__half, 64>(p, dtype, stages, st) : launch_bwd<__half, 128>(p, dtype, stages, st);   // 64 < D <= 128 -> <128>
 }
 
 }  // namespace sfa

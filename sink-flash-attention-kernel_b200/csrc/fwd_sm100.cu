@@ -296,10 +296,10 @@ cudaError_t launch_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
   const int BN = pick_bn(p.W, p.N, P, C::kBNMax);
 
   TileMap mq, mk, mv, mo;
-  if (!make_tile_map(&mq, p.q, dtype, D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mk, p.k, dtype, D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mv, p.v, dtype, D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mo, p.o, dtype, D, p.N, p.Hq, p.B, p.so, P, G)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mq, p.q, dtype, p.D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mk, p.k, dtype, p.D, p.N, p.Hkv, p.B, p.sk, BN, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mv, p.v, dtype, p.D, p.N, p.Hkv, p.B, p.sv, BN, 1)) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mo, p.o, dtype, p.D, p.N, p.Hq, p.B, p.so, P, G)) return cudaErrorInvalidValue;
 
   FwdArgs a;
   a.N = p.N; a.S = p.S; a.W = p.W; a.Hq = p.Hq; a.G = G; a.P = P; a.BN = BN;
@@ -318,7 +318,9 @@ cudaError_t launch_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
 
 bool tc_fwd_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
-  if (p.D != 64 && p.D != 128) return false;
+  // 64 < D <= 128 in steps of 8 (80, 96, 112: north star "head_dim 64/80/128") runs on the head_dim-128 kernel with
+  // TMA zero fill for the missing channels (the reference's Triton kernel cannot run these: tl.arange needs 2^k)
+  if (p.D != 64 && !(p.D > 64 && p.D <= 128 && p.D % 8 == 0)) return false;
   if (p.N < 1) return false;
   return tma_compatible(p.q, p.sq, p.B, p.Hq, p.N) && tma_compatible(p.k, p.sk, p.B, p.Hkv, p.Nkv) && tma_compatible(p.v, p.sv, p.B, p.Hkv, p.Nkv) &&
          tma_compatible(p.o, p.so, p.B, p.Hq, p.N);

@@ -92,7 +92,7 @@ def test_prefill_lowp_vs_oracle(case, dtype):
     qd, kd, vd = (to_dev(t).requires_grad_(True) for t in (ql, kl, vl))
     sd = to_dev(s_aux).requires_grad_(True) if s_aux is not None else None
     o = sa.sink_flash_attention(qd, kd, vd, S, W, sd)
-    assert _lib.last_impl() == ("tcgen05" if D in (64, 128) else "simt")
+    assert _lib.last_impl() == ("tcgen05" if D == 64 or (64 < D <= 128 and D % 8 == 0) else "simt")
     o.backward(to_dev(dol))
     _, lse, _ = _fwd(qd.detach(), kd.detach(), vd.detach(), S, W, sd.detach() if sd is not None else None)
     assert maxdiff(o, o_ref) < 2e-2
@@ -117,6 +117,9 @@ def test_prefill_lowp_vs_oracle(case, dtype):
     (1, 4, 2, 1500, 128, 0, 1500, True),     # full causal (window = N), many KV tiles
     (1, 8, 1, 200, 64, 150, 8, True),        # sinks spanning more than one KV tile of a narrow band
     (1, 2, 2, 130, 64, 0, 1, False),         # window 1: self only
+    (1, 8, 2, 300, 80, 4, 64, True),         # head_dim 80 (north star; the reference's Triton kernel cannot run it): on the
+    (2, 4, 4, 257, 96, 0, 257, True),        # head_dim-128 tensor-core kernels, missing channels = TMA zero fill
+    (1, 4, 1, 200, 112, 2, 33, False),
 ])
 def test_fwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     B, Hq, Hkv, N, D, S, W, use_aux = shape
@@ -171,6 +174,9 @@ def _bwd(q, k, v, o, do, lse, S, W, s_aux, impl=None):
     (1, 8, 1, 200, 64, 150, 8, True),        # sinks spanning more than one key tile
     (1, 2, 2, 130, 64, 0, 1, False),         # window 1: self only
     (1, 8, 8, 96, 64, 7, 0, True),           # window 0: sinks (and s_aux) only
+    (1, 8, 2, 300, 80, 4, 64, True),         # head_dim 80 / 96 / 112 on the head_dim-128 tensor-core kernels
+    (2, 4, 4, 257, 96, 0, 257, True),
+    (1, 4, 1, 200, 112, 2, 33, False),
 ])
 def test_bwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     """dQ/dK/dV of the tensor-core backward against the CUDA-core backward (same 16-bit inputs, fp32 math)
