@@ -36,8 +36,53 @@ struct TileMap {
 // Box = 64 channels x box_n positions x box_h heads x 1 batch, SWIZZLE_128B, OOB -> zero.
 // The two middle dims are ordered by increasing stride, so a multi-head box lands in shared
 // memory as rows (h*box_n + n) when swap_nh == 0 and as rows (n*box_h + h) when swap_nh == 1.
+// Encoded maps are cached per thread, keyed on everything the encoding depends on (base pointer, dtype, extents,
+// strides, box): a training loop calls the operator with the same tensors' geometry (and, with the caching allocator,
+// mostly the same addresses) every step, and each launch needs 4 - 12 maps -- the driver call per map was a visible
+// part of the eager step (0.26 ms of host time around 0.18 ms of kernels in round 1).
+struct TileMapKey {
+  const void* ptr;
+  int64_t sb, sh, sn;
+  int dtype, D, N, H, B, box_n, box_h;
+  bool operator==(const TileMapKey& o) const {
+    return ptr == o.ptr && sb == o.sb && sh == o.sh && sn == o.sn && dtype == o.dtype && D == o.D && N == o.N && H == o.H &&
+           B == o.B && box_n == o.box_n && box_h == o.box_h;
+  }
+};
+struct TileMapCache {
+  static constexpr int kSlots = 64;
+  TileMapKey key[kSlots];
+  TileMap val[kSlots];
+  bool used[kSlots] = {};
+  static unsigned slot_of(const TileMapKey& k) {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= static_cast<uint64_t>(k.box_n) * 0xC2B2AE3D27D4EB4Full + static_cast<uint64_t>(k.sn) * 0x165667B19E3779F9ull +
+         static_cast<uint64_t>(k.N) * 31 + static_cast<uint64_t>(k.box_h);
+    return static_cast<unsigned>(h >> 40) % kSlots;
+  }
+};
+
+inline bool make_tile_map_uncached(TileMap* out, const void* ptr, int dtype, int D, int N, int H, int B, const Strides4& s,
+                                   int box_n, int box_h);
+
 inline bool make_tile_map(TileMap* out, const void* ptr, int dtype, int D, int N, int H, int B, const Strides4& s,
                           int box_n, int box_h) {
+  static thread_local TileMapCache cache;
+  const TileMapKey k{ptr, s.b, s.h, s.n, dtype, D, N, H, B, box_n, box_h};
+  const unsigned slot = TileMapCache::slot_of(k);
+  if (cache.used[slot] && cache.key[slot] == k) {
+    *out = cache.val[slot];
+    return true;
+  }
+  if (!make_tile_map_uncached(out, ptr, dtype, D, N, H, B, s, box_n, box_h)) return false;
+  cache.key[slot] = k;
+  cache.val[slot] = *out;
+  cache.used[slot] = true;
+  return true;
+}
+
+inline bool make_tile_map_uncached(TileMap* out, const void* ptr, int dtype, int D, int N, int H, int B, const Strides4& s,
+                                   int box_n, int box_h) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");

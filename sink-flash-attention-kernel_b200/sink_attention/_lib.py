@@ -274,7 +274,8 @@ def decode(q, k, v, s_aux_f32):
     q, k, v = _unit_last(q), _unit_last(k), _unit_last(v)
     o = torch.empty((B, Hq, 1, D), device=q.device, dtype=q.dtype)
     code = DTYPE_CODE[q.dtype]
-    ws_bytes = lib.sfa_workspace_bytes(OP_DECODE, B, Hq, Hkv, Nkv, D, code)
+    with torch.cuda.device(q.device):       # the work decomposition (hence the workspace) depends on the device's SM count
+        ws_bytes = lib.sfa_workspace_bytes(OP_DECODE, B, Hq, Hkv, Nkv, D, code)
     ws = torch.empty((max(ws_bytes, 1),), device=q.device, dtype=torch.uint8)
     with torch.cuda.device(q.device):
         rc = lib.sfa_decode(
@@ -301,7 +302,8 @@ def decode_ring(q, sink_k, sink_v, win_k, win_v, sink_len: int, window_len: int,
         raise ValueError("K and V cache buffers must share strides")
     o = torch.empty((B, Hq, 1, D), device=q.device, dtype=q.dtype)
     code = DTYPE_CODE[q.dtype]
-    ws_bytes = lib.sfa_workspace_bytes(OP_DECODE, B, Hq, Hkv, sink_len + window_len, D, code)
+    with torch.cuda.device(q.device):
+        ws_bytes = lib.sfa_workspace_bytes(OP_DECODE, B, Hq, Hkv, sink_len + window_len, D, code)
     ws = torch.empty((max(ws_bytes, 1),), device=q.device, dtype=torch.uint8)
     with torch.cuda.device(q.device):
         rc = lib.sfa_decode_ring(
