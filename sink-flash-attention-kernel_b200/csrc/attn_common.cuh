@@ -122,6 +122,22 @@ struct ItemWalkT {
     return true;
   }
   __device__ __forceinline__ bool last_of_tile() const { return t == pl.n_tiles - 1; }
+  // Launches in which EVERY tile has exactly one KV item (no sink tokens, the band fits one tile -- the narrow-window
+  // training shape): hop over `hop` tiles and plan only the one landed on.  Lets a role that owns every second tile
+  // (the forward's ping-pong softmax groups) skip the other group's tile without paying for its plan; the item
+  // counter stays in step with the roles that visit every tile (n == it).
+  __device__ __forceinline__ bool next_single(int hop) {
+    tile += step * hop;
+    it += hop;
+    n += hop;
+    if (tile >= end) return false;
+    advance(a, step * hop, pb, y, b);
+    q0 = pb * a.P;
+    pl = make_plan(q0 + a.q_off, a.P, a.N + a.q_off, a.S, a.W, a.BN, a.bn_mul);
+    if (a.seq_lo != nullptr) clamp_plan(pl, a.seq_lo[b * a.seq_bs + q0], a.W, a.BN, a.bn_mul);
+    t = 0;
+    return true;
+  }
 };
 
 // attended columns [c_lo, c_hi] of query position i inside a tile that starts at key `kstart`

@@ -12,8 +12,8 @@
 //                                  consumed S columns
 //   warps 16-19  epilogue          O / l -> 16-bit -> swizzled smem -> TMA store, LSE = m ln2 + log l
 //   warp 20      TMA producer      Q ring (3 tiles), K and V rings (3 items of up to 144 keys each)
-//   warp 21      UMMA issuer S     S(n) = Q K^T -> S buffer n & 1, two items ahead of the softmax
-//   warp 22      UMMA issuer PV    O(tile & 1) += P(n) V(n)   (TS form, P read from the S buffer)
+//   warp 21      UMMA issuer S     S(n) = Q K^T -> S buffer n % 3, up to two items ahead of the softmax
+//   warp 22      UMMA issuer PV    O += P(n) V(n)   (TS form, P read from the S buffer; one O accumulator)
 //
 // Online softmax in exp2 units seeded with (m, l) = (s_aux, 1) (:139-146); O is rescaled lazily (only when a
 // row max moves by more than 2^8), which never happens for single-item tiles such as window 128.
@@ -38,6 +38,7 @@ struct Fwd64Args {
   int q_off;
   const int* seq_lo;
   int64_t seq_bs;
+  int single_item;   // every tile has exactly one KV item (host-known): the softmax groups hop straight to their tiles
 };
 struct PeerMaps {
   CUtensorMap m[8];
@@ -62,8 +63,14 @@ struct Fwd64Cfg {
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = kBNMax * D * 2;
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kColS = 0;               // S buffers at 0 and kBNMax
-  static constexpr uint32_t kColO = 2 * kBNMax;      // O accumulators at +0 and +D
+  // THREE S buffers (item n uses buffer n % 3) and ONE O accumulator.  With two S buffers S(n + 2) had to wait for
+  // PV(n) -- P(n) aliases the S buffer -- and that chain (P written -> nine PV UMMAs issued at ~140 cycles each -> S
+  // issued) kept each softmax group idle for a third of its period (timeline r1u_trace_fwd64_pingpong.log).  Now
+  // S(n + 2) only waits for PV(n - 1).  The price is a single O accumulator: PV of the next tile starts after the
+  // epilogue has read the previous tile's O (a few hundred cycles, hidden behind the other group's softmax).
+  static constexpr int kSBufs = 3;
+  static constexpr uint32_t kColS = 0;               // S buffers at 0, kBNMax, 2 * kBNMax
+  static constexpr uint32_t kColO = kSBufs * kBNMax; // the O accumulator
   static constexpr int kMaxCh = (kBNMax / 16 + 1) / 2;
   // Two softmax GROUPS take alternate tiles (ping-pong): the warps of one group move in lock-step through a tile
   // (S wait, max exchange, P hand-over), so with a single group every scheduler's warps stall on the same latency
@@ -79,7 +86,7 @@ struct Fwd64Cfg {
   static constexpr int kThreads = (kSoftWarps + 4 + 3) * 32;
   static constexpr int kStatFloats = 2 * 128 + 2 * kParts * 128 + 2 * kParts * 128 + 64;   // row_m, row_l, xch, s_aux (<= 64 heads cached)
   static constexpr int kSmem = 1024 + (kQStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + kStatFloats * 4 + 512;
-  static_assert(2 * kBNMax + 2 * D <= 512, "TMEM budget");
+  static_assert(kSBufs * kBNMax + D <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
 
@@ -116,10 +123,10 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   uint64_t* k_empty = k_full + C::kKStages;
   uint64_t* v_full = k_empty + C::kKStages;
   uint64_t* v_empty = v_full + C::kVStages;
-  uint64_t* s_full = v_empty + C::kVStages;        // [2]  S(n) complete                      (issuer S -> softmax)
-  uint64_t* p_full = s_full + 2;                   // [2]  P(n) written                       (softmax -> issuer PV)
-  uint64_t* sbuf_free = p_full + 2;                // [2]  PV(n) complete: S buffer n & 1 free (issuer PV -> issuer S, softmax rescale)
-  uint64_t* o_done = sbuf_free + 2;                // [2]  tile's O complete                  (issuer PV -> epilogue)
+  uint64_t* s_full = v_empty + C::kVStages;        // [3]  S(n) complete                      (issuer S -> softmax)
+  uint64_t* p_full = s_full + C::kSBufs;           // [3]  P(n) written                       (softmax -> issuer PV)
+  uint64_t* sbuf_free = p_full + C::kSBufs;        // [3]  PV(n) complete: S buffer n % 3 free (issuer PV -> issuer S, softmax rescale)
+  uint64_t* o_done = sbuf_free + C::kSBufs;        // [2]  tile's O complete                  (issuer PV -> epilogue)
   uint64_t* o_free = o_done + 2;                   // [2]  O accumulator + row stats read     (epilogue -> issuer PV, softmax)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
@@ -134,10 +141,12 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     for (int s = 0; s < C::kQStages; ++s) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
     for (int s = 0; s < C::kKStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
     for (int s = 0; s < C::kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < C::kSBufs; ++s) {
       mbar_init(s_full + s, 1);
       mbar_init(p_full + s, C::kGroupWarps * 32);     // an item is handled by ONE group
       mbar_init(sbuf_free + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(o_done + s, 1);
       mbar_init(o_free + s, 128);
     }
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       int tc = 0;
       while (w.next()) {
         tev(a.trace, 1, tc, 1, w.n);
-        const int qs = w.it % C::kQStages, kst = w.n % C::kKStages, sb = w.n & 1;
+        const int qs = w.it % C::kQStages, kst = w.n % C::kKStages, sb = w.n % C::kSBufs;
         int kstart, cols; bool is_sink;
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), 16, 1024);
         if (w.t == 0) mbar_wait(q_full + qs, (w.it / C::kQStages) & 1);
         mbar_wait(k_full + kst, (w.n / C::kKStages) & 1);
-        if (w.n >= 2) mbar_wait(sbuf_free + sb, ((w.n - 2) >> 1) & 1);     // PV(n-2) has consumed P(n-2)
+        if (w.n >= C::kSBufs) mbar_wait(sbuf_free + sb, ((w.n / C::kSBufs) - 1) & 1);     // PV(n-3) has consumed P(n-3)
         tc_fence_after();
         tev(a.trace, 1, tc, 2, w.n);
         const uint32_t ts = tmem + C::kColS + sb * C::kBNMax;
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       int tc = 0;
       while (w.next()) {
         tev(a.trace, 3, tc, 1, w.n);
-        const int vst = w.n % C::kVStages, sb = w.n & 1, tb = w.it & 1;
+        const int vst = w.n % C::kVStages, sb = w.n % C::kSBufs, tb = w.it & 1;
         int kstart, cols; bool is_sink;
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         const uint64_t vd = make_sdesc(smem_u32(v_s + vst * C::kKVBytes), C::kKVBytes, 1024);
@@ -219,14 +228,15 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         int cs[C::kParts + 1];
         part_starts(nk, cs);
         mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
-        mbar_wait(p_full + sb, (w.n >> 1) & 1);
-        if (w.t == 0 && w.it >= 2) mbar_wait(o_free + tb, ((w.it - 2) >> 1) & 1);
+        mbar_wait(p_full + sb, (w.n / C::kSBufs) & 1);
+        // ONE O accumulator: the epilogue must have read the previous tile's O before this tile overwrites it
+        if (w.t == 0 && w.it >= 1) mbar_wait(o_free + (tb ^ 1), ((w.it - 1) >> 1) & 1);
         tc_fence_after();
         tev(a.trace, 3, tc, 2, w.n);
         if (nk == C::kBNMax / 16) {
           // full-width item (every tile of a 128-wide window): no per-UMMA predicates or selects -- this thread's
           // issue time gates S(n + 2), which reuses the S buffer P(n) sits in
-          const uint32_t dO_ = tmem + C::kColO + tb * D;
+          const uint32_t dO_ = tmem + C::kColO;
 #pragma unroll
           for (int kk = 0; kk < C::kBNMax / 16; ++kk) {
             constexpr int kSplit = (C::kBNMax / 16 + C::kParts - 1) / C::kParts;      // cs[1] for kParts == 2
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
               int pstart = 0;
 #pragma unroll
               for (int pp = 1; pp < C::kParts; ++pp) pstart = (kk >= cs[pp]) ? cs[pp] : pstart;
-              umma_ts(tmem + C::kColO + tb * D, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv,
+              umma_ts(tmem + C::kColO, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv,
                       (w.t > 0 || kk > 0));
             }
         }
@@ -264,9 +274,16 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     float m_used = -INFINITY, l = 0.f;
     int i = 0, mtc = 0, row_lo = 0;
     Walk w(a);
-    while (w.next()) {
-      if ((w.it & (C::kGroups - 1)) != grp) continue;      // the other group's tile
-      const int sb = w.n & 1, tb = w.it & 1;
+    bool first_hop = true;
+    while (true) {
+      if (a.single_item) {
+        if (!w.next_single(first_hop ? grp + 1 : C::kGroups)) break;
+        first_hop = false;
+      } else {
+        if (!w.next()) break;
+        if ((w.it & (C::kGroups - 1)) != grp) continue;      // the other group's tile
+      }
+      const int sb = w.n % C::kSBufs, tb = w.it & 1;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
       if (w.t == 0) {
         i = w.q0 + pr;
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       const int pbase = nch / C::kParts, prem = nch % C::kParts;       // same split as part_starts()
       const int ch0 = part * pbase + min(part, prem), ch1 = ch0 + pbase + (part < prem ? 1 : 0);
 
-      mbar_wait(s_full + sb, (w.n >> 1) & 1);
+      mbar_wait(s_full + sb, (w.n / C::kSBufs) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 2, w.n);
       auto wtrace = [&](int code) {
@@ -341,13 +358,13 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         }
         if (w.t > 0) {
           // lazy rescale of this half's O columns: PV(n-1) must have completed
-          mbar_wait(sbuf_free + ((w.n - 1) & 1), ((w.n - 1) >> 1) & 1);
+          mbar_wait(sbuf_free + ((w.n - 1) % C::kSBufs), ((w.n - 1) / C::kSBufs) & 1);
           tc_fence_after();
           if (part < 2) {        // warp-uniform: parts 0 and 1 rescale 32 of the 64 O columns each
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
               uint32_t v[16];
-              const uint32_t oa = tl + C::kColO + tb * D + part * 32 + cc * 16;
+              const uint32_t oa = tl + C::kColO + part * 32 + cc * 16;
               tmem_ld16(oa, v);
               tmem_ld_wait();
 #pragma unroll
@@ -430,7 +447,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[16], pk[8];
-        tmem_ld16(tl + C::kColO + tb * D + cc * 16, v);
+        tmem_ld16(tl + C::kColO + cc * 16, v);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 16; e += 2)
@@ -500,6 +517,10 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
   a.lse = p.lse;
   a.trace = trace_buffer();
   a.q_off = p.q_off; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
+  {
+    const int64_t span = static_cast<int64_t>(p.W < p.Nkv ? p.W : p.Nkv) + P - 1;
+    a.single_item = (p.S == 0 && p.W > 0 && span <= C::kBNMax) ? 1 : 0;
+  }
   a.sp_n = 0;
   PeerMaps pm;
   for (int r = 0; r < 8; ++r) pm.m[r] = mo.map;
