@@ -79,12 +79,16 @@ struct Fwd64Cfg {
   // each owning 1 / kParts of the key columns of its rows.  Measured at the gpt-oss shape: one group x 3 parts
   // 62.2 us, two groups x 2 parts 54.7 us, two groups x 3 parts (992 threads) 60.3 us.  A separate (single) TMEM
   // region for P, so that S(n + 2) need not wait for PV(n), serialises the two groups on that region: 63.3 us.
-  static constexpr int kGroups = 2;
+#ifndef SFA_FWD_GROUPS
+#define SFA_FWD_GROUPS 2
+#endif
+  static constexpr int kGroups = SFA_FWD_GROUPS;
   static constexpr int kParts = 2;
   static constexpr int kGroupWarps = 4 * kParts;
   static constexpr int kSoftWarps = kGroups * kGroupWarps;
   static constexpr int kThreads = (kSoftWarps + 4 + 3) * 32;
-  static constexpr int kStatFloats = 2 * 128 + 2 * kParts * 128 + 2 * kParts * 128 + 64;   // row_m, row_l, xch, s_aux (<= 64 heads cached)
+  static constexpr int kXch = (kGroups > 2 ? kGroups : 2) * kParts * 128;     // row-max exchange: one buffer per group (two for <= 2 groups)
+  static constexpr int kStatFloats = 2 * 128 + 2 * kParts * 128 + kXch + 64;   // row_m, row_l, xch, s_aux (<= 64 heads cached)
   static constexpr int kSmem = 1024 + (kQStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + kStatFloats * 4 + 512;
   static_assert(kSBufs * kBNMax + D <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   float* row_m = reinterpret_cast<float*>(v_s + C::kVStages * C::kKVBytes);   // [2][128]     final running max (log2 units) per tile parity
   float* row_l = row_m + 2 * 128;                                             // [2][kParts][128]  partial row sums of the column parts
   float* xch = row_l + 2 * C::kParts * 128;                                   // [2][kParts][128]  per-item row-max exchange between the parts
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * C::kParts * 128 + 64);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + C::kXch + 64);
   uint64_t* q_full = bars;
   uint64_t* q_empty = q_full + C::kQStages;
   uint64_t* k_full = q_empty + C::kQStages;
@@ -264,9 +268,9 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   } else if (warp < C::kSoftWarps) {
     // ------------------------------------------------------------------ softmax: row == TMEM lane, one part of the columns
     const int quarter = warp & 3, part = (warp >> 2) % C::kParts, grp = warp / C::kGroupWarps;
-    float* saux_s = xch + 2 * C::kParts * 128;          // s_aux * log2e of the first 64 heads (a global load per tile cost ~400 cycles)
+    float* saux_s = xch + C::kXch;          // s_aux * log2e of the first 64 heads (a global load per tile cost ~400 cycles)
     if (a.s_aux != nullptr && threadIdx.x < 64 && threadIdx.x < a.Hq) saux_s[threadIdx.x] = a.s_aux[threadIdx.x] * kLog2e;
-    named_bar_sync(7, C::kSoftWarps * 32);
+    named_bar_sync(15, C::kSoftWarps * 32);
     const int r = quarter * 32 + lane;
     const int pr = a.q_swap ? (r / a.G) : (r % a.P);
     const int gr = a.q_swap ? (r % a.G) : (r / a.P);
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         first_hop = false;
       } else {
         if (!w.next()) break;
-        if ((w.it & (C::kGroups - 1)) != grp) continue;      // the other group's tile
+        if ((w.it % C::kGroups) != grp) continue;      // another group's tile
       }
       const int sb = w.n % C::kSBufs, tb = w.it & 1;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
@@ -340,10 +344,11 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       wtrace(1);
       float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       // ---- the parts of a row agree on its max through shared memory
-      float* xb = xch + (w.n & 1) * (C::kParts * 128);
+      // (with more than two groups two concurrent items can share a parity: one buffer per group then)
+      float* xb = xch + (C::kGroups > 2 ? grp : (w.n & 1)) * (C::kParts * 128);
       xb[part * 128 + r] = mx;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 6, w.n);
-      named_bar_sync(1 + quarter + 8 * grp, C::kParts * 32);      // ids 1-4 (group 0), 9-12 (group 1); 5-7 are taken
+      named_bar_sync(1 + quarter + 4 * grp, C::kParts * 32);      // ids 1-12 (up to three groups); 13-15 are taken
 #pragma unroll
       for (int pp = 0; pp < C::kParts; ++pp) mx = fmaxf(mx, xb[pp * 128 + r]);
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 4, w.n);
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       const int tb = w.it & 1;
       if (et == 0) tev(a.trace, 6, mtc, 1, w.n);
       if (et == 0) tma_store_wait_read0();     // the previous store has finished reading the staging buffer
-      named_bar_sync(6, 128);
+      named_bar_sync(14, 128);
       mbar_wait(o_done + tb, (w.it >> 1) & 1);
       tc_fence_after();
       if (et == 0) tev(a.trace, 6, mtc, 2, w.n);
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         a.lse[(static_cast<int64_t>(w.b) * a.Hq + w.y * a.G + gr) * a.N + i] =
             (l_fin > 0.f) ? m_fin * kLn2 + logf(l_fin) : -INFINITY;
       fence_proxy_async_smem();
-      named_bar_sync(5, 128);
+      named_bar_sync(13, 128);
       if (et == 0) {
         tma_tile_store(&tmO, stage_s, a.o_swap, 0, w.q0, w.y * a.G, w.b);
         if (a.sp_n > 0) {       // Ulysses: the same staged tile goes to the sequence owner over NVLink (TMA store to a peer mapping)
