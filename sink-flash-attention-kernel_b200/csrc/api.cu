@@ -206,7 +206,9 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
     set_impl_name("tcgen05");
     if (tc_fwd64_supported(p, dtype) && !(g_env_fwd_v1 && p.o_route == nullptr && !p.has_ext()))
       return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
-    if (!p.has_ext()) return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");
+    // the one-tile-per-CTA kernel (head_dim > 64) takes packed sequences without sink tokens, not chunk offsets
+    if (p.q_off == 0 && p.Nkv == p.N && !(p.seq_lo != nullptr && p.S > 0))
+      return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");
   }
   set_impl_name("simt");
   return cuda_ret(simt_fwd(p, dtype, st), "sfa_fwd(simt)");

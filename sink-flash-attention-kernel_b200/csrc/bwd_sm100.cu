@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
       int c_lo, c_hi;
       row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+      if (a.seq_lo != nullptr && i < a.N) c_lo = max(c_lo, __ldg(a.seq_lo + w.b * a.seq_bs + i) - kstart);   // packed sequences
       if (i >= a.N) c_hi = -1;
       const int nch = cols / 16;
       const int hch = (nch + 1) / 2;
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         int c_lo, c_hi;
         row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+        if (a.seq_lo != nullptr && i < a.N) c_lo = max(c_lo, __ldg(a.seq_lo + w.b * a.seq_bs + i) - kstart);   // packed sequences
         if (i >= a.N) c_hi = -1;
         const int nch = cols >> 4;
         if (threadIdx.x == 0) trace_ev(a.trace, 4, mtc, 1, w.n);
@@ -750,6 +752,7 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         int c_lo, c_hi;
         row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+        if (a.seq_lo != nullptr && i < a.N) c_lo = max(c_lo, __ldg(a.seq_lo + w.b * a.seq_bs + i) - kstart);   // packed sequences
         if (i >= a.N) c_hi = -1;
         const int nch = cols >> 4;
         if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 1, w.n);
@@ -897,15 +900,18 @@ struct DkvArgs {
   void* dk;
   void* dv;
   Strides4 sdk, sdv;
+  const int* seq_hi;   // packed sequences: one past the last query position that may attend key j (nullptr: none)
+  int64_t seq_bs;
   int Dl;        // logical head_dim (<= the kernel's D): channels Dl .. D-1 are TMA zero fill and are not stored
 };
 
 // position blocks [pb_lo, pb_hi] (P positions each) whose queries can attend a key in [j0, j0+BK)
-__device__ __forceinline__ void chunk_range(const DkvArgs& a, int j0, int bk, int& pb_lo, int& pb_hi) {
+__device__ __forceinline__ void chunk_range(const DkvArgs& a, int b, int j0, int bk, int& pb_lo, int& pb_hi) {
   const int j1 = min(j0 + bk, a.N) - 1;                 // last key of the tile
   int i_max = -1;
   if (j0 < a.S) i_max = a.N - 1;                        // sink keys are seen by every later query
   if (a.W > 0) i_max = max(i_max, min(a.N - 1, j1 + a.W - 1));
+  if (a.seq_hi != nullptr) i_max = min(i_max, __ldg(a.seq_hi + b * a.seq_bs + j1) - 1);   // no row beyond the last key's sequence
   pb_lo = j0 / a.P;
   pb_hi = (i_max >= j0) ? i_max / a.P : pb_lo - 1;
 }
@@ -937,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
   const int j0 = blockIdx.x * C::kBK;
   const int kvh = blockIdx.y, b = blockIdx.z;
   int pb_lo, pb_hi;
-  chunk_range(a, j0, C::kBK, pb_lo, pb_hi);
+  chunk_range(a, b, j0, C::kBK, pb_lo, pb_hi);
   const int npb = max(pb_hi - pb_lo + 1, 0);
   const int nchunks = npb * a.groups_per_kv;             // chunk c -> (group c % gpk, position block pb_lo + c / gpk)
 
@@ -1031,6 +1037,8 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
     const int quarter = warp & 3, half = warp >> 2;
     const int kr = quarter * 32 + lane;                 // key row == TMEM lane
     const int j = j0 + kr;
+    // packed sequences: rows at or beyond e_j belong to a later sequence than key j
+    const int e_j = (a.seq_hi != nullptr && j < a.N) ? __ldg(a.seq_hi + b * a.seq_bs + j) : 0x7fffffff;
     const int jw_lo = j0 + quarter * 32, jw_hi = jw_lo + 31;          // this warp's keys
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int tid = threadIdx.x;                        // 0..255
@@ -1089,8 +1097,8 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
             const float2 dl = *reinterpret_cast<const float2*>(rd + r0);
             float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, l2.x));
             float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, l2.y));
-            const bool ok0 = attended(i0, j, a.S, a.W) && (j < a.N);
-            const bool ok1 = attended(i1, j, a.S, a.W) && (j < a.N);
+            const bool ok0 = attended(i0, j, a.S, a.W) && (j < a.N) && (i0 < e_j);
+            const bool ok1 = attended(i1, j, a.S, a.W) && (j < a.N) && (i1 < e_j);
             p0 = ok0 ? p0 : 0.f;
             p1 = ok1 ? p1 : 0.f;
             const float d0 = ok0 ? p0 * (__uint_as_float(dv[e]) - dl.x) : 0.f;
@@ -1216,7 +1224,7 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
   const int j0 = blockIdx.x * C::kBK;
   const int kvh = blockIdx.y, b = blockIdx.z;
   int pb_lo, pb_hi;
-  chunk_range(a, j0, C::kBK, pb_lo, pb_hi);
+  chunk_range(a, b, j0, C::kBK, pb_lo, pb_hi);
   const int npb = max(pb_hi - pb_lo + 1, 0);
   const int gpk = a.groups_per_kv;
   const int nchunks = npb * gpk;        // chunk c -> (position block pb_lo + c / gpk, group c % gpk); walked with counters
@@ -1358,7 +1366,8 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
     const int j = j0 + kr;
     const int jw_lo = j0 + quarter * 32, jw_hi = jw_lo + 31;          // this warp's keys
     // queries that attend key j: i in [j, i_hi]
-    const int i_hi = (j >= a.N) ? -1 : ((j < a.S) ? 0x7fffffff : ((a.W > 0) ? j + a.W - 1 : -1));
+    int i_hi = (j >= a.N) ? -1 : ((j < a.S) ? 0x7fffffff : ((a.W > 0) ? j + a.W - 1 : -1));
+    if (a.seq_hi != nullptr && j < a.N) i_hi = min(i_hi, __ldg(a.seq_hi + b * a.seq_bs + j) - 1);   // packed sequences
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int tid = threadIdx.x;                        // 0..511
     const int sh_p = 31 - __clz(a.P), sh_g = 31 - __clz(a.G);          // P and G are powers of two
@@ -1619,7 +1628,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.delta = p.delta;
     a.trace = trace_buffer();
     a.bn_mul = bn_magic(BN);
-    a.q_off = 0; a.seq_lo = nullptr; a.seq_bs = 0;
+    a.q_off = 0; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;      // packed sequences (no chunk offset in these kernels)
     a.fuse_delta = (D == 64 && fuses_delta(p, P, BN)) ? 1 : 0;
     a.delta_out = p.delta;
     a.dsrow = (p.s_aux != nullptr && p.ds_aux != nullptr) ? p.dsrow : nullptr;
@@ -1655,6 +1664,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.delta = p.delta;
     a.dk = p.dk; a.dv = p.dv; a.sdk = p.sdk; a.sdv = p.sdv;
     a.Dl = p.D;
+    a.seq_hi = p.seq_hi; a.seq_bs = p.seq_bs;
     a.trace = trace_buffer();
     dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
     if constexpr (D == 64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
@@ -1677,7 +1687,10 @@ bool tc_bwd_fuses_delta(const AttnParams& p, int dtype) {
 
 bool tc_bwd_supported(const AttnParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
-  if (p.has_ext()) return false;               // packed sequences / chunked prefill: fused kernel or CUDA-core path
+  // extended geometry: these kernels take packed sequences (without sink tokens); chunked prefill (q_off / a longer
+  // key axis) is the fused kernel's or the CUDA-core path's
+  if (p.q_off != 0 || p.Nkv != p.N) return false;
+  if (p.seq_lo != nullptr && p.S > 0) return false;
   // head dims 72 .. 120 (multiples of 8: 80, 96, 112, ...) run on the head_dim-128 kernels: the TMA boxes cover 128
   // channels, the tensor only has D, so the tail is hardware zero fill on loads and clipped on stores
   if (p.D != 64 && !(p.D > 64 && p.D <= 128 && p.D % 8 == 0)) return false;

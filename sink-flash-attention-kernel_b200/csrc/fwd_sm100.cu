@@ -44,6 +44,8 @@ struct FwdArgs {
   float sl2;                                   // scale * log2(e)
   const float* s_aux;
   float* lse;
+  const int* seq_lo;     // packed sequences (no sink tokens): first key of the row's sequence; nullptr: none
+  int64_t seq_bs;
 };
 
 template <typename T, int D>
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(192) fwd_kernel(const __grid_constant__ CUtens
   const int kvh = blockIdx.y / a.groups_per_kv;
   const int hq0 = blockIdx.y * a.G;     // == kvh*group + (blockIdx.y % groups_per_kv)*G
   const int b = blockIdx.z;
-  const TilePlan pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN);
+  TilePlan pl = make_plan(q0, a.P, a.N, a.S, a.W, a.BN);
+  if (a.seq_lo != nullptr) clamp_plan(pl, a.seq_lo[b * a.seq_bs + q0], a.W, a.BN, bn_magic(a.BN));
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(192) fwd_kernel(const __grid_constant__ CUtens
       pl.tile(t, a.BN, kstart, cols, is_sink);
       int c_lo, c_hi;   // attended columns of this row inside the tile: [c_lo, c_hi]
       row_range(is_sink, i, kstart, cols, a.S, a.W, c_lo, c_hi);
+      if (a.seq_lo != nullptr && i < a.N) c_lo = max(c_lo, __ldg(a.seq_lo + b * a.seq_bs + i) - kstart);
       mbar_wait(s_full, t & 1);
       tc_fence_after();
       // pass 1: row max over the attended columns
@@ -309,6 +313,7 @@ cudaError_t launch_fwd(const AttnParams& p, int dtype, cudaStream_t st) {
   a.sl2 = p.scale * kLog2e;
   a.s_aux = p.s_aux;
   a.lse = p.lse;
+  a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
   dim3 grid((p.N + P - 1) / P, p.Hq / G, p.B);
   fwd_kernel<T, D><<<grid, 192, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, a);
   return cudaGetLastError();

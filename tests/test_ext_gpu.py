@@ -36,12 +36,16 @@ def _oracle_packed(q, k, v, do, lens, S, W, s_aux):
     # gpt-oss training shape class: head_dim 64, no sink tokens, narrow window -> tcgen05 forward + fused backward
     (torch.bfloat16, 16, 2, 64, 0, 128, [300, 17, 1, 512, 130], ("tcgen05", "tcgen05-fused")),
     (torch.float16, 8, 1, 64, 0, 32, [64, 64, 70], ("tcgen05", "tcgen05-fused")),
-    # full-attention layer over a packed batch (window = longest sequence): tcgen05 forward, CUDA-core backward
-    (torch.bfloat16, 8, 2, 64, 0, 600, [600, 40, 333], ("tcgen05", "simt")),
+    # full-attention layer over a packed batch (window = longest sequence): tcgen05 forward, dQ + dK/dV tensor-core pair
+    (torch.bfloat16, 8, 2, 64, 0, 600, [600, 40, 333], ("tcgen05", "tcgen05")),
+    (torch.float16, 4, 4, 64, 0, 2000, [1, 700, 299, 1000], ("tcgen05", "tcgen05")),
     # per-sequence sink tokens, other head dims, fp32: CUDA-core kernels with the full predicate
     (torch.bfloat16, 8, 2, 64, 3, 16, [50, 2, 90], ("simt", "simt")),
     (torch.float32, 4, 4, 32, 2, 9, [33, 70, 5], ("simt", "simt")),
-    (torch.bfloat16, 8, 2, 128, 0, 64, [100, 156], ("simt", "simt")),
+    # head_dim 128 (and 80 on the same kernels): one-tile-per-CTA forward + kernel pair, all with the sequence bounds
+    (torch.bfloat16, 8, 2, 128, 0, 64, [100, 156], ("tcgen05", "tcgen05")),
+    (torch.bfloat16, 8, 2, 128, 0, 512, [300, 212, 77], ("tcgen05", "tcgen05")),
+    (torch.bfloat16, 4, 1, 80, 0, 100, [130, 90], ("tcgen05", "tcgen05")),
 ])
 def test_packed_sequences_match_per_sequence_oracle(dtype, Hq, Hkv, D, S, W, lens, impls):
     N = sum(lens)
