@@ -32,10 +32,24 @@ _original_flash_attention_forward = None
 
 
 def _is_packed(position_ids: Optional[torch.Tensor]) -> bool:
-    """Packed sequences restart their position ids mid-row (reference :182-193)."""
+    """Packed sequences restart their position ids mid-row (reference :182-193).  Host synchronisation (``.item()``):
+    the verl hook below no longer calls it -- it derives the sequence bounds on the device instead -- the generation
+    hook still does, as the reference."""
     if position_ids is None or position_ids.dim() < 2 or position_ids.size(1) <= 1:
         return False
     return bool((position_ids[:, 1:] < position_ids[:, :-1]).any().item())
+
+
+# HF hands the SAME position_ids tensor to every layer of a forward pass: derive the bounds once per tensor
+_BOUNDS_CACHE = {"key": None, "val": None}
+
+
+def _bounds_from_position_ids(position_ids: torch.Tensor):
+    key = (position_ids.data_ptr(), tuple(position_ids.shape), position_ids._version, position_ids.device)
+    if _BOUNDS_CACHE["key"] != key:
+        _BOUNDS_CACHE["val"] = sequence_bounds_from_position_ids(position_ids)
+        _BOUNDS_CACHE["key"] = key
+    return _BOUNDS_CACHE["val"]
 
 
 def _ulysses_rank(sp_size: int) -> int:
@@ -86,13 +100,17 @@ def _sink_flash_attention_forward(
 ):
     s_aux = kwargs.pop("s_aux", None)
     varlen = all(x is not None for x in (cu_seq_lens_q, cu_seq_lens_k, max_length_q, max_length_k))
-    packed = (not varlen) and position_ids is not None and query_states.size(0) > 0 and _is_packed(position_ids)
     n_q, n_kv, h_q = query_states.shape[1], key_states.shape[1], query_states.shape[2]
+    # position_ids that restart mid-row mark packed sequences (reference :182-193, a `.item()` host sync per layer
+    # call).  Here the bounds are derived ON THE DEVICE and go into the kernels: no sync, and a batch that is not packed
+    # simply gets one sequence per row.  (Self-attention calls only; a cached call, N_q != N_kv, is never packed.)
+    packed = (not varlen) and position_ids is not None and position_ids.dim() == 2 and n_q == n_kv and n_q > 1 and \
+        tuple(position_ids.shape) == (query_states.shape[0], n_q)
     # varlen self-attention only: the same boundaries on both sides (what padding-free training passes)
     varlen_ok = varlen and n_q == n_kv and cu_seq_lens_q.shape == cu_seq_lens_k.shape and \
         (cu_seq_lens_q is cu_seq_lens_k or cu_seq_lens_q.data_ptr() == cu_seq_lens_k.data_ptr() or
          bool(torch.equal(cu_seq_lens_q, cu_seq_lens_k)))
-    if (varlen and not varlen_ok) or (packed and n_q != n_kv) or not is_causal or attention_mask is not None \
+    if (varlen and not varlen_ok) or not is_causal or attention_mask is not None \
             or softcap is not None:
         if s_aux is not None:
             kwargs["s_aux"] = s_aux          # the stock FA path ignores it
@@ -118,7 +136,7 @@ def _sink_flash_attention_forward(
             bounds = sequence_bounds_from_cu_seqlens(cu_seq_lens_q, q.shape[2])
             window = sliding_window if sliding_window is not None else (max_length_q if isinstance(max_length_q, int) else q.shape[2])
         else:
-            bounds = sequence_bounds_from_position_ids(position_ids)
+            bounds = _bounds_from_position_ids(position_ids)
         out = sink_flash_attention_varlen(q, k, v, num_sink=0, window_size=window, s_aux=s_local, seq_bounds=bounds)
         out = out.transpose(1, 2)
         out = out if out.is_contiguous() else out.contiguous()

@@ -215,9 +215,12 @@ def test_verl_forward_routing(monkeypatch):
         assert f(q[:1], kv[:1], kv[:1], None, 10, s_aux=s_aux, **kw) == "orig"
         assert calls[-1][0] == "orig" and calls[-1][1]["s_aux"] is s_aux
     assert f(q, kv, kv, torch.ones(2, 10), 10) == "orig"          # padding mask
-    # monotone position ids are not "packed"
+    # monotone position ids: one sequence per row -- same kernels, bounds [0, N); no host sync decides this any more
     f(q, kv, kv, None, 10, position_ids=torch.arange(10)[None].expand(2, -1))
-    assert calls[-1][0] == "prefill"
+    assert calls[-1][0] == "varlen" and calls[-1][5][0].tolist() == [[0] * 10] * 2 and calls[-1][5][1].tolist() == [[10] * 10] * 2
+    # a cached call (N_q != N_kv) with position ids goes to the chunk / decode kernels
+    f(q[:, :4], kv, kv, None, 4, position_ids=torch.arange(6, 10)[None].expand(2, -1))
+    assert calls[-1][0] == "chunk"
 
 
 def test_sequence_bounds_helpers():

@@ -38,19 +38,27 @@ def test_tiny_gpt_oss_eager_vs_verl_patch(dtype, head_dim, tol):
     with torch.no_grad():
         ref = model(ids).logits.float()
     calls = []
-    orig_fn = sa.verl_patch.sink_flash_attention
+    orig_fn, orig_var = sa.verl_patch.sink_flash_attention, sa.verl_patch.sink_flash_attention_varlen
 
     def spy(q, k, v, num_sink, window_size, s_aux):
-        calls.append((tuple(q.shape), num_sink, window_size, None if s_aux is None else tuple(s_aux.shape), _lib.last_impl))
+        calls.append((tuple(q.shape), num_sink, window_size, None if s_aux is None else tuple(s_aux.shape)))
         return orig_fn(q, k, v, num_sink=num_sink, window_size=window_size, s_aux=s_aux)
+
+    def spy_var(q, k, v, num_sink, window_size, s_aux, seq_bounds):
+        # HF hands position_ids to the hook: the sequence bounds are derived on the device (one sequence per row here)
+        assert seq_bounds[0].unique().tolist() == [0] and seq_bounds[1].unique().tolist() == [q.shape[2]]
+        calls.append((tuple(q.shape), num_sink, window_size, None if s_aux is None else tuple(s_aux.shape)))
+        return orig_var(q, k, v, num_sink=num_sink, window_size=window_size, s_aux=s_aux, seq_bounds=seq_bounds)
     sa.patch_verl_with_sink_attention()
     sa.verl_patch.sink_flash_attention = spy
+    sa.verl_patch.sink_flash_attention_varlen = spy_var
     try:
         model.config._attn_implementation = "flash_attention_2"
         with torch.no_grad():
             got = model(ids).logits.float()
     finally:
         sa.verl_patch.sink_flash_attention = orig_fn
+        sa.verl_patch.sink_flash_attention_varlen = orig_var
         sa.unpatch_verl()
         model.config._attn_implementation = "eager"
     # one call per layer: sliding layer with window 8, full layer with window = N; num_sink = 0; s_aux = sinks [4]
