@@ -237,7 +237,10 @@ __device__ __forceinline__ void fused_delta_rows(const T* ob, const T* dob, floa
   }
 }
 
-template <typename T>
+// kExt: extended geometry (packed sequences / chunk offset) compiled in.  A separate instantiation, not a run-time
+// switch: the two extra live values per math thread pushed the plain kernel over its 72-register budget (36 B of
+// spills -- with 227 KB of shared memory every spill reload is an L2 round trip) and cost 4.5 us at the gpt-oss shape.
+template <typename T, bool kExt>
 __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                              const __grid_constant__ CUtensorMap tmdO,
                                                                              const __grid_constant__ CUtensorMap tmK,
@@ -330,6 +333,8 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   tc_fence_after();
 
   const int P = a.P, nb = a.nb, R = a.R;
+  const int qb = kExt ? a.qb : 0, nkv = kExt ? a.Nkv : a.N;
+  const int* const seq_lo = kExt ? a.seq_lo : nullptr;
 
   if (warp >= 20) {
   if (warp == 20) {
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           ftrace(a.trace, 0, tc, 1, w.it);
           const int s = w.it & 1;
           const uint32_t eph = ((w.it >> 1) & 1) ^ 1;
-          const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb + a.qb - nb + 1) * P;
+          const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb + qb - nb + 1) * P;
           mbar_wait(q_empty + s, eph);
           mbar_expect_tx(q_full + s, C::kQBytes);
           tma_tile(q_s + s * C::kQBytes, &tmQ, q_full + s, a.q_swap, 0, q0, hq0, w.b);
@@ -561,9 +566,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       // first key of the row's packed sequence, in query-row units (absolute - q_off); unused when not packed
       auto load_lo = [&](const FusedWalk& t, bool valid) {
         int v = 0;
-        if (a.seq_lo != nullptr && valid) {
+        if (kExt && seq_lo != nullptr && valid) {
           const int i = t.pb * P + pr;
-          if (i < a.N) v = __ldg(a.seq_lo + t.b * a.seq_bs + i) - a.qb * P;
+          if (i < a.N) v = __ldg(seq_lo + t.b * a.seq_bs + i) - qb * P;
         }
         return v;
       };
@@ -588,8 +593,8 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         // attended keys of the row: [max(i - W + 1, first key of its sequence), i]; keys start at absolute 0
         // (kept as two plain steps: the one-expression form with a -2^30 "no sequence" sentinel folded into a
         // three-way max came out of ptxas 12.9 with the sign of the q_off term lost -- caught by the chunked-prefill tests)
-        int key_lo = -a.qb * P;                            // absolute key 0
-        if (a.seq_lo != nullptr) key_lo = max(key_lo, lo_row);
+        int key_lo = -qb * P;                              // absolute key 0
+        if (kExt && seq_lo != nullptr) key_lo = max(key_lo, lo_row);
         const int c_lo = max(i - a.W + 1, key_lo) - kstart;
         const int c_hi = (i < a.N) ? (i - kstart) : -1;
         int xs = st.slot0 + nb;                            // slot whose block left the window: zero image columns
@@ -819,7 +824,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
 #pragma unroll 1
         for (int jb = 0; jb < nd; ++jb) {
           const int j = w.pb - nb + 1 + jb;                 // key block in query-tile units; absolute block j + qb
-          if (j + a.qb < 0) continue;
+          if (j + qb < 0) continue;
           int slot = st.slot0 + jb;
           if (slot >= R) slot -= R;
 #pragma unroll 1
@@ -836,10 +841,10 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
 #pragma unroll
               for (int e = 0; e < 16; ++e) dst[e * 128] = __uint_as_float(x[e]);
             } else {
-              const int key0 = (j + a.qb) * P + h * 16;
+              const int key0 = (j + qb) * P + h * 16;
               T* dst = okv + static_cast<int64_t>(w.b) * skv.b + static_cast<int64_t>(w.y) * skv.h +
                        static_cast<int64_t>(key0) * skv.n + dch;
-              const int nv = a.Nkv - key0;
+              const int nv = nkv - key0;
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 if (e < nv) *dst = from_f<T>(__uint_as_float(x[e]));
@@ -1014,10 +1019,17 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   }
   a.part = part;
   a.trace = trace_buffer();
-  static std::atomic<unsigned long long> attr_done{0};
-  if (cudaError_t e = ensure_dyn_smem(bwd_fused64_kernel<T>, C::kSmem, attr_done)) return e;
-  bwd_fused64_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (p.has_ext()) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if ((e = ensure_dyn_smem(bwd_fused64_kernel<T, true>, C::kSmem, attr_done)) != cudaSuccess) return e;
+    bwd_fused64_kernel<T, true><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+  } else {
+    static std::atomic<unsigned long long> attr_done{0};
+    if ((e = ensure_dyn_smem(bwd_fused64_kernel<T, false>, C::kSmem, attr_done)) != cudaSuccess) return e;
+    bwd_fused64_kernel<T, false><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+  }
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int nbound = (grid > 1 && nb > 1) ? grid - 1 : 0;   // nb == 1 (window <= one block): no shared key block
   const int nred = (ds_partial != nullptr && ds_nblk > 0) ? p.Hq : 0;
