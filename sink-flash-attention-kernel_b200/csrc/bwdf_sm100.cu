@@ -43,6 +43,12 @@
 namespace sfa {
 namespace {
 
+// The in-kernel delta variant (epilogue groups computing rowsum(dO o O), round 1: 152 us vs 98 + 26 us with the streaming
+// preprocess pass) is compiled in only with -DSFA_FUSED_DELTA_CODE=1: its address arithmetic raised the register pressure
+// of the epilogue role and the default kernel spilled two loop-invariant values that it reloaded every tile.
+#ifndef SFA_FUSED_DELTA_CODE
+#define SFA_FUSED_DELTA_CODE 0
+#endif
 struct FusedCfg {
   static constexpr int D = 64;
   static constexpr int kColsMax = 144;                 // keys per tile (UMMA N of S and dP)
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       auto load_delta = [&](const FusedWalk& t, bool valid) {
         float v = 0.f;
         if (valid) {
-          if (a.fuse_delta) mbar_wait_warp(delta_ready + (t.it & 3), (t.it >> 2) & 1);
+          if (SFA_FUSED_DELTA_CODE && a.fuse_delta) mbar_wait_warp(delta_ready + (t.it & 3), (t.it >> 2) & 1);
           const int i = t.pb * P + pr;
           if (i < a.N) {
             const int64_t row = (static_cast<int64_t>(t.b) * a.Hq + t.y * a.G + gr) * a.N + i;
@@ -752,7 +758,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       int pa = 0;
       // One loop, ONE delta site: two lead-in rounds produce the deltas of the group's first two tiles, every later
       // round is epilogue(tile n) followed by delta(tile n + 4).
-      int lead = a.fuse_delta ? 2 : 0;
+      int lead = (SFA_FUSED_DELTA_CODE && a.fuse_delta) ? 2 : 0;
       while (true) {
         if (lead > 0) {
           --lead;
@@ -870,7 +876,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         if (tr) ftrace(a.trace, trole, tc, 5, w.it);
         }
         // ---- delta of the group's tile four ahead (prefetch for the one after it first)
-        if (!a.fuse_delta) continue;
+        if (!SFA_FUSED_DELTA_CODE || !a.fuse_delta) continue;
         {
           FusedWalk wf = wd;
           wf.next();
@@ -1052,7 +1058,7 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
 // L2-prefetched O / dO rows) costs each epilogue group ~9 000 cycles per tile -- more than its idle time -- and the
 // backward takes 152 us against 108 + 37 us with the separate streaming preprocess kernel.  SFA_FUSED_DELTA=1 enables it.
 bool tc_bwd_fused_computes_delta() {
-  static const bool on = getenv("SFA_FUSED_DELTA") != nullptr;
+  static const bool on = SFA_FUSED_DELTA_CODE && getenv("SFA_FUSED_DELTA") != nullptr;
   return on;
 }
 
