@@ -87,7 +87,7 @@ struct Fwd64Cfg {
   static constexpr int kGroupWarps = 4 * kParts;
   static constexpr int kSoftWarps = kGroups * kGroupWarps;
   static constexpr int kThreads = (kSoftWarps + 4 + 3) * 32;
-  static constexpr int kXch = (kGroups > 2 ? kGroups : 2) * kParts * 128;     // row-max exchange: one buffer per group (two for <= 2 groups)
+  static constexpr int kXch = kGroups * 2 * kParts * 128;     // row-max exchange: two buffers (item parity) per group
   static constexpr int kStatFloats = 2 * 128 + 2 * kParts * 128 + kXch + 64;   // row_m, row_l, xch, s_aux (<= 64 heads cached)
   static constexpr int kSmem = 1024 + (kQStages + 1) * kQBytes + (kKStages + kVStages) * kKVBytes + kStatFloats * 4 + 512;
   static_assert(kSBufs * kBNMax + D <= 512, "TMEM budget");
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   unsigned char* v_s = k_s + C::kKStages * C::kKVBytes;        // [kVStages][kKVBytes]
   float* row_m = reinterpret_cast<float*>(v_s + C::kVStages * C::kKVBytes);   // [2][128]     final running max (log2 units) per tile parity
   float* row_l = row_m + 2 * 128;                                             // [2][kParts][128]  partial row sums of the column parts
-  float* xch = row_l + 2 * C::kParts * 128;                                   // [2][kParts][128]  per-item row-max exchange between the parts
+  float* xch = row_l + 2 * C::kParts * 128;                                   // [kGroups][2][kParts][128]  per-item row-max exchange between the parts
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + C::kXch + 64);
   uint64_t* q_full = bars;
   uint64_t* q_empty = q_full + C::kQStages;
@@ -161,6 +161,13 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+#ifdef SFA_DEBUG_HANG
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("bars at smem 0x%x: q_full +0, q_empty +%d, k_full +%d, k_empty +%d, v_full +%d, v_empty +%d, s_full +%d, p_full +%d, sbuf_free +%d, o_done +%d, o_free +%d (bytes)\n",
+           smem_u32(bars), (int)((q_empty - bars) * 8), (int)((k_full - bars) * 8), (int)((k_empty - bars) * 8), (int)((v_full - bars) * 8),
+           (int)((v_empty - bars) * 8), (int)((s_full - bars) * 8), (int)((p_full - bars) * 8), (int)((sbuf_free - bars) * 8),
+           (int)((o_done - bars) * 8), (int)((o_free - bars) * 8));
+#endif
 
   if (warp == kWProd) {
     // ------------------------------------------------------------------ TMA producer
@@ -285,7 +292,14 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         first_hop = false;
       } else {
         if (!w.next()) break;
-        if ((w.it % C::kGroups) != grp) continue;      // another group's tile
+        if ((w.it % C::kGroups) != grp) {
+          // Another group's tile.  Its items are still WAITED for, one by one: a parity wait is only valid while the
+          // waiter is at most one phase behind the barrier, and a tile of a wide window has many items per S buffer.
+          // (Without this a group that skipped a long tile took S(n - 3)'s completion for S(n)'s: wrong results,
+          // then a protocol deadlock.)
+          mbar_wait(s_full + (w.n % C::kSBufs), (w.n / C::kSBufs) & 1);
+          continue;
+        }
       }
       const int sb = w.n % C::kSBufs, tb = w.it & 1;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
@@ -344,8 +358,8 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       wtrace(1);
       float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       // ---- the parts of a row agree on its max through shared memory
-      // (with more than two groups two concurrent items can share a parity: one buffer per group then)
-      float* xb = xch + (C::kGroups > 2 ? grp : (w.n & 1)) * (C::kParts * 128);
+      // (one pair of buffers per group: with several items per tile the two groups can be on items of equal parity)
+      float* xb = xch + (grp * 2 + (w.n & 1)) * (C::kParts * 128);
       xb[part * 128 + r] = mx;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 6, w.n);
       named_bar_sync(1 + quarter + 4 * grp, C::kParts * 32);      // ids 1-12 (up to three groups); 13-15 are taken

@@ -3,6 +3,7 @@
 // descriptors.  Hand-written inline PTX; bit layouts follow the PTX ISA tcgen05 descriptor
 // tables (same fields as CUTLASS cute/arch/mma_sm100_desc.hpp documents).
 #pragma once
+#include <stdio.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -55,7 +56,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SFA_SPIN_LIMIT) __trap();
+    if (++spins > SFA_SPIN_LIMIT) {
+#ifdef SFA_DEBUG_HANG      // debug builds: name the barrier a role is stuck on before trapping
+      if ((threadIdx.x & 31) == 0 || threadIdx.x >= 640)
+        printf("HANG block %d warp %d lane %d barrier smem 0x%x parity %u\n", blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31,
+               smem_u32(bar), parity);
+#endif
+      __trap();
+    }
   }
 }
 // Whole-warp wait with ONE polling lane: the other 31 lanes park at the warp barrier instead of each keeping a

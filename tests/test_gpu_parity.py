@@ -568,6 +568,35 @@ def test_c2_full_size():
     assert nr >= 1024 and nk >= 96
 
 
+@pytest.mark.parametrize("S,W", [(0, 8192), (4, 2048), (300, 1000)])
+def test_wide_window_head_dim_64_full_size(S, W):
+    """gpt-oss FULL-attention layer (every second layer of the model: the C1 shape with window = N) and wide windows
+    with sink tokens at head_dim 64: tiles of up to 57 KV items on the persistent forward and the dQ + dK/dV pair.
+    (Round 2 found the forward's ping-pong softmax groups losing step with the S barriers on tiles of more than three
+    items -- a parity wait taken one phase early; small shapes never reach that.)"""
+    B, N, Hq, Hkv, D = 1, 8192, 64, 8, 64
+    g = torch.Generator(device="cuda").manual_seed(46 + S)
+    mk = lambda H: torch.randn(B, H, N, D, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    s_aux = torch.randn(Hq, device="cuda", generator=g) * 0.5
+    o, lse, name = _fwd(q, k, v, S, W, s_aux)
+    assert name == "tcgen05"
+    o2, lse2, _ = _fwd(q, k, v, S, W, s_aux)
+    assert torch.equal(o, o2) and torch.equal(lse, lse2)
+    ones = torch.ones_like(v)
+    o1, lse1, _ = _fwd(q, k, ones, S, W, s_aux)
+    assert (o1.float() - (1.0 - torch.exp(s_aux[None, :, None] - lse1))[..., None]).abs().max().item() < 1e-2
+    (dq, dk, dv, ds), name_b = _bwd(q, k, v, o, do, lse, S, W, s_aux)
+    assert name_b == "tcgen05"
+    (dq2, dk2, dv2, ds2), _ = _bwd(q, k, v, o, do, lse, S, W, s_aux)
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2) and torch.equal(ds, ds2)
+    nr, nk = _check_sampled(q, k, v, do, s_aux, S, W, o, lse, (dq, dk, dv), 768, 64, 16, seed=4)
+    assert nr >= 768 and nk >= 64
+    delta = (do.double() * o.double()).sum(-1)
+    ds_ref = -(torch.exp(s_aux.double()[None, :, None] - lse.double()) * delta).sum((0, 2))
+    assert ((ds.double() - ds_ref).abs().max() / ds_ref.abs().max()).item() < 1e-3
+
+
 def test_c4_rank_shard_full_size():
     """Ulysses layout of BASELINE configs[4] at P = 8: one rank's problem after the exchange -- the whole 131072-token
     sequence for 8 q heads / 1 KV head (D=64, W=128, s_aux, bf16) -- forward and fused backward against the CUDA-core

@@ -35,6 +35,8 @@ CONFIGS = {
     # BASELINE.json configs[1], [2], [3]
     "c1": dict(kind="prefill", B=1, N=8192, Hq=64, Hkv=8, D=64, S=0, W=128, s_aux=True),
     "c2": dict(kind="prefill", B=4, N=16384, Hq=32, Hkv=8, D=128, S=4, W=4096, s_aux=False),
+    # gpt-oss full-attention layer (every second layer of the model): same shape, window = N
+    "c1full": dict(kind="prefill", B=1, N=8192, Hq=64, Hkv=8, D=64, S=0, W=8192, s_aux=True),
     "c3": dict(kind="decode", B=64, Nkv=4100, Hq=64, Hkv=8, D=64, s_aux=True),
 }
 

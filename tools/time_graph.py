@@ -15,6 +15,8 @@ from sink_attention import _lib  # noqa: E402
 B, N, Hq, Hkv, D, S, W = 1, 8192, 64, 8, 64, 0, 128
 if len(sys.argv) > 1 and sys.argv[1] == "c2s":
     B, N, Hq, Hkv, D, S, W = 1, 8192, 32, 8, 128, 4, 4096
+if len(sys.argv) > 1 and sys.argv[1] == "c1full":      # gpt-oss FULL-attention layer (every second layer): window = N
+    B, N, Hq, Hkv, D, S, W = 1, 8192, 64, 8, 64, 0, 8192
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(1)
 dt = torch.bfloat16
@@ -93,4 +95,8 @@ def full():
     _lib.bwd(q, k, v, o2, do, lse2, S, W, s_aux)
 
 
-print("fwd+bwd        us:", graph_time(full))
+t_all = graph_time(full)
+print("fwd+bwd        us:", t_all)
+w_, s_ = max(W, 0), max(S, 0)
+pairs = sum(min(i + 1, w_) + min(s_, max(0, i - w_ + 1)) for i in range(N)) * B * Hq
+print(f"masked TFLOP/s fwd+bwd: {14 * D * pairs / (t_all[0] * 1e-6) / 1e12:.1f}  ({14 * D * pairs / (t_all[0] * 1e-6) / 1e12 / 1628.7 * 100:.1f} % of the bf16 burst peak)")
