@@ -869,12 +869,22 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
 }
 
 // ================================================================================== dK/dV kernel
-// One CTA per (128-key tile, kv head, batch).  Keys sit on the TMEM lanes; the packed Q chunks that
-// can see the tile stream through a 2-stage Q/dO ring.
+// One CTA per (128-key tile, kv head, batch).  Keys sit on the TMEM lanes; the packed Q chunks that can see the
+// tile stream through a Q ring (3 tiles) and a dO ring (2 tiles).  TMEM is full at head_dim 128 (S^T, dP^T, dK, dV:
+// 4 x 128 columns), so S^T and dP^T are single-buffered and the overlap comes from the ORDER of the tensor pipe:
+//
+//   tensor pipe:  dV(c) | S(c+1) | dK(c) | dP(c+1) | dV(c+1) | S(c+2) | ...
+//   math warps:           [ dS(c) ]  [   P(c+1)   ]  [ dS(c+1) ]  [  P(c+2)  ] ...
+//
+// P(c+1) (the MUFU-bound pass) runs under dK(c) + dP(c+1), dS(c+1) under dV(c+1) + S(c+2).  P^T overwrites the
+// consumed S^T columns as 16-bit, dS^T the dP^T columns; UMMAs of one thread execute in issue order, so S(c+1) may
+// be issued right behind the dV(c) that still reads P(c) from the same columns.  (Round 1's version ran
+// S, dP -> math -> dV, dK strictly one after the other: 21 % of the tensor peak at BASELINE configs[2].)
 template <int D> struct DkvCfg {
   static constexpr int kDS = D / 64;
   static constexpr int kBK = 128;                       // keys per CTA
-  static constexpr int kQStages = 2;
+  static constexpr int kQStages = 3;                    // Q(c) lives from S(c) to dK(c): two tiles in use + one in flight
+  static constexpr int kDoStages = 2;                   // dO(c) lives from dP(c) to dV(c)
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = kBK * D * 2;
   static constexpr int kSlabQ = 128 * 128;
@@ -884,7 +894,8 @@ template <int D> struct DkvCfg {
   static constexpr uint32_t kColP = 128;                // dP^T (fp32) -> dS^T (16-bit)
   static constexpr uint32_t kColK = 256;                // dK accumulator [keys][D]
   static constexpr uint32_t kColV = 256 + D;            // dV accumulator
-  static constexpr int kSmem = 1024 + 2 * kKVBytes + 2 * kQStages * kQBytes + 2 * 2 * 128 * 4 + 256;
+  // no alignment slack: the dynamic shared memory is declared 1024-byte aligned (checked at kernel entry)
+  static constexpr int kSmem = 2 * kKVBytes + (kQStages + kDoStages) * kQBytes + 2 * 2 * 128 * 4 + 256;
   static_assert(256 + 2 * D <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
@@ -892,6 +903,7 @@ template <int D> struct DkvCfg {
 struct DkvArgs {
   long long* trace;
   int B, N, S, W, Hq, Hkv, G, P, groups_per_kv;
+  int ntiles;    // key tiles per (kv head, batch); the launch is 1-D: tiles holding sink keys first (they see every row)
   int q_swap, k_swap, v_swap;
   int fmt;
   float sl2, scale;
@@ -922,26 +934,45 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap tmK,
                                                            const __grid_constant__ CUtensorMap tmV, const DkvArgs a) {
   using C = DkvCfg<D>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_aligned[];
+  unsigned char* smem = smem_aligned;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();               // SWIZZLE_128B tiles need 1024-byte aligned slabs
   unsigned char* k_s = smem;
   unsigned char* v_s = k_s + C::kKVBytes;
   unsigned char* q_s = v_s + C::kKVBytes;                      // [kQStages][kQBytes]
-  unsigned char* do_s = q_s + C::kQStages * C::kQBytes;
-  float* row_l2 = reinterpret_cast<float*>(do_s + C::kQStages * C::kQBytes);   // [2][128]  -lse*log2e per chunk row
-  float* row_dl = row_l2 + 2 * 128;                                            // [2][128]  delta per chunk row
+  unsigned char* do_s = q_s + C::kQStages * C::kQBytes;        // [kDoStages][kQBytes]
+  float* row_l2 = reinterpret_cast<float*>(do_s + C::kDoStages * C::kQBytes);   // [2][128]  -lse*log2e per chunk row
+  float* row_dl = row_l2 + 2 * 128;                                             // [2][128]  -delta per chunk row
   uint64_t* bars = reinterpret_cast<uint64_t*>(row_dl + 2 * 128);
   uint64_t* kv_full = bars;
-  uint64_t* q_full = kv_full + 1;             // [2]
-  uint64_t* q_empty = q_full + C::kQStages;   // [2]
-  uint64_t* s_full = q_empty + C::kQStages;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* acc_done = p_full + 1;
+  uint64_t* q_full = kv_full + 1;              // [3]
+  uint64_t* q_empty = q_full + C::kQStages;    // [3]  dK(c) complete
+  uint64_t* do_full = q_empty + C::kQStages;   // [2]
+  uint64_t* do_empty = do_full + C::kDoStages; // [2]  dV(c) complete
+  uint64_t* s_full = do_empty + C::kDoStages;  // S^T(c) complete            (issuer -> math)
+  uint64_t* dp_full = s_full + 1;              // dP^T(c) complete           (issuer -> math)
+  uint64_t* p_ready = dp_full + 1;             // P^T(c) written over S^T    (math -> issuer)
+  uint64_t* ds_ready = p_ready + 1;            // dS^T(c) written over dP^T  (math -> issuer)
+  uint64_t* acc_done = ds_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * C::kBK;
-  const int kvh = blockIdx.y, b = blockIdx.z;
+  // 1-D launch: the first Hkv * B CTAs take key tile 0 of every (kv head, batch) -- with sink tokens that tile is
+  // seen by every query row of the sequence (4x the work of a window tile) and must not start in the last wave
+  int tile_x, yz;
+  {
+    const int id = blockIdx.x, heavy = a.Hkv * a.B;
+    if (id < heavy) {
+      tile_x = 0;
+      yz = id;
+    } else {
+      const int r = id - heavy;
+      tile_x = 1 + r % (a.ntiles - 1);
+      yz = r / (a.ntiles - 1);
+    }
+  }
+  const int j0 = tile_x * C::kBK;
+  const int kvh = yz % a.Hkv, b = yz / a.Hkv;
   int pb_lo, pb_hi;
   chunk_range(a, b, j0, C::kBK, pb_lo, pb_hi);
   const int npb = max(pb_hi - pb_lo + 1, 0);
@@ -957,8 +988,14 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
       mbar_init(q_full + s, 1);
       mbar_init(q_empty + s, 1);
     }
+    for (int s = 0; s < C::kDoStages; ++s) {
+      mbar_init(do_full + s, 1);
+      mbar_init(do_empty + s, 1);
+    }
     mbar_init(s_full, 1);
-    mbar_init(p_full, kMathThreads);
+    mbar_init(dp_full, 1);
+    mbar_init(p_ready, kMathThreads);
+    mbar_init(ds_ready, kMathThreads);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -976,58 +1013,90 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
         tma_tile(k_s + s * C::kSlabKV, &tmK, kv_full, a.k_swap, s * 64, j0, kvh, b);
         tma_tile(v_s + s * C::kSlabKV, &tmV, kv_full, a.v_swap, s * 64, j0, kvh, b);
       }
+      int grp = 0, pb = pb_lo, qs = 0, qph = 1, ds = 0, dph = 1;
       for (int c = 0; c < nchunks; ++c) {
-        const int grp = c % a.groups_per_kv, pb = pb_lo + c / a.groups_per_kv;
         const int hq0 = (kvh * a.groups_per_kv + grp) * a.G;
-        const int qs = c % C::kQStages;
-        mbar_wait(q_empty + qs, ((c / C::kQStages) & 1) ^ 1);
-        mbar_expect_tx(q_full + qs, 2 * C::kQBytes);
-        for (int s = 0; s < C::kDS; ++s) {
+        mbar_wait(q_empty + qs, qph);
+        mbar_expect_tx(q_full + qs, C::kQBytes);
+        for (int s = 0; s < C::kDS; ++s)
           tma_tile(q_s + qs * C::kQBytes + s * C::kSlabQ, &tmQ, q_full + qs, a.q_swap, s * 64, pb * a.P, hq0, b);
-          tma_tile(do_s + qs * C::kQBytes + s * C::kSlabQ, &tmdO, q_full + qs, a.q_swap, s * 64, pb * a.P, hq0, b);
-        }
+        mbar_wait(do_empty + ds, dph);
+        mbar_expect_tx(do_full + ds, C::kQBytes);
+        for (int s = 0; s < C::kDS; ++s)
+          tma_tile(do_s + ds * C::kQBytes + s * C::kSlabQ, &tmdO, do_full + ds, a.q_swap, s * 64, pb * a.P, hq0, b);
+        if (++grp == a.groups_per_kv) { grp = 0; ++pb; }
+        if (++qs == C::kQStages) { qs = 0; qph ^= 1; }
+        if (++ds == C::kDoStages) { ds = 0; dph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == kMathWarps + 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && nchunks > 0) {
       const uint32_t idesc_s = make_idesc(a.fmt, 128, 128, 0, 0);    // S^T = K Q^T : M = keys, N = chunk rows
       const uint32_t idesc_acc = make_idesc(a.fmt, 128, D, 0, 1);    // dV += P^T dO : B = dO tile, MN-major
       const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s);
-      mbar_wait(kv_full, 0);
-      tc_fence_after();
-      for (int c = 0; c < nchunks; ++c) {
-        const int qs = c % C::kQStages;
-        const uint32_t qa = smem_u32(q_s + qs * C::kQBytes), doa = smem_u32(do_s + qs * C::kQBytes);
-        mbar_wait(q_full + qs, (c / C::kQStages) & 1);
-        tc_fence_after();
+      auto issue_s = [&](uint32_t qa) {
 #pragma unroll
         for (int s = 0; s < C::kDS; ++s)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_ss(tmem + C::kColS, make_sdesc(ka + s * C::kSlabKV + kk * 32, 16, 1024),
                     make_sdesc(qa + s * C::kSlabQ + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
+      };
+      auto issue_dp = [&](uint32_t doa) {
 #pragma unroll
         for (int s = 0; s < C::kDS; ++s)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_ss(tmem + C::kColP, make_sdesc(va + s * C::kSlabKV + kk * 32, 16, 1024),
                     make_sdesc(doa + s * C::kSlabQ + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, c & 1);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(smem_u32(q_s));
+      umma_commit(s_full);
+      mbar_wait(do_full, 0);
+      tc_fence_after();
+      issue_dp(smem_u32(do_s));
+      umma_commit(dp_full);
+      int qs = 0, qph = 0, ds = 0, dph = 0;       // stage / phase of chunk c
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t qa = smem_u32(q_s + qs * C::kQBytes), doa = smem_u32(do_s + ds * C::kQBytes);
+        int qs1 = qs + 1, qph1 = qph, ds1 = ds + 1, dph1 = dph;
+        if (qs1 == C::kQStages) { qs1 = 0; qph1 ^= 1; }
+        if (ds1 == C::kDoStages) { ds1 = 0; dph1 ^= 1; }
+        const bool more = (c + 1 < nchunks);
+        // dV += P(c)^T dO(c): contraction over the 128 chunk rows, 16 per UMMA; rows [0,64) were packed into 32-bit
+        // columns [0,32) and rows [64,128) into [64,96) of each region (one range per math-warp half)
+        mbar_wait(p_ready, c & 1);
         tc_fence_after();
-        // contraction over the 128 chunk rows, 16 per UMMA; rows [0,64) were packed into 32-bit columns
-        // [0,32) and rows [64,128) into [64,96) of each region (one range per math-warp half)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_ts(tmem + C::kColV, tmem + C::kColS + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
                   make_sdesc(doa + kk * 2048, C::kSlabQ, 1024), idesc_acc, (c > 0 || kk > 0));
+        umma_commit(do_empty + ds);
+        if (more) {            // S(c+1) behind dV(c) in the pipe: it overwrites the columns P(c) is read from
+          mbar_wait(q_full + qs1, qph1);
+          tc_fence_after();
+          issue_s(smem_u32(q_s + qs1 * C::kQBytes));
+          umma_commit(s_full);
+        }
+        mbar_wait(ds_ready, c & 1);
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_ts(tmem + C::kColK, tmem + C::kColP + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
                   make_sdesc(qa + kk * 2048, C::kSlabQ, 1024), idesc_acc, (c > 0 || kk > 0));
         umma_commit(q_empty + qs);
+        if (more) {
+          mbar_wait(do_full + ds1, dph1);
+          tc_fence_after();
+          issue_dp(smem_u32(do_s + ds1 * C::kQBytes));
+          umma_commit(dp_full);
+        }
+        qs = qs1; qph = qph1; ds = ds1; dph = dph1;
       }
       umma_commit(acc_done);
     }
@@ -1043,81 +1112,141 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int tid = threadIdx.x;                        // 0..255
     const int sh_p = 31 - __clz(a.P), sh_g = 31 - __clz(a.G);          // P and G are powers of two
-    for (int c = 0; c < nchunks; ++c) {
-      const int grp = c % a.groups_per_kv, pb = pb_lo + c / a.groups_per_kv;
-      const int hq0 = (kvh * a.groups_per_kv + grp) * a.G, q0 = pb * a.P;
-      // stage -lse*log2e and delta of the 128 chunk rows (row order = the Q tile's box order)
+    const uint64_t sl2_2 = pack_f32x2(a.sl2, a.sl2), one2 = pack_f32x2(1.f, 1.f);
+    // -lse*log2e and -delta of the 128 chunk rows (row order = the Q tile's box order), staged one chunk ahead
+    const int st_pr = a.q_swap ? (tid >> sh_g) : (tid & (a.P - 1));
+    const int st_gr = a.q_swap ? (tid & (a.G - 1)) : (tid >> sh_p);
+    auto load_stats = [&](int grp, int pb, float& nl, float& nd) {
+      nl = -INFINITY;
+      nd = 0.f;
+      const int i = pb * a.P + st_pr;
+      if (tid < 128 && i < a.N) {
+        const int64_t row = (static_cast<int64_t>(b) * a.Hq + (kvh * a.groups_per_kv + grp) * a.G + st_gr) * a.N + i;
+        const float l = __ldg(a.lse + row);
+        nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
+        nd = -__ldg(a.delta + row);
+      }
+    };
+    int grp = 0, pb = pb_lo;
+    if (nchunks > 0) {
+      float nl, nd;
+      load_stats(grp, pb, nl, nd);
       if (tid < 128) {
-        const int pr = a.q_swap ? (tid >> sh_g) : (tid & (a.P - 1));
-        const int gr = a.q_swap ? (tid & (a.G - 1)) : (tid >> sh_p);
-        const int i = q0 + pr;
-        float nl = -INFINITY, dl = 0.f;
-        if (i < a.N) {
-          const int64_t row = (static_cast<int64_t>(b) * a.Hq + hq0 + gr) * a.N + i;
-          const float l = a.lse[row];
-          nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
-          dl = a.delta[row];
-        }
-        row_l2[(c & 1) * 128 + tid] = nl;
-        row_dl[(c & 1) * 128 + tid] = dl;
+        row_l2[tid] = nl;
+        row_dl[tid] = nd;
       }
       named_bar_sync(1, kMathThreads);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int q0 = pb * a.P;
+      int grp_n = grp + 1, pb_n = pb;
+      if (grp_n == a.groups_per_kv) { grp_n = 0; ++pb_n; }
+      float nl_n = -INFINITY, nd_n = 0.f;
+      if (c + 1 < nchunks) load_stats(grp_n, pb_n, nl_n, nd_n);       // in flight during the two passes
       const float* rl = row_l2 + (c & 1) * 128;
       const float* rd = row_dl + (c & 1) * 128;
-      mbar_wait(s_full, c & 1);
-      tc_fence_after();
       // this thread: columns [half*64, half*64+64) of its key row; 16-bit results go to the low half of the
       // 32-bit columns it has already consumed: P^T over S^T, dS^T over dP^T
-#pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 16) {
-        const int c0 = half * 64 + cc;
-        uint32_t sv[16], dv[16], pp[8], pd[8];
-        tmem_ld16(tl + C::kColS + c0, sv);
-        tmem_ld16(tl + C::kColP + c0, dv);
-        tmem_ld_wait();
-        // positions covered by these 16 chunk rows
-        int i_lo, i_hi;
-        if (a.q_swap) {
-          i_lo = q0 + (c0 >> sh_g);
-          i_hi = q0 + ((c0 + 15) >> sh_g);
-        } else {
-          i_lo = q0 + (c0 & (a.P - 1));
-          i_hi = (a.P >= 16) ? i_lo + 15 : q0 + a.P - 1;
-          if (a.P < 16) i_lo = q0;
-        }
-        // warp-uniform skip: no key of this warp is attended by any of these rows
-        const bool any = (jw_lo <= i_hi) && ((jw_lo < a.S) || (jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
-        if (any) {
+      uint32_t pp[32];
+      // ---- pass 1: P^T = exp2(S^T * c - lse), masked
+      mbar_wait(s_full, c & 1);
+      tc_fence_after();
+      {
+        uint32_t sv[2][16];
+        tmem_ld16(tl + C::kColS + half * 64, sv[0]);
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const int r0 = c0 + e, r1 = r0 + 1;
-            const int i0 = q0 + (a.q_swap ? (r0 >> sh_g) : (r0 & (a.P - 1)));
-            const int i1 = q0 + (a.q_swap ? (r1 >> sh_g) : (r1 & (a.P - 1)));
-            const float2 l2 = *reinterpret_cast<const float2*>(rl + r0);
-            const float2 dl = *reinterpret_cast<const float2*>(rd + r0);
-            float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), a.sl2, l2.x));
-            float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), a.sl2, l2.y));
-            const bool ok0 = attended(i0, j, a.S, a.W) && (j < a.N) && (i0 < e_j);
-            const bool ok1 = attended(i1, j, a.S, a.W) && (j < a.N) && (i1 < e_j);
-            p0 = ok0 ? p0 : 0.f;
-            p1 = ok1 ? p1 : 0.f;
-            const float d0 = ok0 ? p0 * (__uint_as_float(dv[e]) - dl.x) : 0.f;
-            const float d1 = ok1 ? p1 * (__uint_as_float(dv[e + 1]) - dl.y) : 0.f;
-            pp[e >> 1] = pack16_fast<T>(p0, p1);
-            pd[e >> 1] = pack16_fast<T>(d0, d1);
+        for (int g = 0; g < 4; ++g) {
+          const int c0 = half * 64 + g * 16;
+          tmem_ld_wait();
+          if (g < 3) tmem_ld16(tl + C::kColS + c0 + 16, sv[(g + 1) & 1]);
+          const uint32_t (&x)[16] = sv[g & 1];
+          // positions covered by these 16 chunk rows
+          int i_lo, i_hi;
+          if (a.q_swap) {
+            i_lo = q0 + (c0 >> sh_g);
+            i_hi = q0 + ((c0 + 15) >> sh_g);
+          } else {
+            i_lo = q0 + (c0 & (a.P - 1));
+            i_hi = (a.P >= 16) ? i_lo + 15 : q0 + a.P - 1;
+            if (a.P < 16) i_lo = q0;
           }
-        } else {
+          // warp-uniform: no key of this warp is attended by any of these rows / every key by every row
+          const bool any = (jw_lo <= i_hi) && ((jw_lo < a.S) || (jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
+          const bool all = (jw_hi <= i_lo) && ((jw_hi < a.S) || (a.W > 0 && jw_lo >= i_hi - a.W + 1)) && (i_hi < a.N) &&
+                           (a.seq_hi == nullptr);
+          uint32_t pk[8];
+          if (all) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) pp[e] = pd[e] = 0u;
+            for (int e = 0; e < 16; e += 2) {
+              const uint64_t l2 = *reinterpret_cast<const uint64_t*>(rl + c0 + e);
+              float x0, x1;
+              unpack_f32x2(fma_f32x2(x[e], x[e + 1], sl2_2, l2), x0, x1);
+              pk[e >> 1] = pack16_fast<T>(fast_exp2(x0), fast_exp2(x1));
+            }
+          } else if (any) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int r0 = c0 + e, r1 = r0 + 1;
+              const int i0 = q0 + (a.q_swap ? (r0 >> sh_g) : (r0 & (a.P - 1)));
+              const int i1 = q0 + (a.q_swap ? (r1 >> sh_g) : (r1 & (a.P - 1)));
+              const float2 l2 = *reinterpret_cast<const float2*>(rl + r0);
+              float p0 = fast_exp2(fmaf(__uint_as_float(x[e]), a.sl2, l2.x));
+              float p1 = fast_exp2(fmaf(__uint_as_float(x[e + 1]), a.sl2, l2.y));
+              const bool ok0 = attended(i0, j, a.S, a.W) && (j < a.N) && (i0 < e_j);
+              const bool ok1 = attended(i1, j, a.S, a.W) && (j < a.N) && (i1 < e_j);
+              pk[e >> 1] = pack16_fast<T>(ok0 ? p0 : 0.f, ok1 ? p1 : 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk[e] = 0u;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pp[g * 8 + e] = pk[e];
+          // each half packs into the front of its OWN source range (32-bit columns [half*64, half*64+32)),
+          // so it never overwrites fp32 columns the other half (or this thread's next load) has yet to read
+          tmem_st8(tl + C::kColS + half * 64 + g * 8, pk);
         }
-        // each half packs into the front of its OWN source range (32-bit columns [half*64, half*64+32)),
-        // so it never overwrites fp32 columns the other half has yet to read
-        tmem_st8(tl + C::kColS + half * 64 + (cc >> 1), pp);
-        tmem_st8(tl + C::kColP + half * 64 + (cc >> 1), pd);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(p_ready);
+      // ---- pass 2: dS^T = P^T o (dP^T - delta): t = dP - delta rounded to 16 bit, then one packed multiply with the
+      // P pair (masked P is exactly 0 and dP is finite there: dS = 0)
+      mbar_wait(dp_full, c & 1);
+      tc_fence_after();
+      {
+        uint32_t dv[2][16];
+        tmem_ld16(tl + C::kColP + half * 64, dv[0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c0 = half * 64 + g * 16;
+          tmem_ld_wait();
+          if (g < 3) tmem_ld16(tl + C::kColP + c0 + 16, dv[(g + 1) & 1]);
+          const uint32_t (&x)[16] = dv[g & 1];
+          uint32_t pd[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const uint64_t nd2 = *reinterpret_cast<const uint64_t*>(rd + c0 + e);
+            float t0, t1;
+            unpack_f32x2(fma_f32x2(x[e], x[e + 1], one2, nd2), t0, t1);
+            pd[e >> 1] = mul16x2<T>(pp[g * 8 + (e >> 1)], pack16_fast<T>(t0, t1));
+          }
+          tmem_st8(tl + C::kColP + half * 64 + g * 8, pd);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+      // next chunk's row statistics: buffer (c + 1) & 1 was last read in chunk c - 1
+      if (c + 1 < nchunks) {
+        if (tid < 128) {
+          row_l2[((c + 1) & 1) * 128 + tid] = nl_n;
+          row_dl[((c + 1) & 1) * 128 + tid] = nd_n;
+        }
+        named_bar_sync(1, kMathThreads);
+      }
+      grp = grp_n;
+      pb = pb_n;
     }
     // ---------------- epilogue: dK * scale, dV -> 16-bit -> global (one key row per thread, half the channels)
     if (nchunks > 0) {
@@ -1667,8 +1796,9 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.seq_hi = p.seq_hi; a.seq_bs = p.seq_bs;
     a.trace = trace_buffer();
     dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
+    a.ntiles = static_cast<int>(grid.x);
     if constexpr (D == 64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
-    else dkdv_kernel<T, D><<<grid, kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    else dkdv_kernel<T, D><<<grid.x * grid.y * grid.z, kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);   // 1-D: heavy tiles first
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
