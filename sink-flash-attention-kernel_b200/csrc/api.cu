@@ -206,6 +206,8 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
     set_impl_name("tcgen05");
     if (tc_fwd64_supported(p, dtype) && !(g_env_fwd_v1 && p.o_route == nullptr && !p.has_ext()))
       return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
+    // 64 < head_dim <= 128: persistent kernel, two query tiles per CTA
+    if (tc_fwd128_supported(p, dtype) && !g_env_fwd_v1) return cuda_ret(tc_fwd128(p, dtype, st), "sfa_fwd(tcgen05/fwd128)");
     // the one-tile-per-CTA kernel (head_dim > 64) takes packed sequences without sink tokens, not chunk offsets
     if (p.q_off == 0 && p.Nkv == p.N && !(p.seq_lo != nullptr && p.S > 0))
       return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");

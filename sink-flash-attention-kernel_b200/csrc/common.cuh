@@ -116,6 +116,8 @@ cudaError_t tc_fwd(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_fwd64_supported(const AttnParams& p, int dtype);   // persistent warp-specialised forward, head_dim 64
 cudaError_t tc_fwd64(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_fwd64_route_supported(const AttnParams& p, int dtype);
+bool tc_fwd128_supported(const AttnParams& p, int dtype);  // persistent two-tile forward, 64 < head_dim <= 128
+cudaError_t tc_fwd128(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_bwd_supported(const AttnParams& p, int dtype);
 bool tc_bwd_fuses_delta(const AttnParams& p, int dtype);   // the dQ kernel derives delta (and ds_aux rows) itself: no preprocess pass
 cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st);
