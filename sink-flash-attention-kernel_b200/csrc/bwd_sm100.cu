@@ -71,27 +71,30 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int& cnt, i
 // ================================================================================== dQ kernel
 // Work items = (packed Q tile, KV tile) pairs in the order of the two-range walk, two TMEM slots:
 // the UMMAs of item n+1 (S, dP) run while the math warps work on item n, and dQ(n) runs under the
-// math of item n+1.  With D = 64 the dQ accumulator is double-buffered too, so a tile's epilogue is
-// deferred by one item and never waits for its own dQ UMMAs.
+// math of item n+1.  (head_dim 64 has its own kernel below; this one serves 64 < D <= 128.)
+//
+// Shared memory at head_dim 128: a tile's Q and dO are 32 KB each, a K or V item 24 KB.  Round 1 held two (Q, dO)
+// stages and only two K slots, so K(n + 2) could be requested only when dQ(n) had completed -- right when S(n + 2)
+// wanted it: one exposed TMA latency per item.  Now THREE 32 KB buffers rotate through the roles
+// Q(t), dO(t), Q(t+1), dO(t+1), ... (use u = 2t / 2t + 1 -> buffer u % 3): Q(t + 1) is prefetched into the buffer
+// dO(t - 1) left (after it served as the staging tile of dQ(t - 1)'s store), dO(t + 1) goes where Q(t) was as soon
+// as the tile's last S is complete; that frees the room for a K ring of three.
 template <int D> struct DqCfg {
+  static_assert(D == 128, "head_dim 64 runs dq64_kernel");
   static constexpr int kDS = D / 64;
   static constexpr int kBNMax = 96;                      // KV rows per item (UMMA N of S and dP)
-  // TMA loads take ~2.4 us under load (measured with the clock64 timeline, tools/trace_dq.py): the rings are
-  // sized so every load is issued two or more items before its first use
-  static constexpr int kKStages = (D == 64) ? 4 : 2;     // K is held from S(n) to dQ(n)
-  static constexpr int kVStages = (D == 64) ? 3 : 2;
-  static constexpr int kQStages = (D == 64) ? 3 : 2;     // Q / dO tiles
-  static constexpr int kDqBufs = (D == 64) ? 2 : 1;
-  static constexpr bool kSepStage = (D == 64);           // own staging buffer for the dQ TMA store
+  static constexpr int kKStages = 3;                     // K is held from S(n) to dQ(n)
+  static constexpr int kVStages = 2;
+  static constexpr int kQBufs = 3;                       // rotating Q / dO / staging buffers
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = kBNMax * D * 2;
   static constexpr int kSlabQ = 128 * 128;
   static constexpr int kSlabKV = kBNMax * 128;
   static constexpr uint32_t kTmemCols = 512;
   static constexpr uint32_t kSlotCols = 2 * kBNMax;      // S then dP
-  static constexpr uint32_t kColQ = 2 * kSlotCols;       // dQ accumulator(s)
-  static constexpr int kSmem = 1024 + (2 * kQStages + (kSepStage ? 1 : 0)) * kQBytes + (kKStages + kVStages) * kKVBytes + 512;
-  static_assert(2 * kSlotCols + kDqBufs * D <= 512, "TMEM budget");
+  static constexpr uint32_t kColQ = 2 * kSlotCols;       // dQ accumulator
+  static constexpr int kSmem = 1024 + kQBufs * kQBytes + (kKStages + kVStages) * kKVBytes + 512;
+  static_assert(2 * kSlotCols + D <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
 
@@ -106,23 +109,21 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
   using C = DqCfg<D>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* q_s = smem;                                   // [kQStages][kQBytes]
-  unsigned char* do_s = q_s + C::kQStages * C::kQBytes;        // [kQStages][kQBytes]
-  unsigned char* stage_s = do_s + C::kQStages * C::kQBytes;    // [kQBytes] if kSepStage
-  unsigned char* k_s = stage_s + (C::kSepStage ? C::kQBytes : 0);
+  unsigned char* qb_s = smem;                                  // [kQBufs][kQBytes]  use u -> buffer u % 3
+  unsigned char* k_s = qb_s + C::kQBufs * C::kQBytes;
   unsigned char* v_s = k_s + C::kKStages * C::kKVBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + C::kVStages * C::kKVBytes);
-  uint64_t* qdo_full = bars;                       // [kQStages]
-  uint64_t* qdo_empty = qdo_full + C::kQStages;    // [kQStages]
-  uint64_t* k_full = qdo_empty + C::kQStages;      // [kKStages]
+  uint64_t* qb_full = bars;                        // [kQBufs]  use u landed: phase u / 3
+  uint64_t* qb_empty = qb_full + C::kQBufs;        // [kQBufs]  Q use: the tile's last S complete; dO use: dQ store has read the staging tile
+  uint64_t* k_full = qb_empty + C::kQBufs;         // [kKStages]
   uint64_t* k_empty = k_full + C::kKStages;
   uint64_t* v_full = k_empty + C::kKStages;        // [kVStages]
   uint64_t* v_empty = v_full + C::kVStages;
   uint64_t* s_full = v_empty + C::kVStages;        // [2]
   uint64_t* p_full = s_full + 2;                   // [2]
-  uint64_t* dq_done = p_full + 2;                  // [kDqBufs]
-  uint64_t* dq_free = dq_done + C::kDqBufs;        // [kDqBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + C::kDqBufs);
+  uint64_t* dq_done = p_full + 2;
+  uint64_t* dq_free = dq_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -132,9 +133,9 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmdQ);
-    for (int s = 0; s < C::kQStages; ++s) {
-      mbar_init(qdo_full + s, 1);
-      mbar_init(qdo_empty + s, 1);
+    for (int s = 0; s < C::kQBufs; ++s) {
+      mbar_init(qb_full + s, 1);
+      mbar_init(qb_empty + s, 1);
     }
     for (int s = 0; s < C::kKStages; ++s) {
       mbar_init(k_full + s, 1);
@@ -148,10 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       mbar_init(s_full + s, 1);
       mbar_init(p_full + s, kMathThreads);
     }
-    for (int s = 0; s < C::kDqBufs; ++s) {
-      mbar_init(dq_done + s, 1);
-      mbar_init(dq_free + s, kMathThreads);
-    }
+    mbar_init(dq_done, 1);
+    mbar_init(dq_free, kMathThreads);
     fence_barrier_init();
   }
   if (warp == kMathWarps + 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -165,17 +164,32 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
     if (lane == 0) {
       ItemWalk w(a);
       int tc = 0;
+      int q_loaded = 0;        // tiles (w.it) whose Q has been requested
+      // Q or dO tile of the tile (pb, y, b) as use u of the rotating buffers
+      auto load_tile = [&](const CUtensorMap* tm, int u, int q0, int hq0, int b) {
+        const int bf = u % C::kQBufs;
+        mbar_wait(qb_empty + bf, ((u / C::kQBufs) & 1) ^ 1);
+        mbar_expect_tx(qb_full + bf, C::kQBytes);
+        for (int s = 0; s < C::kDS; ++s)
+          tma_tile(qb_s + bf * C::kQBytes + s * C::kSlabQ, tm, qb_full + bf, a.q_swap, s * 64, q0, hq0, b);
+      };
       while (w.next()) {
         const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
         if (w.t == 0) {
-          const int qs = w.it % C::kQStages;
-          mbar_wait(qdo_empty + qs, ((w.it / C::kQStages) & 1) ^ 1);
-          trace_ev(a.trace, 0, tc, 1, w.it);      // Q/dO stage free -> loads issued
-          mbar_expect_tx(qdo_full + qs, 2 * C::kQBytes);
-          for (int s = 0; s < C::kDS; ++s) {
-            tma_tile(q_s + qs * C::kQBytes + s * C::kSlabQ, &tmQ, qdo_full + qs, a.q_swap, s * 64, w.q0, hq0, w.b);
-            tma_tile(do_s + qs * C::kQBytes + s * C::kSlabQ, &tmdO, qdo_full + qs, a.q_swap, s * 64, w.q0, hq0, w.b);
+          if (q_loaded <= w.it) {
+            load_tile(&tmQ, 2 * w.it, w.q0, hq0, w.b);
+            q_loaded = w.it + 1;
           }
+          trace_ev(a.trace, 0, tc, 1, w.it);
+          load_tile(&tmdO, 2 * w.it + 1, w.q0, hq0, w.b);       // waits for the previous tile's last S
+        }
+        // prefetch of the NEXT tile's Q, two items into this tile: its buffer was the staging tile of the previous
+        // tile's dQ store (issued by the math warps after this tile's first item)
+        if (w.t == 2 && q_loaded == w.it + 1 && w.tile + w.step < w.end) {
+          int pb = w.pb, y = w.y, b = w.b;
+          ItemWalk::advance(a, w.step, pb, y, b);
+          load_tile(&tmQ, 2 * (w.it + 1), pb * a.P, y * a.G, b);
+          q_loaded = w.it + 2;
         }
         int kstart, cols; bool is_sink;
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
@@ -200,22 +214,20 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       int tc = 0;
       // S = Q K^T and dP = dO V^T of the item `w` points at, into its TMEM slot
       auto issue_sdp = [&](const ItemWalk& w) {
-        const int slot = w.n & 1, qs = w.it % C::kQStages;
-        if (w.t == 0) {
-          mbar_wait(qdo_full + qs, (w.it / C::kQStages) & 1);
-          tc_fence_after();
-          trace_ev(a.trace, 1, tc, 1, w.it);     // Q/dO landed
-        }
+        const int slot = w.n & 1;
+        const int uq = 2 * w.it, ud = 2 * w.it + 1;
+        const int bq = uq % C::kQBufs, bd = ud % C::kQBufs;
         int kstart, cols; bool is_sink;
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         const int kst = w.n % C::kKStages, vst = w.n % C::kVStages;
         const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
         // descriptors of the first K-step; the next ones are +32 B (= +2 in the encoded address field)
-        const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
-        const uint64_t dod = make_sdesc(smem_u32(do_s + qs * C::kQBytes), 16, 1024);
+        const uint64_t qd = make_sdesc(smem_u32(qb_s + bq * C::kQBytes), 16, 1024);
+        const uint64_t dod = make_sdesc(smem_u32(qb_s + bd * C::kQBytes), 16, 1024);
         const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), 16, 1024);
         const uint64_t vd = make_sdesc(smem_u32(v_s + vst * C::kKVBytes), 16, 1024);
         const uint32_t ts = tmem + slot * C::kSlotCols;
+        if (w.t == 0) mbar_wait(qb_full + bq, (uq / C::kQBufs) & 1);
         mbar_wait(k_full + kst, (w.n / C::kKStages) & 1);
         tc_fence_after();
         trace_ev(a.trace, 1, tc, 2, w.n);        // K landed
@@ -224,7 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_ss(ts, qd + ((s * C::kSlabQ + kk * 32) >> 4), kd + ((s * C::kSlabKV + kk * 32) >> 4), idesc_s, (s | kk) != 0);
+        if (w.last_of_tile()) umma_commit(qb_empty + bq);       // Q is only read by S: its buffer takes the next tile's dO
         trace_ev(a.trace, 1, tc, 5, w.n);        // S UMMAs issued
+        if (w.t == 0) mbar_wait(qb_full + bd, (ud / C::kQBufs) & 1);
         mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
         tc_fence_after();
         trace_ev(a.trace, 1, tc, 6, w.n);        // V landed
@@ -243,22 +257,22 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       if (w_sdp.next()) issue_sdp(w_sdp);
       while (w_dq.next()) {
         if (w_sdp.next()) issue_sdp(w_sdp);          // item n+1 runs under the math of item n
-        const int slot = w_dq.n & 1, qs = w_dq.it % C::kQStages, buf = w_dq.it % C::kDqBufs;
+        const int slot = w_dq.n & 1;
         const int kst = w_dq.n % C::kKStages;
         int kstart, cols; bool is_sink;
         w_dq.pl.tile(w_dq.t, a.BN, kstart, cols, is_sink);
         mbar_wait(p_full + slot, (w_dq.n >> 1) & 1);
         tc_fence_after();
         trace_ev(a.trace, 1, tc, 4, w_dq.n);     // dS ready
-        if (w_dq.t == 0 && w_dq.it >= C::kDqBufs) {
-          mbar_wait(dq_free + buf, ((w_dq.it / C::kDqBufs) - 1) & 1);
+        if (w_dq.t == 0 && w_dq.it >= 1) {
+          mbar_wait(dq_free, (w_dq.it - 1) & 1);
           tc_fence_after();
         }
         // dS is held as 16-bit pairs: first half of the key columns over dP, second half over S
         const uint32_t ts = tmem + slot * C::kSlotCols;
         const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), C::kSlabKV, 1024);
         const int hcol = ((cols / 16 + 1) / 2) * 16;
-        const uint32_t dqa = tmem + C::kColQ + buf * D;
+        const uint32_t dqa = tmem + C::kColQ;
         const uint32_t a_lo = ts + C::kBNMax, a_hi = ts + hcol - (hcol >> 1);   // + c0/2 in both halves
         const int nk = cols >> 4;
 #pragma unroll
@@ -267,10 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
             umma_ts(dqa, ((kk * 16 < hcol) ? a_lo : a_hi) + kk * 8, kd + kk * (2048 >> 4), idesc_dq, (w_dq.t > 0 || kk > 0));
         trace_ev(a.trace, 1, tc, 8, w_dq.n);     // dQ UMMAs issued
         umma_commit(k_empty + kst);
-        if (w_dq.last_of_tile()) {
-          umma_commit(dq_done + buf);
-          if (C::kSepStage) umma_commit(qdo_empty + qs);
-        }
+        if (w_dq.last_of_tile()) umma_commit(dq_done);
         trace_ev(a.trace, 1, tc, 9, w_dq.n);     // dQ committed
       }
     }
@@ -299,21 +310,17 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
     };
     struct Pending { int valid, it, q0, hq0, b; } pend = {0, 0, 0, 0, 0};
     auto epilogue = [&](const Pending& e) {
-      const int qs = e.it % C::kQStages, buf = e.it % C::kDqBufs;
-      unsigned char* stage = C::kSepStage ? stage_s : (q_s + qs * C::kQBytes);
-      if (C::kSepStage) {
-        // the previous tile's TMA store must have finished reading the staging buffer
-        if (threadIdx.x == 0) tma_store_wait_read0();
-        named_bar_sync(2, kMathThreads);
-      }
-      mbar_wait(dq_done + buf, (e.it / C::kDqBufs) & 1);
+      // staging tile of the dQ store = the buffer the tile's dO sat in (all of the tile's UMMAs are complete)
+      const int bd = (2 * e.it + 1) % C::kQBufs;
+      unsigned char* stage = qb_s + bd * C::kQBytes;
+      mbar_wait(dq_done, e.it & 1);
       tc_fence_after();
       uint32_t v[D / 32][16];
 #pragma unroll
-      for (int cc = 0; cc < D / 32; ++cc) tmem_ld16(tl + C::kColQ + buf * D + half * (D / 2) + cc * 16, v[cc]);
+      for (int cc = 0; cc < D / 32; ++cc) tmem_ld16(tl + C::kColQ + half * (D / 2) + cc * 16, v[cc]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(dq_free + buf);
+      mbar_arrive(dq_free);
 #pragma unroll
       for (int cc = 0; cc < D / 32; ++cc) {
         const int c0 = half * (D / 2) + cc * 16;
@@ -331,10 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       if (threadIdx.x == 0) {
         for (int s = 0; s < C::kDS; ++s) tma_tile_store(&tmdQ, stage + s * C::kSlabQ, a.dq_swap, s * 64, e.q0, e.hq0, e.b);
         tma_store_commit();
-        if (!C::kSepStage) {
-          tma_store_wait_read0();
-          mbar_arrive(qdo_empty + qs);
-        }
+        tma_store_wait_read0();
+        mbar_arrive(qb_empty + bd);        // the buffer may take the Q of the tile after next
       }
     };
 
@@ -1717,6 +1722,13 @@ inline bool fuses_delta(const AttnParams& p, int P, int BN) {
   return enabled && p.S == 0 && p.W > 0 && span <= BN;
 }
 
+template <int D> struct DqSel {
+  static constexpr int kBNMax = DqCfg<D>::kBNMax, kSmem = DqCfg<D>::kSmem;
+};
+template <> struct DqSel<64> {
+  static constexpr int kBNMax = Dq64Cfg::kBNMax, kSmem = Dq64Cfg::kSmem;
+};
+
 template <typename T, int D>
 cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
   const int group = p.Hq / p.Hkv;
@@ -1729,8 +1741,8 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
   if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;   // guarded by tc_bwd_supported
 
   if (stages & 2) {
-    constexpr int kBNMax = (D == 64) ? Dq64Cfg::kBNMax : DqCfg<D>::kBNMax;
-    constexpr int kSmemDq = (D == 64) ? Dq64Cfg::kSmem : DqCfg<D>::kSmem;
+    constexpr int kBNMax = DqSel<D>::kBNMax;
+    constexpr int kSmemDq = DqSel<D>::kSmem;
     static std::atomic<unsigned long long> attr_done{0};
     {
       cudaError_t e;
