@@ -21,6 +21,7 @@
 // Warp roles (320 threads): warps 0-7 element-wise math + epilogue (two warps per TMEM lane
 // quarter, each taking half of the columns), warp 8 TMA producer, warp 9 tcgen05.mma issuer.
 #include <stdlib.h>
+#include <type_traits>
 
 #include "attn_common.cuh"
 #include "tmap.cuh"
@@ -119,11 +120,12 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
   uint64_t* k_empty = k_full + C::kKStages;
   uint64_t* v_full = k_empty + C::kKStages;        // [kVStages]
   uint64_t* v_empty = v_full + C::kVStages;
-  uint64_t* s_full = v_empty + C::kVStages;        // [2]
+  uint64_t* s_full = v_empty + C::kVStages;        // [2]  S and dP of the slot complete
   uint64_t* p_full = s_full + 2;                   // [2]
   uint64_t* dq_done = p_full + 2;
   uint64_t* dq_free = dq_done + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+  uint64_t* s1_full = dq_free + 1;                 // [2]  S of the slot complete: the exponentials start under the dP UMMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s1_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full + s, 1);
+      mbar_init(s1_full + s, 1);
       mbar_init(p_full + s, kMathThreads);
     }
     mbar_init(dq_done, 1);
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_ss(ts, qd + ((s * C::kSlabQ + kk * 32) >> 4), kd + ((s * C::kSlabKV + kk * 32) >> 4), idesc_s, (s | kk) != 0);
+        umma_commit(s1_full + slot);
         if (w.last_of_tile()) umma_commit(qb_empty + bq);       // Q is only read by S: its buffer takes the next tile's dO
         trace_ev(a.trace, 1, tc, 5, w.n);        // S UMMAs issued
         if (w.t == 0) mbar_wait(qb_full + bd, (ud / C::kQBufs) & 1);
@@ -344,6 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
     };
 
     float l_next, dl_next, neg_l2 = -INFINITY, delta = 0.f;
+    const uint64_t sl2_2 = pack_f32x2(a.sl2, a.sl2), one2 = pack_f32x2(1.f, 1.f);
+    uint64_t negl2_2 = 0, ndelta2 = 0;
     int i = 0, mtc = 0;
     ItemWalk w(a);
     {
@@ -355,6 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       if (w.t == 0) {
         neg_l2 = (l_next == -INFINITY) ? -INFINITY : -l_next * kLog2e;   // lse = -inf: nothing attended, P = 0
         delta = dl_next;
+        negl2_2 = pack_f32x2(neg_l2, neg_l2);
+        ndelta2 = pack_f32x2(-delta, -delta);
         i = w.q0 + pr;
         int pb = w.pb, y = w.y, b = w.b;
         ItemWalk::advance(a, w.step, pb, y, b);
@@ -372,50 +380,65 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       const int hch = (nch + 1) / 2;
       const int hcol = hch * 16;
       const int ch0 = half ? hch : 0, ch1 = half ? nch : hch;
-      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 1, w.n);     // waiting for S, dP
-      mbar_wait(s_full + slot, (w.n >> 1) & 1);
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 1, w.n);     // waiting for S
+      // ---- phase 1 (under the dP UMMAs): P = exp2(S * c - lse) of this thread's columns -> packed 16-bit in registers
+      mbar_wait(s1_full + slot, (w.n >> 1) & 1);
       tc_fence_after();
-      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 2, w.n);     // S, dP complete
-      // all of this thread's S and dP columns are fetched before the first use: one exposed TMEM latency per item
       constexpr int kMaxCh = (C::kBNMax / 16 + 1) / 2;
-      uint32_t sv[kMaxCh][16], dv[kMaxCh][16];
+      uint32_t xv[kMaxCh][16], pp[kMaxCh][8];
+#pragma unroll
+      for (int jj = 0; jj < kMaxCh; ++jj)
+        if (ch0 + jj < ch1) tmem_ld16(ts + (ch0 + jj) * 16, xv[jj]);
+      tmem_ld_wait();
+      // every column of the item attended by every row of the warp (all items but the ends of a band): no per-chunk tests
+      const bool interior = __all_sync(0xffffffffu, c_lo <= 0 && c_hi >= cols - 1);
 #pragma unroll
       for (int jj = 0; jj < kMaxCh; ++jj)
         if (ch0 + jj < ch1) {
-          tmem_ld16(ts + (ch0 + jj) * 16, sv[jj]);
-          tmem_ld16(ts + C::kBNMax + (ch0 + jj) * 16, dv[jj]);
+          const int c0 = (ch0 + jj) * 16;
+          if (interior || __all_sync(0xffffffffu, (c0 >= c_lo) && (c0 + 15 <= c_hi))) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              float x0, x1;
+              unpack_f32x2(fma_f32x2(xv[jj][e], xv[jj][e + 1], sl2_2, negl2_2), x0, x1);
+              pp[jj][e >> 1] = pack16_fast<T>(fast_exp2(x0), fast_exp2(x1));
+            }
+          } else if (c0 + 15 >= c_lo && c0 <= c_hi) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int c = c0 + e;
+              float p0 = fast_exp2(fmaf(__uint_as_float(xv[jj][e]), a.sl2, neg_l2));
+              float p1 = fast_exp2(fmaf(__uint_as_float(xv[jj][e + 1]), a.sl2, neg_l2));
+              p0 = (c >= c_lo && c <= c_hi) ? p0 : 0.f;
+              p1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? p1 : 0.f;
+              pp[jj][e >> 1] = pack16_fast<T>(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pp[jj][e] = 0u;
+          }
+          __syncwarp();
         }
+      // ---- phase 2: dS = P o (dP - delta): t = dP - delta rounded to 16 bit, one packed multiply with the P pair (masked
+      // P is exactly 0 and dP is finite: dS = 0 there)
+      mbar_wait(s_full + slot, (w.n >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 2, w.n);     // S, dP complete
+#pragma unroll
+      for (int jj = 0; jj < kMaxCh; ++jj)
+        if (ch0 + jj < ch1) tmem_ld16(ts + C::kBNMax + (ch0 + jj) * 16, xv[jj]);
       tmem_ld_wait();
 #pragma unroll
       for (int jj = 0; jj < kMaxCh; ++jj)
         if (ch0 + jj < ch1) {
           const int c0 = (ch0 + jj) * 16;
           uint32_t pk[8];
-          const bool full = (c0 >= c_lo) && (c0 + 15 <= c_hi);
-          if (__all_sync(0xffffffffu, full)) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[jj][e]), a.sl2, neg_l2));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[jj][e + 1]), a.sl2, neg_l2));
-              pk[e >> 1] = pack16_fast<T>(p0 * (__uint_as_float(dv[jj][e]) - delta), p1 * (__uint_as_float(dv[jj][e + 1]) - delta));
-            }
-          } else if (c0 + 15 >= c_lo && c0 <= c_hi) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const int c = c0 + e;
-              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[jj][e]), a.sl2, neg_l2));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[jj][e + 1]), a.sl2, neg_l2));
-              float d0 = p0 * (__uint_as_float(dv[jj][e]) - delta);
-              float d1 = p1 * (__uint_as_float(dv[jj][e + 1]) - delta);
-              d0 = (c >= c_lo && c <= c_hi) ? d0 : 0.f;
-              d1 = (c + 1 >= c_lo && c + 1 <= c_hi) ? d1 : 0.f;
-              pk[e >> 1] = pack16_fast<T>(d0, d1);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pk[e] = 0u;
+          for (int e = 0; e < 16; e += 2) {
+            float t0, t1;
+            unpack_f32x2(fma_f32x2(xv[jj][e], xv[jj][e + 1], one2, ndelta2), t0, t1);
+            pk[e >> 1] = mul16x2<T>(pp[jj][e >> 1], pack16_fast<T>(t0, t1));
           }
-          __syncwarp();
           const uint32_t dst = half ? (ts + hcol + ((c0 - hcol) >> 1)) : (ts + C::kBNMax + (c0 >> 1));
           tmem_st8(dst, pk);
         }
@@ -1121,33 +1144,37 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
     // -lse*log2e and -delta of the 128 chunk rows (row order = the Q tile's box order), staged one chunk ahead
     const int st_pr = a.q_swap ? (tid >> sh_g) : (tid & (a.P - 1));
     const int st_gr = a.q_swap ? (tid & (a.G - 1)) : (tid >> sh_p);
-    auto load_stats = [&](int grp, int pb, float& nl, float& nd) {
-      nl = -INFINITY;
-      nd = 0.f;
+    // raw lse / delta of this thread's chunk row (threads 0-127), loaded one chunk ahead; the values are only touched
+    // when they are stored to shared memory at the end of the chunk (no scoreboard wait in between)
+    auto load_stats = [&](int grp, int pb, float& l, float& d) {
+      l = -INFINITY;
+      d = 0.f;
       const int i = pb * a.P + st_pr;
       if (tid < 128 && i < a.N) {
         const int64_t row = (static_cast<int64_t>(b) * a.Hq + (kvh * a.groups_per_kv + grp) * a.G + st_gr) * a.N + i;
-        const float l = __ldg(a.lse + row);
-        nl = (l == -INFINITY) ? -INFINITY : -l * kLog2e;
-        nd = -__ldg(a.delta + row);
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l) : "l"(a.lse + row));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(d) : "l"(a.delta + row));
+      }
+    };
+    auto store_stats = [&](int buf, float l, float d) {
+      if (tid < 128) {
+        row_l2[buf * 128 + tid] = (l == -INFINITY) ? -INFINITY : -l * kLog2e;     // lse = -inf: nothing attended, P = 0
+        row_dl[buf * 128 + tid] = -d;
       }
     };
     int grp = 0, pb = pb_lo;
     if (nchunks > 0) {
-      float nl, nd;
-      load_stats(grp, pb, nl, nd);
-      if (tid < 128) {
-        row_l2[tid] = nl;
-        row_dl[tid] = nd;
-      }
+      float l0, d0;
+      load_stats(grp, pb, l0, d0);
+      store_stats(0, l0, d0);
       named_bar_sync(1, kMathThreads);
     }
     for (int c = 0; c < nchunks; ++c) {
       const int q0 = pb * a.P;
       int grp_n = grp + 1, pb_n = pb;
       if (grp_n == a.groups_per_kv) { grp_n = 0; ++pb_n; }
-      float nl_n = -INFINITY, nd_n = 0.f;
-      if (c + 1 < nchunks) load_stats(grp_n, pb_n, nl_n, nd_n);       // in flight during the two passes
+      float l_n = -INFINITY, d_n = 0.f;
+      if (c + 1 < nchunks) load_stats(grp_n, pb_n, l_n, d_n);         // in flight during the two passes
       const float* rl = row_l2 + (c & 1) * 128;
       const float* rd = row_dl + (c & 1) * 128;
       // this thread: columns [half*64, half*64+64) of its key row; 16-bit results go to the low half of the
@@ -1156,7 +1183,12 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
       // ---- pass 1: P^T = exp2(S^T * c - lse), masked
       mbar_wait(s_full, c & 1);
       tc_fence_after();
-      {
+      // every row of the chunk attends every key of the tile (all but the few chunks at the two ends of the band):
+      // CTA-uniform, so the common chunk pays for no per-group position arithmetic at all
+      const bool interior = (j0 + C::kBK - 1 <= q0) && (q0 + a.P - 1 < a.N) && (a.seq_hi == nullptr) &&
+                            ((j0 + C::kBK - 1 < a.S) || (a.W > 0 && j0 >= q0 + a.P - a.W));
+      auto pass1 = [&](auto tag) {
+        constexpr bool kInterior = decltype(tag)::value;
         uint32_t sv[2][16];
         tmem_ld16(tl + C::kColS + half * 64, sv[0]);
 #pragma unroll
@@ -1165,20 +1197,23 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
           tmem_ld_wait();
           if (g < 3) tmem_ld16(tl + C::kColS + c0 + 16, sv[(g + 1) & 1]);
           const uint32_t (&x)[16] = sv[g & 1];
-          // positions covered by these 16 chunk rows
-          int i_lo, i_hi;
-          if (a.q_swap) {
-            i_lo = q0 + (c0 >> sh_g);
-            i_hi = q0 + ((c0 + 15) >> sh_g);
-          } else {
-            i_lo = q0 + (c0 & (a.P - 1));
-            i_hi = (a.P >= 16) ? i_lo + 15 : q0 + a.P - 1;
-            if (a.P < 16) i_lo = q0;
+          bool any = true, all = true;
+          if constexpr (!kInterior) {
+            // positions covered by these 16 chunk rows
+            int i_lo, i_hi;
+            if (a.q_swap) {
+              i_lo = q0 + (c0 >> sh_g);
+              i_hi = q0 + ((c0 + 15) >> sh_g);
+            } else {
+              i_lo = q0 + (c0 & (a.P - 1));
+              i_hi = (a.P >= 16) ? i_lo + 15 : q0 + a.P - 1;
+              if (a.P < 16) i_lo = q0;
+            }
+            // warp-uniform: no key of this warp is attended by any of these rows / every key by every row
+            any = (jw_lo <= i_hi) && ((jw_lo < a.S) || (jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
+            all = (jw_hi <= i_lo) && ((jw_hi < a.S) || (a.W > 0 && jw_lo >= i_hi - a.W + 1)) && (i_hi < a.N) &&
+                  (a.seq_hi == nullptr);
           }
-          // warp-uniform: no key of this warp is attended by any of these rows / every key by every row
-          const bool any = (jw_lo <= i_hi) && ((jw_lo < a.S) || (jw_hi >= i_lo - a.W + 1)) && (i_lo < a.N);
-          const bool all = (jw_hi <= i_lo) && ((jw_hi < a.S) || (a.W > 0 && jw_lo >= i_hi - a.W + 1)) && (i_hi < a.N) &&
-                           (a.seq_hi == nullptr);
           uint32_t pk[8];
           if (all) {
 #pragma unroll
@@ -1211,7 +1246,9 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
           // so it never overwrites fp32 columns the other half (or this thread's next load) has yet to read
           tmem_st8(tl + C::kColS + half * 64 + g * 8, pk);
         }
-      }
+      };
+      if (interior) pass1(std::true_type{});
+      else pass1(std::false_type{});
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
@@ -1244,10 +1281,7 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
       mbar_arrive(ds_ready);
       // next chunk's row statistics: buffer (c + 1) & 1 was last read in chunk c - 1
       if (c + 1 < nchunks) {
-        if (tid < 128) {
-          row_l2[((c + 1) & 1) * 128 + tid] = nl_n;
-          row_dl[((c + 1) & 1) * 128 + tid] = nd_n;
-        }
+        store_stats((c + 1) & 1, l_n, d_n);
         named_bar_sync(1, kMathThreads);
       }
       grp = grp_n;
