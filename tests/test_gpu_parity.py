@@ -120,6 +120,13 @@ def test_prefill_lowp_vs_oracle(case, dtype):
     (1, 8, 2, 300, 80, 4, 64, True),         # head_dim 80 (north star; the reference's Triton kernel cannot run it): on the
     (2, 4, 4, 257, 96, 0, 257, True),        # head_dim-128 tensor-core kernels, missing channels = TMA zero fill
     (1, 4, 1, 200, 112, 2, 33, False),
+    # the persistent two-tile forward (64 < head_dim <= 128): odd number of position blocks (tile B of the last pair
+    # past N), two packed head groups per KV head, sink tokens spanning several KV tiles, sinks only, one short tile
+    (1, 64, 2, 1000, 128, 0, 300, True),     # group 32 -> G = 16, two groups per KV head, 8 positions per tile
+    (2, 2, 2, 330, 128, 300, 40, True),      # MHA: 128 positions per tile, N / 128 odd, sinks over three KV tiles
+    (1, 8, 2, 200, 128, 9, 0, True),         # window 0: sinks (and s_aux) only
+    (1, 8, 2, 33, 128, 0, 4096, False),      # one pair of tiles, window > N
+    (1, 12, 4, 420, 128, 5, 128, True),      # group 3 -> unpacked tiles
 ])
 def test_fwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     B, Hq, Hkv, N, D, S, W, use_aux = shape
@@ -177,6 +184,15 @@ def _bwd(q, k, v, o, do, lse, S, W, s_aux, impl=None):
     (1, 8, 2, 300, 80, 4, 64, True),         # head_dim 80 / 96 / 112 on the head_dim-128 tensor-core kernels
     (2, 4, 4, 257, 96, 0, 257, True),
     (1, 4, 1, 200, 112, 2, 33, False),
+    # head_dim 128 pair (rotating Q / dO buffers in dQ, ordered tensor pipe in dK/dV): two packed head groups per KV
+    # head, sinks over several key tiles (every chunk of the sequence visits key tile 0..2), sinks only, tiny N
+    # (group 32 x window 300 = 9 600 terms per key: with window 700 the 16-bit rounding of P alone puts dV at 1.03 of the
+    # on-device bar below -- 0.39 of the reference's own bar against the oracle)
+    (1, 64, 2, 1000, 128, 0, 300, True),
+    (2, 2, 2, 330, 128, 300, 40, True),
+    (1, 8, 2, 200, 128, 9, 0, True),
+    (1, 8, 2, 33, 128, 0, 4096, False),
+    (1, 12, 4, 420, 128, 5, 128, True),
 ])
 def test_bwd_tcgen05_vs_simt_and_oracle(shape, dtype):
     """dQ/dK/dV of the tensor-core backward against the CUDA-core backward (same 16-bit inputs, fp32 math)
@@ -351,8 +367,9 @@ def test_mask_bit_exact(N, S, W, dtype):
 # layout: HF [B,N,H,D] transposed views are consumed in place and give identical results
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_strided_hf_layout(dtype):
-    B, N, Hq, Hkv, D, S, W = 2, 300, 8, 2, 64, 2, 96
+@pytest.mark.parametrize("D", [64, 128])
+def test_strided_hf_layout(dtype, D):
+    B, N, Hq, Hkv, S, W = 2, 300, 8, 2, 2, 96
     g = torch.Generator().manual_seed(5)
     qh = torch.randn(B, N, Hq, D, generator=g).to("cuda", dtype)
     kh = torch.randn(B, N, Hkv, D, generator=g).to("cuda", dtype)
