@@ -17,6 +17,14 @@ static std::atomic<int> g_force_impl{SFA_IMPL_AUTO};
 static std::atomic<int> g_bwd_stages{7};
 static std::atomic<int> g_debug[4] = {{0}, {0}, {0}, {0}};
 static const bool g_env_fwd_v1 = getenv("SFA_FWD_V1") != nullptr;   // diagnostics: read once, not per call
+#ifndef SFA_WIDE64_FWD_MIN_W
+#define SFA_WIDE64_FWD_MIN_W 1024
+#endif
+static bool wide_fwd64(const sfa::AttnParams& p) {
+  static const char* env = getenv("SFA_WIDE64_FWD");      // diagnostics: 0 / 1 force the choice
+  if (env != nullptr) return env[0] == '1';
+  return (p.W < p.N ? p.W : p.N) >= SFA_WIDE64_FWD_MIN_W;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -204,10 +212,14 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
   }
   if (g_force_impl != SFA_IMPL_SIMT && tc_fwd_supported(p, dtype)) {
     set_impl_name("tcgen05");
+    // head_dim 64 with a wide window (long KV loop per tile): the two-tile kernel built for that
+    if (p.D == 64 && wide_fwd64(p) && tc_fwd128_supported(p, dtype) && !g_env_fwd_v1)
+      return cuda_ret(tc_fwd128(p, dtype, st), "sfa_fwd(tcgen05/fwd128<64>)");
     if (tc_fwd64_supported(p, dtype) && !(g_env_fwd_v1 && p.o_route == nullptr && !p.has_ext()))
       return cuda_ret(tc_fwd64(p, dtype, st), "sfa_fwd(tcgen05/fwd64)");
     // 64 < head_dim <= 128: persistent kernel, two query tiles per CTA
-    if (tc_fwd128_supported(p, dtype) && !g_env_fwd_v1) return cuda_ret(tc_fwd128(p, dtype, st), "sfa_fwd(tcgen05/fwd128)");
+    if (p.D > 64 && tc_fwd128_supported(p, dtype) && !g_env_fwd_v1)
+      return cuda_ret(tc_fwd128(p, dtype, st), "sfa_fwd(tcgen05/fwd128)");
     // the one-tile-per-CTA kernel (head_dim > 64) takes packed sequences without sink tokens, not chunk offsets
     if (p.q_off == 0 && p.Nkv == p.N && !(p.seq_lo != nullptr && p.S > 0))
       return cuda_ret(tc_fwd(p, dtype, st), "sfa_fwd(tcgen05)");

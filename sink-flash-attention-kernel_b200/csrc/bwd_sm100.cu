@@ -101,7 +101,6 @@ template <typename T> __device__ __forceinline__ uint32_t ds_pair(uint32_t p_pai
 // dO(t - 1) left (after it served as the staging tile of dQ(t - 1)'s store), dO(t + 1) goes where Q(t) was as soon
 // as the tile's last S is complete; that frees the room for a K ring of three.
 template <int D> struct DqCfg {
-  static_assert(D == 128, "head_dim 64 runs dq64_kernel");
   static constexpr int kDS = D / 64;
   static constexpr int kBNMax = 96;                      // KV rows per item (UMMA N of S and dP)
   static constexpr int kKStages = 3;                     // K is held from S(n) to dQ(n)
@@ -1767,14 +1766,19 @@ inline bool fuses_delta(const AttnParams& p, int P, int BN) {
   return enabled && p.S == 0 && p.W > 0 && span <= BN;
 }
 
-template <int D> struct DqSel {
+// kWide: head_dim 64 on the D-generic kernels (dq_kernel / dkdv_kernel: items of 96 / chunks of 128 keys, built for long
+// KV loops) instead of dq64_kernel / dkdv64_kernel (built around short bands)
+#ifndef SFA_WIDE64_MIN_W
+#define SFA_WIDE64_MIN_W 2048
+#endif
+template <int D, bool kWide> struct DqSel {
   static constexpr int kBNMax = DqCfg<D>::kBNMax, kSmem = DqCfg<D>::kSmem;
 };
-template <> struct DqSel<64> {
+template <> struct DqSel<64, false> {
   static constexpr int kBNMax = Dq64Cfg::kBNMax, kSmem = Dq64Cfg::kSmem;
 };
 
-template <typename T, int D>
+template <typename T, int D, bool kWide = false>
 cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
   const int group = p.Hq / p.Hkv;
   int G, P;
@@ -1786,12 +1790,13 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
   if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;   // guarded by tc_bwd_supported
 
   if (stages & 2) {
-    constexpr int kBNMax = DqSel<D>::kBNMax;
-    constexpr int kSmemDq = DqSel<D>::kSmem;
+    constexpr bool k64 = (D == 64) && !kWide;      // the head_dim-64 special kernels
+    constexpr int kBNMax = DqSel<D, kWide>::kBNMax;
+    constexpr int kSmemDq = DqSel<D, kWide>::kSmem;
     static std::atomic<unsigned long long> attr_done{0};
     {
       cudaError_t e;
-      if constexpr (D == 64) e = ensure_dyn_smem(dq64_kernel<T>, kSmemDq, attr_done);
+      if constexpr (k64) e = ensure_dyn_smem(dq64_kernel<T>, kSmemDq, attr_done);
       else e = ensure_dyn_smem(dq_kernel<T, D>, kSmemDq, attr_done);
       if (e != cudaSuccess) return e;
     }
@@ -1815,24 +1820,25 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.trace = trace_buffer();
     a.bn_mul = bn_magic(BN);
     a.q_off = 0; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;      // packed sequences (no chunk offset in these kernels)
-    a.fuse_delta = (D == 64 && fuses_delta(p, P, BN)) ? 1 : 0;
+    a.fuse_delta = (k64 && fuses_delta(p, P, BN)) ? 1 : 0;
     a.delta_out = p.delta;
     a.dsrow = (p.s_aux != nullptr && p.ds_aux != nullptr) ? p.dsrow : nullptr;
     a.s_aux = p.s_aux;
     const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
     a.tiles_per_cta = 0;
-    if constexpr (D == 64) dq64_kernel<T><<<grid, Dq64Cfg::kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
+    if constexpr (k64) dq64_kernel<T><<<grid, Dq64Cfg::kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
     else dq_kernel<T, D><<<grid, kThreads, kSmemDq, st>>>(mq.map, mdo.map, mk.map, mv.map, mdq.map, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   if (stages & 4) {
     constexpr int kBK = 128;
-    constexpr int kSmemKv = (D == 64) ? Dkv64Cfg::kSmem : DkvCfg<D>::kSmem;
+    constexpr bool k64 = (D == 64) && !kWide;
+    constexpr int kSmemKv = k64 ? Dkv64Cfg::kSmem : DkvCfg<D>::kSmem;
     static std::atomic<unsigned long long> attr_done{0};
     {
       cudaError_t e;
-      if constexpr (D == 64) e = ensure_dyn_smem(dkdv64_kernel<T>, kSmemKv, attr_done);
+      if constexpr (k64) e = ensure_dyn_smem(dkdv64_kernel<T>, kSmemKv, attr_done);
       else e = ensure_dyn_smem(dkdv_kernel<T, D>, kSmemKv, attr_done);
       if (e != cudaSuccess) return e;
     }
@@ -1854,7 +1860,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.trace = trace_buffer();
     dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
     a.ntiles = static_cast<int>(grid.x);
-    if constexpr (D == 64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    if constexpr (k64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
     else dkdv_kernel<T, D><<<grid.x * grid.y * grid.z, kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);   // 1-D: heavy tiles first
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1895,10 +1901,32 @@ bool tc_bwd_supported(const AttnParams& p, int dtype) {
   return q_swap == do_swap;
 }
 
+// head_dim 64 with a long chunk loop per key tile (wide window / many sink-seeing rows): dK/dV on the D-generic kernel
+// (ordered tensor pipe, 128-key tiles) -- 2 409 -> 2 033 us at the gpt-oss full-attention shape; the dQ side stays on
+// dq64_kernel (the generic one is slower there: 1 728 vs 1 457 us)
+static bool wide64_dkdv(const AttnParams& p) {
+  static const char* env = getenv("SFA_WIDE64");       // diagnostics: 0 / 1 force the choice
+  if (env != nullptr) return env[0] == '1';
+  // measured at B=1 N=8192 Hq=64 Hkv=8 (tools/time_graph.py c1full, SFA_TG_W): window 1024: 700 vs 621 us, 2048: 998 vs
+  // 1 019, 4096: 1 487 vs 1 669, 8192: 2 033 vs 2 409.  With sink tokens the key tile that holds them visits every row
+  // of the sequence in ONE CTA; at head_dim 64 that CTA outlasts the rest of the launch in either kernel (a known tail:
+  // 4 sink tokens cost ~0.9 ms at this shape), and dkdv64_kernel's shorter chunks make it the lesser evil.
+  return p.S == 0 && (p.W < p.N ? p.W : p.N) >= SFA_WIDE64_MIN_W;
+}
+
+template <typename T>
+cudaError_t tc_bwd_t(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
+  if (p.D != 64) return launch_bwd<T, 128>(p, dtype, stages, st);       // 64 < D <= 128 -> <128>
+  if ((stages & 4) && wide64_dkdv(p) && !tc_bwd_fuses_delta(p, dtype)) {
+    if (stages & 2)
+      if (cudaError_t e = launch_bwd<T, 64>(p, dtype, stages & ~4, st)) return e;
+    return launch_bwd<T, 64, true>(p, dtype, 4, st);
+  }
+  return launch_bwd<T, 64>(p, dtype, stages, st);
+}
+
 cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st) {
-  if (dtype == SFA_DTYPE_BF16)
-    return p.D == 64 ? launch_bwd<__nv_bfloat16, 64>(p, dtype, stages, st) : launch_bwd<__nv_bfloat16, 128>(p, dtype, stages, st);
-  return p.D == 64 ? launch_bwd<__half, 64>(p, dtype, stages, st) : launch_bwd<__half, 128>(p, dtype, stages, st);   // 64 < D <= 128 -> <128>
+  return dtype == SFA_DTYPE_BF16 ? tc_bwd_t<__nv_bfloat16>(p, dtype, stages, st) : tc_bwd_t<__half>(p, dtype, stages, st);
 }
 
 }  // namespace sfa

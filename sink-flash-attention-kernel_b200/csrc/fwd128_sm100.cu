@@ -25,18 +25,18 @@
 namespace sfa {
 namespace {
 
-struct F128Cfg {
-  static constexpr int D = 128;
-  static constexpr int kDS = 2;                          // 64-channel slabs
+template <int D_> struct F128Cfg {
+  static constexpr int D = D_;                           // 128 (also 72 .. 120 by zero fill) or 64 (wide windows)
+  static constexpr int kDS = D / 64;                     // 64-channel slabs
   static constexpr int kBNMax = 128;
-  static constexpr int kKStages = 3, kVStages = 2;
+  static constexpr int kKStages = (D == 64) ? 4 : 3, kVStages = (D == 64) ? 3 : 2;
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = kBNMax * D * 2;
   static constexpr int kSlabQ = 128 * 128;
   static constexpr int kSlabKV = kBNMax * 128;
   static constexpr uint32_t kTmemCols = 512;
   static constexpr uint32_t kColS = 0;                   // S_A at 0, S_B at 128
-  static constexpr uint32_t kColO = 256;                 // O_A at 256, O_B at 384
+  static constexpr uint32_t kColO = 256;                 // O_A at 256, O_B at 256 + D
   static constexpr int kThreads = 320;       // (registers are allocated per four warps: 10 warps get what 12 would)
   // no alignment slack: the dynamic shared memory is declared 1024-byte aligned (checked at kernel entry)
   static constexpr int kSmem = 2 * kQBytes + (kKStages + kVStages) * kKVBytes + 256;
@@ -97,12 +97,12 @@ __device__ __forceinline__ void tmem_st32p(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__(F128Cfg::kThreads, 1) fwd128_kernel(const __grid_constant__ CUtensorMap tmQ,
+template <typename T, int D_>
+__global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                        const __grid_constant__ CUtensorMap tmK,
                                                                        const __grid_constant__ CUtensorMap tmV,
                                                                        const F128Args a) {
-  using C = F128Cfg;
+  using C = F128Cfg<D_>;
   constexpr int D = C::D;
   extern __shared__ __align__(1024) unsigned char smem_al[];
   unsigned char* smem = smem_al;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(F128Cfg::kThreads, 1) fwd128_kernel(const __gr
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           if (kk < nk)
-            umma_ts(tmem + C::kColO + x * 128, tmem + C::kColS + x * 128 + kk * 8,
+            umma_ts(tmem + C::kColO + x * D, tmem + C::kColS + x * 128 + kk * 8,
                     make_sdesc(va + kk * 2048, C::kSlabKV, 1024), idesc_pv, (acc || kk > 0));
       };
       int g = 0, tc = 0;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(F128Cfg::kThreads, 1) fwd128_kernel(const __gr
     const int pr = a.q_swap ? (r / a.G) : (r % a.P);   // position within the tile
     const int gr = a.q_swap ? (r % a.G) : (r / a.P);   // head within the packed group
     const uint32_t tl = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t ts = tl + C::kColS + x * 128, to = tl + C::kColO + x * 128;
+    const uint32_t ts = tl + C::kColS + x * 128, to = tl + C::kColO + x * D;
     const uint64_t sl2_2 = pack_f32x2(a.sl2, a.sl2);
     int g = 0, tc = 0;
     STile st;
@@ -432,11 +432,11 @@ __global__ void __launch_bounds__(F128Cfg::kThreads, 1) fwd128_kernel(const __gr
   if (warp == 9) tmem_dealloc(tmem, C::kTmemCols);
 }
 
-template <typename T>
+template <typename T, int D_>
 cudaError_t launch_fwd128(const AttnParams& p, int dtype, cudaStream_t st) {
-  using C = F128Cfg;
+  using C = F128Cfg<D_>;
   static std::atomic<unsigned long long> attr_done{0};
-  if (cudaError_t e = ensure_dyn_smem(fwd128_kernel<T>, C::kSmem, attr_done)) return e;
+  if (cudaError_t e = ensure_dyn_smem(fwd128_kernel<T, D_>, C::kSmem, attr_done)) return e;
   const int group = p.Hq / p.Hkv;
   int G, P;
   pick_packing(p.Hq, p.Hkv, G, P);
@@ -461,7 +461,7 @@ cudaError_t launch_fwd128(const AttnParams& p, int dtype, cudaStream_t st) {
   a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
   const int sms = device_sm_count();
   const int grid = a.total < sms ? a.total : sms;
-  fwd128_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, a);
+  fwd128_kernel<T, D_><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, a);
   return cudaGetLastError();
 }
 
@@ -470,7 +470,7 @@ cudaError_t launch_fwd128(const AttnParams& p, int dtype, cudaStream_t st) {
 // O rows are written with 16-byte stores straight from the registers (no staging tile: the shared memory holds the Q
 // pair and the K / V rings)
 bool tc_fwd128_supported(const AttnParams& p, int dtype) {
-  if (!tc_fwd_supported(p, dtype) || p.D <= 64) return false;
+  if (!tc_fwd_supported(p, dtype)) return false;      // head_dim 64 or 72 .. 128; the caller picks 64 for wide windows only
   if (p.q_off != 0 || p.Nkv != p.N || (p.seq_lo != nullptr && p.S > 0) || p.o_route != nullptr) return false;
   if (p.S <= 0 && p.W <= 0) return false;      // nothing attended: the one-tile-per-CTA kernel writes the O = 0 rows
   if (reinterpret_cast<uintptr_t>(p.o) % 16 || p.so.n % 8 || p.so.h % 8 || p.so.b % 8) return false;
@@ -478,7 +478,9 @@ bool tc_fwd128_supported(const AttnParams& p, int dtype) {
 }
 
 cudaError_t tc_fwd128(const AttnParams& p, int dtype, cudaStream_t st) {
-  return dtype == SFA_DTYPE_BF16 ? launch_fwd128<__nv_bfloat16>(p, dtype, st) : launch_fwd128<__half>(p, dtype, st);
+  if (p.D == 64)
+    return dtype == SFA_DTYPE_BF16 ? launch_fwd128<__nv_bfloat16, 64>(p, dtype, st) : launch_fwd128<__half, 64>(p, dtype, st);
+  return dtype == SFA_DTYPE_BF16 ? launch_fwd128<__nv_bfloat16, 128>(p, dtype, st) : launch_fwd128<__half, 128>(p, dtype, st);
 }
 
 }  // namespace sfa

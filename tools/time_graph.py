@@ -17,6 +17,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "c2s":
     B, N, Hq, Hkv, D, S, W = 1, 8192, 32, 8, 128, 4, 4096
 if len(sys.argv) > 1 and sys.argv[1] == "c1full":      # gpt-oss FULL-attention layer (every second layer): window = N
     B, N, Hq, Hkv, D, S, W = 1, 8192, 64, 8, 64, 0, 8192
+if os.environ.get("SFA_TG_W"): W = int(os.environ["SFA_TG_W"])
+if os.environ.get("SFA_TG_S"): S = int(os.environ["SFA_TG_S"])
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(1)
 dt = torch.bfloat16
