@@ -282,6 +282,8 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
   float* ds_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes);
   p.dsrow = reinterpret_cast<float*>(static_cast<char*>(workspace) + rows_bytes + align_up((size_t)B * Hq * ((N + 7) / 8) * 4, 256));
   float* fused_part = reinterpret_cast<float*>(reinterpret_cast<char*>(p.dsrow) + rows_bytes);
+  p.kv_part = fused_part;      // the kernel pair and the fused kernel never run in the same call: one region serves both
+  p.kv_part_bytes = tc_bwd_fused_workspace_bytes();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool use_tc = g_force_impl != SFA_IMPL_SIMT && tc_bwd_supported(p, dtype);      // the dQ + dK/dV kernel pair
   // with the extended geometry (packed sequences, chunked prefill) the fused kernel is the only tensor-core path

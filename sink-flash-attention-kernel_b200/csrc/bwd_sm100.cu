@@ -942,6 +942,12 @@ struct DkvArgs {
   long long* trace;
   int B, N, S, W, Hq, Hkv, G, P, groups_per_kv;
   int ntiles;    // key tiles per (kv head, batch); the launch is 1-D: tiles holding sink keys first (they see every row)
+  // Key tiles that hold sink tokens are visited by EVERY later row of the sequence: one CTA walking all N / P
+  // position blocks outlasts the rest of the launch when batch x kv heads is small (4 sink tokens cost 0.9 ms at
+  // B=1 N=8192 Hkv=8 D=64).  Their position-block range is cut into n_split CTAs that leave fp32 partials
+  // [tile][split][key][dK | dV][D]; dkdv_split_reduce_kernel sums them in a fixed order (deterministic).
+  int split_tiles, n_split;
+  float* split_part;
   int q_swap, k_swap, v_swap;
   int fmt;
   float sl2, scale;
@@ -964,6 +970,64 @@ __device__ __forceinline__ void chunk_range(const DkvArgs& a, int b, int j0, int
   if (a.seq_hi != nullptr) i_max = min(i_max, __ldg(a.seq_hi + b * a.seq_bs + j1) - 1);   // no row beyond the last key's sequence
   pb_lo = j0 / a.P;
   pb_hi = (i_max >= j0) ? i_max / a.P : pb_lo - 1;
+}
+
+// 1-D launch of the dK/dV kernels: CTA id -> (key tile, kv head * batch index, split of a sink-holding tile).  The
+// split CTAs come first: they are the longest.
+__device__ __forceinline__ void dkv_block(const DkvArgs& a, int& tile_x, int& kvh, int& b, int& split) {
+  const int id = blockIdx.x;
+  const int heavy = a.split_tiles * a.n_split * a.Hkv * a.B;
+  int yz;
+  if (id < heavy) {
+    int u = id;
+    split = u % a.n_split;
+    u /= a.n_split;
+    tile_x = u % a.split_tiles;
+    yz = u / a.split_tiles;
+  } else {
+    const int r = id - heavy, rest = a.ntiles - a.split_tiles;
+    split = 0;
+    tile_x = a.split_tiles + r % rest;
+    yz = r / rest;
+  }
+  kvh = yz % a.Hkv;
+  b = yz / a.Hkv;
+}
+// this CTA's share of the position blocks [pb_lo, pb_hi] of a split tile
+__device__ __forceinline__ void dkv_split_range(const DkvArgs& a, int tile_x, int split, int& pb_lo, int& pb_hi) {
+  if (a.n_split > 1 && tile_x < a.split_tiles) {
+    const int npb_all = max(pb_hi - pb_lo + 1, 0);
+    const int per = (npb_all + a.n_split - 1) / a.n_split;
+    pb_lo += split * per;
+    pb_hi = min(pb_hi, pb_lo + per - 1);
+  }
+}
+// fp32 partial rows of a split CTA: [(b, kvh)][tile][split][key 0..127][dK (D) | dV (D)]
+__device__ __forceinline__ float* dkv_part_row(const DkvArgs& a, int D, int tile_x, int kvh, int b, int split, int kr) {
+  const size_t slot = ((static_cast<size_t>(b) * a.Hkv + kvh) * a.split_tiles + tile_x) * a.n_split + split;
+  return a.split_part + (slot * 128 + kr) * static_cast<size_t>(2 * D);
+}
+
+// sums the splits of the sink-holding key tiles in a fixed order and writes the 16-bit dK / dV rows
+template <typename T>
+__global__ void dkdv_split_reduce_kernel(const DkvArgs a, int D) {
+  const int tile_x = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int kr = threadIdx.x >> 1, hf = threadIdx.x & 1;      // two threads per key row: dK | dV
+  const int j = tile_x * 128 + kr;
+  if (j >= a.N) return;
+  T* out = static_cast<T*>(hf ? a.dv : a.dk) + b * (hf ? a.sdv.b : a.sdk.b) + kvh * (hf ? a.sdv.h : a.sdk.h) +
+           static_cast<int64_t>(j) * (hf ? a.sdv.n : a.sdk.n);
+  for (int c0 = 0; c0 < a.Dl; c0 += 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < a.n_split; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(dkv_part_row(a, D, tile_x, kvh, b, s, kr) + hf * D + c0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[c0] = from_f<T>(acc.x);
+    out[c0 + 1] = from_f<T>(acc.y);
+    out[c0 + 2] = from_f<T>(acc.z);
+    out[c0 + 3] = from_f<T>(acc.w);
+  }
 }
 
 template <typename T, int D>
@@ -995,24 +1059,13 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 1-D launch: the first Hkv * B CTAs take key tile 0 of every (kv head, batch) -- with sink tokens that tile is
-  // seen by every query row of the sequence (4x the work of a window tile) and must not start in the last wave
-  int tile_x, yz;
-  {
-    const int id = blockIdx.x, heavy = a.Hkv * a.B;
-    if (id < heavy) {
-      tile_x = 0;
-      yz = id;
-    } else {
-      const int r = id - heavy;
-      tile_x = 1 + r % (a.ntiles - 1);
-      yz = r / (a.ntiles - 1);
-    }
-  }
+  int tile_x, kvh, b, split;
+  dkv_block(a, tile_x, kvh, b, split);
   const int j0 = tile_x * C::kBK;
-  const int kvh = yz % a.Hkv, b = yz / a.Hkv;
   int pb_lo, pb_hi;
   chunk_range(a, b, j0, C::kBK, pb_lo, pb_hi);
+  dkv_split_range(a, tile_x, split, pb_lo, pb_hi);
+  const bool to_part = (a.n_split > 1 && tile_x < a.split_tiles);
   const int npb = max(pb_hi - pb_lo + 1, 0);
   const int nchunks = npb * a.groups_per_kv;             // chunk c -> (group c % gpk, position block pb_lo + c / gpk)
 
@@ -1316,6 +1369,18 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
 #pragma unroll
         for (int e = 0; e < 16; ++e) kv_[e] = vv_[e] = 0u;
       }
+      if (to_part) {                       // a split of a sink-holding tile: fp32 partial rows, summed by the reduce kernel
+        float* pr_ = dkv_part_row(a, D, tile_x, kvh, b, split, kr);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          *reinterpret_cast<float4*>(pr_ + c0 + e) =
+              make_float4(__uint_as_float(kv_[e]) * a.scale, __uint_as_float(kv_[e + 1]) * a.scale,
+                          __uint_as_float(kv_[e + 2]) * a.scale, __uint_as_float(kv_[e + 3]) * a.scale);
+          *reinterpret_cast<float4*>(pr_ + D + c0 + e) = make_float4(__uint_as_float(vv_[e]), __uint_as_float(vv_[e + 1]),
+                                                                       __uint_as_float(vv_[e + 2]), __uint_as_float(vv_[e + 3]));
+        }
+        continue;
+      }
 #pragma unroll
       for (int e = 0; e < 16; e += 2) {
         pk[e >> 1] = pack16<T>(__uint_as_float(kv_[e]) * a.scale, __uint_as_float(kv_[e + 1]) * a.scale);
@@ -1391,7 +1456,7 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* const trc = (SFA_TRACE && blockIdx.x == 20 && blockIdx.y == 0 && blockIdx.z == 0) ? a.trace : nullptr;
+  long long* const trc = (SFA_TRACE && blockIdx.x == 20) ? a.trace : nullptr;
   auto tev = [&](int role, int& cnt, int code, int idx) {
     if (SFA_TRACE && trc != nullptr && cnt < 256) {
       trc[(role * 256 + cnt) * 2] = (static_cast<long long>(code) << 32) | static_cast<unsigned>(idx);
@@ -1399,10 +1464,13 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
       ++cnt;
     }
   };
-  const int j0 = blockIdx.x * C::kBK;
-  const int kvh = blockIdx.y, b = blockIdx.z;
+  int tile_x, kvh, b, split;
+  dkv_block(a, tile_x, kvh, b, split);
+  const int j0 = tile_x * C::kBK;
   int pb_lo, pb_hi;
   chunk_range(a, b, j0, C::kBK, pb_lo, pb_hi);
+  dkv_split_range(a, tile_x, split, pb_lo, pb_hi);
+  const bool to_part = (a.n_split > 1 && tile_x < a.split_tiles);
   const int npb = max(pb_hi - pb_lo + 1, 0);
   const int gpk = a.groups_per_kv;
   const int nchunks = npb * gpk;        // chunk c -> (position block pb_lo + c / gpk, group c % gpk); walked with counters
@@ -1730,12 +1798,23 @@ __global__ void __launch_bounds__(Dkv64Cfg::kThreads, 1) dkdv64_kernel(const __g
 #pragma unroll
         for (int e = 0; e < 16; ++e) kv_[e] = vv_[e] = 0u;
       }
+      if (to_part) {                       // a split of a sink-holding tile: fp32 partial rows, summed by the reduce kernel
+        float* pr_ = dkv_part_row(a, D, tile_x, kvh, b, split, kr);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          *reinterpret_cast<float4*>(pr_ + c0 + e) =
+              make_float4(__uint_as_float(kv_[e]) * a.scale, __uint_as_float(kv_[e + 1]) * a.scale,
+                          __uint_as_float(kv_[e + 2]) * a.scale, __uint_as_float(kv_[e + 3]) * a.scale);
+          *reinterpret_cast<float4*>(pr_ + D + c0 + e) = make_float4(__uint_as_float(vv_[e]), __uint_as_float(vv_[e + 1]),
+                                                                       __uint_as_float(vv_[e + 2]), __uint_as_float(vv_[e + 3]));
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 16; e += 2) {
         pk[e >> 1] = pack16<T>(__uint_as_float(kv_[e]) * a.scale, __uint_as_float(kv_[e + 1]) * a.scale);
         pv2[e >> 1] = pack16<T>(__uint_as_float(vv_[e]), __uint_as_float(vv_[e + 1]));
       }
-      if (j < a.N) {
+      if (j < a.N && !to_part) {
         *reinterpret_cast<uint4*>(dkr + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(dkr + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         *reinterpret_cast<uint4*>(dvr + c0) = make_uint4(pv2[0], pv2[1], pv2[2], pv2[3]);
@@ -1860,8 +1939,35 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.trace = trace_buffer();
     dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
     a.ntiles = static_cast<int>(grid.x);
-    if constexpr (k64) dkdv64_kernel<T><<<grid, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
-    else dkdv_kernel<T, D><<<grid.x * grid.y * grid.z, kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);   // 1-D: heavy tiles first
+    // split the position-block range of the tiles that hold sink keys (every later row visits them) over several CTAs
+    a.split_tiles = 0;
+    a.n_split = 1;
+    a.split_part = p.kv_part;
+    if (p.S > 0) {
+      constexpr int Dk = k64 ? 64 : D;
+      a.split_tiles = ((p.S < p.N ? p.S : p.N) + kBK - 1) / kBK;
+      const int npb_all = (p.N + P - 1) / P;                                         // position blocks a sink tile sees
+      const int npb_reg = ((p.W < p.N ? p.W : p.N) + kBK + P - 1) / P + 1;           // ... a window-only tile
+      int want = (npb_all + npb_reg - 1) / npb_reg;
+      const size_t slot_bytes = static_cast<size_t>(128) * 2 * Dk * sizeof(float);
+      const size_t slots = (p.kv_part != nullptr) ? p.kv_part_bytes / slot_bytes : 0;
+      const size_t tiles = static_cast<size_t>(a.split_tiles) * p.Hkv * p.B;
+      const int cap = static_cast<int>(slots / (tiles ? tiles : 1));
+      if (want > cap) want = cap;
+      if (want > 64) want = 64;
+      // only when the unsplit tile would be the tail of the launch: its position blocks against the blocks one SM gets
+      // of everything else (split CTAs re-load K / V and add a reduce launch: 3 % slower where it is not needed)
+      const double per_sm = static_cast<double>(a.ntiles) * p.Hkv * p.B * npb_reg / sm_count();
+      if (npb_all < 0.75 * per_sm) want = 1;
+      a.n_split = want >= 2 ? want : 1;
+    }
+    const int total_ctas = ((a.ntiles - a.split_tiles) + a.split_tiles * a.n_split) * p.Hkv * p.B;
+    if constexpr (k64) dkdv64_kernel<T><<<total_ctas, Dkv64Cfg::kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    else dkdv_kernel<T, D><<<total_ctas, kThreads, kSmemKv, st>>>(mq.map, mdo.map, mk.map, mv.map, a);   // 1-D: longest tiles first
+    if (a.n_split > 1) {
+      if (cudaError_t e2 = cudaGetLastError()) return e2;
+      dkdv_split_reduce_kernel<T><<<dim3(a.split_tiles, p.Hkv, p.B), 256, 0, st>>>(a, k64 ? 64 : D);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -37,6 +37,8 @@ struct AttnParams {
   float* ds_aux;
   float* delta;     // workspace [B,Hq,N]
   float* dsrow;     // workspace [B,Hq,N]: per-row ds_aux contributions when the dQ kernel computes delta itself
+  float* kv_part;   // workspace: fp32 dK / dV partials of split sink-holding key tiles (dQ + dK/dV kernel pair), or nullptr
+  size_t kv_part_bytes;
   Strides4 sq, sk, sv, so, sdo, sdq, sdk, sdv;
   int B, Hq, Hkv, N, D, S, W;      // N: number of QUERY rows (== keys unless Nkv says otherwise)
   float scale;
