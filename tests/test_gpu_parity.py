@@ -807,3 +807,58 @@ def test_errors_are_loud():
         sa.sink_flash_attention(qc, qc[:, :3], qc[:, :3], 0, 8)    # H_q % H_kv != 0
     with pytest.raises(AssertionError):
         sa.sink_decode_attention(qc, qc, qc)                       # N_q != 1
+
+
+# ------------------------------------------------------------------------------------------------
+# randomised shapes: every tensor-core path against the CUDA-core path (same 16-bit inputs, fp32 math)
+# ------------------------------------------------------------------------------------------------
+def _random_shapes(n, seed, long_n=False):
+    import random
+    rnd = random.Random(seed)
+    out = []
+    while len(out) < n:
+        D = rnd.choice([64, 64, 80, 128, 128])
+        Hkv = rnd.choice([1, 2, 3])
+        group = rnd.choice([1, 2, 3, 4, 8, 16])
+        # long_n: long enough for the wide-window routes of head_dim 64 (two-tile forward, D-generic dK/dV)
+        N = rnd.choice([2100, 2500, 3000] if long_n else [1, 7, 31, 33, 129, 255, 300, 517, 700, 1100])
+        S = rnd.choice([0, 0, 1, 5, 130, 300])
+        W = rnd.choice([0, 1, 17, 128, 500, 4096])
+        if S == 0 and W == 0:
+            continue
+        out.append((rnd.choice([1, 2]), Hkv * group, Hkv, N, D, S, W, rnd.random() < 0.6, rnd.random() < 0.4,
+                    rnd.choice([torch.bfloat16, torch.float16])))
+    return out
+
+
+@pytest.mark.parametrize("shape", _random_shapes(48, 2024) + _random_shapes(12, 7, long_n=True), ids=lambda s: "B%d-Hq%d-Hkv%d-N%d-D%d-S%d-W%d-aux%d-hf%d-%s" % (
+    s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], str(s[9])[6:]))
+def test_random_shapes_tcgen05_vs_simt(shape):
+    """Forward and backward of randomly drawn shapes (tile pairs past N, one-row sequences, group sizes that do not
+    pack, sinks over several key tiles -- split over CTAs in dK/dV --, windows from 0 to far beyond N, HF-strided
+    inputs) on the tensor-core kernels against the CUDA-core kernels."""
+    B, Hq, Hkv, N, D, S, W, use_aux, hf, dtype = shape
+    g = torch.Generator().manual_seed(B * 7 + Hq * 13 + N * 3 + D + S + W)
+
+    def mk(H):
+        if hf:
+            return torch.randn(B, N, H, D, generator=g).to("cuda", dtype).transpose(1, 2)
+        return torch.randn(B, H, N, D, generator=g).to("cuda", dtype)
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    s_aux = (torch.randn(Hq, generator=g) * 0.5 + 0.5).cuda() if use_aux else None
+    o_t, lse_t, name_t = _fwd(q, k, v, S, W, s_aux)
+    o_s, lse_s, _ = _fwd(q, k, v, S, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert name_t == "tcgen05"
+    assert maxdiff(o_t, o_s) < 2e-2
+    fin = torch.isfinite(lse_s)
+    assert torch.equal(fin, torch.isfinite(lse_t)) and maxdiff(lse_t[fin], lse_s[fin]) < 2e-3
+    (dq_t, dk_t, dv_t, ds_t), name_b = _bwd(q, k, v, o_t, do, lse_t, S, W, s_aux)
+    (dq_s, dk_s, dv_s, ds_s), _ = _bwd(q, k, v, o_t, do, lse_t, S, W, s_aux, impl=_lib.IMPL_SIMT)
+    assert name_b in ("tcgen05", "tcgen05-fused")
+    # 2e-2 + 1e-2 |x|; the absolute part grows with the size of the sums a key collects (the 16-bit rounding of P and dS
+    # is relative to every TERM: a sink key summing group x N rows reaches |dK| ~ 6 with errors of one bf16 ulp of that)
+    for got, ref in ((dq_t, dq_s), (dk_t, dk_s), (dv_t, dv_s)):
+        atol = 2e-2 * max(1.0, float(ref.float().abs().max()) / 4.0)
+        assert excess(got, ref, atol, 1e-2) <= 1.0
+    if use_aux:
+        assert maxdiff(ds_t, ds_s) < 2e-3 * max(1.0, float(ds_s.abs().max()))
