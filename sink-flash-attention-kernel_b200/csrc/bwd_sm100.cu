@@ -100,11 +100,16 @@ template <typename T> __device__ __forceinline__ uint32_t ds_pair(uint32_t p_pai
 // Q(t), dO(t), Q(t+1), dO(t+1), ... (use u = 2t / 2t + 1 -> buffer u % 3): Q(t + 1) is prefetched into the buffer
 // dO(t - 1) left (after it served as the staging tile of dQ(t - 1)'s store), dO(t + 1) goes where Q(t) was as soon
 // as the tile's last S is complete; that frees the room for a K ring of three.
+#ifndef SFA_DQ_BN
+#define SFA_DQ_BN 96
+#define SFA_DQ_KST 3
+#define SFA_DQ_VST 2
+#endif
 template <int D> struct DqCfg {
   static constexpr int kDS = D / 64;
-  static constexpr int kBNMax = 96;                      // KV rows per item (UMMA N of S and dP)
-  static constexpr int kKStages = 3;                     // K is held from S(n) to dQ(n)
-  static constexpr int kVStages = 2;
+  static constexpr int kBNMax = SFA_DQ_BN;                      // KV rows per item (UMMA N of S and dP)
+  static constexpr int kKStages = SFA_DQ_KST;                     // K is held from S(n) to dQ(n)
+  static constexpr int kVStages = SFA_DQ_VST;
   static constexpr int kQBufs = 3;                       // rotating Q / dO / staging buffers
   static constexpr int kQBytes = 128 * D * 2;
   static constexpr int kKVBytes = kBNMax * D * 2;
