@@ -1,4 +1,4 @@
-// Persistent forward for 64 < head_dim <= 128 (reference kernel being replaced: _sink_flash_attn_fwd_kernel,
+// Persistent forward for 64 < head_dim <= 128, and for head_dim 64 with wide windows (reference kernel being replaced: _sink_flash_attn_fwd_kernel,
 // sink_flash_attention.py:93-194).  At head_dim 128 the tensor pipe and the MUFU pipe need the same number of cycles
 // per score (4 D flops against one exp2), so the kernel is built around keeping BOTH busy: a CTA works on TWO packed
 // query tiles at once (A: position block 2k, B: block 2k + 1 of the same heads -- they share every K / V tile), each
@@ -12,8 +12,9 @@
 // same columns, and a softmax thread that sees S_X(n+1) complete knows PV_X(n) is complete too (lazy O rescale
 // without a further wait).
 //
-//   warps 0-3   softmax + epilogue of tile A   one thread per row (TMEM lane), the whole 128-column row in registers:
-//   warps 4-7   softmax + epilogue of tile B   no cross-thread exchange; O / l -> 16-bit -> global rows directly
+//   warps 0-3   softmax + epilogue of tile A   one thread per row (TMEM lane): 96 of the row's 128 scores stay in
+//   warps 4-7   softmax + epilogue of tile B   registers between the max and the exp pass, no cross-thread exchange;
+//                                              O / l -> 16-bit -> global rows directly
 //   warp 8      TMA producer                   Q pair (single buffer), K ring (3 tiles), V ring (2 tiles)
 //   warp 9      UMMA issuer
 //
