@@ -831,7 +831,11 @@ def _random_shapes(n, seed, long_n=False):
     return out
 
 
-@pytest.mark.parametrize("shape", _random_shapes(48, 2024) + _random_shapes(12, 7, long_n=True), ids=lambda s: "B%d-Hq%d-Hkv%d-N%d-D%d-S%d-W%d-aux%d-hf%d-%s" % (
+_EXTRA = int(__import__("os").environ.get("SFA_TEST_MORE_SHAPES", "0"))     # bug hunts: more draws from another seed
+
+
+@pytest.mark.parametrize("shape", _random_shapes(48, 2024) + _random_shapes(12, 7, long_n=True) + _random_shapes(_EXTRA, 99) +
+                         _random_shapes(_EXTRA // 8, 100, long_n=True), ids=lambda s: "B%d-Hq%d-Hkv%d-N%d-D%d-S%d-W%d-aux%d-hf%d-%s" % (
     s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], str(s[9])[6:]))
 def test_random_shapes_tcgen05_vs_simt(shape):
     """Forward and backward of randomly drawn shapes (tile pairs past N, one-row sequences, group sizes that do not
