@@ -46,6 +46,10 @@ def _oracle_packed(q, k, v, do, lens, S, W, s_aux):
     (torch.bfloat16, 8, 2, 128, 0, 64, [100, 156], ("tcgen05", "tcgen05")),
     (torch.bfloat16, 8, 2, 128, 0, 512, [300, 212, 77], ("tcgen05", "tcgen05")),
     (torch.bfloat16, 4, 1, 80, 0, 100, [130, 90], ("tcgen05", "tcgen05")),
+    # long packed sequences at head_dim 64 with a wide window: the two-tile forward (fwd128_kernel<T, 64>) and the
+    # D-generic dK/dV kernel, both with the sequence bounds
+    (torch.bfloat16, 8, 2, 64, 0, 2048, [1300, 1700], ("tcgen05", "tcgen05")),
+    (torch.bfloat16, 8, 1, 128, 0, 4096, [900, 1, 1400], ("tcgen05", "tcgen05")),
 ])
 def test_packed_sequences_match_per_sequence_oracle(dtype, Hq, Hkv, D, S, W, lens, impls):
     N = sum(lens)
