@@ -574,6 +574,14 @@ def test_c2_full_size():
     del k3, o_l
     (dq, dk, dv, _), name_b = _bwd(q, k, v, o, do, lse, S, W, None)
     assert name_b == "tcgen05"
+    # run-to-run bit identity of the head_dim-128 kernels (persistent two-tile forward, rotating-buffer dQ, ordered-pipe
+    # dK/dV): no atomics, no order that depends on timing
+    o_again, lse_again, _ = _fwd(q, k, v, S, W, None)
+    assert torch.equal(o_again, o) and torch.equal(lse_again, lse)
+    del o_again, lse_again
+    (dq2, dk2, dv2, _), _ = _bwd(q, k, v, o, do, lse, S, W, None)
+    assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
+    del dq2, dk2, dv2
     (dq_s, dk_s, dv_s, _), _ = _bwd(q[:1], k[:1], v[:1], o[:1], do[:1], lse[:1], S, W, None, impl=_lib.IMPL_SIMT)
     for got, ref in ((dq[:1], dq_s), (dk[:1], dk_s), (dv[:1], dv_s)):
         assert excess(got, ref, 5e-2, 2e-2) <= 1.0                  # the reference's gradient bar is atol = rtol = 5e-2
