@@ -54,6 +54,7 @@ struct BwdArgs {
   int q_off;
   const int* seq_lo;
   int64_t seq_bs;
+  int dbg_delay;       // test knob (sfa_set_debug 0): half of the math warps sleep this many ns inside their passes
 };
 
 // Timeline probe for performance work: CTA 0 appends (role, code, index, clock64) records.
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) dq_kernel(const __grid_constant__
       // 0.4 of the on-device bar where dK, summing 22 000 terms per key, needs the single rounding: ds_pair)
       mbar_wait(s_full + slot, (w.n >> 1) & 1);
       tc_fence_after();
+      if (a.dbg_delay && half == 1) __nanosleep(a.dbg_delay);
       if (threadIdx.x == 0) trace_ev(a.trace, 2, mtc, 2, w.n);     // S, dP complete
 #pragma unroll
       for (int jj = 0; jj < kMaxCh; ++jj)
@@ -953,6 +955,7 @@ struct DkvArgs {
   // [tile][split][key][dK | dV][D]; dkdv_split_reduce_kernel sums them in a fixed order (deterministic).
   int split_tiles, n_split;
   float* split_part;
+  int dbg_delay;       // test knob (sfa_set_debug 0): half of the math warps sleep before their passes
   int q_swap, k_swap, v_swap;
   int fmt;
   float sl2, scale;
@@ -1251,6 +1254,7 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
       // ---- pass 1: P^T = exp2(S^T * c - lse), masked
       mbar_wait(s_full, c & 1);
       tc_fence_after();
+      if (a.dbg_delay && half == 1) __nanosleep(a.dbg_delay);
       // every row of the chunk attends every key of the tile (all but the few chunks at the two ends of the band):
       // CTA-uniform, so the common chunk pays for no per-group position arithmetic at all
       const bool interior = (j0 + C::kBK - 1 <= q0) && (q0 + a.P - 1 < a.N) && (a.seq_hi == nullptr) &&
@@ -1324,6 +1328,7 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
       // dS = 0)
       mbar_wait(dp_full, c & 1);
       tc_fence_after();
+      if (a.dbg_delay && half == 0 && (quarter & 1)) __nanosleep(a.dbg_delay);
       {
         uint32_t dv[2][16];
         tmem_ld16(tl + C::kColP + half * 64, dv[0]);
@@ -1904,6 +1909,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.trace = trace_buffer();
     a.bn_mul = bn_magic(BN);
     a.q_off = 0; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;      // packed sequences (no chunk offset in these kernels)
+    a.dbg_delay = debug_knob(0);
     a.fuse_delta = (k64 && fuses_delta(p, P, BN)) ? 1 : 0;
     a.delta_out = p.delta;
     a.dsrow = (p.s_aux != nullptr && p.ds_aux != nullptr) ? p.dsrow : nullptr;
@@ -1941,6 +1947,7 @@ cudaError_t launch_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t 
     a.dk = p.dk; a.dv = p.dv; a.sdk = p.sdk; a.sdv = p.sdv;
     a.Dl = p.D;
     a.seq_hi = p.seq_hi; a.seq_bs = p.seq_bs;
+    a.dbg_delay = debug_knob(0);
     a.trace = trace_buffer();
     dim3 grid((p.N + kBK - 1) / kBK, p.Hkv, p.B);
     a.ntiles = static_cast<int>(grid.x);

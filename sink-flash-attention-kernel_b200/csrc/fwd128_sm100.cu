@@ -57,6 +57,8 @@ struct F128Args {
   int Dl;                // logical head_dim: channels Dl .. 127 are TMA zero fill on loads and are not stored
   const int* seq_lo;     // packed sequences (no sink tokens): first key of the row's sequence; nullptr: none
   int64_t seq_bs;
+  int dbg_delay;         // test knob (sfa_set_debug 0): odd softmax warps sleep this many ns before their exp pass and
+                         // tile B's group before its epilogue -- every result must stay bit-identical
 };
 
 // Super tile t -> (pair of position blocks, packed head group, batch), LAST positions first: the tiles with the longest
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
         if (i >= a.N) c_hi = -1;
         mbar_wait(s_full + x, g & 1);
         tc_fence_after();
+        if (a.dbg_delay && (warp & 1)) __nanosleep(a.dbg_delay);
         // Row sums in both paths: pair k (columns 2k, 2k + 1) goes to accumulator k & 3, masked elements add exactly
         // 0 -- a row gets the same bits whichever path its warp takes (the layout-invariance tests rely on it).
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -405,6 +408,7 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
       // ---------------- epilogue: O / l -> 16-bit -> this row of the output (256 contiguous bytes), LSE
       mbar_wait(o_done + x, tc & 1);
       tc_fence_after();
+      if (a.dbg_delay && x == 1) __nanosleep(a.dbg_delay * 4);
       const float inv = (l > 0.f) ? 1.f / l : 0.f;
       T* orow = static_cast<T*>(a.o) + st.b * a.so.b + static_cast<int64_t>(h) * a.so.h + static_cast<int64_t>(i) * a.so.n;
 #pragma unroll 1
@@ -460,6 +464,7 @@ cudaError_t launch_fwd128(const AttnParams& p, int dtype, cudaStream_t st) {
   a.lse = p.lse;
   a.o = p.o; a.so = p.so; a.Dl = p.D;
   a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
+  a.dbg_delay = debug_knob(0);
   const int sms = device_sm_count();
   const int grid = a.total < sms ? a.total : sms;
   fwd128_kernel<T, D_><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, a);

@@ -302,6 +302,33 @@ def test_bwd_fused_invariant_under_pipeline_delays(delay_ns):
         _lib.set_debug(0, 0)
 
 
+@pytest.mark.parametrize("D,S,W", [(128, 4, 1024), (64, 0, 2048)])
+@pytest.mark.parametrize("delay_ns", [1000, 20000])
+def test_wide_kernels_invariant_under_pipeline_delays(D, S, W, delay_ns):
+    """The same stress for the round-2 kernels of long KV loops (two-tile forward, rotating-buffer dQ, ordered-pipe
+    dK/dV, incl. their head_dim-64 instantiations): knob 0 makes half of the softmax / math warps sleep inside their
+    passes and one softmax group before its epilogue -- a dependency that only holds by timing shows up as a changed
+    bit.  (compute-sanitizer is closed on this pool: profiles/r2_sanitizer_closed.log.)"""
+    B, Hq, Hkv, N = 1, 8, 2, 4096
+    g = torch.Generator().manual_seed(7 + D)
+    mk = lambda H: torch.randn(B, H, N, D, generator=g).to("cuda", torch.bfloat16)
+    q, k, v, do = mk(Hq), mk(Hkv), mk(Hkv), mk(Hq)
+    s_aux = (torch.randn(Hq, generator=g) * 0.5).cuda()
+    o0, lse0, name = _fwd(q, k, v, S, W, s_aux)
+    (dq0, dk0, dv0, ds0), name_b = _bwd(q, k, v, o0, do, lse0, S, W, s_aux)
+    assert (name, name_b) == ("tcgen05", "tcgen05")
+    _lib.set_debug(0, delay_ns)
+    try:
+        for _ in range(2):
+            o1, lse1, _ = _fwd(q, k, v, S, W, s_aux)
+            (dq1, dk1, dv1, ds1), _ = _bwd(q, k, v, o0, do, lse0, S, W, s_aux)
+            torch.cuda.synchronize()
+            assert torch.equal(o1, o0) and torch.equal(lse1, lse0)
+            assert torch.equal(dq1, dq0) and torch.equal(dk1, dk0) and torch.equal(dv1, dv0) and torch.equal(ds1, ds0)
+    finally:
+        _lib.set_debug(0, 0)
+
+
 def test_c1_full_size_backward():
     """gpt-oss shape (BASELINE configs[1]) backward: the fused kernel against the CUDA-core path on the whole
     tensors, plus size-independent properties: linearity in dO, and dV = P^T dO with V-independence."""
