@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
   uint64_t* p_full = s_full + 2;                 // [2]  P_X(n) written over S_X(n)    (softmax X -> issuer)
   uint64_t* o_done = p_full + 2;                 // [2]  last PV_X of the tile done    (issuer -> softmax X)
   uint64_t* o_free = o_done + 2;                 // [2]  O_X read by the epilogue      (softmax X -> issuer)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* p_half = o_free + 2;                 // [2]  first 64 keys of P_X(n) written: PV of those keys starts under
+                                                 //      the second half's exponentials   (softmax X -> issuer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 8 && lane == 0) {
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
     for (int x = 0; x < 2; ++x) {
       mbar_init(s_full + x, 1);
       mbar_init(p_full + x, 128);
+      mbar_init(p_half + x, 128);
       mbar_init(o_done + x, 1);
       mbar_init(o_free + x, 128);
     }
@@ -197,12 +200,13 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
             umma_ss(tmem + C::kColS + x * 128, make_sdesc(qa + s * C::kSlabQ + kk * 32, 16, 1024),
                     make_sdesc(ka + s * C::kSlabKV + kk * 32, 16, 1024), idesc_s, (s | kk) != 0);
       };
-      auto issue_pv = [&](int x, int g, int cols, bool acc) {
+      // key chunks [k0, k1) of PV_X(n): the first four (64 keys) go out as soon as that half of P is written
+      auto issue_pv = [&](int x, int g, int cols, bool acc, int k0, int k1) {
         const uint32_t va = va0 + (g % C::kVStages) * C::kKVBytes;
         const int nk = cols >> 4;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          if (kk < nk)
+          if (kk >= k0 && kk < k1 && kk < nk)
             umma_ts(tmem + C::kColO + x * D, tmem + C::kColS + x * 128 + kk * 8,
                     make_sdesc(va + kk * 2048, C::kSlabKV, 1024), idesc_pv, (acc || kk > 0));
       };
@@ -228,10 +232,13 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
           if (more) st.pl.tile(n + 1, a.BN, kstart, cols_n, is_sink);
           mbar_wait(v_full + g % C::kVStages, (g / C::kVStages) & 1);
           // ---- tile A: PV_A(n), S_A(n + 1)
-          mbar_wait(p_full + 0, g & 1);
+          mbar_wait(p_half + 0, g & 1);
           if (n == 0 && tc > 0) mbar_wait(o_free + 0, (tc - 1) & 1);     // the epilogue has read the previous O_A
           tc_fence_after();
-          issue_pv(0, g, cols, n > 0);
+          issue_pv(0, g, cols, n > 0, 0, 4);
+          mbar_wait(p_full + 0, g & 1);
+          tc_fence_after();
+          issue_pv(0, g, cols, n > 0, 4, 8);
           if (!more) umma_commit(o_done + 0);
           if (more) {
             mbar_wait(k_full + (g + 1) % C::kKStages, ((g + 1) / C::kKStages) & 1);
@@ -240,10 +247,13 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
             umma_commit(s_full + 0);
           }
           // ---- tile B: PV_B(n), S_B(n + 1)
-          mbar_wait(p_full + 1, g & 1);
+          mbar_wait(p_half + 1, g & 1);
           if (n == 0 && tc > 0) mbar_wait(o_free + 1, (tc - 1) & 1);
           tc_fence_after();
-          issue_pv(1, g, cols, n > 0);
+          issue_pv(1, g, cols, n > 0, 0, 4);
+          mbar_wait(p_full + 1, g & 1);
+          tc_fence_after();
+          issue_pv(1, g, cols, n > 0, 4, 8);
           umma_commit(v_empty + g % C::kVStages);
           if (!more) umma_commit(o_done + 1);
           if (more) {
@@ -289,6 +299,7 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
         // Row sums in both paths: pair k (columns 2k, 2k + 1) goes to accumulator k & 3, masked elements add exactly
         // 0 -- a row gets the same bits whichever path its warp takes (the layout-invariance tests rely on it).
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        bool half_done = false;
         if (__all_sync(0xffffffffu, c_lo <= 0 && c_hi >= 127)) {
           // ---- interior tile: 96 of the row's 128 scores stay in registers between the max and the exp pass, the
           // last 32 are read twice (all 128 + the packed P exceed the 168 registers a thread of 12 warps can have)
@@ -343,6 +354,10 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
 #pragma unroll
           for (int k = 16; k < 32; ++k) exp_pair(s[2 * k], s[2 * k + 1], k);
           tmem_st32p(ts, pk);
+          tmem_st_wait();                     // (the reload of the last 32 scores stays in flight: wait::st, not wait::ld)
+          tc_fence_before();
+          mbar_arrive(p_half + x);
+          half_done = true;
 #pragma unroll
           for (int k = 32; k < 48; ++k) exp_pair(s[2 * k], s[2 * k + 1], k);
           tmem_ld_wait();
@@ -403,6 +418,7 @@ __global__ void __launch_bounds__(F128Cfg<D_>::kThreads, 1) fwd128_kernel(const 
         l += (acc[0] + acc[1]) + (acc[2] + acc[3]);
         tmem_st_wait();
         tc_fence_before();
+        if (!half_done) mbar_arrive(p_half + x);      // boundary tiles hand both halves over at once
         mbar_arrive(p_full + x);
       }
       // ---------------- epilogue: O / l -> 16-bit -> this row of the output (256 contiguous bytes), LSE
