@@ -1064,7 +1064,9 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
   uint64_t* p_ready = dp_full + 1;             // P^T(c) written over S^T    (math -> issuer)
   uint64_t* ds_ready = p_ready + 1;            // dS^T(c) written over dP^T  (math -> issuer)
   uint64_t* acc_done = ds_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  uint64_t* p_half = acc_done + 1;             // first two 16-row groups of both column halves of P^T(c) written: the dV
+                                               // k-steps over those rows start under the rest of the exp pass
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile_x, kvh, b, split;
@@ -1094,6 +1096,7 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
     mbar_init(p_ready, kMathThreads);
+    mbar_init(p_half, kMathThreads);
     mbar_init(ds_ready, kMathThreads);
     mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -1169,12 +1172,21 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
         const bool more = (c + 1 < nchunks);
         // dV += P(c)^T dO(c): contraction over the 128 chunk rows, 16 per UMMA; rows [0,64) were packed into 32-bit
         // columns [0,32) and rows [64,128) into [64,96) of each region (one range per math-warp half)
+        // (k-steps 0, 1 and 4, 5 -- the first two row groups of each math-warp half -- as soon as they are written)
+        mbar_wait(p_half, c & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if ((kk & 3) < 2)
+            umma_ts(tmem + C::kColV, tmem + C::kColS + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
+                    make_sdesc(doa + kk * 2048, C::kSlabQ, 1024), idesc_acc, (c > 0 || kk > 0));
         mbar_wait(p_ready, c & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem + C::kColV, tmem + C::kColS + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
-                  make_sdesc(doa + kk * 2048, C::kSlabQ, 1024), idesc_acc, (c > 0 || kk > 0));
+          if ((kk & 3) >= 2)
+            umma_ts(tmem + C::kColV, tmem + C::kColS + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
+                    make_sdesc(doa + kk * 2048, C::kSlabQ, 1024), idesc_acc, 1);
         umma_commit(do_empty + ds);
         if (more) {            // S(c+1) behind dV(c) in the pipe: it overwrites the columns P(c) is read from
           mbar_wait(q_full + qs1, qph1);
@@ -1317,6 +1329,11 @@ __global__ void __launch_bounds__(kThreads, 1) dkdv_kernel(const __grid_constant
           // each half packs into the front of its OWN source range (32-bit columns [half*64, half*64+32)),
           // so it never overwrites fp32 columns the other half (or this thread's next load) has yet to read
           tmem_st8(tl + C::kColS + half * 64 + g * 8, pk);
+          if (g == 1) {            // row groups 0 and 1 of this half are in TMEM
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_half);
+          }
         }
       };
       if (interior) pass1(std::true_type{});
