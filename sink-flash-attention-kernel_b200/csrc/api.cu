@@ -304,7 +304,7 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
   // narrow window, no sink tokens, head_dim 64: ONE kernel computes delta, the ds_aux rows, dQ, dK and dV
   if (use_fused) {
     set_impl_name("tcgen05-fused");
-    if (!tc_bwd_fused_computes_delta()) {
+    if (!tc_bwd_fused_computes_delta(p)) {
       // delta + ds_aux block partials (streaming pass over O and dO), then the fused kernel; the ds_aux partials
       // are reduced by extra blocks of the fused kernel's fix-up launch
       int ds_nblk = 0;
@@ -314,10 +314,9 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
       return cuda_ret(tc_bwd_fused(p, dtype, fused_part, red ? ds_partial : nullptr, red ? ds_nblk : 0, st),
                       "sfa_bwd(tcgen05 fused)");
     }
-    if (int r = cuda_ret(tc_bwd_fused(p, dtype, fused_part, nullptr, 0, st), "sfa_bwd(tcgen05 fused)")) return r;
-    if (p.s_aux && p.ds_aux)
-      return cuda_ret(ds_aux_from_delta(p.delta, p.lse, p.s_aux, p.ds_aux, B, Hq, N, st), "sfa_bwd(ds_aux)");
-    return 0;
+    // delta by the kernel's own delta warps; ds_aux from the delta rows by extra blocks of the fix-up launch
+    const bool red = p.s_aux && p.ds_aux;
+    return cuda_ret(tc_bwd_fused(p, dtype, fused_part, red ? p.delta : nullptr, red ? N : 0, st), "sfa_bwd(tcgen05 fused)");
   }
   // narrow windows (one KV item per tile): the dQ kernel can compute delta = rowsum(P o dP) and the ds_aux rows
   // itself -- no preprocess pass over O and dO

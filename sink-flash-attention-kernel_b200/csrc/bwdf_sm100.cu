@@ -30,11 +30,23 @@
 // its first tile and the last nb - 1 blocks of its run) are written as fp32 partials and summed by a small
 // fix-up kernel: no atomics, no inter-CTA waits, deterministic.
 //
-// Warp roles (24 warps): 0-11 math (lane quarter = warp & 3, a third of the 16-column chunks each), 12-15 and
+// Warp roles (25 warps): 0-11 math (lane quarter = warp & 3, a third of the 16-column chunks each), 12-15 and
 // 16-19 two epilogue groups taking alternate tiles (dQ store, ring drain), 20 TMA producer, 21 UMMA issuer
 // S / dP, 22 UMMA issuer dV^T, 23 UMMA issuer dK^T, 24 UMMA issuer dQ.  An issuing thread spends 100-150 cycles
 // per tcgen05.mma here (9 instructions on the uniform datapath, competing with six busy warps per scheduler)
 // while the tensor pipe needs 55-80: one issuer for all five products ran at ~8000 cycles per tile.
+//
+// delta = rowsum(dO o O) (sink_flash_attention.py:582) is computed IN the kernel -- no separate streaming pass over
+// O and dO (26 us at the gpt-oss shape, with dO read a second time): the epilogue group of tile n computes
+// delta(n + 3) in the idle time after its epilogue, from the dO tile the TMA already put into shared memory and
+// an O tile loaded beside it, into a 128-float buffer the math warps read before pass 2.  The O buffer's 16 KB
+// come from V, which is single-buffered: only dP(n) reads V(n), so its buffer is free again half a tile before
+// V(n + 1) is needed.  The O loads are issued by the group that just consumed the buffer (not by the producer
+// warp: its in-order waits would tie every other load to the delta computation).  What did not work: O and dO
+// rows as 16-byte global loads in the epilogue groups (round 1: 152 us, 8 rows in flight per warp); three
+// dedicated delta warps with the O rows in registers (152 us: two exposed memory round trips per tile, no
+// registers for a second batch in flight); three delta warps reading both tiles from shared memory (149 us:
+// ~4900 cycles per tile for ~500 instructions -- a 26th-28th warp gets an issue slot every ~10 cycles here).
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -43,12 +55,6 @@
 namespace sfa {
 namespace {
 
-// The in-kernel delta variant (epilogue groups computing rowsum(dO o O), round 1: 152 us vs 98 + 26 us with the streaming
-// preprocess pass) is compiled in only with -DSFA_FUSED_DELTA_CODE=1: its address arithmetic raised the register pressure
-// of the epilogue role and the default kernel spilled two loop-invariant values that it reloaded every tile.
-#ifndef SFA_FUSED_DELTA_CODE
-#define SFA_FUSED_DELTA_CODE 0
-#endif
 struct FusedCfg {
   static constexpr int D = 64;
   static constexpr int kColsMax = 144;                 // keys per tile (UMMA N of S and dP)
@@ -65,7 +71,9 @@ struct FusedCfg {
   static constexpr int kThreads = 25 * 32;
   static constexpr int kStageBytes = 8 * 1024;         // dQ store transpose, [32 rows][32 B] per epilogue warp
   static constexpr int kZeroBytes = 1024;              // zero B operand of the slot-clearing UMMAs (P <= 32 columns)
-  static constexpr int kSmem = 1024 + 4 * kQBytes + 4 * kKVBytes + 2 * kPBytes + kStageBytes + kZeroBytes + 512;
+  static constexpr int kDeltaBytes = 2 * 128 * 4;      // delta rows of two tiles in flight
+  // no alignment slack: the dynamic shared memory is declared 1024-byte aligned (checked at kernel entry)
+  static constexpr int kSmem = 5 * kQBytes + 3 * kKVBytes + 2 * kPBytes + kStageBytes + kZeroBytes + kDeltaBytes + 512;
   static constexpr int kPartKeys = 128;                // keys per side of a CTA's fp32 partials
   static constexpr int kMaxCtas = 160;
   static_assert(kColR + kRingCols <= 512, "TMEM budget");
@@ -78,6 +86,9 @@ struct FusedArgs {
   int order_dp;    // issuer A queues dP(n + 1) behind dK^T(n) / dQ(n)
   int prefetch;    // producer warp prefetches tiles into L2 ahead of the TMA loads
   int fuse_delta;  // 1: the epilogue groups compute delta in the kernel; 0: a preprocess kernel wrote it before
+  int write_delta; // fuse_delta only: ds_aux wanted -- per (head, tile[, quarter]) partials of -sum exp(s_aux - lse) * delta
+                   // (sink_flash_attention.py:653-665) go to the workspace, the fix-up launch sums them in a fixed order
+  const float* s_aux;
   int dbg_delay;   // test knob (sfa_set_debug): the part-1 math warps sleep this many ns before pass 2, the epilogue
                    // groups before their dQ stores -- widens every cross-warp window of the pipeline
   int dbg_norace;  // test knob: 1 drops the per-quarter barrier that orders the P-image reads of pass 2(n) before the
@@ -86,10 +97,8 @@ struct FusedArgs {
   float sl2;     // scale * log2(e)
   float scale;
   const float* lse;
-  float* delta;          // [B,Hq,N] workspace: written by the epilogue groups, read back by the math warps
-  const void* o;         // forward output and its gradient, read directly (16-byte loads) for delta
-  const void* dout;
-  Strides4 so, sdo;
+  float* delta;          // [B,Hq,N] workspace
+
   const void* k;         // L2 prefetch of the newest key block
   const void* v;
   Strides4 sk, sv;
@@ -113,7 +122,8 @@ struct FusedArgs {
 #define SFA_TRACE 0
 #endif
 __device__ __forceinline__ void ftrace(long long* trace, int role, int& cnt, int code, int idx) {
-  if (SFA_TRACE && trace != nullptr && blockIdx.x == 0 && cnt < 256) {
+  // trace[2 * 9 * 256]: the CTA to record (sfa_set_debug knob 2; timeline builds only)
+  if (SFA_TRACE && trace != nullptr && static_cast<long long>(blockIdx.x) == trace[2 * 9 * 256] && cnt < 256) {
     trace[(role * 256 + cnt) * 2] = (static_cast<long long>(code) << 32) | static_cast<unsigned>(idx);
     trace[(role * 256 + cnt) * 2 + 1] = clock64();
     ++cnt;
@@ -184,65 +194,6 @@ struct SlotTrack {
   }
 };
 
-// delta = rowsum(dO o O) (sink_flash_attention.py:582) for rows 32 * quarter .. + 31 of one packed tile, written
-// to the workspace.  8 lanes x 16 B per row, 4 rows per warp load, 8 rows (2 per lane group) in flight per batch.
-// Inlined at ONE call site and small on purpose: the kernel is bound by instruction fetch (three inlined copies made
-// it 101 KB of SASS and 1.7x slower), and it must not spill -- with 227 KB of shared memory the L1 that backs local
-// memory is tiny, every spill reload is an L2 round trip (a spilling out-of-line version took 14 000 cycles per tile).
-struct DeltaGeom {
-  int64_t so_h, so_n, sdo_h, sdo_n;
-  int N, P, lgP, lgG, q_swap;
-};
-template <typename T>
-__device__ __forceinline__ void fused_delta_rows(const T* ob, const T* dob, float* drows, const DeltaGeom& g, int i0,
-                                                 int quarter, int lane) {
-  const int dsub = lane & 7, drow = lane >> 3;
-  ob += dsub * 8;
-  dob += dsub * 8;
-#pragma unroll 1
-  for (int bt = 0; bt < 4; ++bt) {
-    uint4 ov[2], gv[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int r2 = quarter * 32 + bt * 8 + j * 4 + drow;
-      const int pr2 = g.q_swap ? (r2 >> g.lgG) : (r2 & (g.P - 1));
-      const int gr2 = g.q_swap ? (r2 & ((1 << g.lgG) - 1)) : (r2 >> g.lgP);
-      const int i = i0 + pr2;
-      ov[j] = gv[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (i < g.N) {
-        const T* po = ob + gr2 * g.so_h + i * g.so_n;
-        const T* pg = dob + gr2 * g.sdo_h + i * g.sdo_n;
-        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(ov[j].x), "=r"(ov[j].y), "=r"(ov[j].z), "=r"(ov[j].w) : "l"(po));
-        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(gv[j].x), "=r"(gv[j].y), "=r"(gv[j].z), "=r"(gv[j].w) : "l"(pg));
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint32_t ou[4] = {ov[j].x, ov[j].y, ov[j].z, ov[j].w}, gu[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float o0, o1, g0, g1;
-        unpack16f<T>(ou[e], o0, o1);
-        unpack16f<T>(gu[e], g0, g1);
-        s0 = fmaf(o0, g0, s0);
-        s1 = fmaf(o1, g1, s1);
-      }
-      float sum = s0 + s1;
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-      const int r2 = quarter * 32 + bt * 8 + j * 4 + drow;
-      const int pr2 = g.q_swap ? (r2 >> g.lgG) : (r2 & (g.P - 1));
-      const int gr2 = g.q_swap ? (r2 & ((1 << g.lgG) - 1)) : (r2 >> g.lgP);
-      const int i = i0 + pr2;
-      if (dsub == 0 && i < g.N) drows[static_cast<int64_t>(gr2) * g.N + i] = sum;
-    }
-  }
-}
-
 // kExt: extended geometry (packed sequences / chunk offset) compiled in.  A separate instantiation, not a run-time
 // switch: the two extra live values per math thread pushed the plain kernel over its 72-register budget (36 B of
 // spills -- with 227 KB of shared memory every spill reload is an L2 round trip) and cost 4.5 us at the gpt-oss shape.
@@ -251,27 +202,31 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
                                                                              const __grid_constant__ CUtensorMap tmdO,
                                                                              const __grid_constant__ CUtensorMap tmK,
                                                                              const __grid_constant__ CUtensorMap tmV,
+                                                                             const __grid_constant__ CUtensorMap tmO,
                                                                              const FusedArgs a) {
   using C = FusedCfg;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_al[];
+  unsigned char* smem = smem_al;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();       // SWIZZLE_128B tiles need 1024-byte aligned slabs
   unsigned char* q_s = smem;                          // [2][kQBytes]
   unsigned char* do_s = q_s + 2 * C::kQBytes;         // [2][kQBytes]
   unsigned char* k_s = do_s + 2 * C::kQBytes;         // [2][kKVBytes]
-  unsigned char* v_s = k_s + 2 * C::kKVBytes;         // [2][kKVBytes]
-  unsigned char* p_s = v_s + 2 * C::kKVBytes;         // P image
+  unsigned char* v_s = k_s + 2 * C::kKVBytes;         // [kKVBytes]
+  unsigned char* o_s = v_s + C::kKVBytes;             // [kQBytes]  O tile (delta)
+  unsigned char* p_s = o_s + C::kQBytes;              // P image
   unsigned char* ds_s = p_s + C::kPBytes;             // dS image
   unsigned char* stage_s = ds_s + C::kPBytes;         // [8 warps][32 rows][32 B]: dQ store transpose
   unsigned char* z_s = stage_s + C::kStageBytes;      // zeros: B operand of the slot-clearing UMMAs
-  uint64_t* bars = reinterpret_cast<uint64_t*>(z_s + C::kZeroBytes);
+  float* delta_s = reinterpret_cast<float*>(z_s + C::kZeroBytes);   // [2][128]: delta of the rows of tiles n, n + 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(z_s + C::kZeroBytes + C::kDeltaBytes);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = q_full + 2;     // [2]  dK^T(n) complete
   uint64_t* k_full = q_empty + 2;
   uint64_t* k_empty = k_full + 2;     //      dQ(n) complete
   uint64_t* do_full = k_empty + 2;
-  uint64_t* do_empty = do_full + 2;   //      dV^T(n) complete
-  uint64_t* v_full = do_empty + 2;
-  uint64_t* v_empty = v_full + 2;     //      dP(n) complete
+  uint64_t* do_empty = do_full + 2;   //      dV^T(n) complete (+ delta(n) computed: the four warps of its epilogue group)
+  uint64_t* v_full = do_empty + 2;    // [0]: V(n), phase n & 1;  [1]: unused
+  uint64_t* v_empty = v_full + 2;     // [0]: dP(n) complete;     [1]: unused
   uint64_t* s_full = v_empty + 2;     // S(n) complete                          (issuer A -> math)
   uint64_t* s_free = s_full + 1;      // S(n) read                              (math -> issuer A)
   uint64_t* dp_full = s_free + 1;     // dP(n) complete                         (issuer A -> math)
@@ -283,13 +238,15 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   uint64_t* dq_done = ds_free + 1;    // [2] all UMMAs of tile n complete       (issuers V + K -> epilogue group n & 1)
   uint64_t* dq_free = dq_done + 2;    // [2] dQ(n) read                         (epilogue group n & 1 -> issuer K)
   uint64_t* drain_done = dq_free + 2; // [2] ring drain of tile n finished      (epilogue group n & 1 -> issuers V, K)
-  uint64_t* delta_ready = drain_done + 2;   // [4] delta rows of tile n in global memory: barrier n & 3, phase n >> 2
-                                            //     (epilogue group n & 1 -> math); four barriers because a group
-                                            //     produces up to two tiles ahead of the consumer (parity aliasing)
-  uint64_t* kq_issued = delta_ready + 4;    // dK^T(n) and dQ(n) have been ISSUED (issuers K, Q -> issuer A): dP(n + 1) is
+  uint64_t* delta_ready = drain_done + 2;   // [2] delta rows of tile n in delta_s[n & 1]   (epilogue group n & 1 -> math)
+  uint64_t* delta_free = delta_ready + 2;   // [2] ... read by every math thread            (math -> epilogue group)
+  uint64_t* kq_issued = delta_free + 2;    // dK^T(n) and dQ(n) have been ISSUED (issuers K, Q -> issuer A): dP(n + 1) is
                                             // queued behind them in the tensor pipe, not in front (both are released
                                             // by the end of pass 2(n), but only dK / dQ gate the next pass 2)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_issued + 1);
+  uint64_t* o_full = kq_issued + 1;         // [8 blocks of 16 rows][2]: O rows of tile n in block j: barrier [j][n & 1], phase
+                                            // (n >> 1) & 1 -- per tile parity because the epilogue groups take alternate
+                                            // tiles (a parity wait cannot tell phase n from phase n - 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const WalkInit wi(a);
@@ -299,7 +256,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
     tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    for (int s = 0; s < 16; ++s) mbar_init(bars + s, 1);
+    if (a.fuse_delta) tma_prefetch_desc(&tmO);
+    // with delta in the kernel: do_empty[s] (bars 10, 11) = dV^T(n) complete + the four warps that computed delta(n)
+    for (int s = 0; s < 16; ++s) mbar_init(bars + s, (a.fuse_delta && (s == 10 || s == 11)) ? 5 : 1);
     mbar_init(s_full, 1);
     mbar_init(s_free, C::kMathWarps * 32);       // per-thread arrivals and waits in the math warps: measured faster than
                                                  // one polling / arriving lane per warp + __syncwarp (fwd64: 62 vs 67 us)
@@ -314,9 +273,10 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       mbar_init(dq_free + g, 4);
       mbar_init(drain_done + g, 4);
       mbar_init(delta_ready + g, 4);
-      mbar_init(delta_ready + 2 + g, 4);
+      mbar_init(delta_free + g, C::kMathWarps * 32);
     }
     mbar_init(kq_issued, 2);
+    for (int j = 0; j < 16; ++j) mbar_init(o_full + j, 1);
     fence_barrier_init();
   }
   if (warp == 21) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -380,18 +340,20 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           const int s = w.it & 1;
           const uint32_t eph = ((w.it >> 1) & 1) ^ 1;
           const int q0 = w.pb * P, hq0 = w.y * a.G, kstart = (w.pb + qb - nb + 1) * P;
+          // dO first: its buffer is released by dV^T(n - 2), half a tile before dK^T(n - 2) / dQ(n - 2) release Q and
+          // K -- and the delta of tile n (epilogue groups) wants dO(n) as early as it can get it
+          mbar_wait(do_empty + s, eph);
+          mbar_expect_tx(do_full + s, C::kQBytes);
+          tma_tile(do_s + s * C::kQBytes, &tmdO, do_full + s, a.q_swap, 0, q0, hq0, w.b);
           mbar_wait(q_empty + s, eph);
           mbar_expect_tx(q_full + s, C::kQBytes);
           tma_tile(q_s + s * C::kQBytes, &tmQ, q_full + s, a.q_swap, 0, q0, hq0, w.b);
           mbar_wait(k_empty + s, eph);
           mbar_expect_tx(k_full + s, kv_bytes);
           tma_tile(k_s + s * C::kKVBytes, &tmK, k_full + s, a.k_swap, 0, kstart, w.y, w.b);
-          mbar_wait(do_empty + s, eph);
-          mbar_expect_tx(do_full + s, C::kQBytes);
-          tma_tile(do_s + s * C::kQBytes, &tmdO, do_full + s, a.q_swap, 0, q0, hq0, w.b);
-          mbar_wait(v_empty + s, eph);
-          mbar_expect_tx(v_full + s, kv_bytes);
-          tma_tile(v_s + s * C::kKVBytes, &tmV, v_full + s, a.v_swap, 0, kstart, w.y, w.b);
+          mbar_wait(v_empty, (w.it & 1) ^ 1);             // single buffer: dP(n - 1) complete
+          mbar_expect_tx(v_full, kv_bytes);
+          tma_tile(v_s, &tmV, v_full, a.v_swap, 0, kstart, w.y, w.b);
           ftrace(a.trace, 0, tc, 3, w.it);
         }
         __syncwarp();
@@ -412,7 +374,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         const int s = w.it & 1;
         const uint32_t fph = (w.it >> 1) & 1;
         const uint64_t qd = qd0 + s * (C::kQBytes >> 4), kd = kd0 + s * (C::kKVBytes >> 4);
-        const uint64_t dod = dod0 + s * (C::kQBytes >> 4), vd = vd0 + s * (C::kKVBytes >> 4);
+        const uint64_t dod = dod0 + s * (C::kQBytes >> 4), vd = vd0;
         mbar_wait(q_full + s, fph);
         mbar_wait(k_full + s, fph);
         if (w.it >= 1) mbar_wait(s_free, (w.it - 1) & 1);
@@ -423,7 +385,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         umma_commit(s_full);
         ftrace(a.trace, 1, tc, 3, w.it);
         mbar_wait(do_full + s, fph);
-        mbar_wait(v_full + s, fph);
+        mbar_wait(v_full, w.it & 1);
         if (w.it >= 1) {
           mbar_wait(dp_free, (w.it - 1) & 1);
           if (a.order_dp) mbar_wait(kq_issued, (w.it - 1) & 1);
@@ -433,7 +395,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + C::kColP, dod + kk * 2, vd + kk * 2, idesc, kk != 0);
         umma_commit(dp_full);
-        umma_commit(v_empty + s);
+        umma_commit(v_empty);
         ftrace(a.trace, 1, tc, 5, w.it);
       }
     }
@@ -550,12 +512,10 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         }
         return v;
       };
-      // delta of tile t was written to global memory by epilogue group (t.it & 1) of THIS CTA: wait for its
-      // mbarrier (release / acquire at CTA scope), then read through L2 (no stale L1 line, no .nc)
+      // delta of tile t from the preprocess pass (fuse_delta == 0); with fuse_delta it comes from delta_s before pass 2
       auto load_delta = [&](const FusedWalk& t, bool valid) {
         float v = 0.f;
-        if (valid) {
-          if (SFA_FUSED_DELTA_CODE && a.fuse_delta) mbar_wait_warp(delta_ready + (t.it & 3), (t.it >> 2) & 1);
+        if (valid && !a.fuse_delta) {
           const int i = t.pb * P + pr;
           if (i < a.N) {
             const int64_t row = (static_cast<int64_t>(t.b) * a.Hq + t.y * a.G + gr) * a.N + i;
@@ -585,9 +545,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       while (w.next()) {
         if (tr) ftrace(a.trace, 3, tc, 1, w.it);
         st.step(w, R);
-        const float lse_i = l_next, dsc = d_next * a.scale;
+        const float lse_i = l_next;
+        float dsc = d_next * a.scale;
         const int lo_row = lo_next;
-        const uint64_t ndsc2 = pack_f32x2(-dsc, -dsc);
         has_next = wn.next();
         l_next = load_row(a.lse, wn, has_next, INFINITY);
         d_next = load_delta(wn, has_next);
@@ -662,6 +622,13 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         mbar_wait(dp_full, w.it & 1);
         tc_fence_after();
         if (w.it >= 1) mbar_wait(ds_free, (w.it - 1) & 1);
+        if (a.fuse_delta) {                                // this row's delta from the delta warps
+          mbar_wait(delta_ready + (w.it & 1), (w.it >> 1) & 1);
+          dsc = delta_s[(w.it & 1) * 128 + r] * a.scale;
+          mbar_arrive(delta_free + (w.it & 1));
+          if (tr) ftrace(a.trace, 3, tc, 6, w.it);
+        }
+        const uint64_t ndsc2 = pack_f32x2(-dsc, -dsc);
         if (a.dbg_delay && part == 1) __nanosleep(a.dbg_delay);
         if (tr) ftrace(a.trace, 3, tc, 4, w.it);
         if (part == 1)
@@ -718,47 +685,129 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         row_pr[t] = pr2;
         row_off[t] = static_cast<int64_t>(gr2) * a.sdq.h + static_cast<int64_t>(pr2) * a.sdq.n + (lane & 1) * 8;
       }
-      // ---- delta = rowsum(dO o O) (sink_flash_attention.py:582) of this group's tiles, computed in the idle time
-      // between two epilogues, four tiles ahead of the epilogue and at least two ahead of the math warps' prefetch:
-      // replaces a separate pass over O and dO (the preprocess kernel, 33 us at the gpt-oss shape).  ds_aux
-      // (:653-665) is reduced from delta and lse by a small kernel afterwards.  8 lanes x 16 B per row, 4 rows per warp load; this
-      // warp owns rows 32 * quarter .. + 31 of the tile.
       int tc = 0;
       const bool tr = SFA_TRACE && (lane == 0) && (quarter == 0);
       const int trole = grp ? 6 : 4;
-      DeltaGeom dgeom;
-      dgeom.so_h = a.so.h; dgeom.so_n = a.so.n; dgeom.sdo_h = a.sdo.h; dgeom.sdo_n = a.sdo.n;
-      dgeom.N = a.N; dgeom.P = P; dgeom.lgP = a.lgP; dgeom.lgG = 7 - a.lgP; dgeom.q_swap = a.q_swap;
-      // L2 prefetch of the O and dO rows of the delta tile after next: this lane's row of the 128
-      auto delta_prefetch = [&](const FusedWalk& t) {
-        const int i = t.pb * P + pr;
-        if (i < a.N) {
-          const int h = t.y * a.G + gr;
-          const T* po = static_cast<const T*>(a.o) + t.b * a.so.b + h * a.so.h + static_cast<int64_t>(i) * a.so.n;
-          const T* pg = static_cast<const T*>(a.dout) + t.b * a.sdo.b + h * a.sdo.h + static_cast<int64_t>(i) * a.sdo.n;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(po));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pg));
-        }
-      };
-      auto delta_tile = [&](const FusedWalk& t) {
-        if (tr) ftrace(a.trace, trole, tc, 7, t.it);
-        const int h0 = t.y * a.G;
-        fused_delta_rows<T>(static_cast<const T*>(a.o) + t.b * a.so.b + h0 * a.so.h,
-                            static_cast<const T*>(a.dout) + t.b * a.sdo.b + h0 * a.sdo.h,
-                            a.delta + (static_cast<int64_t>(t.b) * a.Hq + h0) * a.N, dgeom, t.pb * P, quarter, lane);
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(delta_ready + (t.it & 3));
-      };
-      FusedWalk wd(a, wi);
-      for (int t = 0; t <= grp; ++t) wd.next();          // wd.it == grp: this group's first tile
       FusedWalk w(a, wi);
       SlotTrack st;
       st.slot0 = 0;
       int pa = 0;
-      // One loop, ONE delta site: two lead-in rounds produce the deltas of the group's first two tiles, every later
-      // round is epilogue(tile n) followed by delta(tile n + 4).
-      int lead = (SFA_FUSED_DELTA_CODE && a.fuse_delta) ? 2 : 0;
+      // ---- delta(n + 3) after the epilogue of tile n (i.e. the tiles of the OTHER group): O(n + 3) and dO(n + 3) land
+      // right when this group has finished epilogue(n), a tile before the UMMAs of its next tile n + 2 complete and more
+      // than a tile before pass 2(n + 3).  (delta(n + 2) in front of epilogue(n): the group sat in the wait for the
+      // delta inputs when dQ(n) was ready -- dq_free, the ring drain and with them every issuer ran late: 171 us.)
+      // This warp owns rows 32 * quarter .. + 31.
+      // (the delta tile's coordinates come from two divisions per tile, not from a third walker: registers)
+      int dit = a.fuse_delta ? (grp ^ 1) : (1 << 30);         // index of the group's next delta tile in this CTA's run
+      // O rows arrive as 16-row blocks (2 KB, one TMA box each); the warp that has consumed block j of tile k loads block j
+      // of tile k + 1 into the same place -- for the same quarter's warp of the other group.  (One 16 KB box per tile,
+      // loaded when the whole group had finished: delta(k) -> load -> delta(k + 1) was a chain of ~4600 + ~2000 cycles
+      // per tile, longer than the tile period.)
+      auto o_block = [&](int j, int n_tile, int h_tile, int bt, uint64_t* bar) {
+        const int n0 = n_tile + (a.q_swap ? ((16 * j) >> (7 - a.lgP)) : ((16 * j) & (P - 1)));
+        const int h0 = h_tile + (a.q_swap ? 0 : ((16 * j) >> a.lgP));
+        mbar_expect_tx(bar, 2048);
+        tma_tile(o_s + j * 2048, &tmO, bar, a.q_swap, 0, n0, h0, bt);
+      };
+      if (a.fuse_delta && grp == 1 && lane == 0 && wi.tile < wi.end) {     // O(0): by the warps that will read it
+        o_block(2 * quarter, wi.pb * P, wi.y * a.G, wi.b, o_full + (2 * quarter) * 2);
+        o_block(2 * quarter + 1, wi.pb * P, wi.y * a.G, wi.b, o_full + (2 * quarter + 1) * 2);
+      }
+      auto delta_tile = [&]() {
+        if (wi.tile + dit >= wi.end) return;
+        if (tr) ftrace(a.trace, trole, tc, 7, dit);
+        const int s = dit & 1;
+        // coordinates first (integer divisions), under the wait for the inputs
+        const int dpb = (wi.tile + dit) % a.nblk, dhead = (wi.tile + dit) / a.nblk;   // dhead = b * Hkv + y
+        const int pmax = a.N - 1 - dpb * P;
+        // ds_aux: this row's lse and its head's s_aux, requested now, used after the row sum
+        float lse_r = -INFINITY, sx = 0.f;
+        const int my_pr = a.q_swap ? (lane >> (7 - a.lgP)) + quarter * (32 >> (7 - a.lgP)) : ((quarter * 32 + lane) & (P - 1));
+        const int my_gr = a.q_swap ? (lane & (a.G - 1)) : ((quarter * 32 + lane) >> a.lgP);
+        if (a.write_delta) {
+          if (my_pr <= pmax)
+            lse_r = __ldg(a.lse + (static_cast<int64_t>(dhead) * a.G + my_gr) * a.N + dpb * P + my_pr);
+          sx = __ldg(a.s_aux + (dhead % a.Hkv) * a.G + my_gr);
+        }
+        int on = -1, ohb = 0;                                 // next tile (lane 0 loads its O blocks): position,
+                                                              // head | batch << 12 (registers)
+        if (lane == 0 && wi.tile + dit + 1 < wi.end) {
+          const int tn = wi.tile + dit + 1, hn = tn / a.nblk;
+          on = (tn % a.nblk) * P;
+          ohb = ((hn % a.Hkv) * a.G) | ((hn / a.Hkv) << 12);
+        }
+        const uint32_t ob = smem_u32(o_s), dob = smem_u32(do_s) + s * C::kQBytes;
+        float* const dl = delta_s + s * 128;
+        mbar_wait(do_full + s, (dit >> 1) & 1);               // dO tile
+        if (dit >= 2) mbar_wait(delta_free + s, ((dit - 2) >> 1) & 1);
+        // One lane per row (row 32 * quarter + lane; the 128B swizzle keeps the eight rows of a quarter-warp on distinct
+        // banks): 16 LDS.128 + 1 STS per warp and no shuffles.  The math warps keep the MIO queue (LDS / STS / SHFL /
+        // MUFU / tcgen05.ld) busy, and every MIO instruction of this role waits in it: 8 lanes per row with three
+        // shuffles per row group (48 MIO instructions per warp) took ~4600 cycles per tile; warp-level MMAs
+        // (delta = diag(O dO^T), mma.sync m16n8k16) queue in the tensor pipe between the UMMAs, which is what bounds
+        // this kernel: +1500 cycles per tile.
+        mbar_wait(o_full + (2 * quarter) * 2 + s, (dit >> 1) & 1);
+        mbar_wait(o_full + (2 * quarter + 1) * 2 + s, (dit >> 1) & 1);
+        if (tr) ftrace(a.trace, trole, tc, 8, dit);
+        {
+          const int r2 = quarter * 32 + lane;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            uint4 ov[2], gv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint32_t off = sw128_off(r2, c + u);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(ov[u].x), "=r"(ov[u].y), "=r"(ov[u].z), "=r"(ov[u].w) : "r"(ob + off) : "memory");
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(gv[u].x), "=r"(gv[u].y), "=r"(gv[u].z), "=r"(gv[u].w) : "r"(dob + off) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint32_t ou[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w}, gu[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float o0, o1, g0, g1;
+                unpack16f<T>(ou[e], o0, o1);
+                unpack16f<T>(gu[e], g0, g1);
+                s0 = fmaf(o0, g0, s0);
+                s1 = fmaf(o1, g1, s1);
+              }
+            }
+          }
+          const float sum = s0 + s1;
+          dl[r2] = sum;
+          if (a.write_delta) {
+            // the rows of one head in this warp: P consecutive lanes (P = 16: two heads per warp), or -- swapped layout --
+            // the lanes with equal lane % G; xor-shuffle tree over them, result in the lowest lane of each head
+            float c = (lse_r == -INFINITY) ? 0.f : -__expf(sx - lse_r) * sum;
+            if (a.q_swap) {
+              for (int o = a.G; o < 32; o <<= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            } else {
+              for (int o = 1; o < min(P, 32); o <<= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            }
+            const bool first = a.q_swap ? (lane < a.G) : ((lane & (min(P, 32) - 1)) == 0);
+            // slot (head, tile) -- in the swapped layout every quarter holds rows of every head: (head, tile, quarter)
+            const int nslot = a.q_swap ? 4 : 1;
+            if (first)
+              a.delta[((static_cast<int64_t>(dhead) * a.G + my_gr) * a.nblk + dpb) * nslot + (a.q_swap ? quarter : 0)] = c;
+          }
+        }
+        __syncwarp();                                         // every lane has read its O row
+        if (on >= 0) {
+          o_block(2 * quarter, on, ohb & 4095, ohb >> 12, o_full + (2 * quarter) * 2 + (s ^ 1));
+          o_block(2 * quarter + 1, on, ohb & 4095, ohb >> 12, o_full + (2 * quarter + 1) * 2 + (s ^ 1));
+        }
+        if (lane == 0) {                                      // this warp's rows are in delta_s, its reads of dO are done
+          mbar_arrive(delta_ready + s);
+          mbar_arrive(do_empty + s);
+        }
+        if (tr) ftrace(a.trace, trole, tc, 6, dit);
+        dit += 2;
+      };
+      // lead-in rounds: delta(0), delta(2) by group 1, delta(1) by group 0; then every round is epilogue(n), delta(n + 3)
+      int lead = a.fuse_delta ? 1 + grp : 0;
       while (true) {
         if (lead > 0) {
           --lead;
@@ -875,18 +924,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         if (lane == 0) mbar_arrive(drain_done + grp);
         if (tr) ftrace(a.trace, trole, tc, 5, w.it);
         }
-        // ---- delta of the group's tile four ahead (prefetch for the one after it first)
-        if (!SFA_FUSED_DELTA_CODE || !a.fuse_delta) continue;
-        {
-          FusedWalk wf = wd;
-          wf.next();
-          wf.next();
-          if (wf.tile < wf.end) delta_prefetch(wf);
-        }
-        if (wd.tile < wd.end) delta_tile(wd);
-        wd.next();
-        wd.next();
-        if (tr) ftrace(a.trace, trole, tc, 6, w.it);
+        delta_tile();
       }
     }
   }
@@ -898,8 +936,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
 // Sums the fp32 partials of the key blocks shared by two neighbouring CTAs (tail of c - 1, head of c).
 // grid (boundaries, float4 groups / 256): one float4 per thread -- every load is independent and in flight at once
 // (the first version looped 64 dependent-latency iterations per thread and took 40 us for 2.4 MB).
-// Blocks x >= nbound (y == 0) reduce the ds_aux block partials of head x - nbound instead (fixed order: deterministic;
-// sink_flash_attention.py:653-665) -- one launch less on the backward's critical path.
+// Blocks x >= nbound (y == 0) reduce ds_aux of head x - nbound instead (fixed order: deterministic;
+// sink_flash_attention.py:653-665) -- the block partials of the preprocess pass, or the per-tile partials the fused
+// kernel's epilogue groups left -- one launch less on the backward's critical path.
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_fused_fixup_kernel(const FusedArgs a, const int vec_ok, const int nbound,
                                                               const float* __restrict__ ds_partial, float* ds_aux,
@@ -955,6 +994,7 @@ bool fused_geometry(const AttnParams& p, int& G, int& P, int& nb) {
   pick_packing(p.Hq, p.Hkv, G, P);
   if ((p.Hq / p.Hkv) != G) return false;              // one packed tile must hold the whole GQA group
   if (P != 16 && P != 32) return false;
+  if (p.Hq > 4096 || p.B >= (1 << 19)) return false;   // the O-tile loader packs head | batch << 12 into one register
   if (p.q_off % P != 0) return false;                 // the key-block ring advances in whole query tiles
   const int64_t weff = p.W < p.Nkv ? p.W : p.Nkv;
   const int64_t nb64 = (weff - 1 + P - 1) / P + 1;
@@ -967,6 +1007,7 @@ bool fused_geometry(const AttnParams& p, int& G, int& P, int& nb) {
 template <typename T>
 cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const float* ds_partial, int ds_nblk,
                          cudaStream_t st) {
+  // with the in-kernel delta: ds_partial == p.delta (the kernel leaves per-tile partials there) when ds_aux is wanted
   using C = FusedCfg;
   int G, P, nb;
   if (!fused_geometry(p, G, P, nb)) return cudaErrorInvalidValue;
@@ -988,9 +1029,20 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   if (!make_tile_map(&mk, p.k, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sk, a.cols, 1)) return cudaErrorInvalidValue;
   if (!make_tile_map(&mv, p.v, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sv, a.cols, 1)) return cudaErrorInvalidValue;
   if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;
+  a.fuse_delta = tc_bwd_fused_computes_delta(p) ? 1 : 0;
+  TileMap mo = mq;
+  if (a.fuse_delta) {
+    // 16-row blocks of the packed tile: one head x 16 positions, or (swapped layout) 16 / G positions x G heads
+    const bool o_swap = (p.Hq > 1 && p.N > 1) ? (p.so.h < p.so.n) : false;
+    if (!make_tile_map(&mo, p.o, dtype, C::D, p.N, p.Hq, p.B, p.so, o_swap ? 16 / G : 16, o_swap ? G : 1))
+      return cudaErrorInvalidValue;
+    if (mo.swap_nh != mq.swap_nh) return cudaErrorInvalidValue;
+  }
   a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh;
   a.fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
-  a.fuse_delta = tc_bwd_fused_computes_delta() ? 1 : 0;
+  a.write_delta = (a.fuse_delta && ds_partial != nullptr) ? 1 : 0;
+  a.s_aux = p.s_aux;
+  if (a.write_delta) ds_nblk = a.nblk * (a.q_swap ? 4 : 1);
   a.qb = p.q_off / P; a.Nkv = p.Nkv; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
   a.dbg_delay = debug_knob(0);
   a.dbg_norace = debug_knob(1);
@@ -1003,11 +1055,7 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   a.scale = p.scale;
   a.lse = p.lse;
   a.delta = p.delta;
-  a.o = p.o;
-  a.dout = p.dout;
   a.k = p.k; a.v = p.v; a.sk = p.sk; a.sv = p.sv;
-  a.so = p.so;
-  a.sdo = p.sdo;
   a.dq = p.dq; a.dk = p.dk; a.dv = p.dv;
   a.sdq = p.sdq; a.sdk = p.sdk; a.sdv = p.sdv;
   a.dq_seg_n = 0;
@@ -1029,11 +1077,11 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   if (p.has_ext()) {
     static std::atomic<unsigned long long> attr_done{0};
     if ((e = ensure_dyn_smem(bwd_fused64_kernel<T, true>, C::kSmem, attr_done)) != cudaSuccess) return e;
-    bwd_fused64_kernel<T, true><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    bwd_fused64_kernel<T, true><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mo.map, a);
   } else {
     static std::atomic<unsigned long long> attr_done{0};
     if ((e = ensure_dyn_smem(bwd_fused64_kernel<T, false>, C::kSmem, attr_done)) != cudaSuccess) return e;
-    bwd_fused64_kernel<T, false><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, a);
+    bwd_fused64_kernel<T, false><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mo.map, a);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -1045,8 +1093,8 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
     };
     const int vec_ok = al8(p.dk, p.sdk) && al8(p.dv, p.sdv);
     const int groups = nbound ? (nb - 1) * P * 128 / 4 : 1;
-    bwd_fused_fixup_kernel<T><<<dim3(nbound + nred, (groups + 255) / 256), 256, 0, st>>>(a, vec_ok, nbound, ds_partial,
-                                                                                         p.ds_aux, ds_nblk);
+    bwd_fused_fixup_kernel<T><<<dim3(nbound + nred, (groups + 255) / 256), 256, 0, st>>>(
+        a, vec_ok, nbound, ds_partial, p.ds_aux, ds_nblk);
     e = cudaGetLastError();
   }
   return e;
@@ -1054,12 +1102,14 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
 
 }  // namespace
 
-// Off by default: measured at the gpt-oss shape, delta inside the kernel (epilogue groups, 8 lanes x 16 B per row from
-// L2-prefetched O / dO rows) costs each epilogue group ~9 000 cycles per tile -- more than its idle time -- and the
-// backward takes 152 us against 108 + 37 us with the separate streaming preprocess kernel.  SFA_FUSED_DELTA=1 enables it.
-bool tc_bwd_fused_computes_delta() {
-  static const bool on = SFA_FUSED_DELTA_CODE && getenv("SFA_FUSED_DELTA") != nullptr;
-  return on;
+// delta inside the kernel (three delta warps; the round-1 attempt on the epilogue groups, 8 rows in flight per warp,
+// cost 152 us against 98 + 26 us).  SFA_FUSED_DELTA=0 goes back to the separate preprocess pass.
+bool tc_bwd_fused_computes_delta(const AttnParams& p) {
+  static const bool on = !(getenv("SFA_FUSED_DELTA") != nullptr && atoi(getenv("SFA_FUSED_DELTA")) == 0);
+  if (!on || !tma_compatible(p.o, p.so, p.B, p.Hq, p.N)) return false;
+  const bool q_swap = (p.Hq > 1 && p.N > 1) ? (p.sq.h < p.sq.n) : false;
+  const bool o_swap = (p.Hq > 1 && p.N > 1) ? (p.so.h < p.so.n) : false;
+  return q_swap == o_swap;
 }
 
 size_t tc_bwd_fused_workspace_bytes() {

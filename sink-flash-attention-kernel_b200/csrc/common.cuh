@@ -123,7 +123,7 @@ cudaError_t tc_fwd128(const AttnParams& p, int dtype, cudaStream_t st);
 bool tc_bwd_supported(const AttnParams& p, int dtype);
 bool tc_bwd_fuses_delta(const AttnParams& p, int dtype);   // the dQ kernel derives delta (and ds_aux rows) itself: no preprocess pass
 cudaError_t ds_aux_reduce(const float* partial, float* ds_aux, int B, int Hq, int nblk, cudaStream_t st);
-bool tc_bwd_fused_computes_delta();
+bool tc_bwd_fused_computes_delta(const AttnParams& p);   // delta by the fused kernel's own delta warps
 cudaError_t ds_aux_from_delta(const float* delta, const float* lse, const float* s_aux, float* ds_aux, int B, int Hq,
                               int N, cudaStream_t st);
 cudaError_t tc_bwd(const AttnParams& p, int dtype, int stages, cudaStream_t st);

@@ -25,27 +25,29 @@ lib = _lib.load()
 for _ in range(3):
     _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
 torch.cuda.synchronize()
-buf = torch.zeros(8 * 256 * 2, dtype=torch.int64, device=dev)
+buf = torch.zeros(9 * 256 * 2 + 1, dtype=torch.int64, device=dev)
+buf[-1] = int(os.environ.get('TRACE_CTA', '0'))
 lib.sfa_set_trace_buffer(buf.data_ptr())
 lib.sfa_set_bwd_stages(6)
 _lib.bwd(q, k, v, o, do, lse, S, W, s_aux)
 torch.cuda.synchronize()
 lib.sfa_set_trace_buffer(None)
 lib.sfa_set_bwd_stages(7)
-t = buf.cpu().view(8, 256, 2)
-ROLES = ["PROD", "ISS_A", "ISS_V", "MATH", "EPI0", "ISS_K", "EPI1", "ISS_Q"]
+t = buf.cpu()[:-1].view(9, 256, 2)
+ROLES = ["PROD", "ISS_A", "ISS_V", "MATH", "EPI0", "ISS_K", "EPI1", "ISS_Q", "DELTA"]
 CODES = [
     {1: "begin", 3: "loads issued"},
     {1: "begin", 2: "S inputs ready", 3: "S issued", 4: "dP inputs ready", 5: "dP issued"},
     {1: "begin", 2: "P ready + drain ok", 3: "dV issued"},
-    {1: "begin", 2: "S full + P free", 3: "pass 1 done", 4: "dP full + dS free", 5: "pass 2 done"},
-    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done", 6: "delta(+4) done", 7: "delta begin", 8: "delta loads issued", 9: "delta half done"},
+    {1: "begin", 2: "S full + P free", 3: "pass 1 done", 4: "dP full + dS free", 5: "pass 2 done", 6: "delta read"},
+    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done", 6: "delta done", 7: "delta begin", 8: "delta inputs ready"},
     {1: "begin", 2: "dS ready + drain ok", 3: "dK issued"},
-    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done", 6: "delta(+4) done", 7: "delta begin", 8: "delta loads issued", 9: "delta half done"},
+    {1: "begin", 2: "tile UMMAs complete", 3: "dQ loaded", 4: "dQ stored", 5: "drain done", 6: "delta done", 7: "delta begin", 8: "delta inputs ready"},
     {1: "begin", 2: "dS ready + dq_free ok", 3: "dQ issued"},
+    {1: "begin", 2: "O landed", 3: "dO landed", 4: "delta slot free", 5: "delta done"},
 ]
 ev = []
-for role in range(8):
+for role in range(9):
     for j in range(256):
         tag, clk = int(t[role, j, 0]), int(t[role, j, 1])
         if clk == 0:
