@@ -299,8 +299,8 @@ def run_ours(args):
             o.backward(do)
 
         # The timed step is a CUDA-graph replay of exactly the launches the autograd Function makes (sfa_fwd,
-        # then sfa_bwd: delta/ds_aux preprocess, ds_aux reduce, fused dQ/dK/dV kernel, fix-up): the five kernels take
-        # ~0.2 ms, less than the Python/ctypes launch path around them, so the eager number measures the host.
+        # then sfa_bwd: the fused delta/dQ/dK/dV kernel and its fix-up, which also reduces ds_aux): the three kernels take
+        # ~0.17 ms, less than the Python/ctypes launch path around them, so the eager number measures the host.
         qd_, kd_, vd_, sd_ = q.detach(), k.detach(), v.detach(), s_aux.detach()
 
         def c_abi_step():
@@ -317,8 +317,9 @@ def run_ours(args):
         def step():
             step_graph.replay()
         n_total = N
-        launches_per_step = 4               # fwd; bwd = delta/ds_aux preprocess + fused dQ/dK/dV + its fix-up (which also reduces ds_aux)
-                                            # (wide windows / sinks: preprocess + ds_aux reduce + dQ kernel + dK/dV kernel)
+        # fwd; bwd = fused delta/dQ/dK/dV kernel + its fix-up (which also reduces ds_aux); SFA_FUSED_DELTA=0 puts the
+        # separate delta/ds_aux preprocess pass back (wide windows / sinks: preprocess + ds_aux reduce + dQ kernel + dK/dV kernel)
+        launches_per_step = 4 if os.environ.get("SFA_FUSED_DELTA", "1") == "0" else 3
         workload = ("gpt-oss-20b attention layer fwd+bwd (BASELINE configs[1]): B=1 N=8192 Hq=64 Hkv=8 D=64 window=128 "
                     "s_aux bf16")
         parallelism = "single GPU"
@@ -444,9 +445,10 @@ def run_ours(args):
                 halo_line = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.synchronize()
             dist.barrier()
-        # fwd: 3 scatter + barrier + attention + scatter + barrier (+ clone); bwd: scatter + barrier + preprocess +
-        # fused + fix-up + 3 scatter + barrier (+ 3 copies)  ->  13 kernels of libsinkfa per step (p2p path)
-        launches_per_step = 13 if want_p2p else 1 + 3
+        # fwd: 3 scatter + barrier + attention + scatter + barrier (+ clone); bwd: scatter + barrier +
+        # fused + fix-up + 3 scatter + barrier (+ 3 copies)  ->  12 kernels of libsinkfa per step (p2p path; no preprocess
+        # launch since the fused backward computes delta itself)
+        launches_per_step = 12 if want_p2p else 1 + 2
         workload = (f"gpt-oss-20b attention layer fwd+bwd under Ulysses SP (BASELINE configs[4]): ONE {n_total}-token sequence, "
                     f"{N}-token chunk per rank, Hq=64 Hkv=8 D=64 window=128 s_aux bf16, {exch} each side")
         parallelism = f"ulysses_sp{world}"
@@ -507,7 +509,7 @@ def run_ours(args):
             # dQ, dK and dV (bwdf_sm100.cu) + a small fix-up; otherwise the dQ / dK/dV kernel pair
             _lib.bwd(qd, kd, vd, o_s, do, lse_s, S, W, sd)
             bwd_impl = _lib.last_impl()
-            if bwd_impl == "tcgen05-fused" and os.environ.get("SFA_FUSED_DELTA"):
+            if bwd_impl == "tcgen05-fused" and os.environ.get("SFA_FUSED_DELTA", "1") != "0":
                 stages = (("bwd_fused(delta,ds_aux,dq,dk,dv)", 6),)
             elif bwd_impl == "tcgen05-fused":
                 stages = (("bwd_preprocess(delta,ds_aux)", 1), ("bwd_fused(dq,dk,dv)", 6))

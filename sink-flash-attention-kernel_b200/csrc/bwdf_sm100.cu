@@ -47,6 +47,7 @@
 // dedicated delta warps with the O rows in registers (152 us: two exposed memory round trips per tile, no
 // registers for a second batch in flight); three delta warps reading both tiles from shared memory (149 us:
 // ~4900 cycles per tile for ~500 instructions -- a 26th-28th warp gets an issue slot every ~10 cycles here).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -334,6 +335,15 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       if (a.prefetch)
         for (int i = 0; i < kPrefetchAhead; ++i)
           if (wp.next()) prefetch_tile(wp);
+      if (a.fuse_delta && lane == 0 && wi.tile < wi.end) {        // O(0), as eight 16-row blocks; the epilogue warps load the rest
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          const int n0 = wi.pb * P + (a.q_swap ? ((16 * j) >> (7 - a.lgP)) : ((16 * j) & (P - 1)));
+          const int h0 = wi.y * a.G + (a.q_swap ? 0 : ((16 * j) >> a.lgP));
+          mbar_expect_tx(o_full + j * 2, 2048);
+          tma_load_4d(o_s + j * 2048, &tmO, o_full + j * 2, 0, a.q_swap ? h0 : n0, a.q_swap ? n0 : h0, wi.b);
+        }
+      }
       while (w.next()) {
         if (lane == 0) {
           ftrace(a.trace, 0, tc, 1, w.it);
@@ -703,22 +713,16 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       // of tile k + 1 into the same place -- for the same quarter's warp of the other group.  (One 16 KB box per tile,
       // loaded when the whole group had finished: delta(k) -> load -> delta(k + 1) was a chain of ~4600 + ~2000 cycles
       // per tile, longer than the tile period.)
-      auto o_block = [&](int j, int n_tile, int h_tile, int bt, uint64_t* bar) {
-        const int n0 = n_tile + (a.q_swap ? ((16 * j) >> (7 - a.lgP)) : ((16 * j) & (P - 1)));
-        const int h0 = h_tile + (a.q_swap ? 0 : ((16 * j) >> a.lgP));
-        mbar_expect_tx(bar, 2048);
-        tma_tile(o_s + j * 2048, &tmO, bar, a.q_swap, 0, n0, h0, bt);
-      };
-      if (a.fuse_delta && grp == 1 && lane == 0 && wi.tile < wi.end) {     // O(0): by the warps that will read it
-        o_block(2 * quarter, wi.pb * P, wi.y * a.G, wi.b, o_full + (2 * quarter) * 2);
-        o_block(2 * quarter + 1, wi.pb * P, wi.y * a.G, wi.b, o_full + (2 * quarter + 1) * 2);
-      }
+      // (O(0) comes from the producer warp.  Code size matters here: the roles of this kernel run concurrently out of
+      // one instruction cache -- "no instruction" is among its top stall reasons -- so the loops below are rolled and
+      // the tile coordinates take two divisions, not seven.)
       auto delta_tile = [&]() {
         if (wi.tile + dit >= wi.end) return;
         if (tr) ftrace(a.trace, trole, tc, 7, dit);
         const int s = dit & 1;
         // coordinates first (integer divisions), under the wait for the inputs
-        const int dpb = (wi.tile + dit) % a.nblk, dhead = (wi.tile + dit) / a.nblk;   // dhead = b * Hkv + y
+        const int dhead = (wi.tile + dit) / a.nblk, dpb = wi.tile + dit - dhead * a.nblk;   // dhead = b * Hkv + y
+        const int dbt = dhead / a.Hkv, dy = dhead - dbt * a.Hkv;
         const int pmax = a.N - 1 - dpb * P;
         // ds_aux: this row's lse and its head's s_aux, requested now, used after the row sum
         float lse_r = -INFINITY, sx = 0.f;
@@ -727,14 +731,14 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         if (a.write_delta) {
           if (my_pr <= pmax)
             lse_r = __ldg(a.lse + (static_cast<int64_t>(dhead) * a.G + my_gr) * a.N + dpb * P + my_pr);
-          sx = __ldg(a.s_aux + (dhead % a.Hkv) * a.G + my_gr);
+          sx = __ldg(a.s_aux + dy * a.G + my_gr);
         }
         int on = -1, ohb = 0;                                 // next tile (lane 0 loads its O blocks): position,
                                                               // head | batch << 12 (registers)
         if (lane == 0 && wi.tile + dit + 1 < wi.end) {
-          const int tn = wi.tile + dit + 1, hn = tn / a.nblk;
-          on = (tn % a.nblk) * P;
-          ohb = ((hn % a.Hkv) * a.G) | ((hn / a.Hkv) << 12);
+          const bool wrap = dpb + 1 == a.nblk, wrap_b = wrap && dy + 1 == a.Hkv;
+          on = wrap ? 0 : (dpb + 1) * P;
+          ohb = ((wrap_b ? 0 : dy + (wrap ? 1 : 0)) * a.G) | ((dbt + (wrap_b ? 1 : 0)) << 12);
         }
         const uint32_t ob = smem_u32(o_s), dob = smem_u32(do_s) + s * C::kQBytes;
         float* const dl = delta_s + s * 128;
@@ -752,7 +756,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         {
           const int r2 = quarter * 32 + lane;
           float s0 = 0.f, s1 = 0.f;
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < 8; c += 2) {
             uint4 ov[2], gv[2];
 #pragma unroll
@@ -796,8 +800,15 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         }
         __syncwarp();                                         // every lane has read its O row
         if (on >= 0) {
-          o_block(2 * quarter, on, ohb & 4095, ohb >> 12, o_full + (2 * quarter) * 2 + (s ^ 1));
-          o_block(2 * quarter + 1, on, ohb & 4095, ohb >> 12, o_full + (2 * quarter + 1) * 2 + (s ^ 1));
+#pragma unroll 1
+          for (int j = 2 * quarter; j < 2 * quarter + 2; ++j) {
+            // block j of the packed tile: one head x 16 positions, or (swapped layout) 16 / G positions x G heads
+            const int n0 = on + (a.q_swap ? ((16 * j) >> (7 - a.lgP)) : ((16 * j) & (P - 1)));
+            const int h0 = (ohb & 4095) + (a.q_swap ? 0 : ((16 * j) >> a.lgP));
+            uint64_t* const bar = o_full + j * 2 + (s ^ 1);
+            mbar_expect_tx(bar, 2048);
+            tma_load_4d(o_s + j * 2048, &tmO, bar, 0, a.q_swap ? h0 : n0, a.q_swap ? n0 : h0, ohb >> 12);
+          }
         }
         if (lane == 0) {                                      // this warp's rows are in delta_s, its reads of dO are done
           mbar_arrive(delta_ready + s);
@@ -1010,7 +1021,7 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   // with the in-kernel delta: ds_partial == p.delta (the kernel leaves per-tile partials there) when ds_aux is wanted
   using C = FusedCfg;
   int G, P, nb;
-  if (!fused_geometry(p, G, P, nb)) return cudaErrorInvalidValue;
+  if (!fused_geometry(p, G, P, nb)) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 1, sfa_last_error()); return cudaErrorInvalidValue; }
   FusedArgs a;
   a.B = p.B; a.N = p.N; a.W = p.W; a.Hq = p.Hq; a.Hkv = p.Hkv; a.G = G; a.P = P;
   a.lgP = (P == 16) ? 4 : 5;
@@ -1024,19 +1035,19 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   a.tiles_per_cta = tpc;
   const int grid = (a.total_tiles + tpc - 1) / tpc;
   TileMap mq, mdo, mk, mv;
-  if (!make_tile_map(&mq, p.q, dtype, C::D, p.N, p.Hq, p.B, p.sq, P, G)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mdo, p.dout, dtype, C::D, p.N, p.Hq, p.B, p.sdo, P, G)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mk, p.k, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sk, a.cols, 1)) return cudaErrorInvalidValue;
-  if (!make_tile_map(&mv, p.v, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sv, a.cols, 1)) return cudaErrorInvalidValue;
-  if (mq.swap_nh != mdo.swap_nh) return cudaErrorInvalidValue;
+  if (!make_tile_map(&mq, p.q, dtype, C::D, p.N, p.Hq, p.B, p.sq, P, G)) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 2, sfa_last_error()); return cudaErrorInvalidValue; }
+  if (!make_tile_map(&mdo, p.dout, dtype, C::D, p.N, p.Hq, p.B, p.sdo, P, G)) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 3, sfa_last_error()); return cudaErrorInvalidValue; }
+  if (!make_tile_map(&mk, p.k, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sk, a.cols, 1)) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 4, sfa_last_error()); return cudaErrorInvalidValue; }
+  if (!make_tile_map(&mv, p.v, dtype, C::D, p.Nkv, p.Hkv, p.B, p.sv, a.cols, 1)) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 5, sfa_last_error()); return cudaErrorInvalidValue; }
+  if (mq.swap_nh != mdo.swap_nh) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 6, sfa_last_error()); return cudaErrorInvalidValue; }
   a.fuse_delta = tc_bwd_fused_computes_delta(p) ? 1 : 0;
   TileMap mo = mq;
   if (a.fuse_delta) {
     // 16-row blocks of the packed tile: one head x 16 positions, or (swapped layout) 16 / G positions x G heads
     const bool o_swap = (p.Hq > 1 && p.N > 1) ? (p.so.h < p.so.n) : false;
     if (!make_tile_map(&mo, p.o, dtype, C::D, p.N, p.Hq, p.B, p.so, o_swap ? 16 / G : 16, o_swap ? G : 1))
-      return cudaErrorInvalidValue;
-    if (mo.swap_nh != mq.swap_nh) return cudaErrorInvalidValue;
+      { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 7, sfa_last_error()); return cudaErrorInvalidValue; }
+    if (mo.swap_nh != mq.swap_nh) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 8, sfa_last_error()); return cudaErrorInvalidValue; }
   }
   a.q_swap = mq.swap_nh; a.k_swap = mk.swap_nh; a.v_swap = mv.swap_nh;
   a.fmt = (dtype == SFA_DTYPE_BF16) ? 1 : 0;
@@ -1063,10 +1074,10 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   if (p.dq_route != nullptr) {
     const SpRoute& rt = *p.dq_route;
     if (rt.P < 1 || rt.P > 8 || rt.n_local % P != 0 || static_cast<int64_t>(rt.n_local) * rt.P != p.N)
-      return cudaErrorInvalidValue;
+      { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 9, sfa_last_error()); return cudaErrorInvalidValue; }
     a.sdq = Strides4{static_cast<int64_t>(rt.n_local) * rt.heads_total * C::D, C::D, static_cast<int64_t>(rt.heads_total) * C::D};
     for (int r = 0; r < rt.P; ++r) {
-      if (rt.peer[r] == nullptr || reinterpret_cast<uintptr_t>(rt.peer[r]) % 16 != 0) return cudaErrorInvalidValue;
+      if (rt.peer[r] == nullptr || reinterpret_cast<uintptr_t>(rt.peer[r]) % 16 != 0) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: reject #%d: %s\n", 10, sfa_last_error()); return cudaErrorInvalidValue; }
       a.dq_peer[r] = static_cast<char*>(rt.peer[r]) + static_cast<int64_t>(rt.head_off) * C::D * 2;
     }
     a.dq_seg_n = rt.n_local;
@@ -1084,7 +1095,7 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
     bwd_fused64_kernel<T, false><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mo.map, a);
   }
   e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: kernel launch error %d grid %d\n", (int)e, grid); return e; }
   const int nbound = (grid > 1 && nb > 1) ? grid - 1 : 0;   // nb == 1 (window <= one block): no shared key block
   const int nred = (ds_partial != nullptr && ds_nblk > 0) ? p.Hq : 0;
   if (nbound + nred > 0) {

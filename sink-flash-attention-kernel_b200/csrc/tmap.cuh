@@ -88,6 +88,10 @@ inline bool make_tile_map_uncached(TileMap* out, const void* ptr, int dtype, int
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return false;
   }
+  // The encoder is a DRIVER entry point: it fails with CUDA_ERROR_INVALID_CONTEXT (201) on a thread that has not made a
+  // runtime call yet -- autograd's backward thread, when the first thing the backward does is build a tensor map (it used
+  // to launch the delta preprocess kernel first).  cudaFree(nullptr) binds the device's primary context to this thread.
+  cudaFree(nullptr);
   const CUtensorMapDataType dt = (dtype == SFA_DTYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const bool swap = (H > 1 && N > 1) ? (s.h < s.n) : false;
   cuuint64_t dims[4];
