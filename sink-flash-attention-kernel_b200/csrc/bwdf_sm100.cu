@@ -757,10 +757,10 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           const int r2 = quarter * 32 + lane;
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < 8; c += 2) {
-            uint4 ov[2], gv[2];
+          for (int c = 0; c < 8; c += 1) {
+            uint4 ov[1], gv[1];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 1; ++u) {
               const uint32_t off = sw128_off(r2, c + u);
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(ov[u].x), "=r"(ov[u].y), "=r"(ov[u].z), "=r"(ov[u].w) : "r"(ob + off) : "memory");
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
                            : "=r"(gv[u].x), "=r"(gv[u].y), "=r"(gv[u].z), "=r"(gv[u].w) : "r"(dob + off) : "memory");
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 1; ++u) {
               const uint32_t ou[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w}, gu[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -786,11 +786,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
             // the rows of one head in this warp: P consecutive lanes (P = 16: two heads per warp), or -- swapped layout --
             // the lanes with equal lane % G; xor-shuffle tree over them, result in the lowest lane of each head
             float c = (lse_r == -INFINITY) ? 0.f : -__expf(sx - lse_r) * sum;
-            if (a.q_swap) {
-              for (int o = a.G; o < 32; o <<= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            } else {
-              for (int o = 1; o < min(P, 32); o <<= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            }
+#pragma unroll 1
+            for (int o = a.q_swap ? a.G : 1, hi = a.q_swap ? 32 : min(P, 32); o < hi; o <<= 1)
+              c += __shfl_xor_sync(0xffffffffu, c, o);
             const bool first = a.q_swap ? (lane < a.G) : ((lane & (min(P, 32) - 1)) == 0);
             // slot (head, tile) -- in the swapped layout every quarter holds rows of every head: (head, tile, quarter)
             const int nslot = a.q_swap ? 4 : 1;

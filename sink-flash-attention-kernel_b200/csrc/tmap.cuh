@@ -88,10 +88,6 @@ inline bool make_tile_map_uncached(TileMap* out, const void* ptr, int dtype, int
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return false;
   }
-  // The encoder is a DRIVER entry point: it fails with CUDA_ERROR_INVALID_CONTEXT (201) on a thread that has not made a
-  // runtime call yet -- autograd's backward thread, when the first thing the backward does is build a tensor map (it used
-  // to launch the delta preprocess kernel first).  cudaFree(nullptr) binds the device's primary context to this thread.
-  cudaFree(nullptr);
   const CUtensorMapDataType dt = (dtype == SFA_DTYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const bool swap = (H > 1 && N > 1) ? (s.h < s.n) : false;
   cuuint64_t dims[4];
@@ -126,6 +122,16 @@ inline bool make_tile_map_uncached(TileMap* out, const void* ptr, int dtype, int
   if (D < 64) box[0] = D;
   CUresult r = enc(&out->map, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // The encoder is a DRIVER entry point: it fails on a thread that has not made a runtime call yet -- autograd's
+    // backward thread, when the first thing the backward does is build a tensor map (it used to launch the delta
+    // preprocess kernel first).  cudaFree(nullptr) binds the device's primary context to this thread; retried once.
+    // (Not done up front: cudaFree is not allowed while a stream capture is running, and a capturing thread has a
+    // context.)
+    cudaFree(nullptr);
+    r = enc(&out->map, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u,%u,%u)",
               (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
