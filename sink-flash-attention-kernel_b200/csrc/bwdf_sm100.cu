@@ -84,8 +84,6 @@ struct FusedCfg {
 struct FusedArgs {
   int B, N, W, Hq, Hkv, G, P, lgP, nb, R, cols, nch, nblk, total_tiles, tiles_per_cta;
   int q_swap, k_swap, v_swap;
-  int order_dp;    // issuer A queues dP(n + 1) behind dK^T(n) / dQ(n)
-  int prefetch;    // producer warp prefetches tiles into L2 ahead of the TMA loads
   int fuse_delta;  // 1: the epilogue groups compute delta in the kernel; 0: a preprocess kernel wrote it before
   int write_delta; // fuse_delta only: ds_aux wanted -- per (head, tile[, quarter]) partials of -sum exp(s_aux - lse) * delta
                    // (sink_flash_attention.py:653-665) go to the workspace, the fix-up launch sums them in a fixed order
@@ -307,34 +305,11 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   if (warp == 20) {
     // ------------------------------------------------------------------ TMA producer (lane 0) + L2 prefetch (warp)
     {
-      FusedWalk w(a, wi), wp(a, wi);
+      // (An L2 prefetch of the next tiles ahead of the TMA loads, and dP(n + 1) queued behind dK^T(n) / dQ(n), were both
+      // measured slower in round 1; their code is gone: the size of this kernel's code is a first-order parameter.)
+      FusedWalk w(a, wi);
       const uint32_t kv_bytes = a.cols * C::D * 2;
       int tc = 0;
-      // The shared-memory rings are only two deep, so the HBM latency of a tile's loads sits on the critical cycle
-      // of the pipeline; an L2 prefetch kPrefetchAhead tiles ahead of the loads halves it.  Q / dO tiles by TMA
-      // prefetch; of K / V only the P newest rows are not in L2 yet (the tile before loaded the other nb - 1 blocks).
-      const int kPrefetchAhead = a.prefetch;
-      auto prefetch_tile = [&](const FusedWalk& t) {
-        const int q0 = t.pb * P, hq0 = t.y * a.G;
-        if (lane == 0) {
-          tma_tile_prefetch(&tmQ, a.q_swap, 0, q0, hq0, t.b);
-          tma_tile_prefetch(&tmdO, a.q_swap, 0, q0, hq0, t.b);
-        }
-        for (int r = lane; r < 2 * P; r += 32) {
-          const bool isv = r >= P;
-          const int key = q0 + (isv ? r - P : r);
-          if (key < a.N) {
-            const Strides4& sk = isv ? a.sv : a.sk;
-            const char* ptr = static_cast<const char*>(isv ? a.v : a.k) +
-                              (static_cast<int64_t>(t.b) * sk.b + static_cast<int64_t>(t.y) * sk.h +
-                               static_cast<int64_t>(key) * sk.n) * 2;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-          }
-        }
-      };
-      if (a.prefetch)
-        for (int i = 0; i < kPrefetchAhead; ++i)
-          if (wp.next()) prefetch_tile(wp);
       if (a.fuse_delta && lane == 0 && wi.tile < wi.end) {        // O(0), as eight 16-row blocks; the epilogue warps load the rest
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
@@ -367,7 +342,6 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           ftrace(a.trace, 0, tc, 3, w.it);
         }
         __syncwarp();
-        if (a.prefetch && wp.next()) prefetch_tile(wp);    // behind this tile's loads in the TMA queue, not in front
       }
     }
     __syncwarp();
@@ -398,7 +372,6 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         mbar_wait(v_full, w.it & 1);
         if (w.it >= 1) {
           mbar_wait(dp_free, (w.it - 1) & 1);
-          if (a.order_dp) mbar_wait(kq_issued, (w.it - 1) & 1);
         }
         tc_fence_after();
         ftrace(a.trace, 1, tc, 4, w.it);
@@ -446,7 +419,6 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           rc16 += 256u;
           if (rc16 >= wrap16) rc16 -= wrap16;
         }
-        mbar_arrive(kq_issued);
         umma_commit(ds_free);
         umma_commit(k_empty + s);
         umma_commit(dq_done + s);
@@ -491,7 +463,6 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         // the next tile only when these UMMAs have completed); `unroll 2` cost 4.6 us on the kernel
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_ss(ring, ad + kk * (2048 >> 4), img + kk * (256 >> 4), idesc_ring, 1);
-        if (isK) mbar_arrive(kq_issued);
         umma_commit(a_empty + s);
         umma_commit(isK ? ds_free : p_free);
         umma_commit(dq_done + s);
@@ -1055,11 +1026,6 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   a.qb = p.q_off / P; a.Nkv = p.Nkv; a.seq_lo = p.seq_lo; a.seq_bs = p.seq_bs;
   a.dbg_delay = debug_knob(0);
   a.dbg_norace = debug_knob(1);
-  // measured: 104.1 us with dP(n + 1) queued behind dK^T(n) / dQ(n), 99.3 us without -> off (SFA_ORDER_DP=1 enables)
-  static const int order_dp = getenv("SFA_ORDER_DP") ? atoi(getenv("SFA_ORDER_DP")) : 0;
-  a.order_dp = order_dp;
-  static const int prefetch = getenv("SFA_PREFETCH") ? atoi(getenv("SFA_PREFETCH")) : 0;
-  a.prefetch = prefetch;
   a.sl2 = p.scale * kLog2e;
   a.scale = p.scale;
   a.lse = p.lse;
