@@ -102,7 +102,11 @@ __device__ __forceinline__ void part_starts(int nch, int (&cs)[Fwd64Cfg::kParts 
   for (int p = 0; p < Fwd64Cfg::kParts; ++p) cs[p + 1] = cs[p] + base + (p < rem ? 1 : 0);
 }
 
-template <typename T>
+// kSingle: every tile has exactly one KV item (no sink tokens, the band fits one tile: the narrow-window training shape).
+// A separate instantiation, not a run-time switch: the walker's general planning, the skipped-tile waits and the lazy O
+// rescale drop out of the code -- the roles of this kernel share one instruction cache (see bwdf_sm100.cu: there 10 KB
+// of cold code cost 3 us).
+template <typename T, bool kSingle>
 __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                       const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV,
@@ -173,12 +177,12 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       Walk w(a);
-      while (w.next()) {
+      while (kSingle ? w.next_single(1) : w.next()) {
         const int hq0 = w.y * a.G, kvh = w.y / a.groups_per_kv;
         int kstart, cols; bool is_sink;
         w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
         const int kst = w.n % C::kKStages, vst = w.n % C::kVStages;
-        if (w.t == 0) {
+        if (kSingle || w.t == 0) {
           const int qs = w.it % C::kQStages;
           mbar_wait(q_empty + qs, ((w.it / C::kQStages) & 1) ^ 1);
           mbar_expect_tx(q_full + qs, C::kQBytes);
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     if (lane == 0) {
       Walk w(a);
       int tc = 0;
-      while (w.next()) {
+      while (kSingle ? w.next_single(1) : w.next()) {
         tev(a.trace, 1, tc, 1, w.n);
         const int qs = w.it % C::kQStages, kst = w.n % C::kKStages, sb = w.n % C::kSBufs;
         int kstart, cols; bool is_sink;
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         const uint32_t idesc_s = make_idesc(a.fmt, 128, cols, 0, 0);
         const uint64_t qd = make_sdesc(smem_u32(q_s + qs * C::kQBytes), 16, 1024);
         const uint64_t kd = make_sdesc(smem_u32(k_s + kst * C::kKVBytes), 16, 1024);
-        if (w.t == 0) mbar_wait(q_full + qs, (w.it / C::kQStages) & 1);
+        if (kSingle || w.t == 0) mbar_wait(q_full + qs, (w.it / C::kQStages) & 1);
         mbar_wait(k_full + kst, (w.n / C::kKStages) & 1);
         if (w.n >= C::kSBufs) mbar_wait(sbuf_free + sb, ((w.n / C::kSBufs) - 1) & 1);     // PV(n-3) has consumed P(n-3)
         tc_fence_after();
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         for (int kk = 0; kk < 4; ++kk) umma_ss(ts, qd + kk * 2, kd + kk * 2, idesc_s, kk != 0);
         umma_commit(s_full + sb);
         umma_commit(k_empty + kst);
-        if (w.last_of_tile()) umma_commit(q_empty + qs);
+        if (kSingle || w.last_of_tile()) umma_commit(q_empty + qs);
         tev(a.trace, 1, tc, 3, w.n);
       }
     }
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       const uint32_t idesc_pv = make_idesc(a.fmt, 128, D, 0, 1);
       Walk w(a);
       int tc = 0;
-      while (w.next()) {
+      while (kSingle ? w.next_single(1) : w.next()) {
         tev(a.trace, 3, tc, 1, w.n);
         const int vst = w.n % C::kVStages, sb = w.n % C::kSBufs, tb = w.it & 1;
         int kstart, cols; bool is_sink;
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
         mbar_wait(v_full + vst, (w.n / C::kVStages) & 1);
         mbar_wait(p_full + sb, (w.n / C::kSBufs) & 1);
         // ONE O accumulator: the epilogue must have read the previous tile's O before this tile overwrites it
-        if (w.t == 0 && w.it >= 1) mbar_wait(o_free + (tb ^ 1), ((w.it - 1) >> 1) & 1);
+        if ((kSingle || w.t == 0) && w.it >= 1) mbar_wait(o_free + (tb ^ 1), ((w.it - 1) >> 1) & 1);
         tc_fence_after();
         tev(a.trace, 3, tc, 2, w.n);
         if (nk == C::kBNMax / 16) {
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
           for (int kk = 0; kk < C::kBNMax / 16; ++kk) {
             constexpr int kSplit = (C::kBNMax / 16 + C::kParts - 1) / C::kParts;      // cs[1] for kParts == 2
             const int pstart = (C::kParts == 2) ? (kk >= kSplit ? kSplit : 0) : 0;
-            umma_ts(dO_, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv, (w.t > 0 || kk > 0));
+            umma_ts(dO_, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv, ((!kSingle && w.t > 0) || kk > 0));
           }
         } else {
 #pragma unroll
@@ -262,12 +266,12 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
 #pragma unroll
               for (int pp = 1; pp < C::kParts; ++pp) pstart = (kk >= cs[pp]) ? cs[pp] : pstart;
               umma_ts(tmem + C::kColO, ts + pstart * 16 + (kk - pstart) * 8, vd + kk * (2048 >> 4), idesc_pv,
-                      (w.t > 0 || kk > 0));
+                      ((!kSingle && w.t > 0) || kk > 0));
             }
         }
         umma_commit(sbuf_free + sb);
         umma_commit(v_empty + vst);
-        if (w.last_of_tile()) umma_commit(o_done + tb);
+        if (kSingle || w.last_of_tile()) umma_commit(o_done + tb);
         tev(a.trace, 3, tc, 3, w.n);
       }
     }
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     Walk w(a);
     bool first_hop = true;
     while (true) {
-      if (a.single_item) {
+      if (kSingle) {
         if (!w.next_single(first_hop ? grp + 1 : C::kGroups)) break;
         first_hop = false;
       } else {
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       }
       const int sb = w.n % C::kSBufs, tb = w.it & 1;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
-      if (w.t == 0) {
+      if (kSingle || w.t == 0) {
         i = w.q0 + pr;
         if (a.seq_lo != nullptr) row_lo = (i < a.N) ? __ldg(a.seq_lo + w.b * a.seq_bs + i) : 0;
         const int h = w.y * a.G + gr;
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       int kstart, cols; bool is_sink;
       w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
       int c_lo, c_hi;
-      row_range(is_sink, i + a.q_off, kstart, cols, a.S, a.W, c_lo, c_hi);
+      row_range(!kSingle && is_sink, i + a.q_off, kstart, cols, a.S, a.W, c_lo, c_hi);
       if (a.seq_lo != nullptr) c_lo = max(c_lo, row_lo - kstart);      // never across a packed-sequence boundary
       if (i >= a.N) c_hi = -1;
       const int nch = cols >> 4;
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
           l *= alpha;
           m_used = m_new;
         }
-        if (w.t > 0) {
+        if (!kSingle && w.t > 0) {
           // lazy rescale of this half's O columns: PV(n-1) must have completed
           mbar_wait(sbuf_free + ((w.n - 1) % C::kSBufs), ((w.n - 1) / C::kSBufs) & 1);
           tc_fence_after();
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       l += lsum;
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 7, w.n);
       tmem_st_wait();
-      if (w.last_of_tile()) {
+      if (kSingle || w.last_of_tile()) {
         // hand the row statistics to the epilogue warps (ordered by the p_full -> PV -> o_done chain)
         if (w.it >= 2) mbar_wait(o_free + tb, ((w.it - 2) >> 1) & 1);
         if (part == 0) row_m[tb * 128 + r] = m_used;
@@ -449,8 +453,8 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
     const int et = threadIdx.x - kWEpi * 32;
     Walk w(a);
     int mtc = 0;
-    while (w.next()) {
-      if (!w.last_of_tile()) continue;
+    while (kSingle ? w.next_single(1) : w.next()) {
+      if (!kSingle && !w.last_of_tile()) continue;
       const int tb = w.it & 1;
       if (et == 0) tev(a.trace, 6, mtc, 1, w.n);
       if (et == 0) tma_store_wait_read0();     // the previous store has finished reading the staging buffer
@@ -510,8 +514,9 @@ template <typename T>
 cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
   using C = Fwd64Cfg;
   constexpr int D = 64;
-  static std::atomic<unsigned long long> attr_done{0};
-  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T>, C::kSmem, attr_done)) return e;
+  static std::atomic<unsigned long long> attr_done{0}, attr_done1{0};
+  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, false>, C::kSmem, attr_done)) return e;
+  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, true>, C::kSmem, attr_done1)) return e;
   const int group = p.Hq / p.Hkv;
   int G, P;
   pick_packing(p.Hq, p.Hkv, G, P);
@@ -559,7 +564,8 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
     a.sp_n = rt.n_local;
   }
   const int grid = a.total_tiles < sm_count_fwd() ? a.total_tiles : sm_count_fwd();
-  fwd64_kernel<T><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, pm, a);
+  if (a.single_item) fwd64_kernel<T, true><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, pm, a);
+  else fwd64_kernel<T, false><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, pm, a);
   return cudaGetLastError();
 }
 
