@@ -71,7 +71,8 @@ __device__ __forceinline__ void decode_tile(const A& a, int tile, int& pb, int& 
 // Walks this CTA's work items: tiles blockIdx.x, +gridDim.x, ... (or a contiguous range) and the KV tiles of
 // each, with the tile coordinates kept incrementally (no integer divisions per tile: a division is a
 // ~150-cycle dependent chain on the single-thread TMA / UMMA roles).
-template <class A>
+// kExt = false: the extended geometry (chunk offset, packed-sequence bounds) is compiled out.
+template <class A, bool kExt = true>
 struct ItemWalkT {
   const A& a;
   int tile, it, t, n;        // tile id, tile iteration, KV tile inside the tile, running item count
@@ -114,8 +115,8 @@ struct ItemWalkT {
       advance(a, step, pb, y, b);
       q0 = pb * a.P;
       // the plan lives in ABSOLUTE key positions: row iq of the tile sits at iq + q_off
-      pl = make_plan(q0 + a.q_off, a.P, a.N + a.q_off, a.S, a.W, a.BN, a.bn_mul);
-      if (a.seq_lo != nullptr) clamp_plan(pl, a.seq_lo[b * a.seq_bs + q0], a.W, a.BN, a.bn_mul);
+      pl = make_plan(q0 + (kExt ? a.q_off : 0), a.P, a.N + (kExt ? a.q_off : 0), a.S, a.W, a.BN, a.bn_mul);
+      if (kExt && a.seq_lo != nullptr) clamp_plan(pl, a.seq_lo[b * a.seq_bs + q0], a.W, a.BN, a.bn_mul);
       t = 0;
     }
     ++n;
@@ -133,8 +134,8 @@ struct ItemWalkT {
     if (tile >= end) return false;
     advance(a, step * hop, pb, y, b);
     q0 = pb * a.P;
-    pl = make_plan(q0 + a.q_off, a.P, a.N + a.q_off, a.S, a.W, a.BN, a.bn_mul);
-    if (a.seq_lo != nullptr) clamp_plan(pl, a.seq_lo[b * a.seq_bs + q0], a.W, a.BN, a.bn_mul);
+    pl = make_plan(q0 + (kExt ? a.q_off : 0), a.P, a.N + (kExt ? a.q_off : 0), a.S, a.W, a.BN, a.bn_mul);
+    if (kExt && a.seq_lo != nullptr) clamp_plan(pl, a.seq_lo[b * a.seq_bs + q0], a.W, a.BN, a.bn_mul);
     t = 0;
     return true;
   }

@@ -53,7 +53,6 @@ __device__ __forceinline__ void tev(long long* trace, int role, int& cnt, int co
     ++cnt;
   }
 }
-using Walk = ItemWalkT<Fwd64Args>;
 
 struct Fwd64Cfg {
   // (the full-width fast path of the PV issuer assumes kParts == 2: parts split 9 chunks as 5 + 4)
@@ -106,7 +105,8 @@ __device__ __forceinline__ void part_starts(int nch, int (&cs)[Fwd64Cfg::kParts 
 // A separate instantiation, not a run-time switch: the walker's general planning, the skipped-tile waits and the lazy O
 // rescale drop out of the code -- the roles of this kernel share one instruction cache (see bwdf_sm100.cu: there 10 KB
 // of cold code cost 3 us).
-template <typename T, bool kSingle>
+// kExt: chunk offset / packed-sequence bounds compiled in (same reason).
+template <typename T, bool kSingle, bool kExt>
 __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                       const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV,
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
                                                                       const __grid_constant__ PeerMaps pm,
                                                                       const Fwd64Args a) {
   using C = Fwd64Cfg;
+  using Walk = ItemWalkT<Fwd64Args, kExt>;
   constexpr int D = C::D;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       if (threadIdx.x == 0) tev(a.trace, 4, mtc, 1, w.n);
       if (kSingle || w.t == 0) {
         i = w.q0 + pr;
-        if (a.seq_lo != nullptr) row_lo = (i < a.N) ? __ldg(a.seq_lo + w.b * a.seq_bs + i) : 0;
+        if (kExt && a.seq_lo != nullptr) row_lo = (i < a.N) ? __ldg(a.seq_lo + w.b * a.seq_bs + i) : 0;
         const int h = w.y * a.G + gr;
         m_used = a.s_aux ? (h < 64 ? saux_s[h] : __ldg(a.s_aux + h) * kLog2e) : -INFINITY;
         l = (a.s_aux && part == 0) ? 1.f : 0.f;
@@ -318,8 +319,8 @@ __global__ void __launch_bounds__(Fwd64Cfg::kThreads, 1) fwd64_kernel(const __gr
       int kstart, cols; bool is_sink;
       w.pl.tile(w.t, a.BN, kstart, cols, is_sink);
       int c_lo, c_hi;
-      row_range(!kSingle && is_sink, i + a.q_off, kstart, cols, a.S, a.W, c_lo, c_hi);
-      if (a.seq_lo != nullptr) c_lo = max(c_lo, row_lo - kstart);      // never across a packed-sequence boundary
+      row_range(!kSingle && is_sink, i + (kExt ? a.q_off : 0), kstart, cols, a.S, a.W, c_lo, c_hi);
+      if (kExt && a.seq_lo != nullptr) c_lo = max(c_lo, row_lo - kstart);      // never across a packed-sequence boundary
       if (i >= a.N) c_hi = -1;
       const int nch = cols >> 4;
       const int pbase = nch / C::kParts, prem = nch % C::kParts;       // same split as part_starts()
@@ -514,9 +515,11 @@ template <typename T>
 cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
   using C = Fwd64Cfg;
   constexpr int D = 64;
-  static std::atomic<unsigned long long> attr_done{0}, attr_done1{0};
-  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, false>, C::kSmem, attr_done)) return e;
-  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, true>, C::kSmem, attr_done1)) return e;
+  static std::atomic<unsigned long long> attr_done[4] = {};
+  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, false, false>, C::kSmem, attr_done[0])) return e;
+  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, false, true>, C::kSmem, attr_done[1])) return e;
+  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, true, false>, C::kSmem, attr_done[2])) return e;
+  if (cudaError_t e = ensure_dyn_smem(fwd64_kernel<T, true, true>, C::kSmem, attr_done[3])) return e;
   const int group = p.Hq / p.Hkv;
   int G, P;
   pick_packing(p.Hq, p.Hkv, G, P);
@@ -564,8 +567,11 @@ cudaError_t launch_fwd64(const AttnParams& p, int dtype, cudaStream_t st) {
     a.sp_n = rt.n_local;
   }
   const int grid = a.total_tiles < sm_count_fwd() ? a.total_tiles : sm_count_fwd();
-  if (a.single_item) fwd64_kernel<T, true><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, pm, a);
-  else fwd64_kernel<T, false><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, pm, a);
+  const bool ext = p.has_ext();
+#define SFA_FWD64_LAUNCH(S_, E_) fwd64_kernel<T, S_, E_><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mk.map, mv.map, mo.map, pm, a)
+  if (a.single_item) { if (ext) SFA_FWD64_LAUNCH(true, true); else SFA_FWD64_LAUNCH(true, false); }
+  else { if (ext) SFA_FWD64_LAUNCH(false, true); else SFA_FWD64_LAUNCH(false, false); }
+#undef SFA_FWD64_LAUNCH
   return cudaGetLastError();
 }
 
