@@ -944,25 +944,42 @@ __global__ void __launch_bounds__(256) bwd_fused_fixup_kernel(const FusedArgs a,
   const int t0 = c * a.tiles_per_cta;
   const int pa = t0 % a.nblk;
   if (pa == 0) return;                       // the boundary coincides with a sequence start: nothing shared
-  const int e = (blockIdx.y * 256 + threadIdx.x) * 4;
-  if (e >= (a.nb - 1) * a.P * 128) return;
-  const int key = (pa + a.qb - a.nb + 1) * a.P + (e >> 7);
-  if (key < 0 || key >= a.Nkv) return;
+  // four float4 groups per thread, all eight loads in flight before the first add (one group per thread: 2 352 blocks in
+  // two waves, one memory round trip each: 6.7 us for 19 MB)
   const int seq = t0 / a.nblk, y = seq % a.Hkv, b = seq / a.Hkv;
-  const float4 tl = *reinterpret_cast<const float4*>(a.part + (static_cast<size_t>(c - 1) * 2 + 1) * C::kPartKeys * 128 + e);
-  const float4 hd = *reinterpret_cast<const float4*>(a.part + (static_cast<size_t>(c) * 2 + 0) * C::kPartKeys * 128 + e);
-  const int which = (e >> 6) & 1, d = e & 63;
-  T* o = static_cast<T*>(which ? a.dk : a.dv);
-  const Strides4& s = which ? a.sdk : a.sdv;
-  o += static_cast<int64_t>(b) * s.b + static_cast<int64_t>(y) * s.h + static_cast<int64_t>(key) * s.n + d;
-  const float v0 = tl.x + hd.x, v1 = tl.y + hd.y, v2 = tl.z + hd.z, v3 = tl.w + hd.w;
-  if (vec_ok) {
-    *reinterpret_cast<uint2*>(o) = make_uint2(pack16<T>(v0, v1), pack16<T>(v2, v3));
-  } else {
-    o[0] = from_f<T>(v0);
-    o[1] = from_f<T>(v1);
-    o[2] = from_f<T>(v2);
-    o[3] = from_f<T>(v3);
+  const int nelem = (a.nb - 1) * a.P * 128;
+  const float* const tails = a.part + (static_cast<size_t>(c - 1) * 2 + 1) * C::kPartKeys * 128;
+  const float* const heads = a.part + (static_cast<size_t>(c) * 2 + 0) * C::kPartKeys * 128;
+  float4 tl[4], hd[4];
+  int ee[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ee[k] = ((blockIdx.y * 4 + k) * 256 + threadIdx.x) * 4;
+    const int key = (pa + a.qb - a.nb + 1) * a.P + (ee[k] >> 7);
+    if (ee[k] >= nelem || key < 0 || key >= a.Nkv) ee[k] = -1;
+    if (ee[k] >= 0) {
+      tl[k] = *reinterpret_cast<const float4*>(tails + ee[k]);
+      hd[k] = *reinterpret_cast<const float4*>(heads + ee[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = ee[k];
+    if (e < 0) continue;
+    const int key = (pa + a.qb - a.nb + 1) * a.P + (e >> 7);
+    const int which = (e >> 6) & 1, d = e & 63;
+    T* o = static_cast<T*>(which ? a.dk : a.dv);
+    const Strides4& s = which ? a.sdk : a.sdv;
+    o += static_cast<int64_t>(b) * s.b + static_cast<int64_t>(y) * s.h + static_cast<int64_t>(key) * s.n + d;
+    const float v0 = tl[k].x + hd[k].x, v1 = tl[k].y + hd[k].y, v2 = tl[k].z + hd[k].z, v3 = tl[k].w + hd[k].w;
+    if (vec_ok) {
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack16<T>(v0, v1), pack16<T>(v2, v3));
+    } else {
+      o[0] = from_f<T>(v0);
+      o[1] = from_f<T>(v1);
+      o[2] = from_f<T>(v2);
+      o[3] = from_f<T>(v3);
+    }
   }
 }
 
@@ -1068,7 +1085,7 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
     };
     const int vec_ok = al8(p.dk, p.sdk) && al8(p.dv, p.sdv);
     const int groups = nbound ? (nb - 1) * P * 128 / 4 : 1;
-    bwd_fused_fixup_kernel<T><<<dim3(nbound + nred, (groups + 255) / 256), 256, 0, st>>>(
+    bwd_fused_fixup_kernel<T><<<dim3(nbound + nred, (groups + 1023) / 1024), 256, 0, st>>>(
         a, vec_ok, nbound, ds_partial, p.ds_aux, ds_nblk);
     e = cudaGetLastError();
   }
