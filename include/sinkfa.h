@@ -125,6 +125,22 @@ int sfa_decode(const void* q, const void* k, const void* v, void* o, const float
                const int64_t q_strides[2], const int64_t k_strides[3], const int64_t v_strides[3],
                const int64_t o_strides[2], void* workspace, size_t workspace_bytes, void* stream);
 
+/* Decode with per-batch cache lengths and (optionally) a paged KV cache -- SURVEY section 8 row f4; the reference shares
+ * ONE length across the batch and keeps the cache contiguous (cache.py:11-13, decode_kernel.py:146-149).
+ *   block_table != NULL: k_cache / v_cache are page pools [num_pages, page_size keys] with (page, head, position) element
+ *     strides; logical page j of batch row b is physical page block_table[b * block_table_stride + j] (int32, device);
+ *     page_size: a power of two >= 32.
+ *   block_table == NULL: k_cache / v_cache are [B,Hkv,max_len,D] with (batch, head, position) strides; page_size ignored.
+ *   seq_lens: int32 [B] on the device, keys cached for row b (clamped to max_len); NULL: max_len for every row.  A row
+ *     with no key yields 0 (or attends only the s_aux sink when s_aux is given).
+ * Workspace: sfa_workspace_bytes(SFA_OP_DECODE, B, Hq, Hkv, max_len rounded up to whole pages, D, dtype).
+ * bf16 / fp16, head_dim 64 / 128 / 256 (the tensor-core decode kernel); other cases return -12. */
+int sfa_decode_paged(const void* q, const void* k_cache, const void* v_cache, void* o, const float* s_aux,
+                     const int* block_table, const int* seq_lens, int B, int Hq, int Hkv, int max_len, int D, int dtype,
+                     int page_size, int64_t block_table_stride, const int64_t q_strides[2], const int64_t k_strides[3],
+                     const int64_t v_strides[3], const int64_t o_strides[2], void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* Ring-aware decode: attends sink_k/v[:, :, :sink_len] and window_k/v[:, :, :window_len] in place
  * (softmax is order-invariant, so the ring needs no linearisation).  Buffers are
  * [B,Hkv,num_sink,D] and [B,Hkv,window_size,D] with the given (batch, head, position) strides. */

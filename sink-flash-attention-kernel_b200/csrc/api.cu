@@ -397,7 +397,7 @@ static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t works
       p.sv[s] = p.sv[1 - s];
     }
   if (g_force_impl != SFA_IMPL_SIMT && mma_decode_supported(p, dtype)) {
-    p.splits = mma_decode_splits(p.B, p.Hq, p.Hkv, L);
+    p.splits = mma_decode_splits(p.B, p.Hq, p.Hkv, L, (p.paged && p.block_table != nullptr) ? p.page_size : 1);
     {
       const size_t ml = align_up((size_t)p.B * p.Hq * p.splits * 2 * 4, 256);
       const size_t po = align_up((size_t)p.B * p.Hq * p.splits * p.D * 4, 256);
@@ -410,6 +410,11 @@ static int decode_impl(DecodeParams& p, int dtype, void* workspace, size_t works
     }
     set_impl_name("mma");
     return cuda_ret(mma_decode(p, dtype, st), "sfa_decode(mma)");
+  }
+  if (p.paged) {
+    set_error("per-batch cache lengths / paged KV need the tensor-core decode kernel (bf16 / fp16, head_dim 64 / 128 / 256, "
+              "16-byte aligned rows, page size a power of two >= 32)");
+    return -12;
   }
   p.splits = 1;
   set_impl_name("simt");
@@ -433,6 +438,40 @@ int sfa_decode(const void* q, const void* k, const void* v, void* o, const float
   p.sq_b = q_strides[0]; p.sq_h = q_strides[1]; p.so_b = o_strides[0]; p.so_h = o_strides[1];
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.D = D;
   p.scale = 1.0f / sqrtf((float)D);
+  return decode_impl(p, dtype, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int sfa_decode_paged(const void* q, const void* k_cache, const void* v_cache, void* o, const float* s_aux,
+                     const int* block_table, const int* seq_lens, int B, int Hq, int Hkv, int max_len, int D, int dtype,
+                     int page_size, int64_t block_table_stride, const int64_t q_strides[2], const int64_t k_strides[3],
+                     const int64_t v_strides[3], const int64_t o_strides[2], void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  const int64_t* none[1] = {nullptr};
+  if (int r = check_common(B, Hq, Hkv, max_len, D, dtype, none, 0)) return r;
+  if (!q || !k_cache || !v_cache || !o) {
+    set_error("null tensor pointer");
+    return -6;
+  }
+  if (block_table != nullptr && (page_size < 32 || (page_size & (page_size - 1)) != 0)) {
+    set_error("page_size must be a power of two >= 32, got %d", page_size);
+    return -1;
+  }
+  DecodeParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.o = o; p.s_aux = s_aux;
+  p.k[0] = k_cache; p.v[0] = v_cache;
+  // the planning length: whole pages (ranges start on page boundaries); the rows' own lengths clip it in the kernel
+  p.len[0] = block_table != nullptr ? (max_len + page_size - 1) / page_size * page_size : max_len;
+  p.len[1] = 0;
+  p.sk[0] = mk(k_strides); p.sv[0] = mk(v_strides);
+  p.sq_b = q_strides[0]; p.sq_h = q_strides[1]; p.so_b = o_strides[0]; p.so_h = o_strides[1];
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.D = D;
+  p.scale = 1.0f / sqrtf((float)D);
+  p.paged = 1;
+  p.block_table = block_table; p.bt_stride = block_table_stride; p.seq_lens = seq_lens;
+  p.page_size = block_table != nullptr ? page_size : 0;
+  p.lg_page = 0;
+  while (block_table != nullptr && (1 << p.lg_page) < page_size) ++p.lg_page;
   return decode_impl(p, dtype, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

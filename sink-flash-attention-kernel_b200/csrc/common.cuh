@@ -70,6 +70,15 @@ struct DecodeParams {
   float* part_ml;     // workspace: [B,Hq,splits,2]
   float* part_o;      // workspace: [B,Hq,splits,D]
   int splits;
+  // per-batch cache lengths and paged KV (sfa_decode_paged; the reference shares one length across the batch and keeps
+  // the cache contiguous, cache.py:11-13): k[0] / v[0] are the page pools, sk[0] / sv[0] = (page, head, position) strides,
+  // len[0] = the planning length (max_len rounded up to whole pages), len[1] = 0.
+  int paged;                 // 1: this launch uses the fields below
+  const int* block_table;    // [B][bt_stride] physical page of logical page j of batch row b; nullptr: contiguous cache
+                             // (page == batch row, sk[0].b = batch stride)
+  int64_t bt_stride;
+  const int* seq_lens;       // [B] keys cached for batch row b (device); nullptr: len[0] for every row
+  int page_size, lg_page;    // keys per page (a power of two, a multiple of 32); contiguous cache: unused
 };
 
 void set_error(const char* fmt, ...);
@@ -141,7 +150,7 @@ cudaError_t cache_append(const void* k_new, const void* v_new, void* win_k, void
                          cudaStream_t st);
 
 bool mma_decode_supported(const DecodeParams& p, int dtype);
-int mma_decode_splits(int B, int Hq, int Hkv, int total_len);   // workspace slots per q head
+int mma_decode_splits(int B, int Hq, int Hkv, int total_len, int align = 1);   // workspace slots per q head (align: page size)
 cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st);
 
 void set_trace_buffer(long long* p);   // performance-debug timeline (device buffer, 3*256*2 int64) or nullptr

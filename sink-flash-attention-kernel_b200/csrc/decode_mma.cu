@@ -88,7 +88,11 @@ template <int D> __device__ __forceinline__ int tile_off(int r, int c) { return 
 // second wave.  A CTA's range covers the tail of one unit, possibly whole units, and the head of another: every
 // (unit, key range) segment is one pass of the pipeline below; a unit cut into pieces leaves (m, l, o) partials that
 // the combine kernel merges, a unit inside one range is finished here.
-template <typename T, int D, int V>
+// kPaged: per-batch cache lengths (seq_lens) and / or a page table (block_table) -- a separate instantiation, the plain
+// kernel is unchanged.  The key ranges are planned over the maximal length; a unit's range is clipped to its row's length
+// (ranges past it leave empty partials), and every 32-key block lies inside one page (page_size % 32 == 0, ranges start
+// on page boundaries).
+template <typename T, int D, int V, bool kPaged = false>
 __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chunk_keys, int g_tiles) {
   using C = DecodeCfg<D, V>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -111,6 +115,10 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
   f += k_end - k_begin;
   const int gt = unit % g_tiles;
   const int kvh = (unit / g_tiles) % p.Hkv, b = unit / (g_tiles * p.Hkv);
+  int k_stop = k_end;                               // keys [k_begin, k_stop) exist for this batch row
+  if constexpr (kPaged) {
+    if (p.seq_lens != nullptr) k_stop = min(k_end, max(__ldg(p.seq_lens + b), k_begin));
+  }
   const int h0 = kvh * G + gt * 16;                 // first q head served by this segment
   const int nh = min(16, G - gt * 16);              // real heads among the 16 MMA rows
   // pieces of this unit: CTAs first_cta .. last_cta touch it
@@ -137,13 +145,14 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
   const T* vb[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    kb[s] = static_cast<const T*>(p.k[s]) + b * p.sk[s].b + kvh * p.sk[s].h;
-    vb[s] = static_cast<const T*>(p.v[s]) + b * p.sv[s].b + kvh * p.sv[s].h;
+    // (64-bit batch term: a paged pool or a long contiguous cache exceeds 2^31 elements)
+    kb[s] = static_cast<const T*>(p.k[s]) + ((kPaged && p.block_table != nullptr) ? 0 : static_cast<int64_t>(b) * p.sk[s].b) + kvh * p.sk[s].h;
+    vb[s] = static_cast<const T*>(p.v[s]) + ((kPaged && p.block_table != nullptr) ? 0 : static_cast<int64_t>(b) * p.sv[s].b) + kvh * p.sv[s].h;
   }
   const int len0 = p.len[0];
 
   // blocks of kKB keys; warp w owns blocks w, w+4, ... of this segment
-  const int nblk_total = (k_end - k_begin + KB - 1) / KB;
+  const int nblk_total = (k_stop - k_begin + KB - 1) / KB;
   const int nblk = (nblk_total > warp) ? (nblk_total - warp + 3) / 4 : 0;
 
   // per-lane constants of the block copy: lane owns 16-byte chunk `lch` of rows lr0, lr0 + 32 / (D / 8), ...
@@ -154,6 +163,30 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
     const int key0 = k_begin + (warp + 4 * it) * KB;
     unsigned char* ks_ = ring + (it % C::kStages) * 2 * C::kBlkBytes;
     unsigned char* vs_ = ks_ + C::kBlkBytes;
+    if constexpr (kPaged) {
+      // one page per block: logical page -> physical page, then the same copy as below inside the page
+      int64_t pos0 = key0;
+      int64_t kpage = 0, vpage = 0;
+      if (p.block_table != nullptr) {
+        const int phys = __ldg(p.block_table + b * p.bt_stride + (key0 >> p.lg_page));
+        pos0 = key0 & (p.page_size - 1);
+        kpage = static_cast<int64_t>(phys) * p.sk[0].b;
+        vpage = static_cast<int64_t>(phys) * p.sv[0].b;
+      }
+      const T* ksrc = kb[0] + kpage + (pos0 + lr0) * p.sk[0].n + lch * 8;
+      const T* vsrc = vb[0] + vpage + (pos0 + lr0) * p.sv[0].n + lch * 8;
+      const int64_t kstep = kRowsPerIt * p.sk[0].n, vstep = kRowsPerIt * p.sv[0].n;
+#pragma unroll
+      for (int j = 0; j < KB / kRowsPerIt; ++j) {
+        const int r = lr0 + j * kRowsPerIt;
+        const bool valid = key0 + r < k_stop;           // rows past the row's length: zero fill, never dereferenced
+        cp_async16(ks_ + tile_off<D>(r, lch), valid ? ksrc : kb[0], valid);
+        cp_async16(vs_ + tile_off<D>(r, lch), valid ? vsrc : vb[0], valid);
+        ksrc += kstep;
+        vsrc += vstep;
+      }
+      return;
+    }
     const bool in0 = key0 + KB <= len0, in1 = key0 >= len0;
     if (key0 + KB <= k_end && (in0 || in1)) {
       // fast path (all but the edge blocks): the block lies inside one segment and inside the range -- one pointer
@@ -230,7 +263,7 @@ __global__ void __launch_bounds__(128) decode_mma_kernel(DecodeParams p, int chu
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = key0 + n * 8 + 2 * (lane & 3) + (e & 1);
-        const float s2 = (key < k_end) ? sc[n][e] * sl2 : -INFINITY;
+        const float s2 = (key < k_stop) ? sc[n][e] * sl2 : -INFINITY;
         sc[n][e] = s2;
         mx[e >> 1] = fmaxf(mx[e >> 1], s2);
       }
@@ -386,7 +419,7 @@ __global__ void decode_combine_kernel(DecodeParams p, int chunk_keys, int g_tile
 struct DecodePlan {
   int chunk, ncta, max_pieces;
 };
-DecodePlan make_decode_plan(int B, int Hq, int Hkv, int L) {
+DecodePlan make_decode_plan(int B, int Hq, int Hkv, int L, int align = 1) {
   constexpr int kMinChunk = 256;
   const int g_tiles = (Hq / Hkv + 15) / 16;
   const int64_t total = static_cast<int64_t>(B) * Hkv * g_tiles * L;
@@ -404,6 +437,7 @@ DecodePlan make_decode_plan(int B, int Hq, int Hkv, int L) {
   } else {
     chunk = (total + slots - 1) / slots;          // few units (small batch) or a thin last wave: equal key ranges
   }
+  if (align > 1 && chunk % align != 0) chunk += align - chunk % align;     // paged: ranges start on page boundaries
   DecodePlan pl;
   pl.chunk = static_cast<int>(chunk);
   pl.ncta = static_cast<int>((total + chunk - 1) / chunk);
@@ -411,17 +445,17 @@ DecodePlan make_decode_plan(int B, int Hq, int Hkv, int L) {
   return pl;
 }
 
-template <typename T, int D, int V = 0>
+template <typename T, int D, int V = 0, bool kPaged = false>
 cudaError_t launch(const DecodeParams& p, cudaStream_t st) {
   using C = DecodeCfg<D, V>;
   static std::atomic<unsigned long long> attr_done{0};
-  if (cudaError_t e = ensure_dyn_smem(decode_mma_kernel<T, D, V>, C::kSmem, attr_done)) return e;
+  if (cudaError_t e = ensure_dyn_smem(decode_mma_kernel<T, D, V, kPaged>, C::kSmem, attr_done)) return e;
   const int G = p.Hq / p.Hkv;
   const int g_tiles = (G + 15) / 16;
   const int L = p.len[0] + p.len[1];
-  const DecodePlan pl = make_decode_plan(p.B, p.Hq, p.Hkv, L);
+  const DecodePlan pl = make_decode_plan(p.B, p.Hq, p.Hkv, L, (kPaged && p.block_table != nullptr) ? p.page_size : 1);
   if (pl.max_pieces > p.splits) return cudaErrorInvalidValue;      // workspace carved for fewer pieces
-  decode_mma_kernel<T, D, V><<<pl.ncta, 128, C::kSmem, st>>>(p, pl.chunk, g_tiles);
+  decode_mma_kernel<T, D, V, kPaged><<<pl.ncta, 128, C::kSmem, st>>>(p, pl.chunk, g_tiles);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // units cut by a range boundary are merged here (every unit when the ranges are shorter than a unit; none when
@@ -437,6 +471,7 @@ cudaError_t launch(const DecodeParams& p, cudaStream_t st) {
 bool mma_decode_supported(const DecodeParams& p, int dtype) {
   if (dtype != SFA_DTYPE_BF16 && dtype != SFA_DTYPE_FP16) return false;
   if (p.D != 64 && p.D != 128 && p.D != 256) return false;
+  if (p.paged && p.block_table != nullptr && (p.page_size < 32 || (p.page_size & (p.page_size - 1)) != 0)) return false;
   // 16-byte vector loads: rows must be 16-B aligned
   auto ok = [](const void* ptr, int64_t a, int64_t b, int64_t c) {
     return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (a % 8 == 0) && (b % 8 == 0) && (c % 8 == 0);
@@ -453,11 +488,23 @@ bool mma_decode_supported(const DecodeParams& p, int dtype) {
 // Workspace slots per head (= the most pieces any unit can be cut into) for the balanced decomposition above.
 // History: with one CTA per (unit, split) BASELINE configs[3] measured 112.6 / 118.8 / 120.8 / 118.8 / 127.0 / 133.1 us
 // for 1 / 2 / 3 / 4 / 6 / 8 uniform splits -- every uniform choice leaves a partly filled last wave.
-int mma_decode_splits(int B, int Hq, int Hkv, int total_len) {
-  return make_decode_plan(B, Hq, Hkv, total_len).max_pieces;
+int mma_decode_splits(int B, int Hq, int Hkv, int total_len, int align) {
+  return make_decode_plan(B, Hq, Hkv, total_len, align).max_pieces;
 }
 
 cudaError_t mma_decode(const DecodeParams& p, int dtype, cudaStream_t st) {
+  if (p.paged) {
+#define SFA_DECP(T)                                            \
+  switch (p.D) {                                               \
+    case 64: return launch<T, 64, 0, true>(p, st);             \
+    case 128: return launch<T, 128, 0, true>(p, st);           \
+    case 256: return launch<T, 256, 0, true>(p, st);           \
+  }
+    if (dtype == SFA_DTYPE_BF16) { SFA_DECP(__nv_bfloat16) }
+    if (dtype == SFA_DTYPE_FP16) { SFA_DECP(__half) }
+#undef SFA_DECP
+    return cudaErrorInvalidValue;
+  }
   static const int variant = getenv("SFA_DECODE_VARIANT") ? atoi(getenv("SFA_DECODE_VARIANT")) : 0;   // experiments only
 #define SFA_DEC(T)                                     \
   switch (p.D) {                                       \

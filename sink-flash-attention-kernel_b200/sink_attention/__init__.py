@@ -21,7 +21,7 @@ from .sp_utils import (
     ulysses_head_to_seq,
 )
 from .cache import SinkCacheLayer, SinkAttentionCache
-from .decode_kernel import sink_decode_attention
+from .decode_kernel import sink_decode_attention, sink_decode_attention_varlen, sink_decode_attention_paged
 from .generate_patch import patch_for_generation, unpatch_generation
 from .subprocess_eval import subprocess_generate
 
@@ -48,4 +48,6 @@ __all__ = [
     "HaloSinkAttention",
     "ulysses_seq_to_head",
     "ulysses_head_to_seq",
+    "sink_decode_attention_varlen",
+    "sink_decode_attention_paged",
 ]

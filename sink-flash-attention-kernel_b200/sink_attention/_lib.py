@@ -21,7 +21,7 @@ IMPL_AUTO, IMPL_SIMT = 0, 1
 
 EXPORTS = (
     "sfa_version", "sfa_last_error", "sfa_set_impl", "sfa_set_bwd_stages", "sfa_set_trace_buffer", "sfa_last_impl", "sfa_workspace_bytes",
-    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_set_debug", "sfa_cache_append", "sfa_fwd_ex", "sfa_bwd_ex",
+    "sfa_fwd", "sfa_bwd", "sfa_decode", "sfa_decode_ring", "sfa_decode_paged", "sfa_ulysses_scatter", "sfa_fwd_sp", "sfa_bwd_sp", "sfa_set_debug", "sfa_cache_append", "sfa_fwd_ex", "sfa_bwd_ex",
 )
 
 _lib = None
@@ -119,6 +119,8 @@ def load() -> ctypes.CDLL:
     lib.sfa_decode.restype = i
     lib.sfa_decode_ring.argtypes = [p] * 6 + [f32p] + [i] * 7 + [i64p] * 4 + [p, c.c_size_t, p]
     lib.sfa_decode_ring.restype = i
+    lib.sfa_decode_paged.argtypes = [p, p, p, p, f32p, p, p] + [i] * 7 + [c.c_int64] + [i64p] * 4 + [p, c.c_size_t, p]
+    lib.sfa_decode_paged.restype = i
     lib.sfa_ulysses_scatter.argtypes = [p, c.POINTER(c.c_void_p)] + [i] * 8 + [i64p, i, i, p]
     lib.sfa_ulysses_scatter.restype = i
     lib.sfa_cache_append.argtypes = [p] * 4 + [i] * 4 + [i64p] * 2 + [i, i, p]
@@ -285,6 +287,56 @@ def decode(q, k, v, s_aux_f32):
             _i64(q.stride()[:2]), _i64(k.stride()[:3]), _i64(v.stride()[:3]), _i64(o.stride()[:2]),
             ws.data_ptr(), ws_bytes, _stream(q))
     _check(rc, "sfa_decode")
+    return o
+
+
+def decode_paged(q, k_cache, v_cache, s_aux_f32, seq_lens=None, block_table=None, max_len=None):
+    """Decode with per-batch cache lengths and / or a paged cache (sfa_decode_paged).
+
+    block_table is None: k_cache, v_cache [B,Hkv,Nkv,D] (any batch / head / position strides).
+    block_table [B, max_pages] int32: k_cache, v_cache are page pools [num_pages, page_size, Hkv, D] (the vLLM layout;
+    any page / position / head strides).  seq_lens: int32 [B] on the device or None."""
+    lib = load()
+    _require_cuda(q, k_cache, v_cache, s_aux_f32)
+    B, Hq, _, D = q.shape
+    q = _unit_last(q)
+    if k_cache.stride(-1) != 1 or v_cache.stride(-1) != 1:
+        raise ValueError("cache tensors must have unit channel stride")
+    if block_table is not None:
+        if block_table.dtype != torch.int32 or not block_table.is_cuda or block_table.dim() != 2 or block_table.stride(1) != 1:
+            raise ValueError("block_table must be a CUDA int32 [B, max_pages] tensor with unit inner stride")
+        page_size, Hkv = k_cache.shape[1], k_cache.shape[2]
+        ks = (k_cache.stride(0), k_cache.stride(2), k_cache.stride(1))        # (page, head, position)
+        vs = (v_cache.stride(0), v_cache.stride(2), v_cache.stride(1))
+        cap = block_table.shape[1] * page_size
+        max_len = cap if max_len is None else int(max_len)
+        if max_len > cap:
+            raise ValueError(f"max_len {max_len} exceeds the block table's capacity {cap}")
+        plan_len = (max_len + page_size - 1) // page_size * page_size
+        bt_ptr, bt_stride = block_table.data_ptr(), block_table.stride(0)
+    else:
+        Hkv, page_size = k_cache.shape[1], 0
+        ks, vs = k_cache.stride()[:3], v_cache.stride()[:3]
+        max_len = k_cache.shape[2] if max_len is None else int(max_len)
+        plan_len = max_len
+        bt_ptr, bt_stride = None, 0
+    if seq_lens is not None and (seq_lens.dtype != torch.int32 or not seq_lens.is_cuda or seq_lens.numel() != B
+                                 or not seq_lens.is_contiguous()):
+        raise ValueError("seq_lens must be a contiguous CUDA int32 tensor of B entries")
+    o = torch.empty((B, Hq, 1, D), device=q.device, dtype=q.dtype)
+    code = DTYPE_CODE[q.dtype]
+    with torch.cuda.device(q.device):
+        ws_bytes = lib.sfa_workspace_bytes(OP_DECODE, B, Hq, Hkv, plan_len, D, code)
+    ws = torch.empty((max(ws_bytes, 1),), device=q.device, dtype=torch.uint8)
+    with torch.cuda.device(q.device):
+        rc = lib.sfa_decode_paged(
+            q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), o.data_ptr(),
+            s_aux_f32.data_ptr() if s_aux_f32 is not None else None,
+            bt_ptr, seq_lens.data_ptr() if seq_lens is not None else None,
+            B, Hq, Hkv, max_len, D, code, page_size, bt_stride,
+            _i64(q.stride()[:2]), _i64(ks), _i64(vs), _i64(o.stride()[:2]),
+            ws.data_ptr(), ws_bytes, _stream(q))
+    _check(rc, "sfa_decode_paged")
     return o
 
 

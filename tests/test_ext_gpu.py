@@ -155,3 +155,96 @@ def test_verl_patch_keeps_s_aux_for_packed_batches():
     ref, _ = _oracle_packed(q.cpu().transpose(1, 2).float(), k.cpu().transpose(1, 2).float(), v.cpu().transpose(1, 2).float(),
                             zero, lens, 0, W, s_aux.cpu())
     assert maxdiff(out.transpose(1, 2), ref["o"]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# decode with per-batch cache lengths and a paged KV cache (the reference shares ONE length
+# across the batch and keeps the cache contiguous, cache.py:11-13): every batch row must equal the oracle
+# (decode_kernel.py:205-226 restated, tests/test_decode_kernel.py:19-55) over its own keys
+# ------------------------------------------------------------------------------------------------
+def _decode_rows_oracle(q, k_rows, v_rows, s_aux):
+    """q [B,Hq,1,D] cpu; k_rows / v_rows: per batch row [Hkv, len_b, D] cpu."""
+    outs = []
+    for b in range(q.shape[0]):
+        if k_rows[b].shape[1] == 0:
+            outs.append(torch.zeros_like(q[b:b + 1], dtype=torch.float64))     # nothing (but the s_aux sink) to attend
+        else:
+            outs.append(orc.decode_attention(q[b:b + 1], k_rows[b][None], v_rows[b][None], s_aux))
+    return torch.cat(outs, dim=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,Hq,Hkv,D,Nmax,lens,use_aux", [
+    (4, 16, 2, 64, 700, [700, 1, 333, 64], True),
+    (3, 8, 8, 128, 300, [17, 300, 0], True),            # a row with no key: only the s_aux sink
+    (2, 8, 2, 64, 96, [96, 33], False),
+    (64, 64, 8, 64, 1500, None, True),                   # many units: one CTA per unit
+])
+def test_decode_per_batch_lengths(dtype, B, Hq, Hkv, D, Nmax, lens, use_aux):
+    g = torch.Generator().manual_seed(B + Nmax)
+    if lens is None:
+        lens = torch.randint(1, Nmax + 1, (B,), generator=g).tolist()
+    q = torch.randn(B, Hq, 1, D, generator=g).to(dtype)
+    k = torch.randn(B, Hkv, Nmax, D, generator=g).to(dtype)
+    v = torch.randn(B, Hkv, Nmax, D, generator=g).to(dtype)
+    s_aux = torch.randn(Hq, generator=g) * 0.5 if use_aux else None
+    sl = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    o = sa.sink_decode_attention_varlen(q.cuda(), k.cuda(), v.cuda(), sl, s_aux.cuda() if use_aux else None)
+    assert _lib.last_impl() == "mma"
+    ref = _decode_rows_oracle(q, [k[b, :, :lens[b]] for b in range(B)], [v[b, :, :lens[b]] for b in range(B)], s_aux)
+    assert maxdiff(o, ref) < 1e-2
+    # equal lengths == the reference entry point, bit for bit (same kernel body, same key ranges)
+    full = torch.full((B,), Nmax, dtype=torch.int32, device="cuda")
+    o_full = sa.sink_decode_attention_varlen(q.cuda(), k.cuda(), v.cuda(), full, s_aux.cuda() if use_aux else None)
+    o_plain = sa.sink_decode_attention(q.cuda(), k.cuda(), v.cuda(), s_aux.cuda() if use_aux else None)
+    assert torch.equal(o_full, o_plain)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,Hq,Hkv,D,page,max_pages,lens,use_aux", [
+    (4, 16, 2, 64, 32, 12, [384, 1, 200, 33], True),
+    (3, 8, 4, 128, 64, 5, [320, 65, 0], True),
+    (2, 32, 8, 64, 256, 3, [700, 256], False),
+    (48, 64, 8, 64, 128, 9, None, True),
+])
+def test_decode_paged_kv(dtype, B, Hq, Hkv, D, page, max_pages, lens, use_aux):
+    g = torch.Generator().manual_seed(B * page + max_pages)
+    cap = page * max_pages
+    if lens is None:
+        lens = torch.randint(1, cap + 1, (B,), generator=g).tolist()
+    num_pages = B * max_pages + 3
+    q = torch.randn(B, Hq, 1, D, generator=g).to(dtype)
+    k_cache = torch.randn(num_pages, page, Hkv, D, generator=g).to(dtype)       # the vLLM layout
+    v_cache = torch.randn(num_pages, page, Hkv, D, generator=g).to(dtype)
+    # every logical page gets its own physical page, in a shuffled order; unused table entries point at page 0
+    perm = torch.randperm(num_pages, generator=g)[:B * max_pages].view(B, max_pages).to(torch.int32)
+    for b in range(B):
+        perm[b, (lens[b] + page - 1) // page:] = 0
+    s_aux = torch.randn(Hq, generator=g) * 0.5 if use_aux else None
+    sl = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    o = sa.sink_decode_attention_paged(q.cuda(), k_cache.cuda(), v_cache.cuda(), perm.cuda(), sl,
+                                       s_aux.cuda() if use_aux else None, max_len=max(lens))
+    assert _lib.last_impl() == "mma"
+
+    def rows(cache):
+        out = []
+        for b in range(B):
+            pages = [cache[int(perm[b, j])] for j in range((lens[b] + page - 1) // page)]       # [page, Hkv, D] each
+            flat = torch.cat(pages, dim=0)[:lens[b]] if pages else cache.new_zeros(0, Hkv, D)
+            out.append(flat.transpose(0, 1))                                                      # [Hkv, len, D]
+        return out
+    ref = _decode_rows_oracle(q, rows(k_cache), rows(v_cache), s_aux)
+    assert maxdiff(o, ref) < 1e-2
+    # the default planning length (the table's capacity) gives the same rows
+    o2 = sa.sink_decode_attention_paged(q.cuda(), k_cache.cuda(), v_cache.cuda(), perm.cuda(), sl,
+                                        s_aux.cuda() if use_aux else None)
+    assert maxdiff(o2, ref) < 1e-2
+
+
+def test_decode_paged_rejects_bad_page_size():
+    q = torch.randn(1, 8, 1, 64, device="cuda", dtype=torch.bfloat16)
+    cache = torch.randn(4, 48, 2, 64, device="cuda", dtype=torch.bfloat16)      # 48: not a power of two
+    bt = torch.zeros(1, 2, dtype=torch.int32, device="cuda")
+    sl = torch.tensor([50], dtype=torch.int32, device="cuda")
+    with pytest.raises(ValueError):
+        sa.sink_decode_attention_paged(q, cache, cache, bt, sl)
