@@ -196,7 +196,9 @@ struct SlotTrack {
 // kExt: extended geometry (packed sequences / chunk offset) compiled in.  A separate instantiation, not a run-time
 // switch: the two extra live values per math thread pushed the plain kernel over its 72-register budget (36 B of
 // spills -- with 227 KB of shared memory every spill reload is an L2 round trip) and cost 4.5 us at the gpt-oss shape.
-template <typename T, bool kExt>
+// kLean: the production launch -- delta inside the kernel, no routed dQ, no debug knobs: their branches are compiled out
+// (the size of this kernel's code is a first-order parameter).
+template <typename T, bool kExt, bool kLean>
 __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                              const __grid_constant__ CUtensorMap tmdO,
                                                                              const __grid_constant__ CUtensorMap tmK,
@@ -255,9 +257,9 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
     tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    if (a.fuse_delta) tma_prefetch_desc(&tmO);
+    if ((kLean || a.fuse_delta)) tma_prefetch_desc(&tmO);
     // with delta in the kernel: do_empty[s] (bars 10, 11) = dV^T(n) complete + the four warps that computed delta(n)
-    for (int s = 0; s < 16; ++s) mbar_init(bars + s, (a.fuse_delta && (s == 10 || s == 11)) ? 5 : 1);
+    for (int s = 0; s < 16; ++s) mbar_init(bars + s, ((kLean || a.fuse_delta) && (s == 10 || s == 11)) ? 5 : 1);
     mbar_init(s_full, 1);
     mbar_init(s_free, C::kMathWarps * 32);       // per-thread arrivals and waits in the math warps: measured faster than
                                                  // one polling / arriving lane per warp + __syncwarp (fwd64: 62 vs 67 us)
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       FusedWalk w(a, wi);
       const uint32_t kv_bytes = a.cols * C::D * 2;
       int tc = 0;
-      if (a.fuse_delta && lane == 0 && wi.tile < wi.end) {        // O(0), as eight 16-row blocks; the epilogue warps load the rest
+      if ((kLean || a.fuse_delta) && lane == 0 && wi.tile < wi.end) {        // O(0), as eight 16-row blocks; the epilogue warps load the rest
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           const int n0 = wi.pb * P + (a.q_swap ? ((16 * j) >> (7 - a.lgP)) : ((16 * j) & (P - 1)));
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       // delta of tile t from the preprocess pass (fuse_delta == 0); with fuse_delta it comes from delta_s before pass 2
       auto load_delta = [&](const FusedWalk& t, bool valid) {
         float v = 0.f;
-        if (valid && !a.fuse_delta) {
+        if (valid && !(kLean || a.fuse_delta)) {
           const int i = t.pb * P + pr;
           if (i < a.N) {
             const int64_t row = (static_cast<int64_t>(t.b) * a.Hq + t.y * a.G + gr) * a.N + i;
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         // p_free only orders the tensor pipe's reads; the three warps of a quarter (same rows, all chunks) must agree
         // that pass 2(n) is over before any of them overwrites the image.  Without this barrier a warp that ran a full
         // pass ahead of its neighbour fed P(n + 1) into dS(n): dQ and dK changed from run to run, dV never (round 1).
-        if (w.it >= 1 && !a.dbg_norace) named_bar_sync(1 + quarter, 96);
+        if (w.it >= 1 && !(!kLean && a.dbg_norace)) named_bar_sync(1 + quarter, 96);
         if (part == 1)
           for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(p_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
         const int rc0 = st.slot0 * P;
@@ -603,14 +605,14 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         mbar_wait(dp_full, w.it & 1);
         tc_fence_after();
         if (w.it >= 1) mbar_wait(ds_free, (w.it - 1) & 1);
-        if (a.fuse_delta) {                                // this row's delta from the delta warps
+        if ((kLean || a.fuse_delta)) {                                // this row's delta from the delta warps
           mbar_wait(delta_ready + (w.it & 1), (w.it >> 1) & 1);
           dsc = delta_s[(w.it & 1) * 128 + r] * a.scale;
           mbar_arrive(delta_free + (w.it & 1));
           if (tr) ftrace(a.trace, 3, tc, 6, w.it);
         }
         const uint64_t ndsc2 = pack_f32x2(-dsc, -dsc);
-        if (a.dbg_delay && part == 1) __nanosleep(a.dbg_delay);
+        if (!kLean && a.dbg_delay && part == 1) __nanosleep(a.dbg_delay);
         if (tr) ftrace(a.trace, 3, tc, 4, w.it);
         if (part == 1)
           for (int g8 = 0; g8 < (P >> 3); ++g8) st_shared_v4(ds_a + zoff + g8 * 2048u, 0u, 0u, 0u, 0u);
@@ -679,7 +681,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
       // delta inputs when dQ(n) was ready -- dq_free, the ring drain and with them every issuer ran late: 171 us.)
       // This warp owns rows 32 * quarter .. + 31.
       // (the delta tile's coordinates come from two divisions per tile, not from a third walker: registers)
-      int dit = a.fuse_delta ? (grp ^ 1) : (1 << 30);         // index of the group's next delta tile in this CTA's run
+      int dit = (kLean || a.fuse_delta) ? (grp ^ 1) : (1 << 30);         // index of the group's next delta tile in this CTA's run
       // O rows arrive as 16-row blocks (2 KB, one TMA box each); the warp that has consumed block j of tile k loads block j
       // of tile k + 1 into the same place -- for the same quarter's warp of the other group.  (One 16 KB box per tile,
       // loaded when the whole group had finished: delta(k) -> load -> delta(k + 1) was a chain of ~4600 + ~2000 cycles
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         dit += 2;
       };
       // lead-in rounds: delta(0), delta(2) by group 1, delta(1) by group 0; then every round is epilogue(n), delta(n + 3)
-      int lead = a.fuse_delta ? 1 + grp : 0;
+      int lead = (kLean || a.fuse_delta) ? 1 + grp : 0;
       while (true) {
         if (lead > 0) {
           --lead;
@@ -808,7 +810,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
         {
           T* dq_base = static_cast<T*>(a.dq);
           int il0 = w.pb * P;
-          if (a.dq_seg_n > 0) {       // straight into the sequence owner's buffer over NVLink
+          if (!kLean && a.dq_seg_n > 0) {       // straight into the sequence owner's buffer over NVLink
             const int seg = il0 / a.dq_seg_n;
             dq_base = static_cast<T*>(a.dq_peer[seg]);
             il0 -= seg * a.dq_seg_n;
@@ -816,7 +818,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
           T* const tile_dq = dq_base + static_cast<int64_t>(w.b) * a.sdq.b +
                              static_cast<int64_t>(w.y * a.G) * a.sdq.h + static_cast<int64_t>(il0) * a.sdq.n;
           const bool ok0 = w.pb * P + row_pr[0] < a.N, ok1 = w.pb * P + row_pr[1] < a.N;
-          if (a.dbg_delay && grp == 0) __nanosleep(a.dbg_delay * 4);
+          if (!kLean && a.dbg_delay && grp == 0) __nanosleep(a.dbg_delay * 4);
 #pragma unroll 1
           for (int hq = 0; hq < 4; ++hq) {                  // channels 16 hq .. 16 hq + 15
             uint32_t x[16];
@@ -1066,15 +1068,16 @@ cudaError_t launch_fused(const AttnParams& p, int dtype, float* part, const floa
   a.part = part;
   a.trace = trace_buffer();
   cudaError_t e;
-  if (p.has_ext()) {
-    static std::atomic<unsigned long long> attr_done{0};
-    if ((e = ensure_dyn_smem(bwd_fused64_kernel<T, true>, C::kSmem, attr_done)) != cudaSuccess) return e;
-    bwd_fused64_kernel<T, true><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mo.map, a);
-  } else {
-    static std::atomic<unsigned long long> attr_done{0};
-    if ((e = ensure_dyn_smem(bwd_fused64_kernel<T, false>, C::kSmem, attr_done)) != cudaSuccess) return e;
-    bwd_fused64_kernel<T, false><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mo.map, a);
+  const bool lean = a.fuse_delta && a.dq_seg_n == 0 && a.dbg_delay == 0 && a.dbg_norace == 0 && a.trace == nullptr;
+#define SFA_FUSED_LAUNCH(E_, L_)                                                                                       \
+  {                                                                                                                    \
+    static std::atomic<unsigned long long> attr_done{0};                                                               \
+    if ((e = ensure_dyn_smem(bwd_fused64_kernel<T, E_, L_>, C::kSmem, attr_done)) != cudaSuccess) return e;            \
+    bwd_fused64_kernel<T, E_, L_><<<grid, C::kThreads, C::kSmem, st>>>(mq.map, mdo.map, mk.map, mv.map, mo.map, a);    \
   }
+  if (p.has_ext()) { if (lean) SFA_FUSED_LAUNCH(true, true) else SFA_FUSED_LAUNCH(true, false) }
+  else { if (lean) SFA_FUSED_LAUNCH(false, true) else SFA_FUSED_LAUNCH(false, false) }
+#undef SFA_FUSED_LAUNCH
   e = cudaGetLastError();
   if (e != cudaSuccess) { if (getenv("SFA_DEBUG_LAUNCH")) fprintf(stderr, "launch_fused: kernel launch error %d grid %d\n", (int)e, grid); return e; }
   const int nbound = (grid > 1 && nb > 1) ? grid - 1 : 0;   // nb == 1 (window <= one block): no shared key block
