@@ -98,7 +98,7 @@ struct FusedArgs {
   const float* lse;
   float* delta;          // [B,Hq,N] workspace
 
-  const void* k;         // L2 prefetch of the newest key block
+  const void* k;         // (unused since the L2-prefetch experiment left the kernel)
   const void* v;
   Strides4 sk, sv;
   void* dq;
@@ -241,9 +241,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   uint64_t* drain_done = dq_free + 2; // [2] ring drain of tile n finished      (epilogue group n & 1 -> issuers V, K)
   uint64_t* delta_ready = drain_done + 2;   // [2] delta rows of tile n in delta_s[n & 1]   (epilogue group n & 1 -> math)
   uint64_t* delta_free = delta_ready + 2;   // [2] ... read by every math thread            (math -> epilogue group)
-  uint64_t* kq_issued = delta_free + 2;    // dK^T(n) and dQ(n) have been ISSUED (issuers K, Q -> issuer A): dP(n + 1) is
-                                            // queued behind them in the tensor pipe, not in front (both are released
-                                            // by the end of pass 2(n), but only dK / dQ gate the next pass 2)
+  uint64_t* kq_issued = delta_free + 2;    // unused (the dP-ordering experiment it served is gone); keeps the layout
   uint64_t* o_full = kq_issued + 1;         // [8 blocks of 16 rows][2]: O rows of tile n in block j: barrier [j][n & 1], phase
                                             // (n >> 1) & 1 -- per tile parity because the epilogue groups take alternate
                                             // tiles (a parity wait cannot tell phase n from phase n - 2)
