@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   uint64_t* k_full = q_empty + 2;
   uint64_t* k_empty = k_full + 2;     //      dQ(n) complete
   uint64_t* do_full = k_empty + 2;
-  uint64_t* do_empty = do_full + 2;   //      dV^T(n) complete (+ delta(n) computed: the four warps of its epilogue group)
+  uint64_t* do_empty = do_full + 2;   //      dV^T(n) complete (+ delta(n) computed: the four warps of epilogue group (n & 1) ^ 1)
   uint64_t* v_full = do_empty + 2;    // [0]: V(n), phase n & 1;  [1]: unused
   uint64_t* v_empty = v_full + 2;     // [0]: dP(n) complete;     [1]: unused
   uint64_t* s_full = v_empty + 2;     // S(n) complete                          (issuer A -> math)
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(FusedCfg::kThreads, 1) bwd_fused64_kernel(cons
   uint64_t* dq_done = ds_free + 1;    // [2] all UMMAs of tile n complete       (issuers V + K -> epilogue group n & 1)
   uint64_t* dq_free = dq_done + 2;    // [2] dQ(n) read                         (epilogue group n & 1 -> issuer K)
   uint64_t* drain_done = dq_free + 2; // [2] ring drain of tile n finished      (epilogue group n & 1 -> issuers V, K)
-  uint64_t* delta_ready = drain_done + 2;   // [2] delta rows of tile n in delta_s[n & 1]   (epilogue group n & 1 -> math)
+  uint64_t* delta_ready = drain_done + 2;   // [2] delta rows of tile n in delta_s[n & 1]   (the OTHER epilogue group, (n & 1) ^ 1 -> math)
   uint64_t* delta_free = delta_ready + 2;   // [2] ... read by every math thread            (math -> epilogue group)
   uint64_t* kq_issued = delta_free + 2;    // unused (the dP-ordering experiment it served is gone); keeps the layout
   uint64_t* o_full = kq_issued + 1;         // [8 blocks of 16 rows][2]: O rows of tile n in block j: barrier [j][n & 1], phase
