@@ -26,6 +26,13 @@
 #include "attn_common.cuh"
 #include "tmap.cuh"
 
+// The in-kernel delta variant of dq64_kernel (delta = rowsum(P o dP) in the dS warps; measured slower and less accurate,
+// see fuses_delta below) is compiled in only with -DSFA_DQ64_FUSE_DELTA_CODE=1: cold code in a hot role is not free in
+// these kernels (bwdf_sm100.cu: 10 KB of switched-off experiments cost the fused backward 3 us).
+#ifndef SFA_DQ64_FUSE_DELTA_CODE
+#define SFA_DQ64_FUSE_DELTA_CODE 0
+#endif
+
 namespace sfa {
 namespace {
 
@@ -773,8 +780,8 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
       // ---------------------------------------------------------------- dS warps
       ItemWalk w(a);
       // prefetched per tile: delta of this row (preprocessed), or -- with fused delta -- its lse (for ds_aux)
-      const float* pre_src = a.fuse_delta ? a.lse : a.delta;
-      const bool pre_on = !a.fuse_delta || a.dsrow != nullptr;
+      const float* pre_src = (SFA_DQ64_FUSE_DELTA_CODE && a.fuse_delta) ? a.lse : a.delta;
+      const bool pre_on = !(SFA_DQ64_FUSE_DELTA_CODE && a.fuse_delta) || a.dsrow != nullptr;
       float pre_next, pre_cur = 0.f, delta = 0.f;
       int i = 0, mtc = 0;
       {
@@ -806,7 +813,7 @@ __global__ void __launch_bounds__(Dq64Cfg::kThreads, 1) dq64_kernel(const __grid
         mbar_wait(dp_full, w.n & 1);
         tc_fence_after();
         if (threadIdx.x == 128) trace_ev(a.trace, 5, mtc, 2, w.n);
-        if (a.fuse_delta) {
+        if (SFA_DQ64_FUSE_DELTA_CODE && a.fuse_delta) {
           // delta = sum over the attended columns of P * dP (one extra sweep over this tile's single KV item)
           float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -1867,7 +1874,7 @@ int sm_count() { return device_sm_count(); }
 // (which sit on the dS -> dP -> dS critical chain) 35 us, and delta from 16-bit P puts ds_aux 1.4e-2 away from
 // the fp32 path (the bar is 2e-3).  SFA_FUSE_DELTA=1 enables it for experiments.
 inline bool fuses_delta(const AttnParams& p, int P, int BN) {
-  static const bool enabled = getenv("SFA_FUSE_DELTA") != nullptr;
+  static const bool enabled = SFA_DQ64_FUSE_DELTA_CODE && getenv("SFA_FUSE_DELTA") != nullptr;
   const int64_t span = (int64_t)(p.W < p.N ? p.W : p.N) + P - 1;
   return enabled && p.S == 0 && p.W > 0 && span <= BN;
 }
