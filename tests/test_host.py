@@ -73,6 +73,26 @@ def test_argument_errors_come_back_through_the_abi():
     assert rc < 0 and b"null" in lib.sfa_last_error()
     rc = lib.sfa_set_impl(99)
     assert rc < 0
+    # paged decode: argument checks happen before any CUDA call
+    a2, a3 = (ctypes.c_int64 * 2)(64, 64), (ctypes.c_int64 * 3)(1, 1, 1)
+    dummy = ctypes.c_void_p(16)
+    rc = lib.sfa_decode_paged(dummy, dummy, dummy, dummy, None, dummy, None, 1, 8, 2, 100, 64, 0, 48, 4, a2, a3, a3, a2,
+                              None, 0, None)
+    assert rc < 0 and b"power of two" in lib.sfa_last_error()
+    rc = lib.sfa_decode_paged(dummy, None, dummy, dummy, None, dummy, None, 1, 8, 2, 100, 64, 0, 64, 4, a2, a3, a3, a2,
+                              None, 0, None)
+    assert rc < 0 and b"null" in lib.sfa_last_error()
+
+
+def test_paged_decode_wrappers_refuse_cpu_tensors():
+    q = torch.randn(2, 8, 1, 64)
+    pool = torch.randn(4, 32, 2, 64)
+    bt = torch.zeros(2, 2, dtype=torch.int32)
+    sl = torch.tensor([10, 40], dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sa.sink_decode_attention_paged(q, pool, pool, bt, sl)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sa.sink_decode_attention_varlen(q, torch.randn(2, 2, 40, 64), torch.randn(2, 2, 40, 64), sl)
 
 
 # ------------------------------------------------------------------------------------------------ cache
