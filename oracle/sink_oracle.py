@@ -297,6 +297,36 @@ def decode_attention(q, k, v, s_aux=None, dtype=torch.float64):
     return torch.matmul(p, vf)
 
 
+def decode_attention_paged(q, k_cache, v_cache, block_table, seq_lens, s_aux=None, dtype=torch.float64):
+    """Checker for the paged / per-batch-length decode (SURVEY section 8 row f4 -- beyond the reference, whose cache
+    shares ONE length across the batch and is contiguous, cache.py:11-13): row b attends the first seq_lens[b] keys of
+    the logical sequence block_table[b] spells out over the page pool [num_pages, page_size, H_kv, D]; per row it is
+    exactly decode_attention (decode_kernel.py:205-226 restated).  block_table None: k_cache / v_cache are
+    [B, H_kv, N_max, D].  A row without keys returns zeros (only the s_aux column is attended)."""
+    B = q.shape[0]
+    outs = []
+    for b in range(B):
+        n = int(seq_lens[b]) if seq_lens is not None else None
+        if block_table is None:
+            kb, vb = k_cache[b:b + 1], v_cache[b:b + 1]
+            if n is not None:
+                kb, vb = kb[:, :, :n], vb[:, :, :n]
+        else:
+            page = k_cache.shape[1]
+            n = block_table.shape[1] * page if n is None else n
+            npg = (n + page - 1) // page
+            if npg:
+                kb = torch.cat([k_cache[int(block_table[b, j])] for j in range(npg)], dim=0)[:n].transpose(0, 1)[None]
+                vb = torch.cat([v_cache[int(block_table[b, j])] for j in range(npg)], dim=0)[:n].transpose(0, 1)[None]
+            else:
+                kb = vb = k_cache.new_zeros(1, k_cache.shape[2], 0, k_cache.shape[3])
+        if kb.shape[2] == 0:
+            outs.append(torch.zeros(1, q.shape[1], 1, q.shape[3], dtype=dtype))
+        else:
+            outs.append(decode_attention(q[b:b + 1], kb, vb, s_aux, dtype=dtype))
+    return torch.cat(outs, dim=0)
+
+
 # ---------------------------------------------------------------------------
 # cache (sink buffer + ring window buffer) -- pure-Python model of cache.py
 # ---------------------------------------------------------------------------

@@ -193,6 +193,7 @@ def test_decode_per_batch_lengths(dtype, B, Hq, Hkv, D, Nmax, lens, use_aux):
     assert _lib.last_impl() == "mma"
     ref = _decode_rows_oracle(q, [k[b, :, :lens[b]] for b in range(B)], [v[b, :, :lens[b]] for b in range(B)], s_aux)
     assert maxdiff(o, ref) < 1e-2
+    assert maxdiff(o, orc.decode_attention_paged(q, k, v, None, lens, s_aux)) < 1e-2
     # equal lengths == the reference entry point, bit for bit (same kernel body, same key ranges)
     full = torch.full((B,), Nmax, dtype=torch.int32, device="cuda")
     o_full = sa.sink_decode_attention_varlen(q.cuda(), k.cuda(), v.cuda(), full, s_aux.cuda() if use_aux else None)
@@ -235,6 +236,7 @@ def test_decode_paged_kv(dtype, B, Hq, Hkv, D, page, max_pages, lens, use_aux):
         return out
     ref = _decode_rows_oracle(q, rows(k_cache), rows(v_cache), s_aux)
     assert maxdiff(o, ref) < 1e-2
+    assert maxdiff(o, orc.decode_attention_paged(q, k_cache, v_cache, perm, lens, s_aux)) < 1e-2     # the oracle's own paging
     # the default planning length (the table's capacity) gives the same rows
     o2 = sa.sink_decode_attention_paged(q.cuda(), k_cache.cuda(), v_cache.cuda(), perm.cuda(), sl,
                                         s_aux.cuda() if use_aux else None)

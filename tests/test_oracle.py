@@ -112,3 +112,32 @@ def test_sampled_oracle_matches_full_oracle(shape):
     for got, ref in ((o_s, o), (dq_s, dq), (dk_s, dk), (dv_s, dv)):
         assert (got - ref.reshape(-1, D)).abs().max().item() < 1e-12
     assert (l_s - lse.reshape(-1)).abs().max().item() < 1e-12
+
+
+def test_paged_decode_oracle_equals_contiguous_rows():
+    """The paged / per-batch-length checker is decode_attention per row: an identity block table over a pool cut from a
+    contiguous cache gives the contiguous result, a permuted pool with the matching table gives the same rows, and a
+    shorter seq_len equals decoding over the truncated cache."""
+    g = torch.Generator().manual_seed(5)
+    B, Hq, Hkv, D, page, npg = 3, 8, 2, 16, 4, 5
+    N = page * npg
+    q = torch.randn(B, Hq, 1, D, generator=g)
+    k = torch.randn(B, Hkv, N, D, generator=g)
+    v = torch.randn(B, Hkv, N, D, generator=g)
+    s_aux = torch.randn(Hq, generator=g)
+    full = orc.decode_attention(q, k, v, s_aux)
+    pool_k = k.transpose(1, 2).reshape(B * npg, page, Hkv, D)        # [B, N, Hkv, D] -> pages
+    pool_v = v.transpose(1, 2).reshape(B * npg, page, Hkv, D)
+    table = torch.arange(B * npg).view(B, npg)
+    lens = torch.full((B,), N)
+    assert torch.allclose(orc.decode_attention_paged(q, pool_k, pool_v, table, lens, s_aux), full, atol=1e-12)
+    perm = torch.randperm(B * npg, generator=g)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(B * npg)
+    assert torch.allclose(orc.decode_attention_paged(q, pool_k[perm], pool_v[perm], inv[table], lens, s_aux), full, atol=1e-12)
+    lens = torch.tensor([7, 0, N])
+    out = orc.decode_attention_paged(q, pool_k, pool_v, table, lens, s_aux)
+    assert torch.allclose(out[0:1], orc.decode_attention(q[0:1], k[0:1, :, :7], v[0:1, :, :7], s_aux), atol=1e-12)
+    assert float(out[1].abs().max()) == 0.0
+    assert torch.allclose(out[2:3], full[2:3], atol=1e-12)
+    assert torch.allclose(orc.decode_attention_paged(q, k, v, None, lens, s_aux), out, atol=1e-12)
